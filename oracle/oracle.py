@@ -1,0 +1,366 @@
+"""CPU oracle for eQ's HSL diffusion hot path -- numpy/scipy front end.
+
+TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / ``--impl reference`` legs; never by eq_b200/.
+
+It drives oracle/eq_oracle.c (the C restatement; every function there cites the
+reference file:line it follows) and adds the pieces that live in third-party
+code upstream: the sparse direct solve behind ``LVS->solve()``
+(src/fHSL.cpp:106; DOLFIN 2019.1.0 default "lu" [ext]) is SciPy's SuperLU.
+
+Parity pinning: see the header of eq_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+c_dp = C.POINTER(C.c_double)
+c_lp = C.POINTER(C.c_long)
+c_u8p = C.POINTER(C.c_uint8)
+
+CELL_STRIDE = 16
+NBAND = 7
+
+
+def build(quiet: bool = True) -> None:
+    """Compile libeq_oracle.so (and oracle/_ref when /root/reference exists)."""
+    subprocess.run(["make", "-C", _HERE, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libeq_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.eqo_cg.restype = C.c_long
+        L.eqo_raster_cell.restype = C.c_long
+        L.eqo_boundary_functional.restype = C.c_double
+        L.eqo_boundary_facet.restype = C.c_double
+        L.eqo_deposit_per_point.restype = C.c_double
+        L.eqo_point_in_cell.restype = C.c_int
+        L.eqo_num_threads.restype = C.c_int
+        L.eqo_assemble.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def ref_lib():
+    """The reference's own generated kernels (oracle/_ref), or None."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libeq_ufc_ref.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_boundary_facet.restype = C.c_double
+        _REF = R
+    return _REF
+
+
+# --------------------------------------------------------------------------
+# problem description (mirrors the parameters fenicsInterface reads:
+# src/eQ.h:305-321 and the eQ::data::parameters keys of SURVEY.md 8b)
+# --------------------------------------------------------------------------
+NEUMANN, DIRICHLET, ROBIN, DIRICHLET_CHANNEL = 0, 1, 2, 3
+LEFT, RIGHT, TOP, BOTTOM = 0, 1, 2, 3
+
+
+@dataclass
+class Problem:
+    nW: int
+    nH: int
+    h: float = 0.5
+    dt: float = 0.1
+    D: float = 1200.0
+    # per wall (left,right,top,bottom): type and value (Dirichlet value / Robin rate)
+    bc_type: tuple = (DIRICHLET, DIRICHLET, DIRICHLET, DIRICHLET)
+    bc_value: tuple = (0.0, 0.0, 0.0, 0.0)
+    robin_s: tuple = (0.0, 0.0)
+    # channels (src/fHSL.cpp:110-152)
+    channels: bool = False
+    channel_v: float = 120.0
+    channel_r: tuple = (0.0, 0.0)      # Robin rates at channel ends (left,right)
+    channel_iters: int = 48
+    well_scaling: float = 25.0
+    d11: np.ndarray | None = None
+    d22: np.ndarray | None = None
+    d12: np.ndarray | None = None
+
+    @property
+    def N(self):
+        return self.nW * self.nH
+
+    @property
+    def W(self):
+        return (self.nW - 1) * self.h
+
+    @property
+    def H(self):
+        return (self.nH - 1) * self.h
+
+    @property
+    def use_robin(self):
+        return self.bc_type[LEFT] == ROBIN or self.bc_type[RIGHT] == ROBIN
+
+
+def assemble(p: Problem, u0: np.ndarray | None, want_matrix=True):
+    """Unconstrained (bands, b) as DOLFIN would assemble hslD's a and L."""
+    L = lib()
+    N = p.N
+    bands = np.zeros((NBAND, N)) if want_matrix else None
+    b = np.zeros(N)
+    r1 = p.bc_value[LEFT] if p.bc_type[LEFT] == ROBIN else 0.0
+    r2 = p.bc_value[RIGHT] if p.bc_type[RIGHT] == ROBIN else 0.0
+    rc = L.eqo_assemble(C.c_long(p.nW), C.c_long(p.nH), C.c_double(p.W), C.c_double(p.H),
+                        C.c_double(p.D), C.c_double(p.dt), _dp(p.d11), _dp(p.d22), _dp(p.d12),
+                        C.c_int(1 if p.use_robin else 0), C.c_double(r1), C.c_double(p.robin_s[0]),
+                        C.c_double(r2), C.c_double(p.robin_s[1]),
+                        _dp(u0), C.c_double(0.0), _dp(bands), _dp(b))
+    assert rc == 0
+    return bands, b
+
+
+def dirichlet(p: Problem, top_vals=None, bottom_vals=None):
+    L = lib()
+    is_dir = (C.c_int * 4)(*[1 if t in (DIRICHLET, DIRICHLET_CHANNEL) else 0 for t in p.bc_type])
+    val = (C.c_double * 4)(*[float(v) for v in p.bc_value])
+    mask = np.zeros(p.N, dtype=np.uint8)
+    g = np.zeros(p.N)
+    tv = np.ascontiguousarray(top_vals, dtype=np.float64) if top_vals is not None else None
+    bv = np.ascontiguousarray(bottom_vals, dtype=np.float64) if bottom_vals is not None else None
+    L.eqo_dirichlet_mask(C.c_long(p.nW), C.c_long(p.nH), is_dir, val, _dp(tv), _dp(bv),
+                         mask.ctypes.data_as(c_u8p), _dp(g))
+    return mask, g
+
+
+def bands_to_csr(p: Problem, bands):
+    import scipy.sparse as sp
+    off = (C.c_long * NBAND)()
+    lib().eqo_band_offsets(C.c_long(p.nW), off)
+    N = p.N
+    diags = []
+    offs = []
+    for k in range(NBAND):
+        o = off[k]
+        d = bands[k]
+        # scipy dia: data[k, j] = A[j - o, j]; we hold row-indexed A[i, i+o]
+        arr = np.zeros(N)
+        if o >= 0:
+            arr[o:] = d[:N - o]
+        else:
+            arr[:N + o] = d[-o:]
+        diags.append(arr)
+        offs.append(o)
+    return sp.dia_matrix((np.array(diags), offs), shape=(N, N)).tocsc()
+
+
+def solve_lu(p: Problem, u0, top_vals=None, bottom_vals=None, symmetric=False):
+    """One backward-Euler solve the way src/fHSL.cpp:104-108 does it:
+    assemble, apply DirichletBC (identity rows), sparse direct LU."""
+    import scipy.sparse.linalg as spla
+    bands, b = assemble(p, u0)
+    mask, g = dirichlet(p, top_vals, bottom_vals)
+    L = lib()
+    if mask.any():
+        if symmetric:
+            L.eqo_apply_dirichlet_sym(C.c_long(p.nW), C.c_long(p.nH), _dp(bands), _dp(b),
+                                      mask.ctypes.data_as(c_u8p), _dp(g))
+        else:
+            L.eqo_apply_dirichlet_rows(C.c_long(p.N), _dp(bands), _dp(b),
+                                       mask.ctypes.data_as(c_u8p), _dp(g))
+    A = bands_to_csr(p, bands)
+    lu = spla.splu(A)
+    return lu.solve(b)
+
+
+def solve_cg(p: Problem, u0, top_vals=None, bottom_vals=None, rtol=1e-13, maxit=200000, x0=None):
+    """Same system, symmetric elimination + Jacobi-CG (for meshes too large for LU)."""
+    bands, b = assemble(p, u0)
+    mask, g = dirichlet(p, top_vals, bottom_vals)
+    L = lib()
+    L.eqo_apply_dirichlet_sym(C.c_long(p.nW), C.c_long(p.nH), _dp(bands), _dp(b),
+                              mask.ctypes.data_as(c_u8p), _dp(g))
+    x = np.array(u0 if x0 is None else x0, dtype=np.float64, copy=True)
+    x[mask != 0] = g[mask != 0]
+    rel = C.c_double(0.0)
+    it = L.eqo_cg(C.c_long(p.nW), C.c_long(p.nH), _dp(bands), _dp(b), _dp(x),
+                  C.c_double(rtol), C.c_long(maxit), C.byref(rel))
+    return x, it, rel.value
+
+
+def band_matvec(p: Problem, bands, x):
+    y = np.zeros(p.N)
+    lib().eqo_band_matvec(C.c_long(p.nW), C.c_long(p.nH), _dp(bands), _dp(np.ascontiguousarray(x)), _dp(y))
+    return y
+
+
+def boundary_functional(p: Problem, u):
+    return lib().eqo_boundary_functional(C.c_long(p.nW), C.c_long(p.nH), C.c_double(p.W),
+                                         C.c_double(p.H), _dp(np.ascontiguousarray(u)))
+
+
+def compute_boundary_flux(p: Problem, u):
+    fb = np.zeros(p.nW)
+    ft = np.zeros(p.nW)
+    lib().eqo_compute_boundary_flux(C.c_long(p.nW), C.c_long(p.nH), _dp(np.ascontiguousarray(u)),
+                                    C.c_double(p.h), C.c_double(p.dt), C.c_double(p.D),
+                                    C.c_double(p.well_scaling), _dp(fb), _dp(ft))
+    return fb, ft
+
+
+def channel_substeps(p: Problem, flux, u):
+    u = np.array(u, dtype=np.float64, copy=True)
+    lib().eqo_channel_substeps(C.c_long(p.nW), C.c_double(p.W), C.c_double(p.dt),
+                               C.c_long(p.channel_iters), C.c_double(p.D), C.c_double(p.channel_v),
+                               C.c_double(p.channel_r[0]), C.c_double(0.0),
+                               C.c_double(p.channel_r[1]), C.c_double(0.0),
+                               _dp(np.ascontiguousarray(flux)), _dp(u))
+    return u
+
+
+def robin_rates(v, D, L_left, L_right):
+    a = C.c_double()
+    b = C.c_double()
+    lib().eqo_robin_rates(C.c_double(v), C.c_double(D), C.c_double(L_left), C.c_double(L_right),
+                          C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+@dataclass
+class State:
+    """Mutable solver state of one layer (what fenicsInterface holds)."""
+    u: np.ndarray
+    top: np.ndarray
+    bottom: np.ndarray
+    total_boundary_flux: float = 0.0
+    info: dict = field(default_factory=dict)
+
+
+def new_state(p: Problem) -> State:
+    return State(u=np.zeros(p.N), top=np.zeros(p.nW), bottom=np.zeros(p.nW))
+
+
+def step(p: Problem, s: State, solver="lu") -> State:
+    """fenicsInterface::stepDiffusion, src/fHSL.cpp:98-161.  s.u holds the
+    previous solution plus the cell deposits (what the controller sent)."""
+    top_vals = s.top if p.bc_type[TOP] == DIRICHLET_CHANNEL else None
+    bot_vals = s.bottom if p.bc_type[BOTTOM] == DIRICHLET_CHANNEL else None
+    if solver == "lu":
+        u = solve_lu(p, s.u, top_vals, bot_vals)
+    else:
+        u, it, rel = solve_cg(p, s.u, top_vals, bot_vals)
+        s.info["cg_iters"] = it
+        s.info["cg_relres"] = rel
+    s.u = u
+    if p.channels:
+        fb, ft = compute_boundary_flux(p, u)
+        s.top = channel_substeps(p, ft, s.top)
+        s.bottom = channel_substeps(p, fb, s.bottom)
+    s.total_boundary_flux = p.D * p.dt * boundary_functional(p, u)
+    return s
+
+
+# --------------------------------------------------------------------------
+# cells
+# --------------------------------------------------------------------------
+def make_cells(centers, angles, lengths, trapW, trapH, width=1.0):
+    n = len(angles)
+    rec = np.zeros((n, CELL_STRIDE))
+    L = lib()
+    for k in range(n):
+        L.eqo_make_cell(C.c_double(centers[k][0]), C.c_double(centers[k][1]), C.c_double(angles[k]),
+                        C.c_double(lengths[k]), C.c_double(width), C.c_double(trapW), C.c_double(trapH),
+                        rec[k].ctypes.data_as(c_dp))
+    return rec
+
+
+def nodes_to_edge(npm):
+    # src/abm/eQabm.cpp:75
+    return int(round(npm * 1.0 / 2.0))
+
+
+def raster(cells, npm, nH, nW, cap=512):
+    n = cells.shape[0]
+    counts = np.zeros(n, dtype=np.int64)
+    nodes = np.full((n, cap), -1, dtype=np.int64)
+    lib().eqo_raster(_dp(cells), C.c_long(n), C.c_double(npm), C.c_long(nH), C.c_long(nW),
+                     C.c_long(nodes_to_edge(npm)), counts.ctypes.data_as(c_lp),
+                     nodes.ctypes.data_as(c_lp), C.c_long(cap))
+    return counts, nodes
+
+
+def gather(cells, npm, nH, nW, u):
+    out = np.zeros(cells.shape[0])
+    lib().eqo_gather(_dp(cells), C.c_long(cells.shape[0]), C.c_double(npm), C.c_long(nH), C.c_long(nW),
+                     C.c_long(nodes_to_edge(npm)), _dp(np.ascontiguousarray(u)), _dp(out))
+    return out
+
+
+def scatter(cells, npm, nH, nW, amount_nM, u):
+    u = np.array(u, dtype=np.float64, copy=True)
+    lib().eqo_scatter(_dp(cells), C.c_long(cells.shape[0]), C.c_double(npm), C.c_long(nH), C.c_long(nW),
+                      C.c_long(nodes_to_edge(npm)), _dp(np.ascontiguousarray(amount_nM)), _dp(u))
+    return u
+
+
+def update_cells_sequential(cells, npm, nH, nW, a0, a1, u):
+    u = np.array(u, dtype=np.float64, copy=True)
+    g = np.zeros(cells.shape[0])
+    lib().eqo_update_cells_sequential(_dp(cells), C.c_long(cells.shape[0]), C.c_double(npm),
+                                      C.c_long(nH), C.c_long(nW), C.c_long(nodes_to_edge(npm)),
+                                      _dp(np.ascontiguousarray(a0)), C.c_double(a1), _dp(u), _dp(g))
+    return u, g
+
+
+def synthetic_colony(n, trapW, trapH, seed=12345, min_clear=1.2, margin=3.0):
+    """Config-3 style colony: centres uniform in [margin, W-margin] x
+    [margin, H-margin], angle U[0,2pi), length (1+U)*0.5*4.2 (src/abm/eQabm.cpp:115),
+    rejection-sampled so rods are pairwise separated (scatter order-independent)."""
+    rng = np.random.default_rng(seed)
+    cell = 6.0  # hash-grid pitch > max rod length + clearance
+    gx = int(np.ceil(trapW / cell)) + 1
+    grid: dict = {}
+    centers, angles, lengths = [], [], []
+    tries = 0
+    while len(angles) < n and tries < 200 * n:
+        tries += 1
+        x = rng.uniform(margin, trapW - margin)
+        y = rng.uniform(margin, trapH - margin)
+        a = rng.uniform(0.0, 2 * np.pi)
+        L = (1.0 + rng.uniform()) * 0.5 * 4.2
+        ix, iy = int(x / cell), int(y / cell)
+        ok = True
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for (ox, oy, oL) in grid.get((ix + dx) + gx * (iy + dy), ()):
+                    # conservative: treat rods as discs of radius L/2 + 0.5
+                    if (ox - x) ** 2 + (oy - y) ** 2 < (0.5 * (L + oL) + 1.0 + min_clear) ** 2:
+                        ok = False
+                        break
+                if not ok:
+                    break
+            if not ok:
+                break
+        if not ok:
+            continue
+        grid.setdefault(ix + gx * iy, []).append((x, y, L))
+        centers.append((x, y))
+        angles.append(a)
+        lengths.append(L)
+    return make_cells(centers, angles, lengths, trapW, trapH)

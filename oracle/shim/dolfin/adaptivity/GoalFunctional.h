@@ -1,0 +1,1 @@
+#include "dolfin_stub.h"
