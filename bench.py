@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- HSL diffusion steps/sec at the 2048^2 mesh (BASELINE.json metric).
+
+A "step" = one pass of the hot path over one layer: gather (readHSL) ->
+scatter-add (writeHSL) -> backward-Euler solve to rel. residual 1e-12 ->
+boundary-flux functional, i.e. eQabm::updateCells' lambdas + fenicsInterface::
+stepDiffusion (src/abm/eQabm.cpp:268-359, src/fHSL.cpp:98-161) for BASELINE
+configs[2]: synthetic 2048^2-node trap, 20k rods, single GPU.
+
+N > 1 (torchrun, one rank per GPU): one independent HSL layer per GPU, the
+reference's own MPI model (src/simulation.cpp:628-645) -> weak scaling, no
+data-path collective.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NW = NH = 2048
+NCELLS = 20000
+H, DT, D = 0.5, 0.1, 1200.0
+NPM = 2.0
+METRIC = "hsl_diffusion_steps_per_sec_2048x2048"
+UNIT = "steps/s"
+WORKLOAD = ("configs[2]: synthetic 2048x2048-node trap mesh (h=0.5, dt=0.1, D=1200, Dirichlet-0 walls), "
+            "20k rod cells secreting/sampling, one HSL layer per GPU")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(sample_n=512, threads=1):
+    """Restated reference CPU path ("Fenics-equivalent": re-assemble, DirichletBC, sparse direct LU
+    every step, src/fHSL.cpp:104-108) on a bounded sample, scaled to the 2048^2 metric by DOF count."""
+    from oracle import oracle as O
+    p = O.Problem(nW=sample_n, nH=sample_n, h=H, dt=DT, D=D)
+    cells = O.synthetic_colony(int(NCELLS * (sample_n / NW) ** 2), p.W, p.H)
+    u = np.zeros(p.N)
+    t0 = time.perf_counter()
+    amount = 100.0 + 0.0 * O.gather(cells, NPM, p.nH, p.nW, u)
+    u = O.scatter(cells, NPM, p.nH, p.nW, amount, u)
+    s = O.new_state(p)
+    s.u = u
+    O.step(p, s, solver="lu")
+    dt = time.perf_counter() - t0
+    value = (1.0 / dt) * (p.N / float(NW * NH))
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"one full step (gather+scatter+assemble+DirichletBC+SuperLU factor/solve+flux) on a "
+                       f"{sample_n}x{sample_n} mesh with {len(cells)} rods in {dt:.2f} s, scaled by DOF ratio "
+                       f"{p.N}/{NW * NH} to the 2048^2 metric (LU cost is superlinear, so this flatters the CPU)"),
+            "seconds": dt}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; the Fenics/PETSc original cannot be
+    built here) timed on the host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    n = 320
+    p = O.Problem(nW=n, nH=n, h=H, dt=DT, D=D)
+    cells = O.synthetic_colony(int(NCELLS * (n / NW) ** 2), p.W, p.H)
+    s = O.new_state(p)
+
+    def one():
+        amount = 100.0 + 0.0 * O.gather(cells, NPM, p.nH, p.nW, s.u)
+        s.u = O.scatter(cells, NPM, p.nH, p.nW, amount, s.u)
+        O.step(p, s, solver="lu")
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = (1.0 / dt) * (p.N / float(NW * NH))
+    sample = (f"each step = one full step on a {n}x{n} mesh with {len(cells)} rods (SuperLU, 1 thread: one MPI "
+              f"rank per layer upstream), scaled by DOF ratio to 2048^2")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (NW * NH) / p.N,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="eq_b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import eq_b200 as E
+    from oracle import oracle as O  # synthetic colony generator + cpu_baseline only
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    g = E.GpuHSL(NW, NH, h=H, dt=DT, D=D, device=local_rank, stream=stream.cuda_stream)
+    W = (NW - 1) * H
+    cells = O.synthetic_colony(NCELLS, W, W, seed=12345 + rank)
+    ncells = len(cells)
+    amount = np.full(ncells, 100.0)  # nM per step
+    g.upload_cells(cells, NPM)
+    g.set_amounts(amount)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        g.gather_resident()
+        g.scatter_resident()
+        g.step()
+
+    # pinned host buffers for the end-to-end legs
+    rec_pin = torch.from_numpy(cells.copy()).pin_memory()
+    amt_pin = torch.from_numpy(amount.copy()).pin_memory()
+    out_pin = torch.zeros(ncells, dtype=torch.float64).pin_memory()
+    fld_pin = torch.zeros(NW * NH, dtype=torch.float64).pin_memory()
+    import ctypes as C
+    dpp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    L = E.lib()
+
+    def step_e2e():
+        # fused drop-in: only per-cell data crosses PCIe (cell records in, sampled HSL out, deposits in)
+        g._ck(L.eqgpu_cells_upload(g._h, dpp(rec_pin), C.c_int64(ncells), C.c_double(NPM)))
+        g._ck(L.eqgpu_cells_gather(g._h, dpp(out_pin)))
+        g._ck(L.eqgpu_cells_scatter(g._h, dpp(amt_pin)))
+        g.step()
+        return g.stats().total_boundary_flux
+
+    def step_compat():
+        # strict drop-in: fenicsInterface's host solution_vector in and out every step
+        g.step_host_ptr(fld_pin.data_ptr())
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = g.stats().kernel_launches
+    ms = timed(step_resident, args.steps)
+    launches = g.stats().kernel_launches - l0
+    iters = g.stats().iterations
+    relres = g.stats().relres
+    clocks = sampler.stop()
+    ms_step = ms / args.steps
+    value = world * args.steps / (ms / 1e3)
+
+    for _ in range(3):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    g.set_field(np.zeros(NW * NH))
+    for _ in range(3):
+        step_compat()
+    ms_compat = timed(step_compat, max(3, args.steps // 5)) / max(3, args.steps // 5)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # dominant kernel, timed alone with CUDA events on the launching stream
+        roof = {}
+        for name in ("jacobi", "apply", "update_xr"):
+            kms, kbytes = g.bench_kernel(name, 50)
+            roof[name] = {"ms": kms, "bytes": kbytes, "gbs": kbytes / (kms * 1e-3) / 1e9}
+        dom = "jacobi"
+        N = NW * NH
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rods": ncells, "pcg_iterations": int(iters),
+                       "relres": relres, "rtol": 1e-12, "mg_levels": int(g.stats().levels),
+                       "parallelism": f"layer-per-gpu x{world}",
+                       "l2": "working set (6 fine fp64 vectors = 201 MB + MG hierarchy) exceeds the 126 MB L2; no explicit flush",
+                       "dof_updates_per_sec": value * N},
+            "clocks": clocks,
+            "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(rec_pin.numel() * 8 + amt_pin.numel() * 8),
+                    "d2h_bytes_per_step": int(out_pin.numel() * 8 + 8),
+                    "path": "eqgpu_cells_upload+gather+scatter+step with pinned host buffers (field stays in HBM)"},
+            "e2e_compat": {"value": world * 1e3 / ms_compat, "unit": UNIT,
+                           "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
+                           "path": "eqgpu_step_host: fenicsInterface::stepDiffusion contract, full solution_vector in/out"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": f"k_{dom} (level-0)", "achieved": roof[dom]["gbs"],
+                         "peak": peak, "unit": "GB/s", "frac": roof[dom]["gbs"] / peak, "traffic": None,
+                         "peak_source": peak_src, "kernels": roof,
+                         "step_ideal_frac": (16.0 * N / (ms_step * 1e-3) / 1e9) / peak},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,279 @@
+"""eq_b200 -- B200-native drop-in for eQ's HSL diffusion hot path.
+
+Python is plumbing only: this module loads ``eq_b200/csrc/libeqgpu.so`` (the
+C-ABI declared in ``include/eqgpu.h``) with ctypes and mirrors the public
+surface of the reference's ``fenicsInterface`` (src/fHSL.h:333-449) --
+``initDiffusion / stepDiffusion / solution_vector / totalBoundaryFlux /
+setBoundaryValues`` -- so the parity tests read like calls on the reference
+class.  There is no CPU path: if the CUDA library is missing or no GPU is
+present the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libeqgpu.so")
+
+NEUMANN, DIRICHLET, ROBIN, DIRICHLET_CHANNEL = 0, 1, 2, 3
+LEFT, RIGHT, TOP, BOTTOM = 0, 1, 2, 3
+CELL_STRIDE = 16
+
+API_SYMBOLS = [
+    "eqgpu_default_params", "eqgpu_create", "eqgpu_destroy", "eqgpu_last_error",
+    "eqgpu_set_field", "eqgpu_get_field", "eqgpu_set_tensor", "eqgpu_set_boundary_value",
+    "eqgpu_step", "eqgpu_step_host", "eqgpu_get_stats", "eqgpu_get_channels",
+    "eqgpu_set_channels", "eqgpu_get_channel_flux", "eqgpu_cells_upload", "eqgpu_cells_raster",
+    "eqgpu_cells_gather", "eqgpu_cells_scatter", "eqgpu_apply_operator", "eqgpu_build_rhs",
+    "eqgpu_field_device_ptr", "eqgpu_sync", "eqgpu_cells_set_amounts",
+    "eqgpu_cells_gather_resident", "eqgpu_cells_scatter_resident", "eqgpu_cells_get_gathered",
+    "eqgpu_bench_kernel",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("nW", C.c_int32), ("nH", C.c_int32),
+        ("hx", C.c_double), ("hy", C.c_double), ("dt", C.c_double), ("D", C.c_double),
+        ("bc_type", C.c_int32 * 4), ("bc_value", C.c_double * 4), ("robin_s", C.c_double * 2),
+        ("channels", C.c_int32), ("channel_iters", C.c_int32), ("channel_v", C.c_double),
+        ("channel_r", C.c_double * 2), ("well_scaling", C.c_double), ("rtol", C.c_double),
+        ("max_iters", C.c_int32), ("device", C.c_int32), ("stream", C.c_void_p),
+        ("smooth_sweeps", C.c_int32), ("max_levels", C.c_int32), ("reserved", C.c_int32 * 8),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int32), ("levels", C.c_int32), ("relres", C.c_double),
+        ("total_boundary_flux", C.c_double), ("kernel_launches", C.c_int64), ("steps", C.c_int64),
+    ]
+
+
+class EqGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libeqgpu.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j4", "all"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded C-ABI.  Fails loudly when the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EqGpuError(f"{LIB_PATH} is missing: build it with eq_b200.build() "
+                             "(__graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.eqgpu_last_error.restype = C.c_char_p
+        L.eqgpu_last_error.argtypes = [C.c_void_p]
+        L.eqgpu_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+        L.eqgpu_destroy.argtypes = [C.c_void_p]
+        L.eqgpu_destroy.restype = None
+        L.eqgpu_default_params.restype = None
+        for name in API_SYMBOLS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def default_params() -> Params:
+    p = Params()
+    lib().eqgpu_default_params(C.byref(p))
+    return p
+
+
+class GpuHSL:
+    """One HSL layer on one GPU: the Python face of ``gpuHSL`` (eq_b200/host/gpuHSL.h),
+    itself the drop-in for ``fenicsInterface`` (src/fHSL.h:333-449)."""
+
+    def __init__(self, nW, nH, h=0.5, dt=0.1, D=1200.0,
+                 bc_type=(DIRICHLET,) * 4, bc_value=(0.0,) * 4, robin_s=(0.0, 0.0),
+                 channels=False, channel_v=120.0, channel_r=(0.0, 0.0), channel_iters=48,
+                 well_scaling=25.0, rtol=1e-12, max_iters=200, device=0, stream=None,
+                 smooth_sweeps=0, max_levels=0, hy=None):
+        L = lib()
+        p = default_params()
+        p.nW, p.nH, p.hx, p.hy, p.dt, p.D = nW, nH, h, (hy if hy else h), dt, D
+        for w in range(4):
+            p.bc_type[w] = int(bc_type[w])
+            p.bc_value[w] = float(bc_value[w])
+        p.robin_s[0], p.robin_s[1] = robin_s
+        p.channels = 1 if channels else 0
+        p.channel_v = channel_v
+        p.channel_r[0], p.channel_r[1] = channel_r
+        p.channel_iters = channel_iters
+        p.well_scaling = well_scaling
+        p.rtol, p.max_iters, p.device = rtol, max_iters, device
+        p.stream = stream
+        p.smooth_sweeps, p.max_levels = smooth_sweeps, max_levels
+        self.params = p
+        self.nW, self.nH, self.N = nW, nH, nW * nH
+        self._h = C.c_void_p()
+        rc = L.eqgpu_create(C.byref(p), C.byref(self._h))
+        if rc != 0:
+            raise EqGpuError(f"eqgpu_create failed ({rc}): {L.eqgpu_last_error(None).decode()}")
+        # the members simulation.cpp touches
+        self.solution_vector = np.zeros(self.N)
+        self.totalBoundaryFlux = 0.0
+        self.ncells = 0
+
+    # -- plumbing ----------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise EqGpuError(f"eqgpu error {rc}: {lib().eqgpu_last_error(self._h).decode()}")
+
+    def close(self):
+        if self._h:
+            lib().eqgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- fenicsInterface surface --------------------------------------------
+    def stepDiffusion(self):
+        """src/fHSL.cpp:98-161 with the host-vector contract (solution_vector in/out)."""
+        self.solution_vector = _f64(self.solution_vector)
+        self._ck(lib().eqgpu_step_host(self._h, _dp(self.solution_vector)))
+        self.totalBoundaryFlux = self.stats().total_boundary_flux
+        return self.solution_vector
+
+    def setBoundaryValues(self, v: float):
+        self._ck(lib().eqgpu_set_boundary_value(self._h, C.c_double(v)))
+
+    def getBoundaryFlux(self):
+        return {"totalFlux": self.totalBoundaryFlux}
+
+    # -- device-resident path -----------------------------------------------
+    def set_field(self, u):
+        u = _f64(u)
+        assert u.size == self.N
+        self._ck(lib().eqgpu_set_field(self._h, _dp(u)))
+
+    def get_field(self):
+        u = np.empty(self.N)
+        self._ck(lib().eqgpu_get_field(self._h, _dp(u)))
+        return u
+
+    def step(self):
+        self._ck(lib().eqgpu_step(self._h))
+        self.totalBoundaryFlux = self.stats().total_boundary_flux
+
+    def step_host_ptr(self, ptr: int):
+        """eqgpu_step_host on a raw host pointer (e.g. a pinned buffer)."""
+        self._ck(lib().eqgpu_step_host(self._h, C.cast(ptr, C.POINTER(C.c_double))))
+
+    def set_tensor(self, d11=None, d22=None, d12=None):
+        if d11 is None:
+            self._ck(lib().eqgpu_set_tensor(self._h, None, None, None))
+        else:
+            a, b, c = _f64(d11), _f64(d22), _f64(d12)
+            self._ck(lib().eqgpu_set_tensor(self._h, _dp(a), _dp(b), _dp(c)))
+
+    def stats(self) -> Stats:
+        st = Stats()
+        self._ck(lib().eqgpu_get_stats(self._h, C.byref(st)))
+        return st
+
+    def channels(self):
+        t, b = np.empty(self.nW), np.empty(self.nW)
+        self._ck(lib().eqgpu_get_channels(self._h, _dp(t), _dp(b)))
+        return t, b
+
+    def set_channels(self, top, bottom):
+        t, b = _f64(top), _f64(bottom)
+        self._ck(lib().eqgpu_set_channels(self._h, _dp(t), _dp(b)))
+
+    def channel_flux(self):
+        t, b = np.empty(self.nW), np.empty(self.nW)
+        self._ck(lib().eqgpu_get_channel_flux(self._h, _dp(t), _dp(b)))
+        return t, b
+
+    def apply_operator(self, x, constrained=False):
+        x = _f64(x)
+        y = np.empty(self.N)
+        self._ck(lib().eqgpu_apply_operator(self._h, _dp(x), _dp(y), C.c_int(1 if constrained else 0)))
+        return y
+
+    def build_rhs(self, u0):
+        u0 = _f64(u0)
+        b = np.empty(self.N)
+        self._ck(lib().eqgpu_build_rhs(self._h, _dp(u0), _dp(b)))
+        return b
+
+    def field_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._ck(lib().eqgpu_field_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def sync(self):
+        self._ck(lib().eqgpu_sync(self._h))
+
+    # -- cells (eQabm::updateCells lambdas) ----------------------------------
+    def upload_cells(self, records, nodes_per_micron):
+        rec = _f64(records).reshape(-1, CELL_STRIDE)
+        self.ncells = rec.shape[0]
+        self._ck(lib().eqgpu_cells_upload(self._h, _dp(rec), C.c_int64(self.ncells),
+                                          C.c_double(nodes_per_micron)))
+
+    def raster(self, cap=512):
+        counts = np.zeros(self.ncells, dtype=np.int32)
+        nodes = np.full((self.ncells, cap), -1, dtype=np.int64)
+        self._ck(lib().eqgpu_cells_raster(self._h, counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          nodes.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int32(cap)))
+        return counts, nodes
+
+    def gather(self):
+        out = np.empty(self.ncells)
+        self._ck(lib().eqgpu_cells_gather(self._h, _dp(out)))
+        return out
+
+    def scatter(self, amount_nM):
+        a = _f64(amount_nM)
+        assert a.size == self.ncells
+        self._ck(lib().eqgpu_cells_scatter(self._h, _dp(a)))
+
+    # -- device-resident cell ops (no host copies inside) ---------------------
+    def set_amounts(self, amount_nM):
+        a = _f64(amount_nM)
+        assert a.size == self.ncells
+        self._ck(lib().eqgpu_cells_set_amounts(self._h, _dp(a)))
+
+    def gather_resident(self):
+        self._ck(lib().eqgpu_cells_gather_resident(self._h))
+
+    def scatter_resident(self):
+        self._ck(lib().eqgpu_cells_scatter_resident(self._h))
+
+    def get_gathered(self):
+        out = np.empty(self.ncells)
+        self._ck(lib().eqgpu_cells_get_gathered(self._h, _dp(out)))
+        return out
+
+    def bench_kernel(self, name: str, reps: int = 20):
+        ms, nbytes = C.c_double(), C.c_double()
+        self._ck(lib().eqgpu_bench_kernel(self._h, name.encode(), C.c_int(reps), C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value

@@ -1,0 +1,213 @@
+// Cell <-> mesh coupling: the lambdas of eQabm::updateCells
+// (src/abm/eQabm.cpp:268-359) -- findInteriorPoints, readHSL, writeHSL -- with
+// one warp per rod.  The point-in-rod predicate restates cpmEcoli::pointIsInCell
+// (src/abm/cpmEcoli.cpp:313-327) on top of Chipmunk 7.0.1's cpBodyWorldToLocal
+// and cpvcross [ext]; all of its arithmetic uses explicit round-to-nearest
+// mul/add/sub intrinsics so that nvcc cannot contract a*b+c into an FMA: the
+// node set must equal the CPU's bit for bit.
+#include "eqgpu_internal.cuh"
+
+#define CELLS_PER_BLOCK 8  // warps per block
+
+struct CellBox { int i1, i2, j1, j2; };
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+
+// src/eQ.h:119-130: size_t(round(x*n)), C round() = half away from zero
+__device__ __forceinline__ long long ij_round(double x, double n) { return (long long)round(mul(x, n)); }
+
+__device__ __forceinline__ bool point_in_cell(const double *c, double px, double py)
+{
+    const double posx = c[0], posy = c[1], rx = c[2], ry = c[3];
+    const double off = c[4], noff = c[5], rad = c[6];
+    // body->transform = (a=rot.x, b=rot.y, c=-rot.y, d=rot.x, tx=p.x, ty=p.y);
+    // cpTransformRigidInverse, then cpTransformPoint (left-to-right sums)
+    const double tc = -ry;
+    const double ia = rx, ic = -tc, itx = sub(mul(tc, posy), mul(posx, rx));
+    const double ib = -ry, id = rx, ity = sub(mul(posx, ry), mul(rx, posy));
+    const double lx = add(add(mul(ia, px), mul(ic, py)), itx);
+    const double ly = add(add(mul(ib, px), mul(id, py)), ity);
+    // vertsA (cpmEcoli.cpp:127-130,177-180,413-415) and edges (:71-76)
+    const double v0x = -off, v0y = rad, v1x = noff, v1y = rad;
+    const double v2x = noff, v2y = -rad, v3x = -off, v3y = -rad;
+    const double e0x = sub(v1x, v0x), e0y = sub(v1y, v0y);
+    const double e1x = sub(v2x, v1x), e1y = sub(v2y, v1y);
+    const double e2x = sub(v3x, v2x), e2y = sub(v3y, v2y);
+    const double e3x = sub(v0x, v3x), e3y = sub(v0y, v3y);
+    const double p0x = sub(lx, v1x), p0y = sub(ly, v1y);
+    const double p1x = sub(lx, v2x), p1y = sub(ly, v2y);
+    const double p2x = sub(lx, v3x), p2y = sub(ly, v3y);
+    const double p3x = sub(lx, v0x), p3y = sub(ly, v0y);
+    return (sub(mul(e0x, p0y), mul(e0y, p0x)) < 0.0) && (sub(mul(e1x, p1y), mul(e1y, p1x)) < 0.0) &&
+           (sub(mul(e2x, p2y), mul(e2y, p2x)) < 0.0) && (sub(mul(e3x, p3y), mul(e3y, p3x)) < 0.0);
+}
+
+// search box of findInteriorPoints (src/abm/eQabm.cpp:274-287)
+__device__ __forceinline__ CellBox cell_box(const double *c, double npm, int nH, int nW, int nte)
+{
+    long long ai = ij_round(c[8], npm), aj = ij_round(c[7], npm);
+    long long bi = ij_round(c[10], npm), bj = ij_round(c[9], npm);
+    long long i1 = min(ai, bi), i2 = max(ai, bi), j1 = min(aj, bj), j2 = max(aj, bj);
+    i1 = (i1 >= nte) ? (i1 - nte) : 0;
+    j1 = (j1 >= nte) ? (j1 - nte) : 0;
+    i2 = ((i2 + nte) >= (long long)(nH - 1)) ? (nH - 1) : (i2 + nte);
+    j2 = ((j2 + nte) >= (long long)(nW - 1)) ? (nW - 1) : (j2 + nte);
+    CellBox b; b.i1 = (int)i1; b.i2 = (int)i2; b.j1 = (int)j1; b.j2 = (int)j2;
+    return b;
+}
+
+// Walks the search box 32 nodes at a time in the reference's row-major order.
+// visit(node, inside_mask, lane_is_inside) is called once per chunk by the
+// whole warp; returns the number of interior points.
+template <class F>
+__device__ __forceinline__ int raster_walk(const double *c, double npm, int nH, int nW, int nte, F visit)
+{
+    const int lane = threadIdx.x & 31;
+    const CellBox b = cell_box(c, npm, nH, nW, nte);
+    const int bw = b.j2 - b.j1 + 1, bh = b.i2 - b.i1 + 1;
+    const int total = (b.i2 >= b.i1 && b.j2 >= b.j1) ? bw * bh : 0;
+    int count = 0;
+    for (int base = 0; base < total; base += 32) {
+        const int t = base + lane;
+        bool in = false;
+        long long node = -1;
+        if (t < total) {
+            const int pi = b.i1 + t / bw, pj = b.j1 + t % bw;
+            // src/eQ.h:115-118 xy_from_ij
+            const double x = __ddiv_rn((double)pj, npm), y = __ddiv_rn((double)pi, npm);
+            in = point_in_cell(c, x, y);
+            node = (long long)pi * nW + pj;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        visit(node, m, in, count);
+        count += __popc(m);
+    }
+    return count;
+}
+
+// fallback point when no node is inside (src/abm/eQabm.cpp:299-303)
+__device__ __forceinline__ long long centre_node(const double *c, double npm, int nW)
+{
+    return ij_round(c[12], npm) * (long long)nW + ij_round(c[11], npm);
+}
+
+__global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
+k_cells_raster(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
+               int *__restrict__ counts, long long *__restrict__ nodes, int cap)
+{
+    const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
+    if (k >= ncells) return;
+    const int lane = threadIdx.x & 31;
+    const double *c = cells + k * EQGPU_CELL_STRIDE;
+    long long *out = nodes ? nodes + k * cap : nullptr;
+    int n = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned m, bool in, int count) {
+        if (in && out) {
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) out[pos] = node;
+        }
+    });
+    if (n == 0) {
+        if (lane == 0 && out && cap > 0) out[0] = centre_node(c, npm, nW);
+        n = 1;
+    }
+    if (lane == 0) counts[k] = n;
+}
+
+// readHSL (src/abm/eQabm.cpp:326-337): mean over the cell's points, summed in
+// the reference's order (every lane carries the same running sum).
+__global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
+k_cells_gather(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
+               const double *__restrict__ u, double *__restrict__ out)
+{
+    const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
+    if (k >= ncells) return;
+    const int lane = threadIdx.x & 31;
+    const double *c = cells + k * EQGPU_CELL_STRIDE;
+    double HSL = 0.0;
+    int n = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned m, bool in, int) {
+        const double v = in ? __ldg(u + node) : 0.0;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            HSL = add(HSL, __shfl_sync(0xffffffffu, v, src));
+            m &= m - 1;
+        }
+    });
+    if (n == 0) { HSL = __ldg(u + centre_node(c, npm, nW)); n = 1; }
+    if (lane == 0) out[k] = __ddiv_rn(HSL, (double)n);
+}
+
+// src/eQcell.h:40-93 (poleRadius = 1/2)
+__device__ __forceinline__ double cell_volume(double L)
+{
+    const double poleRadius = 1.0 / 2.0;
+    const double cyl = 3.14159265358979323846 * (poleRadius * poleRadius);
+    const double poleVolume = 4.0 / 3.0 * 3.14159265358979323846 * (poleRadius * poleRadius * poleRadius);
+    return add(mul(sub(L, 1.0), cyl), poleVolume);
+}
+
+// writeHSL (src/abm/eQabm.cpp:338-359): nM -> molecules -> per-node increment,
+// same amount on every interior point.  Rods of one colony do not overlap, so
+// each node receives at most a handful of (usually one) atomic adds.
+__global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
+k_cells_scatter(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
+                const double *__restrict__ amount, const int *__restrict__ counts,
+                double *__restrict__ u)
+{
+    const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
+    if (k >= ncells) return;
+    const int lane = threadIdx.x & 31;
+    const double *c = cells + k * EQGPU_CELL_STRIDE;
+    const int n = counts[k];
+    const double L = c[13];
+    const double vol = cell_volume(L);
+    const double nanoMolarPerMoleculePerCubicMicron = 1.0 / 0.602;
+    const double numberHSL = mul(__ddiv_rn(amount[k], nanoMolarPerMoleculePerCubicMicron), vol);
+    const double extra = sub(1.0, __ddiv_rn(vol, mul(mul(L, 1.0), 1.0)));
+    const double perSquareMicron = __ddiv_rn(numberHSL, extra);
+    const double onePoint = mul(mul(perSquareMicron, npm), npm);
+    const double dHSL = __ddiv_rn(onePoint, (double)n);
+    int found = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned, bool in, int) {
+        if (in) atomicAdd(u + node, dHSL);
+    });
+    if (found == 0 && lane == 0) atomicAdd(u + centre_node(c, npm, nW), dHSL);
+}
+
+static int nte_of(double npm) { return (int)llround(npm * 1.0 / 2.0); }  // src/abm/eQabm.cpp:75
+
+int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap)
+{
+    if (s->ncells == 0) return 0;
+    const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
+    k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
+        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), d_counts, d_nodes, cap);
+    s->launches++;
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int cells_gather(eqgpu_solver *s, double *d_out)
+{
+    if (s->ncells == 0) return 0;
+    const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
+    k_cells_gather<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
+        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->u, d_out);
+    s->launches++;
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int cells_scatter(eqgpu_solver *s, const double *d_amount)
+{
+    if (s->ncells == 0) return 0;
+    const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
+    // point counts first (the per-node amount divides by them)
+    k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
+        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->cell_counts, nullptr, 0);
+    k_cells_scatter<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
+        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), d_amount, s->cell_counts, s->u);
+    s->launches += 2;
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}

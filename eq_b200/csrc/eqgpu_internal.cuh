@@ -1,0 +1,339 @@
+// Internal declarations shared by the translation units of libeqgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/eqgpu.h"
+
+#define EQ_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            s->set_error(std::string(#call) + ": " + cudaGetErrorString(e__)); \
+            return EQGPU_ECUDA;                                                \
+        }                                                                      \
+    } while (0)
+
+// Stencil band order (same as oracle/eq_oracle.c).
+enum { B_C = 0, B_E, B_W, B_N, B_S, B_NE, B_SW, NBAND };
+
+// One grid of the multigrid hierarchy: a tensor-product mesh of nx x ny nodes
+// whose rectangles are split by the BL->TR diagonal ("right" RectangleMesh,
+// src/fHSL.cpp:171).  Level 0 is uniform; coarse levels keep every even node
+// plus the last one, so only their last cell can be narrower.
+struct LevelDev {
+    int nx, ny;
+    // padded cell sizes: hx[j] = width of the cell WEST of node j (hx[0] = 0),
+    // hx[j+1] = width of the cell EAST of node j (hx[nx] = 0).  ihx = 1/hx or 0.
+    const double *hx, *ihx, *hy, *ihy;
+    double tau;           // dt * D
+    double rob_l, rob_r;  // dt * r_left, dt * r_right (0 when the wall is not Robin)
+    unsigned dirmask;     // bit0 left, bit1 right, bit2 top, bit3 bottom are Dirichlet
+    // uniform fast path: nodes 1<=j<=jreg_hi, 1<=i<=ireg_hi see four regular cells
+    int jreg_hi, ireg_hi;
+    double cC, cEW, cNS, cD;
+    // optional nodal tensor fields (level-local, injected); null = isotropic
+    const double *d11, *d22, *d12;
+};
+
+struct CGScalars {
+    double rz_old, rz_new, pAp, rr, bnorm2, stop2, rr0;
+    int iters, done, max_iters, pad;
+};
+
+struct Level {
+    LevelDev dev;
+    std::vector<double> hx_host, hy_host;  // unpadded cell sizes
+    double *d_hx = nullptr, *d_ihx = nullptr, *d_hy = nullptr, *d_ihy = nullptr;
+    double *x = nullptr, *b = nullptr, *t = nullptr;  // solution, rhs, scratch
+    double *t11 = nullptr, *t22 = nullptr, *t12 = nullptr;
+    size_t n() const { return (size_t)dev.nx * dev.ny; }
+};
+
+struct eqgpu_solver {
+    eqgpu_params p;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    size_t N = 0;
+    std::vector<Level> levels;
+    // fine-level vectors
+    double *u = nullptr;   // resident field == PCG iterate x
+    double *r = nullptr, *pv = nullptr, *Ap = nullptr, *z = nullptr;
+    double *d11 = nullptr, *d22 = nullptr, *d12 = nullptr;
+    // Dirichlet data
+    double dir_val[4] = {0, 0, 0, 0};
+    double *chan_top = nullptr, *chan_bot = nullptr;       // channel u (nW)
+    double *flux_top = nullptr, *flux_bot = nullptr;       // per-step channel flux
+    double *chan_coef = nullptr;                           // tridiagonal factors
+    // reductions
+    double *partials = nullptr;  // [nslots][max_blocks]
+    unsigned *counters = nullptr;
+    CGScalars *sc = nullptr;
+    CGScalars *sc_host = nullptr;  // pinned
+    double *flux_dev = nullptr;    // total boundary functional
+    double *flux_host = nullptr;   // pinned
+    int max_blocks = 0;
+    // cells
+    double *cells = nullptr;
+    int64_t ncells = 0, cells_cap = 0;
+    double npm = 0;
+    double *cell_vals = nullptr;   // device per-cell gather result
+    double *cell_amt = nullptr;    // device per-cell deposit amounts (nM)
+    int32_t *cell_counts = nullptr;
+    double *stage_host = nullptr;  // pinned staging for field copies
+    // stats
+    eqgpu_stats st{};
+    int64_t launches = 0;
+    int nu = 2, ncoarse = 24;
+    double omega = 0.8;
+    bool tensor = false;
+
+    void set_error(const std::string &m) { err = m; }
+};
+
+// ---- solver.cu ----
+int solver_setup(eqgpu_solver *s);
+void solver_teardown(eqgpu_solver *s);
+int solver_step(eqgpu_solver *s);
+int solver_apply(eqgpu_solver *s, const double *dx, double *dy, bool constrained);
+int solver_rhs(eqgpu_solver *s, const double *du0, double *db);
+int solver_refresh_levels(eqgpu_solver *s);
+int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes);
+// ---- cells.cu ----
+int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap);
+int cells_gather(eqgpu_solver *s, double *d_out);
+int cells_scatter(eqgpu_solver *s, const double *d_amount);
+// ---- channels.cu ----
+int channels_setup(eqgpu_solver *s);
+int channels_step(eqgpu_solver *s);
+int boundary_functional(eqgpu_solver *s);
+
+#ifdef __CUDACC__
+// --------------------------------------------------------------------------
+// device helpers
+// --------------------------------------------------------------------------
+__device__ __forceinline__ bool is_dirichlet(const LevelDev &L, int i, int j)
+{
+    unsigned m = L.dirmask;
+    return ((m & 1u) && j == 0) || ((m & 2u) && j == L.nx - 1) ||
+           ((m & 4u) && i == L.ny - 1) || ((m & 8u) && i == 0);
+}
+
+// Row of A = M + dt*K + dt*R at node (i,j) of a tensor-product "right" mesh,
+// isotropic constant tensor (closed form of fenics/hslD.h:3123-3350 summed over
+// the six triangles around the node; DESIGN.md "operator").
+__device__ __forceinline__ void stencil_iso(const LevelDev &L, int i, int j, double c[NBAND])
+{
+    if (i >= 1 && i <= L.ireg_hi && j >= 1 && j <= L.jreg_hi) {
+        c[B_C] = L.cC; c[B_E] = L.cEW; c[B_W] = L.cEW; c[B_N] = L.cNS; c[B_S] = L.cNS;
+        c[B_NE] = L.cD; c[B_SW] = L.cD;
+        return;
+    }
+    const double aw = L.hx[j], ae = L.hx[j + 1], bs = L.hy[i], bn = L.hy[i + 1];
+    const double iaw = L.ihx[j], iae = L.ihx[j + 1], ibs = L.ihy[i], ibn = L.ihy[i + 1];
+    const double sy = 0.5 * L.tau * (bs + bn), sx = 0.5 * L.tau * (aw + ae);
+    const double my = (bs + bn) * (1.0 / 24.0), mx = (aw + ae) * (1.0 / 24.0);
+    c[B_E] = ae * my - sy * iae;
+    c[B_W] = aw * my - sy * iaw;
+    c[B_N] = bn * mx - sx * ibn;
+    c[B_S] = bs * mx - sx * ibs;
+    c[B_NE] = ae * bn * (1.0 / 12.0);
+    c[B_SW] = aw * bs * (1.0 / 12.0);
+    double cc = sy * (iae + iaw) + sx * (ibn + ibs) +
+                (2.0 * aw * bs + ae * bs + aw * bn + 2.0 * ae * bn) * (1.0 / 12.0);
+    // Robin edge mass dt*r*|e|*{1/3,1/6} (fenics/hslD.h:3284-3441)
+    if (j == 0 && L.rob_l != 0.0) {
+        cc += L.rob_l * (bs + bn) * (1.0 / 3.0);
+        c[B_N] += L.rob_l * bn * (1.0 / 6.0);
+        c[B_S] += L.rob_l * bs * (1.0 / 6.0);
+    }
+    if (j == L.nx - 1 && L.rob_r != 0.0) {
+        cc += L.rob_r * (bs + bn) * (1.0 / 3.0);
+        c[B_N] += L.rob_r * bn * (1.0 / 6.0);
+        c[B_S] += L.rob_r * bs * (1.0 / 6.0);
+    }
+    c[B_C] = cc;
+}
+
+// Consistent P1 mass row only (for the load vector b = M u0).
+__device__ __forceinline__ void stencil_mass(const LevelDev &L, int i, int j, double c[NBAND])
+{
+    const double aw = L.hx[j], ae = L.hx[j + 1], bs = L.hy[i], bn = L.hy[i + 1];
+    const double my = (bs + bn) * (1.0 / 24.0), mx = (aw + ae) * (1.0 / 24.0);
+    c[B_E] = ae * my; c[B_W] = aw * my; c[B_N] = bn * mx; c[B_S] = bs * mx;
+    c[B_NE] = ae * bn * (1.0 / 12.0);
+    c[B_SW] = aw * bs * (1.0 / 12.0);
+    c[B_C] = (2.0 * aw * bs + ae * bs + aw * bn + 2.0 * ae * bn) * (1.0 / 12.0);
+}
+
+// General-tensor row: six triangles around the node, each with the mean of its
+// three vertex tensor values (fenics/hslD.h:3181-3259; the 3-point rule with P1
+// weights integrates a P1 coefficient exactly = area * vertex mean).
+// T(i,j) reads the nodal tensor (d11,d22,d12) at a node, already times tau.
+struct Ten { double a, b, c; };
+__device__ __forceinline__ Ten ten_at(const LevelDev &L, int i, int j)
+{
+    const size_t g = (size_t)i * L.nx + j;
+    Ten t; t.a = __ldg(L.d11 + g); t.b = __ldg(L.d22 + g); t.c = __ldg(L.d12 + g);
+    return t;
+}
+__device__ __forceinline__ Ten ten_mean(const Ten &p, const Ten &q, const Ten &r, double tau)
+{
+    Ten t;
+    t.a = tau * (p.a + q.a + r.a) * (1.0 / 3.0);
+    t.b = tau * (p.b + q.b + r.b) * (1.0 / 3.0);
+    t.c = tau * (p.c + q.c + r.c) * (1.0 / 3.0);
+    return t;
+}
+__device__ __forceinline__ void stencil_tensor(const LevelDev &L, int i, int j, double c[NBAND])
+{
+    stencil_mass(L, i, j, c);
+    const double aw = L.hx[j], ae = L.hx[j + 1], bs = L.hy[i], bn = L.hy[i + 1];
+    const double iaw = L.ihx[j], iae = L.ihx[j + 1], ibs = L.ihy[i], ibn = L.ihy[i + 1];
+    const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
+    const Ten P = ten_at(L, i, j);
+    Ten E = P, W = P, N = P, S = P, NE = P, SW = P;
+    if (hasE) E = ten_at(L, i, j + 1);
+    if (hasW) W = ten_at(L, i, j - 1);
+    if (hasN) N = ten_at(L, i + 1, j);
+    if (hasS) S = ten_at(L, i - 1, j);
+    if (hasN && hasE) NE = ten_at(L, i + 1, j + 1);
+    if (hasS && hasW) SW = ten_at(L, i - 1, j - 1);
+    double cc = 0.0;
+    // K_e entries for a rectangle a x b:
+    //  lower (BL,BR,TR): BL-BL (b/2a)d11; BL-BR -(b/2a)d11+d12/2; BL-TR -d12/2;
+    //                    BR-BR (b/2a)d11-d12+(a/2b)d22; BR-TR d12/2-(a/2b)d22; TR-TR (a/2b)d22
+    //  upper (BL,TL,TR): BL-BL (a/2b)d22; BL-TL d12/2-(a/2b)d22; BL-TR -d12/2;
+    //                    TL-TL (b/2a)d11-d12+(a/2b)d22; TL-TR -(b/2a)d11+d12/2; TR-TR (b/2a)d11
+    if (hasS && hasW) {  // SW cell (aw x bs), node is TR; BL=SW, BR=S, TL=W
+        const double ba = 0.5 * bs * iaw, ab = 0.5 * aw * ibs;
+        Ten tl = ten_mean(SW, S, P, L.tau), tu = ten_mean(SW, W, P, L.tau);
+        cc += ab * tl.b + ba * tu.a;
+        c[B_S] += 0.5 * tl.c - ab * tl.b;
+        c[B_W] += 0.5 * tu.c - ba * tu.a;
+        c[B_SW] += -0.5 * tl.c - 0.5 * tu.c;
+    }
+    if (hasS && hasE) {  // SE cell (ae x bs), node is TL (upper only); BL=S, TR=E
+        const double ba = 0.5 * bs * iae, ab = 0.5 * ae * ibs;
+        Ten tu = ten_mean(S, P, E, L.tau);
+        cc += ba * tu.a - tu.c + ab * tu.b;
+        c[B_S] += 0.5 * tu.c - ab * tu.b;
+        c[B_E] += 0.5 * tu.c - ba * tu.a;
+    }
+    if (hasN && hasW) {  // NW cell (aw x bn), node is BR (lower only); BL=W, TR=N
+        const double ba = 0.5 * bn * iaw, ab = 0.5 * aw * ibn;
+        Ten tl = ten_mean(W, P, N, L.tau);
+        cc += ba * tl.a - tl.c + ab * tl.b;
+        c[B_W] += 0.5 * tl.c - ba * tl.a;
+        c[B_N] += 0.5 * tl.c - ab * tl.b;
+    }
+    if (hasN && hasE) {  // NE cell (ae x bn), node is BL; BR=E, TL=N, TR=NE
+        const double ba = 0.5 * bn * iae, ab = 0.5 * ae * ibn;
+        Ten tl = ten_mean(P, E, NE, L.tau), tu = ten_mean(P, N, NE, L.tau);
+        cc += ba * tl.a + ab * tu.b;
+        c[B_E] += 0.5 * tl.c - ba * tl.a;
+        c[B_N] += 0.5 * tu.c - ab * tu.b;
+        c[B_NE] += -0.5 * tl.c - 0.5 * tu.c;
+    }
+    if (j == 0 && L.rob_l != 0.0) {
+        cc += L.rob_l * (bs + bn) * (1.0 / 3.0);
+        c[B_N] += L.rob_l * bn * (1.0 / 6.0);
+        c[B_S] += L.rob_l * bs * (1.0 / 6.0);
+    }
+    if (j == L.nx - 1 && L.rob_r != 0.0) {
+        cc += L.rob_r * (bs + bn) * (1.0 / 3.0);
+        c[B_N] += L.rob_r * bn * (1.0 / 6.0);
+        c[B_S] += L.rob_r * bs * (1.0 / 6.0);
+    }
+    c[B_C] += cc;
+}
+
+template <bool TENSOR>
+__device__ __forceinline__ void stencil_row(const LevelDev &L, int i, int j, double c[NBAND])
+{
+    if (TENSOR) stencil_tensor(L, i, j, c);
+    else stencil_iso(L, i, j, c);
+}
+
+// sum_k c[k] * x[nbr_k]; neighbours outside the grid carry zero coefficients
+// and are not read.
+__device__ __forceinline__ double stencil_dot(const LevelDev &L, int i, int j,
+                                              const double c[NBAND], const double *__restrict__ x)
+{
+    const size_t g = (size_t)i * L.nx + j;
+    const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
+    double s = c[B_C] * __ldg(x + g);
+    if (hasE) s += c[B_E] * __ldg(x + g + 1);
+    if (hasW) s += c[B_W] * __ldg(x + g - 1);
+    if (hasN) s += c[B_N] * __ldg(x + g + L.nx);
+    if (hasS) s += c[B_S] * __ldg(x + g - L.nx);
+    if (hasN && hasE) s += c[B_NE] * __ldg(x + g + L.nx + 1);
+    if (hasS && hasW) s += c[B_SW] * __ldg(x + g - L.nx - 1);
+    return s;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic grid reduction of NV values per thread: warp shuffles, one
+// shared-memory pass per block, block partials to global, and the last block
+// to finish sums the partials in a fixed order.  Returns true in thread 0 of
+// that last block, with the totals in out[].
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, unsigned *counter,
+                                            double (&out)[NV])
+{
+    __shared__ double sm[NV][32];
+    __shared__ bool last;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const int nblocks = gridDim.x * gridDim.y;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double w = warp_sum(v[k]);
+        if (lane == 0) sm[k][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double w = lane < nwarps ? sm[k][lane] : 0.0;
+            w = warp_sum(w);
+            if (lane == 0) partials[(size_t)k * nblocks + bid] = w;
+        }
+    }
+    if (tid == 0) {
+        __threadfence();
+        unsigned t = atomicAdd(counter, 1u);
+        last = (t == (unsigned)nblocks - 1u);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double w = 0.0;
+        for (int b = tid; b < nblocks; b += nthreads) w += __ldcg(partials + (size_t)k * nblocks + b);
+        w = warp_sum(w);
+        __syncthreads();
+        if (lane == 0) sm[k][warp] = w;
+        __syncthreads();
+        if (warp == 0) {
+            double q = lane < nwarps ? sm[k][lane] : 0.0;
+            q = warp_sum(q);
+            out[k] = q;
+        }
+    }
+    if (tid == 0) *counter = 0u;
+    return tid == 0;
+}
+#endif

@@ -1,0 +1,710 @@
+// Matrix-free P1-FEM operator, load vector, and the multigrid-preconditioned CG
+// that replaces LinearVariationalSolver::solve() (src/fHSL.cpp:104-108).
+//
+// System solved each step (fenics/hslD.ufl:36-42):
+//   (M + dt*K(D) + dt*R) u = M u0 + dt*r*s*e,  Dirichlet rows u_i = g_i.
+// DOLFIN assembles it and runs a sparse LU; here A is never formed: every
+// kernel evaluates the 7-point row of the "right"-diagonal mesh in registers.
+#include "eqgpu_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#define BX 32
+#define BY 8
+
+struct DirData {
+    double val[4];
+    const double *top, *bot;  // per-node channel values or null
+};
+
+__device__ __forceinline__ double dir_value(const LevelDev &L, const DirData &d, int i, int j)
+{
+    // DirichletBC objects are applied in the order left,right,top,bottom
+    // (src/fHSL.cpp:468-539); the last one applied wins at a corner.
+    const unsigned m = L.dirmask;
+    if ((m & 8u) && i == 0) return d.bot ? d.bot[j] : d.val[3];
+    if ((m & 4u) && i == L.ny - 1) return d.top ? d.top[j] : d.val[2];
+    if ((m & 2u) && j == L.nx - 1) return d.val[1];
+    return d.val[0];
+}
+
+// ---------------------------------------------------------------------------
+// operator apply: y = A x on free rows (Dirichlet rows -> 0), optional x.y
+// ---------------------------------------------------------------------------
+template <bool TENSOR, bool DOT>
+__global__ void __launch_bounds__(BX *BY)
+k_apply(LevelDev L, const double *__restrict__ x, double *__restrict__ y, CGScalars *sc,
+        double *partials, unsigned *counter)
+{
+    if (DOT && sc->done) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    double v[1] = {0.0};
+    if (i < L.ny && j < L.nx) {
+        const size_t g = (size_t)i * L.nx + j;
+        double out = 0.0;
+        if (!is_dirichlet(L, i, j)) {
+            double c[NBAND];
+            stencil_row<TENSOR>(L, i, j, c);
+            out = stencil_dot(L, i, j, c, x);
+            if (DOT) v[0] = out * __ldg(x + g);
+        }
+        y[g] = out;
+    }
+    if (DOT) {
+        double tot[1];
+        if (grid_reduce<1>(v, partials, counter, tot)) sc->pAp = tot[0];
+    }
+}
+
+// Verification hook: y = A x with explicit handling of constrained rows/cols.
+// mode 0: unconstrained operator.  mode 1: Dirichlet rows = identity, columns
+// to Dirichlet nodes dropped (the symmetric elimination CG works with).
+template <bool TENSOR>
+__global__ void k_apply_check(LevelDev L, const double *__restrict__ x, double *__restrict__ y, int mode)
+{
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.ny || j >= L.nx) return;
+    const size_t g = (size_t)i * L.nx + j;
+    if (mode == 1 && is_dirichlet(L, i, j)) { y[g] = x[g]; return; }
+    double c[NBAND];
+    stencil_row<TENSOR>(L, i, j, c);
+    if (mode == 1) {
+        if (j + 1 < L.nx && is_dirichlet(L, i, j + 1)) c[B_E] = 0.0;
+        if (j > 0 && is_dirichlet(L, i, j - 1)) c[B_W] = 0.0;
+        if (i + 1 < L.ny && is_dirichlet(L, i + 1, j)) c[B_N] = 0.0;
+        if (i > 0 && is_dirichlet(L, i - 1, j)) c[B_S] = 0.0;
+        if (i + 1 < L.ny && j + 1 < L.nx && is_dirichlet(L, i + 1, j + 1)) c[B_NE] = 0.0;
+        if (i > 0 && j > 0 && is_dirichlet(L, i - 1, j - 1)) c[B_SW] = 0.0;
+    }
+    y[g] = stencil_dot(L, i, j, c, x);
+}
+
+// b = M u0 + Robin load (unconstrained load vector L(phi_g), fenics/hslD.h:3466-3689)
+__device__ __forceinline__ double load_row(const LevelDev &L, int i, int j,
+                                           const double *__restrict__ u0, double rs_l, double rs_r)
+{
+    double c[NBAND];
+    stencil_mass(L, i, j, c);
+    double b = stencil_dot(L, i, j, c, u0);
+    if (j == 0) b += rs_l * 0.5 * (L.hy[i] + L.hy[i + 1]);
+    if (j == L.nx - 1) b += rs_r * 0.5 * (L.hy[i] + L.hy[i + 1]);
+    return b;
+}
+
+__global__ void k_rhs_check(LevelDev L, const double *__restrict__ u0, double *__restrict__ b,
+                            double rs_l, double rs_r)
+{
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.ny || j >= L.nx) return;
+    b[(size_t)i * L.nx + j] = load_row(L, i, j, u0, rs_l, rs_r);
+}
+
+// ---------------------------------------------------------------------------
+// PCG start.  Reduced system on the free rows: A_ff x_f = b_f - A_fd g_d with
+// b = M u0 + load.  Two starting guesses are evaluated in one pass:
+//   (A) x0 = u0 (the previous field plus deposits)  -> rA = b - A x0
+//   (B) x0 = 0                                      -> rB = b - A_fd g_d
+// (Dirichlet nodes hold g in both.)  rB is also the right-hand side of the
+// reduced system, so ||rB|| is the norm the stopping test is relative to.
+// k_impose keeps whichever guess has the smaller residual: u0 is excellent in
+// quasi-steady state and poor right after large point deposits, where the
+// huge A*u0 would cap the attainable accuracy.
+// ---------------------------------------------------------------------------
+template <bool TENSOR>
+__global__ void __launch_bounds__(BX *BY)
+k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict__ rA,
+       double *__restrict__ rB, double rs_l, double rs_r, CGScalars *sc, double *partials,
+       unsigned *counter)
+{
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    double v[2] = {0.0, 0.0};
+    if (i < L.ny && j < L.nx) {
+        const size_t g = (size_t)i * L.nx + j;
+        double resA = 0.0, resB = 0.0;
+        if (!is_dirichlet(L, i, j)) {
+            const double b = load_row(L, i, j, u, rs_l, rs_r);
+            double c[NBAND];
+            stencil_row<TENSOR>(L, i, j, c);
+            const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
+            double ax = c[B_C] * __ldg(u + g), ag = 0.0;
+            auto acc = [&](int ii, int jj, double ck) {
+                if (is_dirichlet(L, ii, jj)) {
+                    const double t = ck * dir_value(L, dd, ii, jj);
+                    ax += t; ag += t;
+                } else ax += ck * __ldg(u + (size_t)ii * L.nx + jj);
+            };
+            if (hasE) acc(i, j + 1, c[B_E]);
+            if (hasW) acc(i, j - 1, c[B_W]);
+            if (hasN) acc(i + 1, j, c[B_N]);
+            if (hasS) acc(i - 1, j, c[B_S]);
+            if (hasN && hasE) acc(i + 1, j + 1, c[B_NE]);
+            if (hasS && hasW) acc(i - 1, j - 1, c[B_SW]);
+            resA = b - ax;
+            resB = b - ag;
+            v[0] = resA * resA;
+            v[1] = resB * resB;
+        }
+        rA[g] = resA;
+        rB[g] = resB;
+    }
+    double tot[2];
+    if (grid_reduce<2>(v, partials, counter, tot)) {
+        sc->rr0 = tot[0];
+        sc->bnorm2 = tot[1];
+    }
+}
+
+// Pick the starting guess, impose u_d = g_d, set up the PCG scalars.
+__global__ void __launch_bounds__(BX *BY)
+k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
+         const double *__restrict__ rB, CGScalars *sc, double rtol, int max_iters)
+{
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    const bool useB = sc->bnorm2 < sc->rr0;
+    if (i < L.ny && j < L.nx) {
+        const size_t g = (size_t)i * L.nx + j;
+        if (is_dirichlet(L, i, j)) u[g] = dir_value(L, dd, i, j);
+        else if (useB) { u[g] = 0.0; r[g] = rB[g]; }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
+        const double rr = useB ? sc->bnorm2 : sc->rr0;
+        const double stop2 = rtol * rtol * sc->bnorm2;
+        // every block has read bnorm2/rr0 before this block can be the last to
+        // finish only if we do not overwrite them: keep them, write the rest.
+        sc->rr = rr;
+        sc->stop2 = stop2;
+        sc->iters = 0;
+        sc->max_iters = max_iters;
+        sc->done = (rr <= stop2) ? 1 : 0;
+        sc->rz_old = 1.0;
+        sc->rz_new = 0.0;
+    }
+}
+
+// rz_new = r . z
+__global__ void __launch_bounds__(256)
+k_dot(size_t n, const double *__restrict__ a, const double *__restrict__ b, CGScalars *sc,
+      double *partials, unsigned *counter)
+{
+    if (sc->done) return;
+    double v[1] = {0.0};
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n;
+         g += (size_t)gridDim.x * blockDim.x)
+        v[0] += __ldg(a + g) * __ldg(b + g);
+    double tot[1];
+    if (grid_reduce<1>(v, partials, counter, tot)) sc->rz_new = tot[0];
+}
+
+// p = z + beta p
+__global__ void __launch_bounds__(256)
+k_update_p(size_t n, const double *__restrict__ z, double *__restrict__ p, const CGScalars *sc)
+{
+    if (sc->done) return;
+    const double beta = sc->iters == 0 ? 0.0 : sc->rz_new / sc->rz_old;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n;
+         g += (size_t)gridDim.x * blockDim.x)
+        p[g] = __ldg(z + g) + beta * p[g];
+}
+
+// x += alpha p ; r -= alpha Ap ; rr = r.r ; bookkeeping in the last block
+__global__ void __launch_bounds__(256)
+k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+            const double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter)
+{
+    if (sc->done) return;
+    const double alpha = sc->rz_new / sc->pAp;
+    double v[1] = {0.0};
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n;
+         g += (size_t)gridDim.x * blockDim.x) {
+        x[g] += alpha * __ldg(p + g);
+        const double rn = r[g] - alpha * __ldg(Ap + g);
+        r[g] = rn;
+        v[0] += rn * rn;
+    }
+    double tot[1];
+    if (grid_reduce<1>(v, partials, counter, tot)) {
+        sc->rr = tot[0];
+        sc->rz_old = sc->rz_new;
+        sc->iters += 1;
+        if (tot[0] <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// multigrid pieces
+// ---------------------------------------------------------------------------
+// x = omega * D^-1 b   (first sweep from a zero guess)
+template <bool TENSOR>
+__global__ void __launch_bounds__(BX *BY)
+k_jacobi0(LevelDev L, const double *__restrict__ b, double *__restrict__ x, double omega,
+          const CGScalars *sc)
+{
+    if (sc->done) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.ny || j >= L.nx) return;
+    const size_t g = (size_t)i * L.nx + j;
+    double out = 0.0;
+    if (!is_dirichlet(L, i, j)) {
+        double c[NBAND];
+        stencil_row<TENSOR>(L, i, j, c);
+        out = omega * __ldg(b + g) / c[B_C];
+    }
+    x[g] = out;
+}
+
+// xout = xin + omega * D^-1 (b - A xin);  RESID: xout = b - A xin instead
+template <bool TENSOR, bool RESID>
+__global__ void __launch_bounds__(BX *BY)
+k_jacobi(LevelDev L, const double *__restrict__ b, const double *__restrict__ xin,
+         double *__restrict__ xout, double omega, const CGScalars *sc)
+{
+    if (sc->done) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.ny || j >= L.nx) return;
+    const size_t g = (size_t)i * L.nx + j;
+    double out = 0.0;
+    if (!is_dirichlet(L, i, j)) {
+        double c[NBAND];
+        stencil_row<TENSOR>(L, i, j, c);
+        const double res = __ldg(b + g) - stencil_dot(L, i, j, c, xin);
+        out = RESID ? res : __ldg(xin + g) + omega * res / c[B_C];
+    }
+    xout[g] = out;
+}
+
+// coarse node J <-> fine node min(2J, nf-1)
+__device__ __forceinline__ int fine_of(int J, int nf) { return min(2 * J, nf - 1); }
+// is fine index f a "midpoint" node (odd and not the last node)?
+__device__ __forceinline__ bool is_mid(int f, int nf) { return (f & 1) && f != nf - 1; }
+
+// bc = P^T rf  (P = P1 interpolation on the "right" mesh: midpoints of the
+// E-W, N-S and SW-NE edges take half of each end)
+__global__ void __launch_bounds__(BX *BY)
+k_restrict(LevelDev F, LevelDev Cc, const double *__restrict__ rf, double *__restrict__ bc,
+           const CGScalars *sc)
+{
+    if (sc->done) return;
+    const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
+    if (I >= Cc.ny || J >= Cc.nx) return;
+    double out = 0.0;
+    if (!is_dirichlet(Cc, I, J)) {
+        const int fi = fine_of(I, F.ny), fj = fine_of(J, F.nx);
+        const size_t g = (size_t)fi * F.nx + fj;
+        const bool e = fj + 1 < F.nx && is_mid(fj + 1, F.nx);
+        const bool w = fj - 1 >= 0 && is_mid(fj - 1, F.nx);
+        const bool n = fi + 1 < F.ny && is_mid(fi + 1, F.ny);
+        const bool s = fi - 1 >= 0 && is_mid(fi - 1, F.ny);
+        out = __ldg(rf + g);
+        double h = 0.0;
+        if (e) h += __ldg(rf + g + 1);
+        if (w) h += __ldg(rf + g - 1);
+        if (n) h += __ldg(rf + g + F.nx);
+        if (s) h += __ldg(rf + g - F.nx);
+        if (n && e) h += __ldg(rf + g + F.nx + 1);
+        if (s && w) h += __ldg(rf + g - F.nx - 1);
+        out += 0.5 * h;
+    }
+    bc[(size_t)I * Cc.nx + J] = out;
+}
+
+// xf += P xc
+__global__ void __launch_bounds__(BX *BY)
+k_prolong_add(LevelDev F, LevelDev Cc, const double *__restrict__ xc, double *__restrict__ xf,
+              const CGScalars *sc)
+{
+    if (sc->done) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= F.ny || j >= F.nx) return;
+    if (is_dirichlet(F, i, j)) return;
+    const bool mi = is_mid(i, F.ny), mj = is_mid(j, F.nx);
+    // coarse index of the coincident / lower neighbour node
+    const int I0 = (i == F.ny - 1 && !(i & 1)) ? i / 2 : (i == F.ny - 1 ? Cc.ny - 1 : i / 2);
+    const int J0 = (j == F.nx - 1 && !(j & 1)) ? j / 2 : (j == F.nx - 1 ? Cc.nx - 1 : j / 2);
+    const double *c0 = xc + (size_t)I0 * Cc.nx + J0;
+    double add;
+    if (!mi && !mj) add = __ldg(c0);
+    else if (!mi && mj) add = 0.5 * (__ldg(c0) + __ldg(c0 + 1));
+    else if (mi && !mj) add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx));
+    else add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx + 1));
+    xf[(size_t)i * F.nx + j] += add;
+}
+
+// nodal injection of a tensor component to the coarse grid
+__global__ void k_inject(LevelDev F, LevelDev Cc, const double *__restrict__ f, double *__restrict__ c)
+{
+    const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
+    if (I >= Cc.ny || J >= Cc.nx) return;
+    c[(size_t)I * Cc.nx + J] = f[(size_t)fine_of(I, F.ny) * F.nx + fine_of(J, F.nx)];
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static dim3 grid2d(const LevelDev &L) { return dim3((L.nx + BX - 1) / BX, (L.ny + BY - 1) / BY); }
+
+static std::vector<double> coarsen_cells(const std::vector<double> &h)
+{
+    const int n = (int)h.size() + 1;  // nodes
+    const int nc = n / 2 + 1;
+    std::vector<double> hc(nc - 1);
+    for (int J = 0; J < nc - 1; ++J) {
+        const int f0 = std::min(2 * J, n - 1), f1 = std::min(2 * J + 2, n - 1);
+        double w = 0.0;
+        for (int k = f0; k < f1; ++k) w += h[k];
+        hc[J] = w;
+    }
+    return hc;
+}
+
+static int upload_padded(eqgpu_solver *s, const std::vector<double> &h, double **d_h, double **d_ih)
+{
+    const int n = (int)h.size() + 1;
+    std::vector<double> pad(n + 1, 0.0), ipad(n + 1, 0.0);
+    for (int k = 0; k < n - 1; ++k) { pad[k + 1] = h[k]; ipad[k + 1] = 1.0 / h[k]; }
+    EQ_CUDA(cudaMalloc(d_h, sizeof(double) * (n + 1)));
+    EQ_CUDA(cudaMalloc(d_ih, sizeof(double) * (n + 1)));
+    EQ_CUDA(cudaMemcpy(*d_h, pad.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
+    EQ_CUDA(cudaMemcpy(*d_ih, ipad.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int leading_regular(const std::vector<double> &h)
+{
+    int k = 0;
+    while (k < (int)h.size() && h[k] == h[0]) ++k;
+    return k;  // cells 0..k-1 are regular
+}
+
+static void fill_level_consts(eqgpu_solver *s, Level &lv)
+{
+    LevelDev &L = lv.dev;
+    const eqgpu_params &p = s->p;
+    L.tau = p.dt * p.D;
+    L.rob_l = p.bc_type[EQGPU_LEFT] == EQGPU_BC_ROBIN ? p.dt * p.bc_value[EQGPU_LEFT] : 0.0;
+    L.rob_r = p.bc_type[EQGPU_RIGHT] == EQGPU_BC_ROBIN ? p.dt * p.bc_value[EQGPU_RIGHT] : 0.0;
+    unsigned m = 0;
+    for (int w = 0; w < 4; ++w)
+        if (p.bc_type[w] == EQGPU_BC_DIRICHLET || p.bc_type[w] == EQGPU_BC_DIRICHLET_CHANNEL)
+            m |= 1u << w;
+    L.dirmask = m;
+    const double a = lv.hx_host[0], b = lv.hy_host[0];
+    // node j (1 <= j) is regular when cells j-1 and j are: j <= leading_regular-1
+    L.jreg_hi = std::min(leading_regular(lv.hx_host) - 1, L.nx - 2);
+    L.ireg_hi = std::min(leading_regular(lv.hy_host) - 1, L.ny - 2);
+    L.cC = 2.0 * L.tau * (b / a + a / b) + a * b * 0.5;
+    L.cEW = a * b / 12.0 - L.tau * b / a;
+    L.cNS = a * b / 12.0 - L.tau * a / b;
+    L.cD = a * b / 12.0;
+    L.hx = lv.d_hx; L.ihx = lv.d_ihx; L.hy = lv.d_hy; L.ihy = lv.d_ihy;
+    L.d11 = lv.t11; L.d22 = lv.t22; L.d12 = lv.t12;
+}
+
+int solver_setup(eqgpu_solver *s)
+{
+    const eqgpu_params &p = s->p;
+    s->N = (size_t)p.nW * p.nH;
+    const double hx0 = p.hx, hy0 = p.hy > 0 ? p.hy : p.hx;
+    s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 2;
+    // ---- hierarchy -------------------------------------------------------
+    Level l0;
+    l0.dev.nx = p.nW; l0.dev.ny = p.nH;
+    l0.hx_host.assign(p.nW - 1, hx0);
+    l0.hy_host.assign(p.nH - 1, hy0);
+    s->levels.clear();
+    s->levels.push_back(l0);
+    const int maxl = p.max_levels > 0 ? p.max_levels : 12;
+    const double tau = p.dt * p.D;
+    while ((int)s->levels.size() < maxl) {
+        const Level &f = s->levels.back();
+        if (std::min(f.dev.nx, f.dev.ny) < 5) break;
+        // stop once the mass term dominates: Jacobi alone converges fast there
+        if (tau / (f.hx_host[0] * f.hy_host[0]) < 0.1) break;
+        Level c;
+        c.hx_host = coarsen_cells(f.hx_host);
+        c.hy_host = coarsen_cells(f.hy_host);
+        c.dev.nx = (int)c.hx_host.size() + 1;
+        c.dev.ny = (int)c.hy_host.size() + 1;
+        s->levels.push_back(c);
+    }
+    for (size_t l = 0; l < s->levels.size(); ++l) {
+        Level &lv = s->levels[l];
+        if (upload_padded(s, lv.hx_host, &lv.d_hx, &lv.d_ihx)) return EQGPU_ECUDA;
+        if (upload_padded(s, lv.hy_host, &lv.d_hy, &lv.d_ihy)) return EQGPU_ECUDA;
+        const size_t bytes = sizeof(double) * lv.n();
+        EQ_CUDA(cudaMalloc(&lv.t, bytes));
+        if (l > 0) {
+            EQ_CUDA(cudaMalloc(&lv.x, bytes));
+            EQ_CUDA(cudaMalloc(&lv.b, bytes));
+        }
+        fill_level_consts(s, lv);
+    }
+    // ---- fine vectors ----------------------------------------------------
+    const size_t bytes = sizeof(double) * s->N;
+    EQ_CUDA(cudaMalloc(&s->u, bytes));
+    EQ_CUDA(cudaMalloc(&s->r, bytes));
+    EQ_CUDA(cudaMalloc(&s->pv, bytes));
+    EQ_CUDA(cudaMalloc(&s->Ap, bytes));
+    EQ_CUDA(cudaMalloc(&s->z, bytes));
+    EQ_CUDA(cudaMemset(s->u, 0, bytes));
+    EQ_CUDA(cudaMemset(s->pv, 0, bytes));
+    s->levels[0].x = s->z;
+    s->levels[0].b = s->r;
+    // ---- reductions ------------------------------------------------------
+    dim3 g0 = grid2d(s->levels[0].dev);
+    s->max_blocks = std::max<int>(g0.x * g0.y, 8 * s->num_sms);
+    EQ_CUDA(cudaMalloc(&s->partials, sizeof(double) * 4 * s->max_blocks));
+    EQ_CUDA(cudaMalloc(&s->counters, sizeof(unsigned) * 16));
+    EQ_CUDA(cudaMemset(s->counters, 0, sizeof(unsigned) * 16));
+    EQ_CUDA(cudaMalloc(&s->sc, sizeof(CGScalars)));
+    EQ_CUDA(cudaMemset(s->sc, 0, sizeof(CGScalars)));
+    EQ_CUDA(cudaMallocHost(&s->sc_host, sizeof(CGScalars)));
+    EQ_CUDA(cudaMalloc(&s->chan_top, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMalloc(&s->chan_bot, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMalloc(&s->flux_top, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMalloc(&s->flux_bot, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMemset(s->chan_top, 0, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMemset(s->chan_bot, 0, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMemset(s->flux_top, 0, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMemset(s->flux_bot, 0, sizeof(double) * p.nW));
+    EQ_CUDA(cudaMalloc(&s->flux_dev, sizeof(double)));
+    EQ_CUDA(cudaMallocHost(&s->flux_host, sizeof(double)));
+    s->st.levels = (int)s->levels.size();
+    for (int w = 0; w < 4; ++w) s->dir_val[w] = p.bc_value[w];
+    return 0;
+}
+
+void solver_teardown(eqgpu_solver *s)
+{
+    for (auto &lv : s->levels) {
+        cudaFree(lv.d_hx); cudaFree(lv.d_ihx); cudaFree(lv.d_hy); cudaFree(lv.d_ihy);
+        cudaFree(lv.t);
+        if (&lv != &s->levels[0]) { cudaFree(lv.x); cudaFree(lv.b); }
+        if (&lv != &s->levels[0]) { cudaFree(lv.t11); cudaFree(lv.t22); cudaFree(lv.t12); }
+    }
+    s->levels.clear();
+    cudaFree(s->u); cudaFree(s->r); cudaFree(s->pv); cudaFree(s->Ap); cudaFree(s->z);
+    cudaFree(s->d11); cudaFree(s->d22); cudaFree(s->d12);
+    cudaFree(s->partials); cudaFree(s->counters); cudaFree(s->sc);
+    cudaFree(s->chan_top); cudaFree(s->chan_bot); cudaFree(s->flux_top); cudaFree(s->flux_bot);
+    cudaFree(s->chan_coef); cudaFree(s->flux_dev);
+    if (s->sc_host) cudaFreeHost(s->sc_host);
+    if (s->flux_host) cudaFreeHost(s->flux_host);
+}
+
+// (re)build the coarse tensor fields after eqgpu_set_tensor
+int solver_refresh_levels(eqgpu_solver *s)
+{
+    Level &l0 = s->levels[0];
+    l0.t11 = s->d11; l0.t22 = s->d22; l0.t12 = s->d12;
+    for (size_t l = 0; l < s->levels.size(); ++l) {
+        Level &lv = s->levels[l];
+        if (l > 0) {
+            if (s->tensor) {
+                const size_t bytes = sizeof(double) * lv.n();
+                if (!lv.t11) {
+                    EQ_CUDA(cudaMalloc(&lv.t11, bytes));
+                    EQ_CUDA(cudaMalloc(&lv.t22, bytes));
+                    EQ_CUDA(cudaMalloc(&lv.t12, bytes));
+                }
+                Level &f = s->levels[l - 1];
+                fill_level_consts(s, lv);
+                k_inject<<<grid2d(lv.dev), dim3(BX, BY), 0, s->stream>>>(f.dev, lv.dev, f.t11, lv.t11);
+                k_inject<<<grid2d(lv.dev), dim3(BX, BY), 0, s->stream>>>(f.dev, lv.dev, f.t22, lv.t22);
+                k_inject<<<grid2d(lv.dev), dim3(BX, BY), 0, s->stream>>>(f.dev, lv.dev, f.t12, lv.t12);
+                s->launches += 3;
+            }
+        }
+        fill_level_consts(s, lv);
+    }
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static DirData make_dirdata(eqgpu_solver *s)
+{
+    DirData d;
+    for (int w = 0; w < 4; ++w) d.val[w] = s->dir_val[w];
+    d.top = s->p.bc_type[EQGPU_TOP] == EQGPU_BC_DIRICHLET_CHANNEL ? s->chan_top : nullptr;
+    d.bot = s->p.bc_type[EQGPU_BOTTOM] == EQGPU_BC_DIRICHLET_CHANNEL ? s->chan_bot : nullptr;
+    return d;
+}
+
+template <bool T>
+static void vcycle(eqgpu_solver *s)
+{
+    const dim3 blk(BX, BY);
+    cudaStream_t st = s->stream;
+    const int nl = (int)s->levels.size();
+    const double om = s->omega;
+    // sweeps sweeps from a zero guess, result left in lv.x (uses lv.t as ping-pong)
+    auto smooth_from_zero = [&](Level &lv, int sweeps) {
+        const dim3 g = grid2d(lv.dev);
+        double *cur = (sweeps & 1) ? lv.x : lv.t;  // so that the last write lands in lv.x
+        k_jacobi0<T><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, om, s->sc);
+        s->launches++;
+        for (int k = 1; k < sweeps; ++k) {
+            double *nxt = (cur == lv.x) ? lv.t : lv.x;
+            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, om, s->sc);
+            s->launches++;
+            cur = nxt;
+        }
+    };
+    auto smooth = [&](Level &lv, int sweeps) {  // in: lv.x, out: lv.x
+        const dim3 g = grid2d(lv.dev);
+        double *cur = lv.x;
+        for (int k = 0; k < sweeps; ++k) {
+            double *nxt = (cur == lv.x) ? lv.t : lv.x;
+            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, om, s->sc);
+            s->launches++;
+            cur = nxt;
+        }
+        if (cur != lv.x) {  // odd sweep count: one more would break symmetry, so copy
+            cudaMemcpyAsync(lv.x, lv.t, sizeof(double) * lv.n(), cudaMemcpyDeviceToDevice, st);
+        }
+    };
+    for (int l = 0; l < nl - 1; ++l) {
+        Level &lv = s->levels[l], &cv = s->levels[l + 1];
+        smooth_from_zero(lv, s->nu);
+        k_jacobi<T, true><<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, lv.b, lv.x, lv.t, om, s->sc);
+        k_restrict<<<grid2d(cv.dev), blk, 0, st>>>(lv.dev, cv.dev, lv.t, cv.b, s->sc);
+        s->launches += 2;
+    }
+    smooth_from_zero(s->levels[nl - 1], nl > 1 ? s->ncoarse : std::max(s->ncoarse, 2 * s->nu));
+    for (int l = nl - 2; l >= 0; --l) {
+        Level &lv = s->levels[l], &cv = s->levels[l + 1];
+        k_prolong_add<<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, cv.dev, cv.x, lv.x, s->sc);
+        s->launches++;
+        smooth(lv, s->nu);
+    }
+}
+
+template <bool T>
+static int pcg(eqgpu_solver *s)
+{
+    const eqgpu_params &p = s->p;
+    cudaStream_t st = s->stream;
+    Level &l0 = s->levels[0];
+    const LevelDev &L = l0.dev;
+    const dim3 blk(BX, BY), g0 = grid2d(L);
+    const double rtol = p.rtol > 0 ? p.rtol : 1e-12;
+    const int max_iters = p.max_iters > 0 ? p.max_iters : 200;
+    const double rs_l = L.rob_l * p.robin_s[0], rs_r = L.rob_r * p.robin_s[1];
+    DirData dd = make_dirdata(s);
+    const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+
+    k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, s->sc, s->partials,
+                                  s->counters + 0);
+    k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->sc, rtol, max_iters);
+    s->launches += 2;
+
+    int issued = 0;
+    int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
+    while (true) {
+        for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
+            vcycle<T>(s);
+            k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
+            k_update_p<<<nb1, 256, 0, st>>>(s->N, s->z, s->pv, s->sc);
+            k_apply<T, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, s->sc, s->partials, s->counters + 2);
+            k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials,
+                                             s->counters + 3);
+            s->launches += 4;
+        }
+        EQ_CUDA(cudaMemcpyAsync(s->sc_host, s->sc, sizeof(CGScalars), cudaMemcpyDeviceToHost, st));
+        EQ_CUDA(cudaStreamSynchronize(st));
+        if (s->sc_host->done || issued >= max_iters) break;
+        chunk = 2;
+    }
+    s->st.iterations = s->sc_host->iters;
+    const double ref = s->sc_host->bnorm2;
+    s->st.relres = ref > 0 ? std::sqrt(s->sc_host->rr / ref) : 0.0;
+    if (s->sc_host->rr > s->sc_host->stop2) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "PCG did not converge: %d iterations, relres %.3e (rtol %.1e)",
+                 s->sc_host->iters, s->st.relres, rtol);
+        s->set_error(buf);
+        return EQGPU_ENOCONV;
+    }
+    return 0;
+}
+
+int solver_step(eqgpu_solver *s)
+{
+    int rc = s->tensor ? pcg<true>(s) : pcg<false>(s);
+    if (rc) return rc;
+    if (s->p.channels) {
+        rc = channels_step(s);
+        if (rc) return rc;
+    }
+    rc = boundary_functional(s);
+    if (rc) return rc;
+    s->st.steps++;
+    s->st.kernel_launches = s->launches;
+    return 0;
+}
+
+int solver_apply(eqgpu_solver *s, const double *dx, double *dy, bool constrained)
+{
+    const LevelDev &L = s->levels[0].dev;
+    if (s->tensor)
+        k_apply_check<true><<<grid2d(L), dim3(BX, BY), 0, s->stream>>>(L, dx, dy, constrained ? 1 : 0);
+    else
+        k_apply_check<false><<<grid2d(L), dim3(BX, BY), 0, s->stream>>>(L, dx, dy, constrained ? 1 : 0);
+    s->launches++;
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int solver_rhs(eqgpu_solver *s, const double *du0, double *db)
+{
+    const LevelDev &L = s->levels[0].dev;
+    k_rhs_check<<<grid2d(L), dim3(BX, BY), 0, s->stream>>>(L, du0, db, L.rob_l * s->p.robin_s[0],
+                                                            L.rob_r * s->p.robin_s[1]);
+    s->launches++;
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Times one named kernel in isolation (bench.py roofline line).  The vectors
+// used are the solver's own work vectors; the field u is not touched.
+int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes)
+{
+    Level &l0 = s->levels[0];
+    const LevelDev &L = l0.dev;
+    const dim3 blk(BX, BY), g0 = grid2d(L);
+    cudaStream_t st = s->stream;
+    const std::string nm(name);
+    cudaEvent_t e0, e1;
+    EQ_CUDA(cudaEventCreate(&e0));
+    EQ_CUDA(cudaEventCreate(&e1));
+    EQ_CUDA(cudaMemsetAsync(&s->sc->done, 0, sizeof(int), st));
+    auto launch = [&](int k) -> bool {
+        if (nm == "apply") {  // read p, write Ap (+ p.Ap): 16 B/DOF
+            k_apply<false, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, s->sc, s->partials, s->counters + 2);
+            *alg_bytes = 16.0 * s->N;
+        } else if (nm == "jacobi") {  // read x, b, write x': 24 B/DOF
+            double *a = (k & 1) ? l0.t : s->z, *b = (k & 1) ? s->z : l0.t;
+            k_jacobi<false, false><<<g0, blk, 0, st>>>(L, s->r, a, b, s->omega, s->sc);
+            *alg_bytes = 24.0 * s->N;
+        } else if (nm == "update_xr") {  // read x,r,p,Ap write x,r: 48 B/DOF
+            const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+            k_update_xr<<<nb1, 256, 0, st>>>(s->N, l0.t, s->z, s->pv, s->Ap, s->sc, s->partials, s->counters + 3);
+            *alg_bytes = 48.0 * s->N;
+        } else return false;
+        return true;
+    };
+    if (!launch(0)) { s->set_error("unknown kernel name"); return EQGPU_EINVAL; }
+    EQ_CUDA(cudaMemsetAsync(&s->sc->done, 0, sizeof(int), st));
+    EQ_CUDA(cudaEventRecord(e0, st));
+    for (int k = 0; k < reps; ++k) { launch(k); EQ_CUDA(cudaMemsetAsync(&s->sc->done, 0, sizeof(int), st)); }
+    EQ_CUDA(cudaEventRecord(e1, st));
+    EQ_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    EQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *avg_ms = ms / reps;
+    s->launches += reps + 1;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}

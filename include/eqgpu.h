@@ -1,0 +1,175 @@
+/*
+ * eqgpu.h -- C ABI of the B200 (sm_100a) HSL diffusion solver.
+ *
+ * This is the drop-in boundary for ONE hot path of jwinkle/eQ: the per-timestep
+ * implicit HSL solve and the cell<->mesh coupling around it.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference
+ * root).  The C++ host class eq_b200/host/gpuHSL.h wraps these behind eQ's own
+ * `eQ::diffusionSolver` interface (src/eQ.h:302-330); INTEGRATION.md shows the
+ * edits a maintainer makes in src/simulation.{h,cpp}.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host
+ * buffer; all fields are fp64 in natural node order g = iy*nW + jx (the
+ * identity dof map, src/fHSL.h:89-114 / src/simulation.cpp:367-386); one
+ * solver <-> one CUDA device and stream, no process-global state.  Every
+ * function returns 0 on success or a negative EQGPU_E* code;
+ * eqgpu_last_error() gives the message.  There is NO CPU fallback: without a
+ * usable CUDA device eqgpu_create fails with EQGPU_ECUDA.
+ */
+#ifndef EQGPU_H
+#define EQGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQGPU_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define EQGPU_API __attribute__((visibility("default")))
+#else
+#define EQGPU_API
+#endif
+
+enum {
+    EQGPU_OK = 0,
+    EQGPU_EINVAL = -1,   /* bad argument / configuration           */
+    EQGPU_ECUDA = -2,    /* CUDA runtime error or no device        */
+    EQGPU_ENOCONV = -3,  /* PCG hit max_iters before reaching rtol */
+    EQGPU_ESTATE = -4    /* call made in the wrong state           */
+};
+
+/* Wall order everywhere: LEFT (x=0), RIGHT (x=W), TOP (y=H), BOTTOM (y=0). */
+enum { EQGPU_LEFT = 0, EQGPU_RIGHT = 1, EQGPU_TOP = 2, EQGPU_BOTTOM = 3 };
+
+/* Boundary types = the decode of parameters["boundaries"][wall][1] = {a,b,v}
+ * in src/fHSL.cpp:468-539 (a==0 Dirichlet value v, v==-1 on top/bottom means
+ * "the channel Function"; b==0 homogeneous Neumann; else Robin), and of the
+ * legacy DIRICHLET_0 / DIRICHLET_UPDATE paths (:545-569). */
+enum {
+    EQGPU_BC_NEUMANN = 0,
+    EQGPU_BC_DIRICHLET = 1,          /* bc_value = boundary value            */
+    EQGPU_BC_ROBIN = 2,              /* bc_value = rate r (left/right only)  */
+    EQGPU_BC_DIRICHLET_CHANNEL = 3   /* top/bottom only: value = channel u   */
+};
+
+/* What fenicsInterface::initDiffusion reads from eQ::diffusionSolver::params
+ * (src/eQ.h:305-321) and from eQ::data::parameters (SURVEY.md 8b "globals"). */
+typedef struct eqgpu_params {
+    int32_t abi_version;      /* EQGPU_ABI_VERSION */
+    int32_t nW, nH;           /* node counts = cells+1 (src/fHSL.cpp:242-243,281-283) */
+    double hx, hy;            /* node spacing; hy <= 0 means hy = hx (1/nodesPerMicron) */
+    double dt;                /* params.dt                                   */
+    double D;                 /* params.D_HSL                                */
+    int32_t bc_type[4];       /* EQGPU_BC_* per wall                         */
+    double bc_value[4];       /* Dirichlet value or Robin rate per wall      */
+    double robin_s[2];        /* s_left, s_right (src/fHSL.cpp:359-360)      */
+    int32_t channels;         /* 1: MICROFLUIDIC_TRAP && !H_TRAP branch of stepDiffusion (:110-152) */
+    int32_t channel_iters;    /* channelSolverNumberIterations (src/main.cpp:426-429) */
+    double channel_v;         /* simulationFlowRate (src/fHSL.cpp:336)       */
+    double channel_r[2];      /* Robin rates at the channel ends (:342-362)  */
+    double well_scaling;      /* src/fHSL.cpp:47                             */
+    double rtol;              /* PCG relative residual target; <=0 -> 1e-12  */
+    int32_t max_iters;        /* <=0 -> 200                                  */
+    int32_t device;           /* CUDA device ordinal                         */
+    void *stream;             /* cudaStream_t to run on, or NULL for an own stream */
+    int32_t smooth_sweeps;    /* multigrid pre/post sweeps; <=0 -> default   */
+    int32_t max_levels;       /* <=0 -> automatic                            */
+    int32_t reserved[8];
+} eqgpu_params;
+
+typedef struct eqgpu_stats {
+    int32_t iterations;        /* PCG iterations of the last step            */
+    int32_t levels;            /* multigrid levels in use                    */
+    double relres;             /* ||r|| / ||b|| reached                      */
+    double total_boundary_flux;/* fenicsInterface::totalBoundaryFlux (src/fHSL.cpp:160) */
+    int64_t kernel_launches;   /* kernels launched by this solver so far     */
+    int64_t steps;             /* steps taken so far                         */
+} eqgpu_stats;
+
+typedef struct eqgpu_solver eqgpu_solver;
+
+/* Fills *p with the shipped defaults (src/main.cpp:457-548, src/eQinit.h:12). */
+EQGPU_API void eqgpu_default_params(eqgpu_params *p);
+
+/* ctor + initDiffusion (src/fHSL.cpp:17-24,37-53,195-328). */
+EQGPU_API int eqgpu_create(const eqgpu_params *p, eqgpu_solver **out);
+/* dtor / finalize (src/fHSL.cpp:655-661). */
+EQGPU_API void eqgpu_destroy(eqgpu_solver *s);
+/* Message of the last failure on this solver (s == NULL: last create failure). */
+EQGPU_API const char *eqgpu_last_error(const eqgpu_solver *s);
+
+/* solution_vector access (src/fHSL.h:412; the buffer Simulation Isend/Irecv's,
+ * src/simulation.cpp:491-505).  Host <-> device copies of nW*nH doubles. */
+EQGPU_API int eqgpu_set_field(eqgpu_solver *s, const double *host_u);
+EQGPU_API int eqgpu_get_field(eqgpu_solver *s, double *host_u);
+
+/* D11/D22/D12 (src/fHSL.h:434, src/simulation.cpp:503-505).  All NULL restores
+ * the isotropic 1,1,0 default (src/fHSL.cpp:313-323). */
+EQGPU_API int eqgpu_set_tensor(eqgpu_solver *s, const double *d11, const double *d22, const double *d12);
+
+/* fenicsInterface::setBoundaryValues (src/fHSL.cpp:601-604): every Dirichlet
+ * wall takes value v from the next step on (DIRICHLET_UPDATE). */
+EQGPU_API int eqgpu_set_boundary_value(eqgpu_solver *s, double v);
+
+/* fenicsInterface::stepDiffusion (src/fHSL.cpp:98-161) on the device-resident
+ * field: trap solve, channel flux + sub-steps, boundary-flux functional. */
+EQGPU_API int eqgpu_step(eqgpu_solver *s);
+/* Same with the reference's host-vector contract: solution_vector in, solved
+ * field out (H2D + step + D2H inside the call). */
+EQGPU_API int eqgpu_step_host(eqgpu_solver *s, double *solution_vector);
+
+EQGPU_API int eqgpu_get_stats(eqgpu_solver *s, eqgpu_stats *out);
+
+/* topChannelData / bottomChannelData (src/fHSL.cpp:145-151), nW doubles each. */
+EQGPU_API int eqgpu_get_channels(eqgpu_solver *s, double *top, double *bottom);
+EQGPU_API int eqgpu_set_channels(eqgpu_solver *s, const double *top, const double *bottom);
+/* fluxTopChannel / fluxBottomChannel of the last step (src/fHSL.cpp:54-96). */
+EQGPU_API int eqgpu_get_channel_flux(eqgpu_solver *s, double *flux_top, double *flux_bottom);
+
+/* ---- cells: eQabm::updateCells' lambdas (src/abm/eQabm.cpp:268-359) -------
+ * A cell record is EQGPU_CELL_STRIDE doubles:
+ *  0,1 bodyA position   2,3 bodyA rot (cos,sin)   4 offset   5 newOffset
+ *  6 radius   7,8 polePositionA   9,10 polePositionB   11,12 centre   13 length
+ * (what findInteriorPoints / pointIsInCell read: src/abm/cpmEcoli.cpp:313-327,
+ *  src/abm/Ecoli.cpp:36-63). */
+#define EQGPU_CELL_STRIDE 16
+EQGPU_API int eqgpu_cells_upload(eqgpu_solver *s, const double *records, int64_t ncells, double nodes_per_micron);
+/* findInteriorPoints: counts[k] points of cell k, node ids (iy*nW+jx) in the
+ * reference's push_back order into nodes[k*cap .. ] (at most cap written). */
+EQGPU_API int eqgpu_cells_raster(eqgpu_solver *s, int32_t *counts, int64_t *nodes, int32_t cap);
+/* readHSL for every cell: out[k] = mean of the field over the cell's points. */
+EQGPU_API int eqgpu_cells_gather(eqgpu_solver *s, double *out);
+/* writeHSL for every cell: amount_nM[k] is Strain's deltaHSL for this layer. */
+EQGPU_API int eqgpu_cells_scatter(eqgpu_solver *s, const double *amount_nM);
+
+/* Device-resident variants (no host copy inside): gather into the solver's
+ * per-cell buffer / scatter the amounts last given to eqgpu_cells_set_amounts.
+ * eqgpu_cells_get_gathered copies the last gather result to the host. */
+EQGPU_API int eqgpu_cells_set_amounts(eqgpu_solver *s, const double *amount_nM);
+EQGPU_API int eqgpu_cells_gather_resident(eqgpu_solver *s);
+EQGPU_API int eqgpu_cells_scatter_resident(eqgpu_solver *s);
+EQGPU_API int eqgpu_cells_get_gathered(eqgpu_solver *s, double *out);
+
+/* ---- verification hooks (used by the parity tests) ------------------------
+ * y = A x with A = M + dt*K(D) + dt*R exactly as DOLFIN would assemble it
+ * (unconstrained, constrained = 0) or with Dirichlet rows replaced by identity
+ * and columns eliminated (constrained = 1). */
+EQGPU_API int eqgpu_apply_operator(eqgpu_solver *s, const double *host_x, double *host_y, int constrained);
+/* b = L(u0) = M u0 + Robin load (unconstrained load vector). */
+EQGPU_API int eqgpu_build_rhs(eqgpu_solver *s, const double *host_u0, double *host_b);
+/* Device pointer to the resident field (for benchmarks that stage inputs in HBM). */
+EQGPU_API int eqgpu_field_device_ptr(eqgpu_solver *s, void **dev_ptr);
+EQGPU_API int eqgpu_sync(eqgpu_solver *s);
+/* Times `reps` back-to-back launches of one named kernel on the solver's
+ * stream with CUDA events (for bench.py's roofline line).  Returns the average
+ * milliseconds per launch and the algorithmic bytes one launch must move
+ * (DESIGN.md "kernels").  Unknown name -> EQGPU_EINVAL. */
+EQGPU_API int eqgpu_bench_kernel(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQGPU_H */

@@ -292,7 +292,8 @@ def make_cells(centers, angles, lengths, trapW, trapH, width=1.0):
 
 def nodes_to_edge(npm):
     # src/abm/eQabm.cpp:75
-    return int(round(npm * 1.0 / 2.0))
+    import math
+    return int(math.floor(npm * 1.0 / 2.0 + 0.5))  # C round(): half away from zero
 
 
 def raster(cells, npm, nH, nW, cap=512):

@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, eq_b200.GpuHSL) against the
+CPU oracle on identical meshes, fields, cells and dt.
+
+Bars (BASELINE.json north_star): fields and per-cell sampled concentrations
+rel-L2 <= 1e-8 against the direct (LU) solve; cell -> node lookup bit-exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import eq_b200 as E
+
+TOL = 1e-8  # relative L2, north_star
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def field(p, seed=0, smooth=True):
+    rng = np.random.default_rng(seed)
+    if not smooth:
+        return rng.uniform(0, 10, p.N)
+    y, x = np.mgrid[0:p.nH, 0:p.nW]
+    u = 5 + 3 * np.sin(2 * np.pi * x / p.nW) * np.cos(np.pi * y / p.nH) + rng.uniform(0, 1, (p.nH, p.nW))
+    return u.ravel()
+
+
+def make(oracle, nW, nH, **kw):
+    p = oracle.Problem(nW=nW, nH=nH, **kw)
+    g = E.GpuHSL(nW, nH, h=p.h, dt=p.dt, D=p.D, bc_type=p.bc_type, bc_value=p.bc_value,
+                 robin_s=p.robin_s, channels=p.channels, channel_v=p.channel_v,
+                 channel_r=p.channel_r, channel_iters=p.channel_iters, well_scaling=p.well_scaling)
+    return p, g
+
+
+BCS = {
+    "dirichlet0": dict(bc_type=(1, 1, 1, 1), bc_value=(0, 0, 0, 0)),
+    "neumann": dict(bc_type=(0, 0, 0, 0), bc_value=(0, 0, 0, 0)),
+    "robin_lr": dict(bc_type=(2, 2, 0, 0), bc_value=(120.0, 120.0, 0, 0)),
+    "robin_lr_dir_tb": dict(bc_type=(2, 2, 1, 1), bc_value=(138.78, 18.78, 2.0, 0.5), robin_s=(0.3, 0.1)),
+    "threewall": dict(bc_type=(0, 0, 0, 1), bc_value=(0, 0, 0, 0)),
+    "dir_values": dict(bc_type=(1, 1, 1, 1), bc_value=(1.0, 2.0, 3.0, 4.0)),
+}
+
+
+@pytest.mark.parametrize("bc", list(BCS))
+@pytest.mark.parametrize("shape", [(201, 41), (64, 37), (17, 16)])
+def test_operator_matches_assembled_matrix(oracle, bc, shape):
+    """(1) matrix-free stencil == the Fenics-style assembled matrix (unconstrained and constrained)."""
+    p, g = make(oracle, *shape, **BCS[bc])
+    bands, _ = oracle.assemble(p, None)
+    x = field(p, 1, smooth=False)
+    y_ref = oracle.band_matvec(p, bands, x)
+    y = g.apply_operator(x)
+    assert rel(y, y_ref) < 1e-13
+    # constrained operator vs symmetric elimination of the same matrix
+    import ctypes as C
+    mask, gv = oracle.dirichlet(p)
+    b = np.zeros(p.N)
+    oracle.lib().eqo_apply_dirichlet_sym(C.c_long(p.nW), C.c_long(p.nH), oracle._dp(bands), oracle._dp(b),
+                                         mask.ctypes.data_as(oracle.c_u8p), oracle._dp(gv))
+    assert rel(g.apply_operator(x, constrained=True), oracle.band_matvec(p, bands, x)) < 1e-13
+    g.close()
+
+
+@pytest.mark.parametrize("bc", ["dirichlet0", "robin_lr_dir_tb"])
+def test_rhs_matches_assembled_load(oracle, bc):
+    p, g = make(oracle, 201, 41, **BCS[bc])
+    u0 = field(p, 2)
+    _, b_ref = oracle.assemble(p, u0, want_matrix=False)
+    assert rel(g.build_rhs(u0), b_ref) < 1e-13
+    g.close()
+
+
+@pytest.mark.parametrize("bc", list(BCS))
+@pytest.mark.parametrize("shape", [(201, 41), (257, 257), (130, 75)])
+def test_step_matches_direct_solve(oracle, bc, shape):
+    """(2) one backward-Euler step == assemble + DirichletBC + sparse LU (src/fHSL.cpp:104-108)."""
+    p, g = make(oracle, *shape, **BCS[bc])
+    u0 = field(p, 3)
+    ref = oracle.solve_lu(p, u0)
+    g.solution_vector[:] = u0
+    out = g.stepDiffusion()
+    st = g.stats()
+    assert rel(out, ref) < TOL, (st.iterations, st.relres)
+    # flux functional (src/fHSL.cpp:156-160)
+    want = p.D * p.dt * oracle.boundary_functional(p, ref)
+    assert abs(g.totalBoundaryFlux - want) <= 1e-7 * max(abs(want), 1.0)
+    g.close()
+
+
+def test_multi_step_default_trap(oracle):
+    """Config 1: default trap 201x41, Dirichlet-0, 32 cells depositing, 20 steps."""
+    p, g = make(oracle, 201, 41, **BCS["dirichlet0"])
+    rng = np.random.default_rng(5)
+    n = 32
+    centers = np.c_[rng.uniform(3, p.W - 3, n), rng.uniform(3, p.H - 3, n)]
+    cells = oracle.make_cells(centers, rng.uniform(0, 2 * np.pi, n), (1 + rng.uniform(size=n)) * 2.1, p.W, p.H)
+    npm = 1.0 / p.h
+    g.upload_cells(cells, npm)
+    s = oracle.new_state(p)
+    for k in range(20):
+        amount = 100.0 + 5.0 * oracle.gather(cells, npm, p.nH, p.nW, s.u)
+        s.u = oracle.scatter(cells, npm, p.nH, p.nW, amount, s.u)
+        s = oracle.step(p, s)
+        ga = 100.0 + 5.0 * g.gather()
+        g.scatter(ga)
+        g.step()
+    assert rel(g.get_field(), s.u) < TOL
+    assert rel(g.gather(), oracle.gather(cells, npm, p.nH, p.nW, s.u)) < TOL
+    g.close()
+
+
+def test_channels_config4_small(oracle):
+    """Microfluidic trap: Robin left/right, top/bottom Dirichlet from the 1-D channels,
+    CN channel sub-steps driven by the FD wall flux (src/fHSL.cpp:110-152)."""
+    rl, rr = oracle.robin_rates(120.0, 1200.0, 20.0, 20.0)
+    kw = dict(bc_type=(2, 2, 3, 3), bc_value=(rl, rr, 0, 0), channels=True, channel_v=120.0,
+              channel_r=(rl, rr), channel_iters=48, well_scaling=10.0 * (25.0 / 5.0) * 0.5)
+    p, g = make(oracle, 201, 41, **kw)
+    s = oracle.new_state(p)
+    rng = np.random.default_rng(7)
+    for k in range(6):
+        dep = np.zeros(p.N)
+        dep[rng.integers(0, p.N, 50)] += rng.uniform(10, 100, 50)
+        s.u = s.u + dep
+        s = oracle.step(p, s)
+        g.set_field(g.get_field() + dep)
+        g.step()
+    t, b = g.channels()
+    assert rel(g.get_field(), s.u) < TOL
+    assert rel(t, s.top) < TOL and rel(b, s.bottom) < TOL
+    assert abs(g.totalBoundaryFlux - s.total_boundary_flux) <= 1e-7 * abs(s.total_boundary_flux)
+    g.close()
+
+
+def test_tensor_operator_and_step(oracle):
+    """Variable anisotropic tensor D*[[D11,D12],[D12,D22]] (fenics/hslD.ufl:34)."""
+    p, g = make(oracle, 97, 65, **BCS["robin_lr_dir_tb"])
+    rng = np.random.default_rng(11)
+    th = rng.uniform(0, np.pi, p.N)
+    dx, dy = 1.5, 0.6
+    p.d11 = dx * np.cos(th) ** 2 + dy * np.sin(th) ** 2
+    p.d22 = dx * np.sin(th) ** 2 + dy * np.cos(th) ** 2
+    p.d12 = (dx - dy) * np.sin(th) * np.cos(th)
+    g.set_tensor(p.d11, p.d22, p.d12)
+    bands, _ = oracle.assemble(p, None)
+    x = field(p, 1, smooth=False)
+    assert rel(g.apply_operator(x), oracle.band_matvec(p, bands, x)) < 1e-12
+    u0 = field(p, 4)
+    ref = oracle.solve_lu(p, u0)
+    g.solution_vector[:] = u0
+    assert rel(g.stepDiffusion(), ref) < TOL
+    g.close()
+
+
+@pytest.mark.parametrize("npm,shape", [(2.0, (201, 41)), (1.0, (101, 21)), (4.0, (401, 81))])
+def test_raster_bit_exact(oracle, npm, shape):
+    """Cell -> node lookup must be bit-exact (north_star): identical node lists, order included."""
+    nW, nH = shape
+    h = 1.0 / npm
+    W, H = (nW - 1) * h, (nH - 1) * h
+    rng = np.random.default_rng(21)
+    n = 4000
+    # include rods poking through the walls (clamped poles) and tiny rods (empty set fallback)
+    centers = np.c_[rng.uniform(-0.5, W + 0.5, n), rng.uniform(-0.5, H + 0.5, n)]
+    centers = np.clip(centers, 0.0, [W, H])
+    lengths = np.where(rng.uniform(size=n) < 0.1, 1.05, (1 + rng.uniform(size=n)) * 2.1)
+    cells = oracle.make_cells(centers, rng.uniform(0, 2 * np.pi, n), lengths, W, H)
+    # grown rods: newOffset ratcheted beyond offset (src/abm/cpmEcoli.cpp:407-415)
+    cells[::3, 5] += 0.05 * rng.integers(0, 20, len(cells[::3]))
+    # nodes exactly on the rectangle edge: axis-aligned rods centred on nodes
+    cells[:50, 2], cells[:50, 3] = 1.0, 0.0
+    cells[:50, 0] = np.round(cells[:50, 0] * npm) / npm
+    cells[:50, 1] = np.round(cells[:50, 1] * npm) / npm
+    g = E.GpuHSL(nW, nH, h=h)
+    g.upload_cells(cells, npm)
+    cnt, nodes = g.raster(cap=256)
+    cnt_ref, nodes_ref = oracle.raster(cells, npm, nH, nW, cap=256)
+    assert np.array_equal(cnt, cnt_ref)
+    assert np.array_equal(nodes, nodes_ref)
+    assert cnt.min() >= 1
+    # gather is summed in the reference's order -> bit-exact; scatter adds the same per-node amount
+    u = rng.uniform(0, 50, nW * nH)
+    g.set_field(u)
+    assert np.array_equal(g.gather(), oracle.gather(cells, npm, nH, nW, u))
+    g.close()
+
+
+def test_scatter_conserves_and_matches(oracle):
+    nW = nH = 512
+    p = oracle.Problem(nW=nW, nH=nH)
+    cells = oracle.synthetic_colony(1500, p.W, p.H, seed=3)
+    g = E.GpuHSL(nW, nH)
+    npm = 2.0
+    g.upload_cells(cells, npm)
+    rng = np.random.default_rng(9)
+    amount = rng.uniform(10, 200, len(cells))
+    u0 = rng.uniform(0, 5, p.N)
+    g.set_field(u0)
+    g.scatter(amount)
+    ref = oracle.scatter(cells, npm, nH, nW, amount, u0)
+    out = g.get_field()
+    # rods are separated: each node gets one add -> bit-exact
+    assert np.array_equal(out, ref)
+    g.close()
+
+
+def test_full_size_2048_properties(oracle):
+    """Config 3 at full size: properties that need no direct solve.
+    (a) residual of the returned field in the ORACLE's assembled operator;
+    (b) mass conservation under all-Neumann walls (sum M u is invariant);
+    (c) oracle CG (independent code) agreement."""
+    nW = nH = 2048
+    p, g = make(oracle, nW, nH, **BCS["neumann"])
+    cells = oracle.synthetic_colony(20000, p.W, p.H)
+    npm = 2.0
+    g.upload_cells(cells, npm)
+    amount = np.full(len(cells), 100.0)
+    g.scatter(amount)
+    u0 = g.get_field()
+    assert np.array_equal(u0, oracle.scatter(cells, npm, nH, nW, amount, np.zeros(p.N)))
+    g.step()
+    u1 = g.get_field()
+    bands, b = oracle.assemble(p, u0)
+    r = b - oracle.band_matvec(p, bands, u1)
+    assert np.linalg.norm(r) / np.linalg.norm(b) < 1e-11
+    # (b) 1^T M u1 = 1^T M u0  (K 1 = 0)
+    _, m1 = oracle.assemble(p, u1, want_matrix=False)
+    assert abs(m1.sum() - b.sum()) <= 1e-10 * abs(b.sum())
+    # (c) Dirichlet-0 variant against the oracle's own CG
+    p2, g2 = make(oracle, nW, nH, **BCS["dirichlet0"])
+    g2.solution_vector[:] = u0
+    out = g2.stepDiffusion()
+    ref, it, relres = oracle.solve_cg(p2, u0, rtol=1e-13)
+    assert it > 0
+    assert rel(out, ref) < TOL
+    g.close(); g2.close()
