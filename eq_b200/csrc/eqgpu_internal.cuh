@@ -32,7 +32,7 @@ struct LevelDev {
     unsigned dirmask;     // bit0 left, bit1 right, bit2 top, bit3 bottom are Dirichlet
     // uniform fast path: nodes 1<=j<=jreg_hi, 1<=i<=ireg_hi see four regular cells
     int jreg_hi, ireg_hi;
-    double cC, cEW, cNS, cD;
+    double cC, cEW, cNS, cD, icC;
     // optional nodal tensor fields (level-local, injected); null = isotropic
     const double *d11, *d22, *d12;
 };
@@ -61,7 +61,11 @@ struct eqgpu_solver {
     std::vector<Level> levels;
     // fine-level vectors
     double *u = nullptr;   // resident field == PCG iterate x
-    double *r = nullptr, *pv = nullptr, *Ap = nullptr, *z = nullptr;
+    double *r = nullptr, *pv = nullptr, *pv2 = nullptr, *Ap = nullptr, *z = nullptr;
+    LevelDev *d_levels = nullptr;  // device copy of every level descriptor (k_tail)
+    int tail_first = 0;            // first level handled by the single-CTA tail kernel
+    size_t tail_smem = 0;
+    bool fused = true;
     double *d11 = nullptr, *d22 = nullptr, *d12 = nullptr;
     // Dirichlet data
     double dir_val[4] = {0, 0, 0, 0};
@@ -122,18 +126,31 @@ __device__ __forceinline__ bool is_dirichlet(const LevelDev &L, int i, int j)
            ((m & 4u) && i == L.ny - 1) || ((m & 8u) && i == 0);
 }
 
+// Where a kernel reads the padded cell sizes from: global memory (jo = io = 0)
+// or a shared-memory copy of the window [jo, jo+n) x [io, io+m) of a tile.
+struct Spacing {
+    const double *hx, *ihx, *hy, *ihy;
+    int jo, io;
+};
+__device__ __forceinline__ Spacing global_spacing(const LevelDev &L)
+{
+    Spacing S; S.hx = L.hx; S.ihx = L.ihx; S.hy = L.hy; S.ihy = L.ihy; S.jo = 0; S.io = 0;
+    return S;
+}
+
 // Row of A = M + dt*K + dt*R at node (i,j) of a tensor-product "right" mesh,
 // isotropic constant tensor (closed form of fenics/hslD.h:3123-3350 summed over
 // the six triangles around the node; DESIGN.md "operator").
-__device__ __forceinline__ void stencil_iso(const LevelDev &L, int i, int j, double c[NBAND])
+__device__ __forceinline__ void stencil_iso(const LevelDev &L, const Spacing &S, int i, int j, double c[NBAND])
 {
     if (i >= 1 && i <= L.ireg_hi && j >= 1 && j <= L.jreg_hi) {
         c[B_C] = L.cC; c[B_E] = L.cEW; c[B_W] = L.cEW; c[B_N] = L.cNS; c[B_S] = L.cNS;
         c[B_NE] = L.cD; c[B_SW] = L.cD;
         return;
     }
-    const double aw = L.hx[j], ae = L.hx[j + 1], bs = L.hy[i], bn = L.hy[i + 1];
-    const double iaw = L.ihx[j], iae = L.ihx[j + 1], ibs = L.ihy[i], ibn = L.ihy[i + 1];
+    const int jj = j - S.jo, ii = i - S.io;
+    const double aw = S.hx[jj], ae = S.hx[jj + 1], bs = S.hy[ii], bn = S.hy[ii + 1];
+    const double iaw = S.ihx[jj], iae = S.ihx[jj + 1], ibs = S.ihy[ii], ibn = S.ihy[ii + 1];
     const double sy = 0.5 * L.tau * (bs + bn), sx = 0.5 * L.tau * (aw + ae);
     const double my = (bs + bn) * (1.0 / 24.0), mx = (aw + ae) * (1.0 / 24.0);
     c[B_E] = ae * my - sy * iae;
@@ -156,6 +173,11 @@ __device__ __forceinline__ void stencil_iso(const LevelDev &L, int i, int j, dou
         c[B_S] += L.rob_r * bs * (1.0 / 6.0);
     }
     c[B_C] = cc;
+}
+
+__device__ __forceinline__ void stencil_iso(const LevelDev &L, int i, int j, double c[NBAND])
+{
+    stencil_iso(L, global_spacing(L), i, j, c);
 }
 
 // Consistent P1 mass row only (for the load vector b = M u0).

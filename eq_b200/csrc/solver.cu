@@ -6,6 +6,7 @@
 // DOLFIN assembles it and runs a sparse LU; here A is never formed: every
 // kernel evaluates the 7-point row of the "right"-diagonal mesh in registers.
 #include "eqgpu_internal.cuh"
+#include "mg_fused.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -274,10 +275,6 @@ k_jacobi(LevelDev L, const double *__restrict__ b, const double *__restrict__ xi
     xout[g] = out;
 }
 
-// coarse node J <-> fine node min(2J, nf-1)
-__device__ __forceinline__ int fine_of(int J, int nf) { return min(2 * J, nf - 1); }
-// is fine index f a "midpoint" node (odd and not the last node)?
-__device__ __forceinline__ bool is_mid(int f, int nf) { return (f & 1) && f != nf - 1; }
 
 // bc = P^T rf  (P = P1 interpolation on the "right" mesh: midpoints of the
 // E-W, N-S and SW-NE edges take half of each end)
@@ -319,16 +316,8 @@ k_prolong_add(LevelDev F, LevelDev Cc, const double *__restrict__ xc, double *__
     if (i >= F.ny || j >= F.nx) return;
     if (is_dirichlet(F, i, j)) return;
     const bool mi = is_mid(i, F.ny), mj = is_mid(j, F.nx);
-    // coarse index of the coincident / lower neighbour node
-    const int I0 = (i == F.ny - 1 && !(i & 1)) ? i / 2 : (i == F.ny - 1 ? Cc.ny - 1 : i / 2);
-    const int J0 = (j == F.nx - 1 && !(j & 1)) ? j / 2 : (j == F.nx - 1 ? Cc.nx - 1 : j / 2);
-    const double *c0 = xc + (size_t)I0 * Cc.nx + J0;
-    double add;
-    if (!mi && !mj) add = __ldg(c0);
-    else if (!mi && mj) add = 0.5 * (__ldg(c0) + __ldg(c0 + 1));
-    else if (mi && !mj) add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx));
-    else add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx + 1));
-    xf[(size_t)i * F.nx + j] += add;
+    (void)mi; (void)mj;
+    xf[(size_t)i * F.nx + j] += prolong_at(F, Cc, xc, i, j);
 }
 
 // nodal injection of a tensor component to the coarse grid
@@ -397,6 +386,7 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
     L.cEW = a * b / 12.0 - L.tau * b / a;
     L.cNS = a * b / 12.0 - L.tau * a / b;
     L.cD = a * b / 12.0;
+    L.icC = 1.0 / L.cC;
     L.hx = lv.d_hx; L.ihx = lv.d_ihx; L.hy = lv.d_hy; L.ihy = lv.d_ihy;
     L.d11 = lv.t11; L.d22 = lv.t22; L.d12 = lv.t12;
 }
@@ -406,7 +396,7 @@ int solver_setup(eqgpu_solver *s)
     const eqgpu_params &p = s->p;
     s->N = (size_t)p.nW * p.nH;
     const double hx0 = p.hx, hy0 = p.hy > 0 ? p.hy : p.hx;
-    s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 2;
+    s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 3;
     // ---- hierarchy -------------------------------------------------------
     Level l0;
     l0.dev.nx = p.nW; l0.dev.ny = p.nH;
@@ -420,7 +410,7 @@ int solver_setup(eqgpu_solver *s)
         const Level &f = s->levels.back();
         if (std::min(f.dev.nx, f.dev.ny) < 5) break;
         // stop once the mass term dominates: Jacobi alone converges fast there
-        if (tau / (f.hx_host[0] * f.hy_host[0]) < 0.1) break;
+        if (tau / (f.hx_host[0] * f.hy_host[0]) < 0.6) break;
         Level c;
         c.hx_host = coarsen_cells(f.hx_host);
         c.hy_host = coarsen_cells(f.hy_host);
@@ -445,6 +435,8 @@ int solver_setup(eqgpu_solver *s)
     EQ_CUDA(cudaMalloc(&s->u, bytes));
     EQ_CUDA(cudaMalloc(&s->r, bytes));
     EQ_CUDA(cudaMalloc(&s->pv, bytes));
+    EQ_CUDA(cudaMalloc(&s->pv2, bytes));
+    EQ_CUDA(cudaMemset(s->pv2, 0, bytes));
     EQ_CUDA(cudaMalloc(&s->Ap, bytes));
     EQ_CUDA(cudaMalloc(&s->z, bytes));
     EQ_CUDA(cudaMemset(s->u, 0, bytes));
@@ -472,6 +464,42 @@ int solver_setup(eqgpu_solver *s)
     EQ_CUDA(cudaMallocHost(&s->flux_host, sizeof(double)));
     s->st.levels = (int)s->levels.size();
     for (int w = 0; w < 4; ++w) s->dir_val[w] = p.bc_value[w];
+    // ---- single-CTA tail: the deepest levels that fit one CTA's shared memory
+    EQ_CUDA(cudaMalloc(&s->d_levels, sizeof(LevelDev) * MAX_LEVELS));
+    {
+        const size_t budget = 200 * 1024;
+        const int nl = (int)s->levels.size();
+        int first = nl - 1;
+        auto need = [&](int l) {
+            const Level &lv = s->levels[l];
+            return sizeof(double) * (3 * lv.n() + 2 * (lv.dev.nx + 1) + 2 * (lv.dev.ny + 1));
+        };
+        size_t used = need(nl - 1);
+        while (first > 0 && used + need(first - 1) <= budget) {
+            --first;
+            used += need(first);
+        }
+        if (used > budget) { s->fused = false; }  // coarsest level alone too big: unfused path
+        s->tail_first = first;
+        s->tail_smem = used;
+    }
+    if (s->fused) {
+        EQ_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tail_smem));
+        const int nu = s->nu;
+        if (nu > 4) { s->set_error("smooth_sweeps must be <= 4"); return EQGPU_EINVAL; }
+        const int tsm = 2 * TN * (int)sizeof(double);
+#define SET_SMEM(NU)                                                                                         \
+    case NU:                                                                                                 \
+        EQ_CUDA(cudaFuncSetAttribute((k_presmooth<NU, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));       \
+        EQ_CUDA(cudaFuncSetAttribute((k_presmooth<NU, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));        \
+        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
+        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
+        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));  \
+        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
+        break;
+        switch (nu) { SET_SMEM(1) SET_SMEM(2) SET_SMEM(3) SET_SMEM(4) }
+#undef SET_SMEM
+    }
     return 0;
 }
 
@@ -484,6 +512,7 @@ void solver_teardown(eqgpu_solver *s)
         if (&lv != &s->levels[0]) { cudaFree(lv.t11); cudaFree(lv.t22); cudaFree(lv.t12); }
     }
     s->levels.clear();
+    cudaFree(s->d_levels); cudaFree(s->pv2);
     cudaFree(s->u); cudaFree(s->r); cudaFree(s->pv); cudaFree(s->Ap); cudaFree(s->z);
     cudaFree(s->d11); cudaFree(s->d22); cudaFree(s->d12);
     cudaFree(s->partials); cudaFree(s->counters); cudaFree(s->sc);
@@ -517,6 +546,13 @@ int solver_refresh_levels(eqgpu_solver *s)
             }
         }
         fill_level_consts(s, lv);
+    }
+    {
+        std::vector<LevelDev> host(MAX_LEVELS);
+        for (size_t l = 0; l < s->levels.size() && l < MAX_LEVELS; ++l) host[l] = s->levels[l].dev;
+        EQ_CUDA(cudaMemcpyAsync(s->d_levels, host.data(), sizeof(LevelDev) * MAX_LEVELS, cudaMemcpyHostToDevice,
+                                s->stream));
+        EQ_CUDA(cudaStreamSynchronize(s->stream));
     }
     EQ_CUDA(cudaGetLastError());
     return 0;
@@ -580,6 +616,86 @@ static void vcycle(eqgpu_solver *s)
     }
 }
 
+// Chebyshev-root Jacobi weights: n sweeps x <- x + w_k D^-1 (b - A x) whose
+// error polynomial is the scaled Chebyshev polynomial on [lo, hi] (eigenvalue
+// range of D^-1 A to damp).  Roots are taken alternately from both ends.
+static void cheb_weights(int n, double lo, double hi, double *w)
+{
+    const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo);
+    std::vector<double> r(n);
+    for (int k = 0; k < n; ++k) r[k] = 1.0 / (theta - delta * std::cos(M_PI * (2 * k + 1) / (2.0 * n)));
+    for (int k = 0, a = 0, b = n - 1; k < n; ++k) w[k] = (k & 1) ? r[b--] : r[a++];
+}
+
+static SmoothW smooth_weights(eqgpu_solver *s)
+{
+    SmoothW sw{};
+    // high-frequency range of D^-1 A on this stencil is [0.5, 2] (DESIGN.md "smoother")
+    cheb_weights(s->nu, 0.5, 2.0, sw.w);
+    return sw;
+}
+
+static CoarseW coarse_weights(eqgpu_solver *s)
+{
+    CoarseW cw{};
+    const Level &c = s->levels.back();
+    const double F = s->p.dt * s->p.D / (c.hx_host[0] * c.hy_host[0]);
+    // smallest eigenvalue of D^-1 A >= (mass row sum)/(diagonal) = 1/(0.5 + 4F) on square cells
+    const double lo = 0.8 / (0.5 + 4.0 * F), hi = 2.0;
+    const double sigma = (hi + lo) / (hi - lo);
+    int n = (int)std::ceil(std::acosh(50.0) / std::acosh(sigma));
+    n = std::max(2, std::min(n, MAX_CHEB));
+    cw.n = n;
+    cheb_weights(n, lo, hi, cw.w);
+    return cw;
+}
+
+// Fused V-cycle (isotropic): two kernels per large level + one tail CTA.
+// Leaves z = B r in levels[0].x and (when the fine level is tiled) r.z in sc->rz_new.
+template <int NU>
+static void vcycle_fused(eqgpu_solver *s)
+{
+    cudaStream_t st = s->stream;
+    const int lt = s->tail_first, nl = (int)s->levels.size();
+    const size_t tsm = 2 * TN * sizeof(double);
+    const SmoothW sw = smooth_weights(s);
+    const CoarseW cw = coarse_weights(s);
+    auto tgrid = [](const LevelDev &L, int to) { return dim3((L.nx + to - 1) / to, (L.ny + to - 1) / to); };
+    constexpr int TO_PRE = TS - 2 * (NU + 1), TO_POST = TS - 2 * NU;
+    for (int l = 0; l < lt; ++l) {
+        Level &lv = s->levels[l], &cv = s->levels[l + 1];
+        const dim3 g = tgrid(lv.dev, TO_PRE);
+        if ((int)(g.x * g.y) >= 2 * s->num_sms)
+            k_presmooth<NU, 8><<<g, 512, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
+        else
+            k_presmooth<NU, 4><<<g, 1024, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
+        s->launches++;
+    }
+    TailDesc td;
+    td.first = lt; td.last = nl - 1;
+    int off = 0;
+    for (int l = lt; l < nl; ++l) { td.off[l] = off; off += 3 * (int)s->levels[l].n(); }
+    for (int l = lt; l < nl; ++l) {
+        td.soff[l] = off;
+        off += 2 * (s->levels[l].dev.nx + 1) + 2 * (s->levels[l].dev.ny + 1);
+    }
+    k_tail<<<1, TAIL_THREADS, s->tail_smem, st>>>(s->d_levels, td, s->levels[lt].b, s->levels[lt].x, s->nu, sw, cw,
+                                                  s->sc);
+    s->launches++;
+    for (int l = lt - 1; l >= 0; --l) {
+        Level &lv = s->levels[l], &cv = s->levels[l + 1];
+        const dim3 g = tgrid(lv.dev, TO_POST);
+        const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
+#define POST(DOT, R, NT)                                                                                          \
+    k_postsmooth<NU, DOT, R><<<g, NT, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, lv.x, cv.x, sw, s->sc, s->partials, \
+                                                 s->counters + 1)
+        if (l == 0) { if (big) POST(true, 8, 512); else POST(true, 4, 1024); }
+        else { if (big) POST(false, 8, 512); else POST(false, 4, 1024); }
+#undef POST
+        s->launches++;
+    }
+}
+
 template <bool T>
 static int pcg(eqgpu_solver *s)
 {
@@ -603,6 +719,25 @@ static int pcg(eqgpu_solver *s)
     int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
     while (true) {
         for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
+            if (!T && s->fused) {
+                switch (s->nu) {
+                case 1: vcycle_fused<1>(s); break;
+                case 2: vcycle_fused<2>(s); break;
+                case 3: vcycle_fused<3>(s); break;
+                default: vcycle_fused<4>(s); break;
+                }
+                if (s->tail_first == 0) {
+                    k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
+                    s->launches++;
+                }
+                const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
+                k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
+                std::swap(s->pv, s->pv2);
+                k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials,
+                                                 s->counters + 3);
+                s->launches += 2;
+                continue;
+            }
             vcycle<T>(s);
             k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
             k_update_p<<<nb1, 256, 0, st>>>(s->N, s->z, s->pv, s->sc);
@@ -691,6 +826,27 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
             const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
             k_update_xr<<<nb1, 256, 0, st>>>(s->N, l0.t, s->z, s->pv, s->Ap, s->sc, s->partials, s->counters + 3);
             *alg_bytes = 48.0 * s->N;
+        } else if (nm == "apply_p") {  // read z,p write p',Ap: 32 B/DOF
+            const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
+            k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
+            *alg_bytes = 32.0 * s->N;
+        } else if (nm == "presmooth" || nm == "postsmooth") {
+            if (!s->fused || s->tail_first == 0 || s->nu != 3) return false;
+            Level &cv = s->levels[1];
+            const size_t tsm = 2 * TN * sizeof(double);
+            const SmoothW sw = smooth_weights(s);
+            if (nm == "presmooth") {  // read b, write x and b_coarse: 16 + 2 B/DOF
+                const int to = TS - 8;
+                const dim3 tg((L.nx + to - 1) / to, (L.ny + to - 1) / to);
+                k_presmooth<3, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, cv.b, sw, s->sc);
+                *alg_bytes = 18.0 * s->N;
+            } else {  // read x, b, x_coarse, write x: 24 + 2 B/DOF
+                const int to = TS - 6;
+                const dim3 tg((L.nx + to - 1) / to, (L.ny + to - 1) / to);
+                k_postsmooth<3, true, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, s->z, cv.x, sw, s->sc,
+                                                                    s->partials, s->counters + 1);
+                *alg_bytes = 26.0 * s->N;
+            }
         } else return false;
         return true;
     };
