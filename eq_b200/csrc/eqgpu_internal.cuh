@@ -66,6 +66,8 @@ struct eqgpu_solver {
     int tail_first = 0;            // first level handled by the single-CTA tail kernel
     size_t tail_smem = 0;
     bool fused = true;
+    cudaGraphExec_t graph_exec = nullptr;  // two fused PCG iterations
+    int graph_launches = 0;
     double *d11 = nullptr, *d22 = nullptr, *d12 = nullptr;
     // Dirichlet data
     double dir_val[4] = {0, 0, 0, 0};

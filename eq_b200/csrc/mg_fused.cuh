@@ -502,34 +502,63 @@ struct TailDesc {
     int first, last;            // level range [first, last]
     int off[MAX_LEVELS];        // start of the level's three arrays in the smem block (doubles)
     int soff[MAX_LEVELS];       // start of the level's cell-size copies (hx, ihx, hy, ihy)
+    int total;                  // doubles of shared memory in use
 };
 
+// Tail levels live in shared memory as padded arrays: row stride nx+2, a zero
+// ring around the grid, node (i,j) at (i+1)*(nx+2) + j+1.
+__device__ __forceinline__ int lidx(const LevelDev &L, int i, int j) { return (i + 1) * (L.nx + 2) + j + 1; }
+
+// One sweep over a whole tail level.  All nodes take the constant-coefficient
+// update (warps walk rows; lanes walk columns), then the irregular nodes (rows
+// 0, ireg_hi+1.., columns 0, jreg_hi+1.., Dirichlet nodes) are recomputed with
+// the general row.
 template <int MODE>
 __device__ __forceinline__ void lvl_sweep(const LevelDev &L, const Spacing &S, const double *b, const double *src,
                                           double *dst, double w)
 {
-    const int n = L.nx * L.ny;
-    for (int g = threadIdx.x; g < n; g += TAIL_THREADS) {
-        const int i = g / L.nx, j = g - i * L.nx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sx = L.nx + 2;
+    const double cC = L.cC, cEW = L.cEW, cNS = L.cNS, cD = L.cD, wd = w * L.icC;
+    for (int i = warp; i < L.ny; i += TAIL_THREADS / 32) {
+        for (int j = lane; j < L.nx; j += 32) {
+            const int c = (i + 1) * sx + j + 1;
+            double out;
+            if (MODE == 0) out = wd * b[c];
+            else {
+                const double ax = cC * src[c] + cEW * (src[c + 1] + src[c - 1]) + cNS * (src[c + sx] + src[c - sx]) +
+                                  cD * (src[c + sx + 1] + src[c - sx - 1]);
+                const double res = b[c] - ax;
+                out = MODE == 2 ? res : src[c] + wd * res;
+            }
+            dst[c] = out;
+        }
+    }
+    __syncthreads();
+    const int nr = L.ny - L.ireg_hi, ncol = L.nx - L.jreg_hi;
+    const int span = max(L.nx, L.ny);
+    const int items = (nr + ncol) * span;
+    for (int it = threadIdx.x; it < items; it += TAIL_THREADS) {
+        const int k = it / span, e = it - k * span;
+        int i, j;
+        if (k < nr) { i = k == 0 ? 0 : L.ireg_hi + k; j = e; }
+        else { const int kk = k - nr; j = kk == 0 ? 0 : L.jreg_hi + kk; i = e; }
+        if (i >= L.ny || j >= L.nx) continue;
+        const int c = (i + 1) * sx + j + 1;
         double out = 0.0;
         if (!is_dirichlet(L, i, j)) {
             double cf[NBAND];
             stencil_iso(L, S, i, j, cf);
-            if (MODE == 0) out = w * b[g] * inv_diag(L, i, j, cf);
+            const double id = inv_diag(L, i, j, cf);
+            if (MODE == 0) out = w * id * b[c];
             else {
-                const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
-                double ax = cf[B_C] * src[g];
-                if (hasE) ax += cf[B_E] * src[g + 1];
-                if (hasW) ax += cf[B_W] * src[g - 1];
-                if (hasN) ax += cf[B_N] * src[g + L.nx];
-                if (hasS) ax += cf[B_S] * src[g - L.nx];
-                if (hasN && hasE) ax += cf[B_NE] * src[g + L.nx + 1];
-                if (hasS && hasW) ax += cf[B_SW] * src[g - L.nx - 1];
-                const double res = b[g] - ax;
-                out = MODE == 2 ? res : src[g] + w * res * inv_diag(L, i, j, cf);
+                const double ax = cf[B_C] * src[c] + cf[B_E] * src[c + 1] + cf[B_W] * src[c - 1] +
+                                  cf[B_N] * src[c + sx] + cf[B_S] * src[c - sx] + cf[B_NE] * src[c + sx + 1] +
+                                  cf[B_SW] * src[c - sx - 1];
+                const double res = b[c] - ax;
+                out = MODE == 2 ? res : src[c] + w * id * res;
             }
         }
-        dst[g] = out;
+        dst[c] = out;
     }
     __syncthreads();
 }
@@ -548,7 +577,7 @@ __device__ __forceinline__ void lvl_smooth(const LevelDev &L, const Spacing &S, 
         cur = first; oth = (first == x) ? t : x;
         k = 1;
     } else if (sweeps & 1) {
-        const int n = L.nx * L.ny;
+        const int n = (L.nx + 2) * (L.ny + 2);
         for (int g = threadIdx.x; g < n; g += TAIL_THREADS) t[g] = x[g];
         __syncthreads();
         cur = t; oth = x;
@@ -565,9 +594,10 @@ k_tail(const LevelDev *__restrict__ levels, TailDesc td, const double *__restric
 {
     if (sc->done) return;
     extern __shared__ double sm[];
+    auto PN = [&](int l) { return (levels[l].nx + 2) * (levels[l].ny + 2); };
     auto X = [&](int l) { return sm + td.off[l]; };
-    auto B = [&](int l) { return sm + td.off[l] + levels[l].nx * levels[l].ny; };
-    auto T = [&](int l) { return sm + td.off[l] + 2 * levels[l].nx * levels[l].ny; };
+    auto B = [&](int l) { return sm + td.off[l] + PN(l); };
+    auto T = [&](int l) { return sm + td.off[l] + 2 * PN(l); };
     auto SP = [&](int l) {
         const LevelDev &L = levels[l];
         double *q = sm + td.soff[l];
@@ -575,6 +605,9 @@ k_tail(const LevelDev *__restrict__ levels, TailDesc td, const double *__restric
         S.jo = 0; S.io = 0;
         return S;
     };
+    // zero everything once (pad rings must be zero), stage the cell sizes and the right-hand side
+    for (int g = threadIdx.x; g < td.total; g += TAIL_THREADS) sm[g] = 0.0;
+    __syncthreads();
     for (int l = td.first; l <= td.last; ++l) {
         const LevelDev &L = levels[l];
         double *q = sm + td.soff[l];
@@ -584,9 +617,10 @@ k_tail(const LevelDev *__restrict__ levels, TailDesc td, const double *__restric
     }
     {
         const LevelDev &L = levels[td.first];
-        const int n = L.nx * L.ny;
         double *b0 = B(td.first);
-        for (int g = threadIdx.x; g < n; g += TAIL_THREADS) b0[g] = __ldg(b_in + g);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int i = warp; i < L.ny; i += TAIL_THREADS / 32)
+            for (int j = lane; j < L.nx; j += 32) b0[lidx(L, i, j)] = __ldg(b_in + (size_t)i * L.nx + j);
         __syncthreads();
     }
     for (int l = td.first; l < td.last; ++l) {
@@ -595,25 +629,25 @@ k_tail(const LevelDev *__restrict__ levels, TailDesc td, const double *__restric
         lvl_sweep<2>(F, SP(l), B(l), X(l), T(l), 0.0);
         const double *rf = T(l);
         double *bc = B(l + 1);
-        const int nc = Cc.nx * Cc.ny;
+        const int nc = Cc.nx * Cc.ny, fs = F.nx + 2;
         for (int g = threadIdx.x; g < nc; g += TAIL_THREADS) {
             const int I = g / Cc.nx, J = g - I * Cc.nx;
             double out = 0.0;
             if (!is_dirichlet(Cc, I, J)) {
                 const int fi = fine_of(I, F.ny), fj = fine_of(J, F.nx);
-                const int c = fi * F.nx + fj;
+                const int c = lidx(F, fi, fj);
                 const bool e = fj + 1 < F.nx && is_mid(fj + 1, F.nx), w = fj >= 1 && is_mid(fj - 1, F.nx);
                 const bool n = fi + 1 < F.ny && is_mid(fi + 1, F.ny), s = fi >= 1 && is_mid(fi - 1, F.ny);
                 double h = 0.0;
                 if (e) h += rf[c + 1];
                 if (w) h += rf[c - 1];
-                if (n) h += rf[c + F.nx];
-                if (s) h += rf[c - F.nx];
-                if (n && e) h += rf[c + F.nx + 1];
-                if (s && w) h += rf[c - F.nx - 1];
+                if (n) h += rf[c + fs];
+                if (s) h += rf[c - fs];
+                if (n && e) h += rf[c + fs + 1];
+                if (s && w) h += rf[c - fs - 1];
                 out = rf[c] + 0.5 * h;
             }
-            bc[g] = out;
+            bc[lidx(Cc, I, J)] = out;
         }
         __syncthreads();
     }
@@ -622,26 +656,27 @@ k_tail(const LevelDev *__restrict__ levels, TailDesc td, const double *__restric
         const LevelDev &F = levels[l], &Cc = levels[l + 1];
         double *xf = X(l);
         const double *xc = X(l + 1);
-        const int n = F.nx * F.ny;
+        const int n = F.nx * F.ny, cs = Cc.nx + 2;
         for (int g = threadIdx.x; g < n; g += TAIL_THREADS) {
             const int i = g / F.nx, j = g - i * F.nx;
             if (is_dirichlet(F, i, j)) continue;
             const bool mi = is_mid(i, F.ny), mj = is_mid(j, F.nx);
-            const double *c0 = xc + coarse_lo(i, F.ny, Cc.ny) * Cc.nx + coarse_lo(j, F.nx, Cc.nx);
+            const double *c0 = xc + lidx(Cc, coarse_lo(i, F.ny, Cc.ny), coarse_lo(j, F.nx, Cc.nx));
             double add;
             if (!mi && !mj) add = c0[0];
             else if (!mi && mj) add = 0.5 * (c0[0] + c0[1]);
-            else if (mi && !mj) add = 0.5 * (c0[0] + c0[Cc.nx]);
-            else add = 0.5 * (c0[0] + c0[Cc.nx + 1]);
-            xf[g] += add;
+            else if (mi && !mj) add = 0.5 * (c0[0] + c0[cs]);
+            else add = 0.5 * (c0[0] + c0[cs + 1]);
+            xf[lidx(F, i, j)] += add;
         }
         __syncthreads();
         lvl_smooth<false>(F, SP(l), B(l), X(l), T(l), nu, sw.w);
     }
     {
         const LevelDev &L = levels[td.first];
-        const int n = L.nx * L.ny;
         const double *x0 = X(td.first);
-        for (int g = threadIdx.x; g < n; g += TAIL_THREADS) x_out[g] = x0[g];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int i = warp; i < L.ny; i += TAIL_THREADS / 32)
+            for (int j = lane; j < L.nx; j += 32) x_out[(size_t)i * L.nx + j] = x0[lidx(L, i, j)];
     }
 }

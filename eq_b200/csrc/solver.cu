@@ -209,7 +209,8 @@ k_update_p(size_t n, const double *__restrict__ z, double *__restrict__ p, const
         p[g] = __ldg(z + g) + beta * p[g];
 }
 
-// x += alpha p ; r -= alpha Ap ; rr = r.r ; bookkeeping in the last block
+// x += alpha p ; r -= alpha Ap ; rr = r.r ; bookkeeping in the last block.
+// 128-bit accesses, two independent double2 per thread per trip.
 __global__ void __launch_bounds__(256)
 k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
             const double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter)
@@ -217,11 +218,32 @@ k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const doub
     if (sc->done) return;
     const double alpha = sc->rz_new / sc->pAp;
     double v[1] = {0.0};
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n;
-         g += (size_t)gridDim.x * blockDim.x) {
-        x[g] += alpha * __ldg(p + g);
-        const double rn = r[g] - alpha * __ldg(Ap + g);
-        r[g] = rn;
+    const size_t n2 = n >> 1, stride = (size_t)gridDim.x * blockDim.x;
+    double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p), *A2 = reinterpret_cast<const double2 *>(Ap);
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + stride < n2; g += 2 * stride) {
+        const size_t h = g + stride;
+        double2 xa = x2[g], xb = x2[h], ra = r2[g], rb = r2[h];
+        const double2 pa = __ldg(p2 + g), pb = __ldg(p2 + h), aa = __ldg(A2 + g), ab = __ldg(A2 + h);
+        xa.x += alpha * pa.x; xa.y += alpha * pa.y; xb.x += alpha * pb.x; xb.y += alpha * pb.y;
+        ra.x -= alpha * aa.x; ra.y -= alpha * aa.y; rb.x -= alpha * ab.x; rb.y -= alpha * ab.y;
+        x2[g] = xa; x2[h] = xb; r2[g] = ra; r2[h] = rb;
+        v[0] += ra.x * ra.x + ra.y * ra.y + rb.x * rb.x + rb.y * rb.y;
+    }
+    for (; g < n2; g += stride) {
+        double2 xa = x2[g], ra = r2[g];
+        const double2 pa = __ldg(p2 + g), aa = __ldg(A2 + g);
+        xa.x += alpha * pa.x; xa.y += alpha * pa.y;
+        ra.x -= alpha * aa.x; ra.y -= alpha * aa.y;
+        x2[g] = xa; r2[g] = ra;
+        v[0] += ra.x * ra.x + ra.y * ra.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t t = n - 1;
+        x[t] += alpha * p[t];
+        const double rn = r[t] - alpha * Ap[t];
+        r[t] = rn;
         v[0] += rn * rn;
     }
     double tot[1];
@@ -472,7 +494,8 @@ int solver_setup(eqgpu_solver *s)
         int first = nl - 1;
         auto need = [&](int l) {
             const Level &lv = s->levels[l];
-            return sizeof(double) * (3 * lv.n() + 2 * (lv.dev.nx + 1) + 2 * (lv.dev.ny + 1));
+            return sizeof(double) * (3 * (size_t)(lv.dev.nx + 2) * (lv.dev.ny + 2) + 2 * (lv.dev.nx + 1) +
+                                     2 * (lv.dev.ny + 1));
         };
         size_t used = need(nl - 1);
         while (first > 0 && used + need(first - 1) <= budget) {
@@ -512,6 +535,7 @@ void solver_teardown(eqgpu_solver *s)
         if (&lv != &s->levels[0]) { cudaFree(lv.t11); cudaFree(lv.t22); cudaFree(lv.t12); }
     }
     s->levels.clear();
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     cudaFree(s->d_levels); cudaFree(s->pv2);
     cudaFree(s->u); cudaFree(s->r); cudaFree(s->pv); cudaFree(s->Ap); cudaFree(s->z);
     cudaFree(s->d11); cudaFree(s->d22); cudaFree(s->d12);
@@ -653,9 +677,8 @@ static CoarseW coarse_weights(eqgpu_solver *s)
 // Fused V-cycle (isotropic): two kernels per large level + one tail CTA.
 // Leaves z = B r in levels[0].x and (when the fine level is tiled) r.z in sc->rz_new.
 template <int NU>
-static void vcycle_fused(eqgpu_solver *s)
+static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
 {
-    cudaStream_t st = s->stream;
     const int lt = s->tail_first, nl = (int)s->levels.size();
     const size_t tsm = 2 * TN * sizeof(double);
     const SmoothW sw = smooth_weights(s);
@@ -674,11 +697,15 @@ static void vcycle_fused(eqgpu_solver *s)
     TailDesc td;
     td.first = lt; td.last = nl - 1;
     int off = 0;
-    for (int l = lt; l < nl; ++l) { td.off[l] = off; off += 3 * (int)s->levels[l].n(); }
+    for (int l = lt; l < nl; ++l) {
+        td.off[l] = off;
+        off += 3 * (s->levels[l].dev.nx + 2) * (s->levels[l].dev.ny + 2);
+    }
     for (int l = lt; l < nl; ++l) {
         td.soff[l] = off;
         off += 2 * (s->levels[l].dev.nx + 1) + 2 * (s->levels[l].dev.ny + 1);
     }
+    td.total = off;
     k_tail<<<1, TAIL_THREADS, s->tail_smem, st>>>(s->d_levels, td, s->levels[lt].b, s->levels[lt].x, s->nu, sw, cw,
                                                   s->sc);
     s->launches++;
@@ -696,6 +723,52 @@ static void vcycle_fused(eqgpu_solver *s)
     }
 }
 
+// One PCG iteration of the fused (isotropic) path, enqueued on `st`.
+static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
+{
+    const LevelDev &L = s->levels[0].dev;
+    const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+    switch (s->nu) {
+    case 1: vcycle_fused<1>(s, st); break;
+    case 2: vcycle_fused<2>(s, st); break;
+    case 3: vcycle_fused<3>(s, st); break;
+    default: vcycle_fused<4>(s, st); break;
+    }
+    if (s->tail_first == 0) {
+        k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
+        s->launches++;
+    }
+    const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
+    k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
+    std::swap(s->pv, s->pv2);
+    k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials, s->counters + 3);
+    s->launches += 2;
+}
+
+// Two iterations (so the p ping-pong returns to its starting buffers) captured
+// once into a CUDA graph; every kernel re-reads its scalars from device memory
+// and exits at once when the converged flag is set, so the graph is replayed
+// without any host decision in between.
+static int build_iteration_graph(eqgpu_solver *s)
+{
+    if (s->graph_exec) return 0;
+    cudaStream_t cap;
+    EQ_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    const int64_t l0 = s->launches;
+    EQ_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    enqueue_fused_iteration(s, cap);
+    enqueue_fused_iteration(s, cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    s->graph_launches = (int)(s->launches - l0);
+    s->launches = l0;
+    if (e != cudaSuccess) { s->set_error(std::string("graph capture: ") + cudaGetErrorString(e)); return EQGPU_ECUDA; }
+    EQ_CUDA(cudaGraphInstantiate(&s->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    return 0;
+}
+
 template <bool T>
 static int pcg(eqgpu_solver *s)
 {
@@ -709,6 +782,11 @@ static int pcg(eqgpu_solver *s)
     const double rs_l = L.rob_l * p.robin_s[0], rs_r = L.rob_r * p.robin_s[1];
     DirData dd = make_dirdata(s);
     const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+    const bool fused = !T && s->fused;
+    if (fused) {
+        int rc = build_iteration_graph(s);
+        if (rc) return rc;
+    }
 
     k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, s->sc, s->partials,
                                   s->counters + 0);
@@ -718,33 +796,21 @@ static int pcg(eqgpu_solver *s)
     int issued = 0;
     int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
     while (true) {
-        for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
-            if (!T && s->fused) {
-                switch (s->nu) {
-                case 1: vcycle_fused<1>(s); break;
-                case 2: vcycle_fused<2>(s); break;
-                case 3: vcycle_fused<3>(s); break;
-                default: vcycle_fused<4>(s); break;
-                }
-                if (s->tail_first == 0) {
-                    k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
-                    s->launches++;
-                }
-                const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
-                k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
-                std::swap(s->pv, s->pv2);
+        if (fused) {
+            for (int k = 0; k < chunk && issued < max_iters; k += 2, issued += 2) {
+                EQ_CUDA(cudaGraphLaunch(s->graph_exec, st));
+                s->launches += s->graph_launches;
+            }
+        } else {
+            for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
+                vcycle<T>(s);
+                k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
+                k_update_p<<<nb1, 256, 0, st>>>(s->N, s->z, s->pv, s->sc);
+                k_apply<T, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, s->sc, s->partials, s->counters + 2);
                 k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials,
                                                  s->counters + 3);
-                s->launches += 2;
-                continue;
+                s->launches += 4;
             }
-            vcycle<T>(s);
-            k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
-            k_update_p<<<nb1, 256, 0, st>>>(s->N, s->z, s->pv, s->sc);
-            k_apply<T, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, s->sc, s->partials, s->counters + 2);
-            k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials,
-                                             s->counters + 3);
-            s->launches += 4;
         }
         EQ_CUDA(cudaMemcpyAsync(s->sc_host, s->sc, sizeof(CGScalars), cudaMemcpyDeviceToHost, st));
         EQ_CUDA(cudaStreamSynchronize(st));
