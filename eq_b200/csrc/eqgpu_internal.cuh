@@ -15,7 +15,7 @@
         }                                                                      \
     } while (0)
 
-// Stencil band order (same as oracle/eq_oracle.c).
+// Stencil band order: centre, E, W, N, S, NE, SW on the "right"-diagonal mesh.
 enum { B_C = 0, B_E, B_W, B_N, B_S, B_NE, B_SW, NBAND };
 
 // One grid of the multigrid hierarchy: a tensor-product mesh of nx x ny nodes

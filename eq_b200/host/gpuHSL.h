@@ -1,0 +1,93 @@
+// gpuHSL -- drop-in for fenicsInterface (src/fHSL.h:333-449) on a B200.
+//
+// It implements eQ's own solver interface, eQ::diffusionSolver
+// (src/eQ.h:302-330), and additionally exposes the de-facto members that
+// src/simulation.cpp reaches into on the Fenics class:
+//   solution_vector, D11/D22/D12, totalBoundaryFlux, setBoundaryValues(),
+//   topChannelData/bottomChannelData, nodesH/nodesW, and a `shell` carrying
+//   mesh_coords / dof_from_vertex (identity) / num_vertices().
+// All numerical work goes through the C ABI in include/eqgpu.h.
+//
+// The reference reads its configuration from the global eQ::data::parameters
+// JSON (src/fHSL.cpp:45-47,110,117,336-341,446-570); here the same keys arrive
+// as an explicit gpuHSL::config filled by the caller (INTEGRATION.md shows the
+// six lines that copy them from the JSON inside Simulation::create_HSLgrid).
+#pragma once
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/eqgpu.h"
+#include "eq_compat.h"
+
+class gpuHSL : public eQ::diffusionSolver {
+public:
+    // the eQ::data::parameters keys fenicsInterface reads
+    struct config {
+        std::string boundaryType = "DIRICHLET_0";  // "DIRICHLET_0" | "DIRICHLET_UPDATE" | "MICROFLUIDIC_TRAP" | ...
+        std::string trapType = "NOWALLED";         // "NOWALLED" | "THREEWALLED" | "TWOWALLED" | "ONEWALLED" | "H_TRAP"
+        // parameters["boundaries"][wall][1] = {a, b, v} (src/eQ.h:399-419), order left,right,top,bottom
+        double boundaries[4][3] = {{0, 1, 0}, {0, 1, 0}, {0, 1, 0}, {0, 1, 0}};
+        double lengthScaling = 5.0;                 // src/main.cpp:511
+        double simulationFlowRate = 120.0;          // src/main.cpp:364
+        double simulationChannelLengthLeft = 20.0;  // src/main.cpp:333-336
+        double simulationChannelLengthRight = 20.0;
+        int channelSolverNumberIterations = 48;     // src/main.cpp:426-429
+        int device = 0;                             // CUDA device of this layer
+        double rtol = 1e-12;
+    };
+
+    // what simulation.cpp reads through `diffusionSolver->shell->...` (src/simulation.cpp:298-308)
+    struct meshShell {
+        struct meshInfo {
+            size_t n = 0;
+            size_t num_vertices() const { return n; }
+        };
+        std::shared_ptr<meshInfo> mesh = std::make_shared<meshInfo>();
+        std::vector<double> mesh_coords;   // 2N doubles, vertex order, x then y
+        std::vector<int> dof_from_vertex;  // identity
+    };
+
+    gpuHSL() = default;
+    explicit gpuHSL(const config &c) : cfg(c) {}
+    ~gpuHSL() override;
+
+    config cfg;
+    eQ::diffusionSolver::params myParams;
+    std::shared_ptr<meshShell> shell = std::make_shared<meshShell>();
+
+    // eQ::diffusionSolver
+    void initDiffusion(eQ::diffusionSolver::params &) override;  // src/fHSL.cpp:37-53
+    void stepDiffusion() override;                               // src/fHSL.cpp:98-161
+    eQ::data::parametersType getBoundaryFlux(void) override;     // {"totalFlux": totalBoundaryFlux}
+    void writeDiffusionFiles(double timestamp) override;         // src/fHSL.cpp:630-636 (VTK ImageData instead of PVD)
+    void finalize(void) override;
+
+    // fenicsInterface's extra surface
+    void setBoundaryValues(const double);    // src/fHSL.cpp:601-604
+    void setRobinBoundaryConditions();       // src/fHSL.cpp:331-364
+    size_t nodesH = 0, nodesW = 0;
+    std::vector<double> solution_vector;     // N doubles; Simulation Isend/Irecv's into it
+    std::vector<double> topChannelData, bottomChannelData;
+    std::shared_ptr<std::vector<double>> D11, D22, D12;
+    double totalBoundaryFlux = 0.0;
+    double wellScaling = 0.0;
+
+    // device-resident path (controller-side fusion): eQabm::updateCells' lambdas on the GPU
+    void uploadCells(const double *records, size_t ncells);  // EQGPU_CELL_STRIDE doubles each
+    void readHSL(double *out);                               // src/abm/eQabm.cpp:326-337, all cells
+    void writeHSL(const double *amount_nM);                  // src/abm/eQabm.cpp:338-359, all cells
+    void stepDiffusionResident();                            // stepDiffusion without the host round trip
+    void fetchSolution();                                    // device field -> solution_vector
+
+    eqgpu_solver *handle() { return h; }
+    int lastIterations() const;
+
+private:
+    eqgpu_solver *h = nullptr;
+    double leftRate = 0.0, rightRate = 0.0, channelFlowVelocity = 0.0;
+    bool tensorDirty = false;
+    void check(int rc, const char *what);
+    void pushTensorIfChanged();
+};

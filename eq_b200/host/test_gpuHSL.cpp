@@ -1,0 +1,92 @@
+// Driver used by tests/test_host_class.py: exercises gpuHSL exactly the way
+// Simulation does (src/simulation.cpp:207,244,466-476,491-505) and dumps the
+// fields for comparison with the oracle.
+//   test_gpuHSL <case> <in.bin> <out.bin>
+// in.bin : doubles [W, H, npm, dt, D, nsteps, ncells, <ncells*16 records>, <N deposits added before each step>]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "gpuHSL.h"
+
+static std::vector<double> read_all(const char *path)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { perror(path); exit(2); }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<double> v(n / sizeof(double));
+    if (fread(v.data(), sizeof(double), v.size(), f) != v.size()) { perror("read"); exit(2); }
+    fclose(f);
+    return v;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 4) { fprintf(stderr, "usage: %s case in.bin out.bin\n", argv[0]); return 2; }
+    const std::string kase = argv[1];
+    std::vector<double> in = read_all(argv[2]);
+    const double W = in[0], H = in[1], npm = in[2], dt = in[3], D = in[4];
+    const int nsteps = int(in[5]);
+    const size_t ncells = size_t(in[6]);
+    const double *cells = in.data() + 7;
+    const double *deposit = cells + ncells * EQGPU_CELL_STRIDE;
+
+    gpuHSL::config cfg;
+    if (kase == "default") { cfg.boundaryType = "DIRICHLET_0"; cfg.trapType = "NOWALLED"; }
+    else if (kase == "threewall") { cfg.boundaryType = "DIRICHLET_0"; cfg.trapType = "THREEWALLED"; }
+    else if (kase == "htrap") {  // MICROFLUIDIC_TRAP + H_TRAP: Robin left/right = flow rate, top/bottom Neumann
+        cfg.boundaryType = "MICROFLUIDIC_TRAP"; cfg.trapType = "H_TRAP";
+        const double rob[3] = {1.0, 1.0, 0.0}, neu[3] = {1.0, 0.0, 0.0};
+        memcpy(cfg.boundaries[0], rob, sizeof rob); memcpy(cfg.boundaries[1], rob, sizeof rob);
+        memcpy(cfg.boundaries[2], neu, sizeof neu); memcpy(cfg.boundaries[3], neu, sizeof neu);
+    } else if (kase == "channels") {  // MICROFLUIDIC_TRAP, default trap: Robin left/right, channel Dirichlet top/bottom
+        cfg.boundaryType = "MICROFLUIDIC_TRAP"; cfg.trapType = "NOWALLED";
+        const double rob[3] = {1.0, 1.0, 0.0}, chan[3] = {0.0, 1.0, -1.0};
+        memcpy(cfg.boundaries[0], rob, sizeof rob); memcpy(cfg.boundaries[1], rob, sizeof rob);
+        memcpy(cfg.boundaries[2], chan, sizeof chan); memcpy(cfg.boundaries[3], chan, sizeof chan);
+    } else { fprintf(stderr, "unknown case\n"); return 2; }
+
+    eQ::diffusionSolver::params p{};
+    p.dt = dt; p.D_HSL = D; p.trapHeightMicrons = H; p.trapWidthMicrons = W; p.nodesPerMicron = npm;
+    p.uniqueID = 0; p.comm = 0;
+
+    std::shared_ptr<gpuHSL> solver = std::make_shared<gpuHSL>(cfg);  // simulation.cpp:207
+    try {
+        solver->initDiffusion(p);                                    // simulation.cpp:244
+        const size_t N = solver->solution_vector.size();
+        if (solver->shell->mesh->num_vertices() != N) return 3;      // simulation.cpp:298-301
+        std::vector<double> flux;
+        for (int s = 0; s < nsteps; ++s) {
+            for (size_t k = 0; k < N; ++k) solver->solution_vector[k] += deposit[k];  // controller's writeHSL result arrives
+            solver->stepDiffusion();                                 // simulation.cpp:475
+            flux.push_back(solver->getBoundaryFlux()["totalFlux"]);
+        }
+        FILE *f = fopen(argv[3], "wb");
+        double hdr[3] = {double(solver->nodesW), double(solver->nodesH), double(solver->lastIterations())};
+        fwrite(hdr, sizeof(double), 3, f);
+        fwrite(solver->solution_vector.data(), sizeof(double), N, f);
+        fwrite(solver->topChannelData.data(), sizeof(double), solver->nodesW, f);
+        fwrite(solver->bottomChannelData.data(), sizeof(double), solver->nodesW, f);
+        fwrite(flux.data(), sizeof(double), flux.size(), f);
+        // fused path: cells on the GPU
+        if (ncells) {
+            std::vector<double> g(ncells), amt(ncells, 100.0);
+            solver->uploadCells(cells, ncells);
+            solver->readHSL(g.data());
+            solver->writeHSL(amt.data());
+            solver->stepDiffusionResident();
+            solver->fetchSolution();
+            fwrite(g.data(), sizeof(double), ncells, f);
+            fwrite(solver->solution_vector.data(), sizeof(double), N, f);
+        }
+        fclose(f);
+        solver->finalize();
+    } catch (const std::exception &e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,90 @@
+"""The C++ drop-in class gpuHSL (eq_b200/host), driven the way Simulation drives fenicsInterface
+(src/simulation.cpp:207,244,466-476), against the oracle's stepDiffusion."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "eq_b200", "host", "test_gpuHSL")
+
+
+def run_case(oracle, tmp_path, kase, W, H, npm, dt, D, nsteps, cells, deposit):
+    if not os.path.exists(EXE):
+        subprocess.run(["make", "-C", os.path.dirname(EXE), "all"], check=True)
+    inp = np.concatenate([[W, H, npm, dt, D, nsteps, len(cells)], cells.ravel(), deposit])
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    inp.astype(np.float64).tofile(fin)
+    subprocess.run([EXE, kase, str(fin), str(fout)], check=True)
+    out = np.fromfile(fout)
+    nW, nH = int(out[0]), int(out[1])
+    N = nW * nH
+    o = 3
+    res = {"nW": nW, "nH": nH, "iters": int(out[2]), "u": out[o:o + N]}
+    o += N
+    res["top"], res["bottom"] = out[o:o + nW], out[o + nW:o + 2 * nW]
+    o += 2 * nW
+    res["flux"] = out[o:o + nsteps]
+    o += nsteps
+    if len(cells):
+        res["gathered"] = out[o:o + len(cells)]
+        res["u_fused"] = out[o + len(cells):o + len(cells) + N]
+    return res
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+CASES = {
+    "default": dict(bc_type=(1, 1, 1, 1)),
+    "threewall": dict(bc_type=(0, 0, 0, 1)),
+    "htrap": dict(bc_type=(2, 2, 0, 0), bc_value=(120.0, 120.0, 0, 0)),
+}
+
+
+@pytest.mark.parametrize("kase", list(CASES))
+def test_gpuHSL_matches_oracle(oracle, tmp_path, kase):
+    W, H, npm, dt, D, nsteps = 100.0, 20.0, 2.0, 0.1, 1200.0, 4
+    p = oracle.Problem(nW=201, nH=41, h=0.5, dt=dt, D=D, **CASES[kase])
+    rng = np.random.default_rng(8)
+    n = 40
+    cells = oracle.make_cells(np.c_[rng.uniform(3, W - 3, n), rng.uniform(3, H - 3, n)], rng.uniform(0, 2 * np.pi, n),
+                              (1 + rng.uniform(size=n)) * 2.1, W, H)
+    deposit = oracle.scatter(cells, npm, p.nH, p.nW, np.full(n, 100.0), np.zeros(p.N))
+    got = run_case(oracle, tmp_path, kase, W, H, npm, dt, D, nsteps, cells, deposit)
+    assert (got["nW"], got["nH"]) == (201, 41)
+    s = oracle.new_state(p)
+    flux = []
+    for _ in range(nsteps):
+        s.u = s.u + deposit
+        s = oracle.step(p, s)
+        flux.append(s.total_boundary_flux)
+    assert rel(got["u"], s.u) < 1e-8
+    assert np.allclose(got["flux"], flux, rtol=1e-7)
+    # fused tail of the driver: gather, scatter 100 nM, one resident step
+    g = oracle.gather(cells, npm, p.nH, p.nW, s.u)
+    assert rel(got["gathered"], g) < 1e-8
+    s.u = oracle.scatter(cells, npm, p.nH, p.nW, np.full(n, 100.0), s.u)
+    s = oracle.step(p, s)
+    assert rel(got["u_fused"], s.u) < 1e-8
+
+
+def test_gpuHSL_microfluidic_trap_with_channels(oracle, tmp_path):
+    W, H, npm, dt, D, nsteps = 100.0, 20.0, 2.0, 0.1, 1200.0, 5
+    rl, rr = oracle.robin_rates(120.0, D, 20.0, 20.0)
+    p = oracle.Problem(nW=201, nH=41, h=0.5, dt=dt, D=D, bc_type=(2, 2, 3, 3), bc_value=(rl, rr, 0, 0), channels=True,
+                       channel_v=120.0, channel_r=(rl, rr), channel_iters=48, well_scaling=10.0 * (25.0 / 5.0) * 0.5)
+    rng = np.random.default_rng(9)
+    deposit = np.zeros(p.N)
+    deposit[rng.integers(0, p.N, 80)] = rng.uniform(10, 100, 80)
+    got = run_case(oracle, tmp_path, "channels", W, H, npm, dt, D, nsteps, np.zeros((0, 16)), deposit)
+    s = oracle.new_state(p)
+    for _ in range(nsteps):
+        s.u = s.u + deposit
+        s = oracle.step(p, s)
+    assert rel(got["u"], s.u) < 1e-8
+    assert rel(got["top"], s.top) < 1e-8 and rel(got["bottom"], s.bottom) < 1e-8
