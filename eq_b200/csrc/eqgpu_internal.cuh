@@ -66,6 +66,9 @@ struct eqgpu_solver {
     int tail_first = 0;            // first level handled by the single-CTA tail kernel
     size_t tail_smem = 0;
     bool fused = true;
+    bool use_cluster = false;      // deepest levels on a 16-CTA cluster (k_ctail) instead of one CTA (k_tail)
+    int ctail_first = 0, ctail_ncta = 0;
+    size_t ctail_smem = 0;
     cudaGraphExec_t graph_exec = nullptr;  // two fused PCG iterations
     int graph_launches = 0;
     double *d11 = nullptr, *d22 = nullptr, *d12 = nullptr;

@@ -7,9 +7,11 @@
 // kernel evaluates the 7-point row of the "right"-diagonal mesh in registers.
 #include "eqgpu_internal.cuh"
 #include "mg_fused.cuh"
+#include "mg_cluster.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #define BX 32
 #define BY 8
@@ -413,6 +415,8 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
     L.d11 = lv.t11; L.d22 = lv.t22; L.d12 = lv.t12;
 }
 
+static CTailDesc make_ctail_desc(eqgpu_solver *s, int first, int ncta);
+
 int solver_setup(eqgpu_solver *s)
 {
     const eqgpu_params &p = s->p;
@@ -507,6 +511,34 @@ int solver_setup(eqgpu_solver *s)
         s->tail_smem = used;
     }
     if (s->fused) {
+        // Cluster tail.  Measured at 2048^2 (profiles/r01_cluster_tail.md): the ~1.5 us cluster barrier per
+        // sweep makes it lose against the tile kernels for levels >= 129^2, and win (388 vs 381 steps/s)
+        // when it takes exactly the levels the single-CTA tail would take.  EQGPU_CTAIL_FIRST overrides.
+        const int nl = (int)s->levels.size();
+        int cf = s->tail_first;
+        if (const char *e = getenv("EQGPU_CTAIL_FIRST")) {
+            cf = std::max(0, std::min(atoi(e), nl - 1));
+            while (cf < nl - 1 && (size_t)make_ctail_desc(s, cf, CT_MAX_CTAS).total * sizeof(double) > 200 * 1024) ++cf;
+        }
+        const CTailDesc td = make_ctail_desc(s, cf, CT_MAX_CTAS);
+        const size_t csm = (size_t)td.total * sizeof(double);
+        s->use_cluster = false;
+        if (csm <= 200 * 1024 &&
+            cudaFuncSetAttribute(k_ctail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaFuncSetAttribute(k_ctail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm) == cudaSuccess) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(CT_MAX_CTAS); cfg.blockDim = dim3(CT_THREADS); cfg.dynamicSmemBytes = csm;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CT_MAX_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_ctail, &cfg) == cudaSuccess && nclusters >= 1) {
+                s->use_cluster = true;
+                s->ctail_first = cf; s->ctail_ncta = CT_MAX_CTAS; s->ctail_smem = csm;
+            }
+        }
+        cudaGetLastError();  // a refused attribute is not an error of the solver
         EQ_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tail_smem));
         const int nu = s->nu;
         if (nu > 4) { s->set_error("smooth_sweeps must be <= 4"); return EQGPU_EINVAL; }
@@ -640,6 +672,30 @@ static void vcycle(eqgpu_solver *s)
     }
 }
 
+static CTailDesc make_ctail_desc(eqgpu_solver *s, int first, int ncta)
+{
+    CTailDesc td{};
+    const int nl = (int)s->levels.size();
+    td.first = first; td.last = nl - 1; td.ncta = ncta;
+    int off = 0, maxnx = 0;
+    for (int l = first; l < nl; ++l) {
+        const LevelDev &L = s->levels[l].dev;
+        td.rp[l] = (L.ny + ncta - 1) / ncta;
+        td.off[l] = off;
+        off += 3 * td.rp[l] * (L.nx + 2);
+        maxnx = std::max(maxnx, L.nx);
+    }
+    for (int l = first; l < nl; ++l) {
+        const LevelDev &L = s->levels[l].dev;
+        td.soff[l] = off;
+        off += 2 * (L.nx + 1) + 2 * (L.ny + 1);
+    }
+    td.zoff = off;
+    off += maxnx + 2;
+    td.total = off;
+    return td;
+}
+
 // Chebyshev-root Jacobi weights: n sweeps x <- x + w_k D^-1 (b - A x) whose
 // error polynomial is the scaled Chebyshev polynomial on [lo, hi] (eigenvalue
 // range of D^-1 A to damp).  Roots are taken alternately from both ends.
@@ -679,7 +735,7 @@ static CoarseW coarse_weights(eqgpu_solver *s)
 template <int NU>
 static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
 {
-    const int lt = s->tail_first, nl = (int)s->levels.size();
+    const int lt = s->use_cluster ? s->ctail_first : s->tail_first, nl = (int)s->levels.size();
     const size_t tsm = 2 * TN * sizeof(double);
     const SmoothW sw = smooth_weights(s);
     const CoarseW cw = coarse_weights(s);
@@ -694,6 +750,23 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
             k_presmooth<NU, 4><<<g, 1024, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
         s->launches++;
     }
+    if (s->use_cluster) {
+        const CTailDesc ctd = make_ctail_desc(s, lt, s->ctail_ncta);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(s->ctail_ncta); cfg.blockDim = dim3(CT_THREADS); cfg.dynamicSmemBytes = s->ctail_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = s->ctail_ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const LevelDev *dl = s->d_levels;
+        const double *bin = s->levels[lt].b;
+        double *xout = s->levels[lt].x;
+        int nu = s->nu;
+        const CGScalars *scp = s->sc;
+        cudaLaunchKernelEx(&cfg, k_ctail, dl, ctd, bin, xout, nu, sw, cw, scp);
+        s->launches++;
+    } else {
     TailDesc td;
     td.first = lt; td.last = nl - 1;
     int off = 0;
@@ -709,6 +782,7 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
     k_tail<<<1, TAIL_THREADS, s->tail_smem, st>>>(s->d_levels, td, s->levels[lt].b, s->levels[lt].x, s->nu, sw, cw,
                                                   s->sc);
     s->launches++;
+    }
     for (int l = lt - 1; l >= 0; --l) {
         Level &lv = s->levels[l], &cv = s->levels[l + 1];
         const dim3 g = tgrid(lv.dev, TO_POST);
@@ -734,7 +808,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     case 3: vcycle_fused<3>(s, st); break;
     default: vcycle_fused<4>(s, st); break;
     }
-    if (s->tail_first == 0) {
+    if ((s->use_cluster ? s->ctail_first : s->tail_first) == 0) {
         k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
         s->launches++;
     }
@@ -897,7 +971,7 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
             k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
             *alg_bytes = 32.0 * s->N;
         } else if (nm == "presmooth" || nm == "postsmooth") {
-            if (!s->fused || s->tail_first == 0 || s->nu != 3) return false;
+            if (!s->fused || (s->use_cluster ? s->ctail_first : s->tail_first) == 0 || s->nu != 3) return false;
             Level &cv = s->levels[1];
             const size_t tsm = 2 * TN * sizeof(double);
             const SmoothW sw = smooth_weights(s);
