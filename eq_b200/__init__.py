@@ -31,7 +31,7 @@ API_SYMBOLS = [
     "eqgpu_cells_gather", "eqgpu_cells_scatter", "eqgpu_apply_operator", "eqgpu_build_rhs",
     "eqgpu_field_device_ptr", "eqgpu_sync", "eqgpu_cells_set_amounts",
     "eqgpu_cells_gather_resident", "eqgpu_cells_scatter_resident", "eqgpu_cells_get_gathered",
-    "eqgpu_bench_kernel",
+    "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
 ]
 
 
@@ -79,6 +79,7 @@ def lib():
         L.eqgpu_last_error.restype = C.c_char_p
         L.eqgpu_last_error.argtypes = [C.c_void_p]
         L.eqgpu_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+        L.eqgpu_create_slab.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
         L.eqgpu_destroy.argtypes = [C.c_void_p]
         L.eqgpu_destroy.restype = None
         L.eqgpu_default_params.restype = None
@@ -96,6 +97,15 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id for eqgpu_create_slab; make it on rank 0 and hand it to the other ranks."""
+    buf = C.create_string_buffer(128)
+    rc = lib().eqgpu_nccl_unique_id(buf)
+    if rc != 0:
+        raise EqGpuError("eqgpu_nccl_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
 def default_params() -> Params:
     p = Params()
     lib().eqgpu_default_params(C.byref(p))
@@ -110,7 +120,8 @@ class GpuHSL:
                  bc_type=(DIRICHLET,) * 4, bc_value=(0.0,) * 4, robin_s=(0.0, 0.0),
                  channels=False, channel_v=120.0, channel_r=(0.0, 0.0), channel_iters=48,
                  well_scaling=25.0, rtol=1e-12, max_iters=200, device=0, stream=None,
-                 smooth_sweeps=0, max_levels=0, hy=None):
+                 smooth_sweeps=0, max_levels=0, hy=None, slab=None):
+        """slab = (rank, world, nccl_id_bytes) selects the row-slab decomposition (eqgpu_create_slab)."""
         L = lib()
         p = default_params()
         p.nW, p.nH, p.hx, p.hy, p.dt, p.D = nW, nH, h, (hy if hy else h), dt, D
@@ -129,7 +140,12 @@ class GpuHSL:
         self.params = p
         self.nW, self.nH, self.N = nW, nH, nW * nH
         self._h = C.c_void_p()
-        rc = L.eqgpu_create(C.byref(p), C.byref(self._h))
+        if slab is None:
+            rc = L.eqgpu_create(C.byref(p), C.byref(self._h))
+        else:
+            rank, world, uid = slab
+            rc = L.eqgpu_create_slab(C.byref(p), C.c_int(rank), C.c_int(world),
+                                     C.c_char_p(uid) if uid is not None else None, C.byref(self._h))
         if rc != 0:
             raise EqGpuError(f"eqgpu_create failed ({rc}): {L.eqgpu_last_error(None).decode()}")
         # the members simulation.cpp touches
@@ -173,8 +189,18 @@ class GpuHSL:
         assert u.size == self.N
         self._ck(lib().eqgpu_set_field(self._h, _dp(u)))
 
-    def get_field(self):
-        u = np.empty(self.N)
+    def slab_rows(self):
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(lib().eqgpu_slab_rows(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_field(self, out=None):
+        """Whole-field host array; in slab mode only this rank's owned rows are (over)written."""
+        if out is not None:
+            u = _f64(out)
+            self._ck(lib().eqgpu_get_field(self._h, _dp(u)))
+            return u
+        u = np.zeros(self.N)
         self._ck(lib().eqgpu_get_field(self._h, _dp(u)))
         return u
 

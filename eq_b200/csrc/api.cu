@@ -28,7 +28,30 @@ void eqgpu_default_params(eqgpu_params *p)
 
 const char *eqgpu_last_error(const eqgpu_solver *s) { return s ? s->err.c_str() : g_create_error.c_str(); }
 
-int eqgpu_create(const eqgpu_params *p, eqgpu_solver **out)
+static int create_common(const eqgpu_params *p, int rank, int world, const void *nccl_id, eqgpu_solver **out);
+
+int eqgpu_create(const eqgpu_params *p, eqgpu_solver **out) { return create_common(p, 0, 1, nullptr, out); }
+
+int eqgpu_create_slab(const eqgpu_params *p, int rank, int world, const void *nccl_unique_id, eqgpu_solver **out)
+{
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !nccl_unique_id)) {
+        g_create_error = "bad slab rank/world/id";
+        return EQGPU_EINVAL;
+    }
+    if (p && p->channels) { g_create_error = "row-slab mode does not run the flow channels yet"; return EQGPU_EINVAL; }
+    return create_common(p, rank, world, nccl_unique_id, out);
+}
+
+int eqgpu_nccl_unique_id(void *out128) { return out128 ? slab_unique_id(out128) : EQGPU_EINVAL; }
+
+int eqgpu_slab_rows(eqgpu_solver *s, int32_t *g0, int32_t *g1)
+{
+    if (!s || !g0 || !g1) return EQGPU_EINVAL;
+    *g0 = s->levels[0].g0; *g1 = s->levels[0].g1;
+    return 0;
+}
+
+static int create_common(const eqgpu_params *p, int rank, int world, const void *nccl_id, eqgpu_solver **out)
 {
     if (!p || !out) { g_create_error = "null argument"; return EQGPU_EINVAL; }
     *out = nullptr;
@@ -57,8 +80,12 @@ int eqgpu_create(const eqgpu_params *p, eqgpu_solver **out)
     if (!s) { g_create_error = "out of host memory"; return EQGPU_EINVAL; }
     s->p = *p;
     if (!(s->p.hy > 0)) s->p.hy = s->p.hx;
+    s->slab = world > 1;
+    s->slab_rank = rank;
+    s->slab_world = world;
     auto fail = [&](int rc) {
         g_create_error = s->err;
+        slab_destroy_comm(s);
         solver_teardown(s);
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
         delete s;
@@ -76,7 +103,12 @@ int eqgpu_create(const eqgpu_params *p, eqgpu_solver **out)
         }
         s->own_stream = true;
     }
-    int rc = solver_setup(s);
+    int rc = 0;
+    if (s->slab) {
+        rc = slab_init_comm(s, nccl_id);
+        if (rc) return fail(rc);
+    }
+    rc = solver_setup(s);
     if (rc) return fail(rc);
     rc = channels_setup(s);
     if (rc) return fail(rc);
@@ -92,6 +124,7 @@ void eqgpu_destroy(eqgpu_solver *s)
     if (!s) return;
     cudaSetDevice(s->p.device);
     cudaStreamSynchronize(s->stream);
+    slab_destroy_comm(s);
     solver_teardown(s);
     cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt);
     if (s->own_stream) cudaStreamDestroy(s->stream);
@@ -104,7 +137,9 @@ int eqgpu_set_field(eqgpu_solver *s, const double *h)
 {
     CHECK_S(s);
     if (!h) { s->set_error("null field"); return EQGPU_EINVAL; }
-    EQ_CUDA(cudaMemcpyAsync(s->u, h, sizeof(double) * s->N, cudaMemcpyHostToDevice, s->stream));
+    // the host array is always the whole nW x nH field; a slab takes its window (owned + halo rows)
+    EQ_CUDA(cudaMemcpyAsync(s->u, h + (size_t)s->levels[0].dev.row0 * s->p.nW, sizeof(double) * s->N,
+                            cudaMemcpyHostToDevice, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -113,7 +148,10 @@ int eqgpu_get_field(eqgpu_solver *s, double *h)
 {
     CHECK_S(s);
     if (!h) { s->set_error("null field"); return EQGPU_EINVAL; }
-    EQ_CUDA(cudaMemcpyAsync(h, s->u, sizeof(double) * s->N, cudaMemcpyDeviceToHost, s->stream));
+    // ... and gives back its owned rows only
+    const Level &l0 = s->levels[0];
+    EQ_CUDA(cudaMemcpyAsync(h + (size_t)l0.g0 * s->p.nW, s->u + (size_t)l0.dev.own0 * s->p.nW,
+                            sizeof(double) * (size_t)(l0.g1 - l0.g0) * s->p.nW, cudaMemcpyDeviceToHost, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -126,6 +164,7 @@ int eqgpu_set_tensor(eqgpu_solver *s, const double *d11, const double *d22, cons
         return solver_refresh_levels(s);
     }
     if (!d11 || !d22 || !d12) { s->set_error("give all three tensor components or none"); return EQGPU_EINVAL; }
+    if (s->slab) { s->set_error("variable tensor is single-GPU only for now"); return EQGPU_ESTATE; }
     const size_t bytes = sizeof(double) * s->N;
     if (!s->d11) {
         EQ_CUDA(cudaMalloc(&s->d11, bytes));
@@ -160,10 +199,13 @@ int eqgpu_step_host(eqgpu_solver *s, double *v)
 {
     CHECK_S(s);
     if (!v) { s->set_error("null solution_vector"); return EQGPU_EINVAL; }
-    EQ_CUDA(cudaMemcpyAsync(s->u, v, sizeof(double) * s->N, cudaMemcpyHostToDevice, s->stream));
+    const Level &l0 = s->levels[0];
+    EQ_CUDA(cudaMemcpyAsync(s->u, v + (size_t)l0.dev.row0 * s->p.nW, sizeof(double) * s->N, cudaMemcpyHostToDevice,
+                            s->stream));
     int rc = solver_step(s);
     if (rc) return rc;
-    EQ_CUDA(cudaMemcpyAsync(v, s->u, sizeof(double) * s->N, cudaMemcpyDeviceToHost, s->stream));
+    EQ_CUDA(cudaMemcpyAsync(v + (size_t)l0.g0 * s->p.nW, s->u + (size_t)l0.dev.own0 * s->p.nW,
+                            sizeof(double) * (size_t)(l0.g1 - l0.g0) * s->p.nW, cudaMemcpyDeviceToHost, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -317,6 +359,7 @@ int eqgpu_apply_operator(eqgpu_solver *s, const double *hx, double *hy, int cons
 {
     CHECK_S(s);
     if (!hx || !hy) return EQGPU_EINVAL;
+    if (s->slab) { s->set_error("verification hooks are single-GPU only"); return EQGPU_ESTATE; }
     const size_t bytes = sizeof(double) * s->N;
     EQ_CUDA(cudaMemcpyAsync(s->pv, hx, bytes, cudaMemcpyHostToDevice, s->stream));
     int rc = solver_apply(s, s->pv, s->Ap, constrained != 0);
@@ -331,6 +374,7 @@ int eqgpu_build_rhs(eqgpu_solver *s, const double *hu0, double *hb)
 {
     CHECK_S(s);
     if (!hu0 || !hb) return EQGPU_EINVAL;
+    if (s->slab) { s->set_error("verification hooks are single-GPU only"); return EQGPU_ESTATE; }
     const size_t bytes = sizeof(double) * s->N;
     EQ_CUDA(cudaMemcpyAsync(s->pv, hu0, bytes, cudaMemcpyHostToDevice, s->stream));
     int rc = solver_rhs(s, s->pv, s->Ap);

@@ -119,22 +119,28 @@ k_cells_raster(const double *__restrict__ cells, long long ncells, double npm, i
 // the reference's order (every lane carries the same running sum).
 __global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
 k_cells_gather(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
-               const double *__restrict__ u, double *__restrict__ out)
+               const double *__restrict__ u, double *__restrict__ out, int row0, int g0, int g1)
 {
     const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
     if (k >= ncells) return;
     const int lane = threadIdx.x & 31;
     const double *c = cells + k * EQGPU_CELL_STRIDE;
     double HSL = 0.0;
+    // row-slab mode: only nodes in owned rows [g0, g1) are read (the partial means are summed over ranks)
+    auto owned = [&](long long node) { const int gi = (int)(node / nW); return gi >= g0 && gi < g1; };
     int n = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned m, bool in, int) {
-        const double v = in ? __ldg(u + node) : 0.0;
+        const double v = (in && owned(node)) ? __ldg(u + node - (long long)row0 * nW) : 0.0;
         while (m) {
             const int src = __ffs(m) - 1;
             HSL = add(HSL, __shfl_sync(0xffffffffu, v, src));
             m &= m - 1;
         }
     });
-    if (n == 0) { HSL = __ldg(u + centre_node(c, npm, nW)); n = 1; }
+    if (n == 0) {
+        const long long cn = centre_node(c, npm, nW);
+        HSL = owned(cn) ? __ldg(u + cn - (long long)row0 * nW) : 0.0;
+        n = 1;
+    }
     if (lane == 0) out[k] = __ddiv_rn(HSL, (double)n);
 }
 
@@ -153,7 +159,7 @@ __device__ __forceinline__ double cell_volume(double L)
 __global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
 k_cells_scatter(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
                 const double *__restrict__ amount, const int *__restrict__ counts,
-                double *__restrict__ u)
+                double *__restrict__ u, int row0, int g0, int g1)
 {
     const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
     if (k >= ncells) return;
@@ -168,10 +174,14 @@ k_cells_scatter(const double *__restrict__ cells, long long ncells, double npm, 
     const double perSquareMicron = __ddiv_rn(numberHSL, extra);
     const double onePoint = mul(mul(perSquareMicron, npm), npm);
     const double dHSL = __ddiv_rn(onePoint, (double)n);
+    auto owned = [&](long long node) { const int gi = (int)(node / nW); return gi >= g0 && gi < g1; };
     int found = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned, bool in, int) {
-        if (in) atomicAdd(u + node, dHSL);
+        if (in && owned(node)) atomicAdd(u + node - (long long)row0 * nW, dHSL);
     });
-    if (found == 0 && lane == 0) atomicAdd(u + centre_node(c, npm, nW), dHSL);
+    if (found == 0 && lane == 0) {
+        const long long cn = centre_node(c, npm, nW);
+        if (owned(cn)) atomicAdd(u + cn - (long long)row0 * nW, dHSL);
+    }
 }
 
 static int nte_of(double npm) { return (int)llround(npm * 1.0 / 2.0); }  // src/abm/eQabm.cpp:75
@@ -192,9 +202,14 @@ int cells_gather(eqgpu_solver *s, double *d_out)
     if (s->ncells == 0) return 0;
     const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
     k_cells_gather<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
-        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->u, d_out);
+        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->u, d_out, s->levels[0].dev.row0,
+        s->levels[0].g0, s->levels[0].g1);
     s->launches++;
     EQ_CUDA(cudaGetLastError());
+    if (s->slab) {
+        int rc = slab_allreduce(s, d_out, d_out, (int)s->ncells);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -206,7 +221,8 @@ int cells_scatter(eqgpu_solver *s, const double *d_amount)
     k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
         s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->cell_counts, nullptr, 0);
     k_cells_scatter<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
-        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), d_amount, s->cell_counts, s->u);
+        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), d_amount, s->cell_counts, s->u,
+        s->levels[0].dev.row0, s->levels[0].g0, s->levels[0].g1);
     s->launches += 2;
     EQ_CUDA(cudaGetLastError());
     return 0;

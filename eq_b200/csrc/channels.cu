@@ -130,29 +130,26 @@ k_channel_substeps(int n, int num_iter, double h, double dtx, double D, double v
     for (int j = threadIdx.x; j < n; j += CH_THREADS) ug[j] = u[j];
 }
 
-// -oint grad(u).n ds over the four walls (fenics/boundary.h:2652-2741 on the
-// "right" mesh: each wall facet sees the one-sided difference of the triangle
-// it belongs to).  Single block, deterministic.
+// -oint grad(u).n ds over the four walls (fenics/boundary.h:2652-2741 on the "right" mesh: each wall
+// facet sees the one-sided difference of the triangle it belongs to).  u holds global rows
+// [row0, row0+ny_loc); every facet term is added by the rank that owns the row it is attached to
+// (left facet i -> row i+1, right facet i -> row i, bottom -> row 0, top -> row nH-1).
+// Single block, deterministic.
 __global__ void __launch_bounds__(1024)
-k_boundary_functional(int nW, int nH, double hx, double hy, const double *__restrict__ u, double *out)
+k_boundary_functional(int nW, int nH, double hx, double hy, const double *__restrict__ u, double *out,
+                      int row0, int g0, int g1)
 {
     double acc = 0.0;
     const double ry = hx / hy, rx = hy / hx;
-    const int nb = nW - 1, nl = nH - 1;
-    for (int t = threadIdx.x; t < 2 * nb + 2 * nl; t += blockDim.x) {
-        if (t < nb) {  // bottom: lower triangle (v0,v1,v3): du/dy = (u_TR - u_BR)/hy
-            const int j = t;
-            acc += (u[(size_t)nW + j + 1] - u[j + 1]) * ry;
-        } else if (t < 2 * nb) {  // top: upper triangle (v0,v2,v3): -du/dy = (u_BL - u_TL)/hy
-            const int j = t - nb;
-            acc += (u[(size_t)(nH - 2) * nW + j] - u[(size_t)(nH - 1) * nW + j]) * ry;
-        } else if (t < 2 * nb + nl) {  // left: upper triangle: du/dx = (u_TR - u_TL)/hx
-            const int i = t - 2 * nb;
-            acc += (u[(size_t)(i + 1) * nW + 1] - u[(size_t)(i + 1) * nW]) * rx;
-        } else {  // right: lower triangle: -du/dx = (u_BL - u_BR)/hx
-            const int i = t - 2 * nb - nl;
-            acc += (u[(size_t)i * nW + nW - 2] - u[(size_t)i * nW + nW - 1]) * rx;
-        }
+    const int nb = nW - 1;
+    auto U = [&](int gi, int j) { return u[(size_t)(gi - row0) * nW + j]; };
+    if (g0 == 0)  // bottom: lower triangle (v0,v1,v3): du/dy = (u_TR - u_BR)/hy
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) acc += (U(1, j + 1) - U(0, j + 1)) * ry;
+    if (g1 == nH)  // top: upper triangle (v0,v2,v3): -du/dy = (u_BL - u_TL)/hy
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) acc += (U(nH - 2, j) - U(nH - 1, j)) * ry;
+    for (int gi = g0 + threadIdx.x; gi < g1; gi += blockDim.x) {
+        if (gi >= 1) acc += (U(gi, 1) - U(gi, 0)) * rx;                     // left facet gi-1: du/dx = (u_TR - u_TL)/hx
+        if (gi <= nH - 2) acc += (U(gi, nW - 2) - U(gi, nW - 1)) * rx;      // right facet gi: -du/dx = (u_BL - u_BR)/hx
     }
     __shared__ double sm[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -225,8 +222,14 @@ int boundary_functional(eqgpu_solver *s)
 {
     const eqgpu_params &p = s->p;
     const double hy = p.hy > 0 ? p.hy : p.hx;
-    k_boundary_functional<<<1, 1024, 0, s->stream>>>(p.nW, p.nH, p.hx, hy, s->u, s->flux_dev);
+    const Level &l0 = s->levels[0];
+    k_boundary_functional<<<1, 1024, 0, s->stream>>>(p.nW, p.nH, p.hx, hy, s->u, s->flux_dev, l0.dev.row0, l0.g0,
+                                                     l0.g1);
     s->launches++;
+    if (s->slab) {
+        int rc = slab_allreduce(s, s->flux_dev, s->flux_dev, 1);
+        if (rc) return rc;
+    }
     EQ_CUDA(cudaMemcpyAsync(s->flux_host, s->flux_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));
     // src/fHSL.cpp:160

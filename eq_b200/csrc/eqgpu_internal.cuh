@@ -35,16 +35,23 @@ struct LevelDev {
     double cC, cEW, cNS, cD, icC;
     // optional nodal tensor fields (level-local, injected); null = isotropic
     const double *d11, *d22, *d12;
+    // row-slab decomposition: the arrays hold global rows [row0, row0+ny) of a gny-row grid, of
+    // which local rows [own0, own1) are owned (the others are halo copies).  Single GPU: 0, ny, 0, ny.
+    int row0, gny, own0, own1;
 };
 
 struct CGScalars {
     double rz_old, rz_new, pAp, rr, bnorm2, stop2, rr0;
+    // slab mode: kernels leave their rank-local sums here; an out-of-place all-reduce then writes the
+    // global value into the field above (idempotent when replayed after convergence)
+    double part_rz, part_pAp, part_rr, part_b2, part_rr0;
     int iters, done, max_iters, pad;
 };
 
 struct Level {
     LevelDev dev;
-    std::vector<double> hx_host, hy_host;  // unpadded cell sizes
+    std::vector<double> hx_host, hy_host;  // unpadded cell sizes (global grid)
+    int g0 = 0, g1 = 0;                    // owned global rows [g0, g1)
     double *d_hx = nullptr, *d_ihx = nullptr, *d_hy = nullptr, *d_ihy = nullptr;
     double *x = nullptr, *b = nullptr, *t = nullptr;  // solution, rhs, scratch
     double *t11 = nullptr, *t22 = nullptr, *t12 = nullptr;
@@ -66,6 +73,11 @@ struct eqgpu_solver {
     int tail_first = 0;            // first level handled by the single-CTA tail kernel
     size_t tail_smem = 0;
     bool fused = true;
+    // row-slab mode (eqgpu_create_slab): this rank owns rows [levels[l].g0, levels[l].g1) of every level
+    bool slab = false;
+    int slab_rank = 0, slab_world = 1;
+    void *nccl_comm = nullptr;
+    double *cell_cnt = nullptr;    // per-cell owned-point counts (slab gather)
     bool use_cluster = false;      // deepest levels on a 16-CTA cluster (k_ctail) instead of one CTA (k_tail)
     int ctail_first = 0, ctail_ncta = 0;
     size_t ctail_smem = 0;
@@ -111,6 +123,12 @@ int solver_apply(eqgpu_solver *s, const double *dx, double *dy, bool constrained
 int solver_rhs(eqgpu_solver *s, const double *du0, double *db);
 int solver_refresh_levels(eqgpu_solver *s);
 int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes);
+// ---- slab.cu ----
+int slab_init_comm(eqgpu_solver *s, const void *unique_id);
+void slab_destroy_comm(eqgpu_solver *s);
+int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v);          // one-row halos of a level vector
+int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count);  // sum over ranks, stream-ordered
+int slab_unique_id(void *out128);
 // ---- cells.cu ----
 int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap);
 int cells_gather(eqgpu_solver *s, double *d_out);

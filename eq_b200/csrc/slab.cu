@@ -1,0 +1,121 @@
+// Row-slab decomposition plumbing: one-row halo exchange and scalar all-reduce over NCCL
+// (NVLink 5 / NVSwitch between the GPUs of one box).  The reference's precedent is the PETSc DMDA
+// star-stencil halo of diffuclass.cpp:364-370,659-669 and the KSP's internal dot-product
+// MPI_Allreduce (diffuclass.cpp:410 [ext]).
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2 -- the copy torch has already loaded in the
+// calling process, or the system one), so libeqgpu.so itself has no link-time dependency on it and
+// single-GPU use never touches it.
+#include "eqgpu_internal.cuh"
+#include <dlfcn.h>
+#include <cstring>
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclSum = 0 };
+
+static struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+static bool nccl_load(std::string &err)
+{
+    if (g_nccl.lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);  // already in the process (torch)?
+        if (!h) h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(field, name)                                                     \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                              \
+    if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = h;
+    return true;
+}
+
+#define EQ_NCCL(call)                                                                       \
+    do {                                                                                    \
+        ncclResult_t r__ = (call);                                                          \
+        if (r__ != 0) {                                                                     \
+            s->set_error(std::string(#call) + ": " + g_nccl.GetErrorString(r__));           \
+            return EQGPU_ECUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+int slab_unique_id(void *out128)
+{
+    std::string err;
+    if (!nccl_load(err)) return EQGPU_ECUDA;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return EQGPU_ECUDA;
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+int slab_init_comm(eqgpu_solver *s, const void *unique_id)
+{
+    std::string err;
+    if (!nccl_load(err)) { s->set_error(err); return EQGPU_ECUDA; }
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclComm_t comm = nullptr;
+    EQ_NCCL(g_nccl.CommInitRank(&comm, s->slab_world, id, s->slab_rank));
+    s->nccl_comm = comm;
+    return 0;
+}
+
+void slab_destroy_comm(eqgpu_solver *s)
+{
+    if (s->nccl_comm && g_nccl.lib) g_nccl.CommDestroy((ncclComm_t)s->nccl_comm);
+    s->nccl_comm = nullptr;
+}
+
+// Refresh the halo rows of a level vector: my first/last owned rows go to the neighbours below/above,
+// theirs arrive in my halo rows.  Stream-ordered; every rank issues the same sequence.
+int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v)
+{
+    ncclComm_t comm = (ncclComm_t)s->nccl_comm;
+    const bool below = L.own0 > 0, above = L.own1 < L.ny;
+    if (!below && !above) return 0;
+    const size_t nx = (size_t)L.nx;
+    EQ_NCCL(g_nccl.GroupStart());
+    if (below) {
+        EQ_NCCL(g_nccl.Send(v + (size_t)L.own0 * nx, nx, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+        EQ_NCCL(g_nccl.Recv(v, nx, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+    }
+    if (above) {
+        EQ_NCCL(g_nccl.Send(v + (size_t)(L.own1 - 1) * nx, nx, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+        EQ_NCCL(g_nccl.Recv(v + (size_t)L.own1 * nx, nx, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+    }
+    EQ_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count)
+{
+    EQ_NCCL(g_nccl.AllReduce(src, dst, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)s->nccl_comm, s->stream));
+    return 0;
+}

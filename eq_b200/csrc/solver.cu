@@ -38,12 +38,12 @@ __device__ __forceinline__ double dir_value(const LevelDev &L, const DirData &d,
 template <bool TENSOR, bool DOT>
 __global__ void __launch_bounds__(BX *BY)
 k_apply(LevelDev L, const double *__restrict__ x, double *__restrict__ y, CGScalars *sc,
-        double *partials, unsigned *counter)
+        double *partials, unsigned *counter, double *out_pAp)
 {
     if (DOT && sc->done) return;
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     double v[1] = {0.0};
-    if (i < L.ny && j < L.nx) {
+    if (i >= L.own0 && i < L.own1 && j < L.nx) {
         const size_t g = (size_t)i * L.nx + j;
         double out = 0.0;
         if (!is_dirichlet(L, i, j)) {
@@ -56,7 +56,7 @@ k_apply(LevelDev L, const double *__restrict__ x, double *__restrict__ y, CGScal
     }
     if (DOT) {
         double tot[1];
-        if (grid_reduce<1>(v, partials, counter, tot)) sc->pAp = tot[0];
+        if (grid_reduce<1>(v, partials, counter, tot)) *out_pAp = tot[0];
     }
 }
 
@@ -118,11 +118,11 @@ template <bool TENSOR>
 __global__ void __launch_bounds__(BX *BY)
 k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict__ rA,
        double *__restrict__ rB, double rs_l, double rs_r, CGScalars *sc, double *partials,
-       unsigned *counter)
+       unsigned *counter, double *out_rr0, double *out_b2)
 {
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     double v[2] = {0.0, 0.0};
-    if (i < L.ny && j < L.nx) {
+    if (i >= L.own0 && i < L.own1 && j < L.nx) {
         const size_t g = (size_t)i * L.nx + j;
         double resA = 0.0, resB = 0.0;
         if (!is_dirichlet(L, i, j)) {
@@ -153,8 +153,8 @@ k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict_
     }
     double tot[2];
     if (grid_reduce<2>(v, partials, counter, tot)) {
-        sc->rr0 = tot[0];
-        sc->bnorm2 = tot[1];
+        *out_rr0 = tot[0];
+        *out_b2 = tot[1];
     }
 }
 
@@ -165,7 +165,7 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
 {
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     const bool useB = sc->bnorm2 < sc->rr0;
-    if (i < L.ny && j < L.nx) {
+    if (i >= L.own0 && i < L.own1 && j < L.nx) {
         const size_t g = (size_t)i * L.nx + j;
         if (is_dirichlet(L, i, j)) u[g] = dir_value(L, dd, i, j);
         else if (useB) { u[g] = 0.0; r[g] = rB[g]; }
@@ -189,7 +189,7 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
 // rz_new = r . z
 __global__ void __launch_bounds__(256)
 k_dot(size_t n, const double *__restrict__ a, const double *__restrict__ b, CGScalars *sc,
-      double *partials, unsigned *counter)
+      double *partials, unsigned *counter, double *out)
 {
     if (sc->done) return;
     double v[1] = {0.0};
@@ -197,7 +197,7 @@ k_dot(size_t n, const double *__restrict__ a, const double *__restrict__ b, CGSc
          g += (size_t)gridDim.x * blockDim.x)
         v[0] += __ldg(a + g) * __ldg(b + g);
     double tot[1];
-    if (grid_reduce<1>(v, partials, counter, tot)) sc->rz_new = tot[0];
+    if (grid_reduce<1>(v, partials, counter, tot)) *out = tot[0];
 }
 
 // p = z + beta p
@@ -215,12 +215,22 @@ k_update_p(size_t n, const double *__restrict__ z, double *__restrict__ p, const
 // 128-bit accesses, two independent double2 per thread per trip.
 __global__ void __launch_bounds__(256)
 k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
-            const double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter)
+            const double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter, int book,
+            double *out_rr)
 {
     if (sc->done) return;
     const double alpha = sc->rz_new / sc->pAp;
     double v[1] = {0.0};
-    const size_t n2 = n >> 1, stride = (size_t)gridDim.x * blockDim.x;
+    const bool aligned = ((((size_t)x) | ((size_t)r) | ((size_t)p) | ((size_t)Ap)) & 15) == 0;
+    const size_t n2 = aligned ? n >> 1 : 0, stride = (size_t)gridDim.x * blockDim.x;
+    if (!aligned) {  // a slab whose first owned row starts at an odd element: scalar accesses
+        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+            x[t] += alpha * __ldg(p + t);
+            const double rn = r[t] - alpha * __ldg(Ap + t);
+            r[t] = rn;
+            v[0] += rn * rn;
+        }
+    }
     double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
     const double2 *p2 = reinterpret_cast<const double2 *>(p), *A2 = reinterpret_cast<const double2 *>(Ap);
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,7 +251,7 @@ k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const doub
         x2[g] = xa; r2[g] = ra;
         v[0] += ra.x * ra.x + ra.y * ra.y;
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (aligned && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const size_t t = n - 1;
         x[t] += alpha * p[t];
         const double rn = r[t] - alpha * Ap[t];
@@ -250,11 +260,36 @@ k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const doub
     }
     double tot[1];
     if (grid_reduce<1>(v, partials, counter, tot)) {
-        sc->rr = tot[0];
-        sc->rz_old = sc->rz_new;
-        sc->iters += 1;
-        if (tot[0] <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
+        *out_rr = tot[0];
+        if (book) {
+            sc->rz_old = sc->rz_new;
+            sc->iters += 1;
+            if (tot[0] <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
+        }
     }
+}
+
+// iteration bookkeeping when ||r||^2 had to be summed over ranks first (slab mode)
+__global__ void k_book(CGScalars *sc)
+{
+    if (sc->done) return;
+    sc->rz_old = sc->rz_new;
+    sc->iters += 1;
+    if (sc->rr <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
+}
+
+// PCG setup from the (already rank-summed) start residuals (slab mode; single GPU does this in k_impose)
+__global__ void k_cg_setup(CGScalars *sc, double rtol, int max_iters)
+{
+    const bool useB = sc->bnorm2 < sc->rr0;
+    const double rr = useB ? sc->bnorm2 : sc->rr0;
+    sc->rr = rr;
+    sc->stop2 = rtol * rtol * sc->bnorm2;
+    sc->iters = 0;
+    sc->max_iters = max_iters;
+    sc->done = (rr <= sc->stop2) ? 1 : 0;
+    sc->rz_old = 1.0;
+    sc->rz_new = 0.0;
 }
 
 // ---------------------------------------------------------------------------
@@ -268,7 +303,7 @@ k_jacobi0(LevelDev L, const double *__restrict__ b, double *__restrict__ x, doub
 {
     if (sc->done) return;
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.ny || j >= L.nx) return;
+    if (i < L.own0 || i >= L.own1 || j >= L.nx) return;
     const size_t g = (size_t)i * L.nx + j;
     double out = 0.0;
     if (!is_dirichlet(L, i, j)) {
@@ -287,7 +322,7 @@ k_jacobi(LevelDev L, const double *__restrict__ b, const double *__restrict__ xi
 {
     if (sc->done) return;
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.ny || j >= L.nx) return;
+    if (i < L.own0 || i >= L.own1 || j >= L.nx) return;
     const size_t g = (size_t)i * L.nx + j;
     double out = 0.0;
     if (!is_dirichlet(L, i, j)) {
@@ -301,22 +336,24 @@ k_jacobi(LevelDev L, const double *__restrict__ b, const double *__restrict__ xi
 
 
 // bc = P^T rf  (P = P1 interpolation on the "right" mesh: midpoints of the
-// E-W, N-S and SW-NE edges take half of each end)
+// E-W, N-S and SW-NE edges take half of each end).  Row logic uses global rows
+// (row0/gny) so the same kernel serves a row slab.
 __global__ void __launch_bounds__(BX *BY)
 k_restrict(LevelDev F, LevelDev Cc, const double *__restrict__ rf, double *__restrict__ bc,
            const CGScalars *sc)
 {
     if (sc->done) return;
     const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
-    if (I >= Cc.ny || J >= Cc.nx) return;
+    if (I < Cc.own0 || I >= Cc.own1 || J >= Cc.nx) return;
     double out = 0.0;
     if (!is_dirichlet(Cc, I, J)) {
-        const int fi = fine_of(I, F.ny), fj = fine_of(J, F.nx);
+        const int gfi = fine_of(I + Cc.row0, F.gny), fj = fine_of(J, F.nx);
+        const int fi = gfi - F.row0;
         const size_t g = (size_t)fi * F.nx + fj;
         const bool e = fj + 1 < F.nx && is_mid(fj + 1, F.nx);
         const bool w = fj - 1 >= 0 && is_mid(fj - 1, F.nx);
-        const bool n = fi + 1 < F.ny && is_mid(fi + 1, F.ny);
-        const bool s = fi - 1 >= 0 && is_mid(fi - 1, F.ny);
+        const bool n = gfi + 1 < F.gny && is_mid(gfi + 1, F.gny);
+        const bool s = gfi - 1 >= 0 && is_mid(gfi - 1, F.gny);
         out = __ldg(rf + g);
         double h = 0.0;
         if (e) h += __ldg(rf + g + 1);
@@ -337,11 +374,17 @@ k_prolong_add(LevelDev F, LevelDev Cc, const double *__restrict__ xc, double *__
 {
     if (sc->done) return;
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= F.ny || j >= F.nx) return;
+    if (i < F.own0 || i >= F.own1 || j >= F.nx) return;
     if (is_dirichlet(F, i, j)) return;
-    const bool mi = is_mid(i, F.ny), mj = is_mid(j, F.nx);
-    (void)mi; (void)mj;
-    xf[(size_t)i * F.nx + j] += prolong_at(F, Cc, xc, i, j);
+    const int gi = i + F.row0;
+    const bool mi = is_mid(gi, F.gny), mj = is_mid(j, F.nx);
+    const double *c0 = xc + (size_t)(coarse_lo(gi, F.gny, Cc.gny) - Cc.row0) * Cc.nx + coarse_lo(j, F.nx, Cc.nx);
+    double add;
+    if (!mi && !mj) add = __ldg(c0);
+    else if (!mi && mj) add = 0.5 * (__ldg(c0) + __ldg(c0 + 1));
+    else if (mi && !mj) add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx));
+    else add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx + 1));
+    xf[(size_t)i * F.nx + j] += add;
 }
 
 // nodal injection of a tensor component to the coarse grid
@@ -349,7 +392,7 @@ __global__ void k_inject(LevelDev F, LevelDev Cc, const double *__restrict__ f, 
 {
     const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
     if (I >= Cc.ny || J >= Cc.nx) return;
-    c[(size_t)I * Cc.nx + J] = f[(size_t)fine_of(I, F.ny) * F.nx + fine_of(J, F.nx)];
+    c[(size_t)I * Cc.nx + J] = f[(size_t)(fine_of(I + Cc.row0, F.gny) - F.row0) * F.nx + fine_of(J, F.nx)];
 }
 
 // ---------------------------------------------------------------------------
@@ -371,15 +414,18 @@ static std::vector<double> coarsen_cells(const std::vector<double> &h)
     return hc;
 }
 
-static int upload_padded(eqgpu_solver *s, const std::vector<double> &h, double **d_h, double **d_ih)
+// Padded cell sizes of nodes [first, first+count): entry k = size of the cell below/left of node first+k.
+static int upload_padded(eqgpu_solver *s, const std::vector<double> &h, double **d_h, double **d_ih,
+                         int first = 0, int count = -1)
 {
     const int n = (int)h.size() + 1;
+    if (count < 0) count = n;
     std::vector<double> pad(n + 1, 0.0), ipad(n + 1, 0.0);
     for (int k = 0; k < n - 1; ++k) { pad[k + 1] = h[k]; ipad[k + 1] = 1.0 / h[k]; }
-    EQ_CUDA(cudaMalloc(d_h, sizeof(double) * (n + 1)));
-    EQ_CUDA(cudaMalloc(d_ih, sizeof(double) * (n + 1)));
-    EQ_CUDA(cudaMemcpy(*d_h, pad.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
-    EQ_CUDA(cudaMemcpy(*d_ih, ipad.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
+    EQ_CUDA(cudaMalloc(d_h, sizeof(double) * (count + 1)));
+    EQ_CUDA(cudaMalloc(d_ih, sizeof(double) * (count + 1)));
+    EQ_CUDA(cudaMemcpy(*d_h, pad.data() + first, sizeof(double) * (count + 1), cudaMemcpyHostToDevice));
+    EQ_CUDA(cudaMemcpy(*d_ih, ipad.data() + first, sizeof(double) * (count + 1), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -401,11 +447,14 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
     for (int w = 0; w < 4; ++w)
         if (p.bc_type[w] == EQGPU_BC_DIRICHLET || p.bc_type[w] == EQGPU_BC_DIRICHLET_CHANNEL)
             m |= 1u << w;
+    // a slab sees the top/bottom walls only if its local first/last row IS the global wall row
+    if (L.row0 > 0) m &= ~8u;
+    if (L.row0 + L.ny < L.gny) m &= ~4u;
     L.dirmask = m;
     const double a = lv.hx_host[0], b = lv.hy_host[0];
     // node j (1 <= j) is regular when cells j-1 and j are: j <= leading_regular-1
     L.jreg_hi = std::min(leading_regular(lv.hx_host) - 1, L.nx - 2);
-    L.ireg_hi = std::min(leading_regular(lv.hy_host) - 1, L.ny - 2);
+    L.ireg_hi = std::min(leading_regular(lv.hy_host) - 1, L.gny - 2) - L.row0;  // local index
     L.cC = 2.0 * L.tau * (b / a + a / b) + a * b * 0.5;
     L.cEW = a * b / 12.0 - L.tau * b / a;
     L.cNS = a * b / 12.0 - L.tau * a / b;
@@ -420,34 +469,57 @@ static CTailDesc make_ctail_desc(eqgpu_solver *s, int first, int ncta);
 int solver_setup(eqgpu_solver *s)
 {
     const eqgpu_params &p = s->p;
-    s->N = (size_t)p.nW * p.nH;
+    s->N = (size_t)p.nW * p.nH;  // replaced by the local size once the slab window is known
     const double hx0 = p.hx, hy0 = p.hy > 0 ? p.hy : p.hx;
     s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 3;
     // ---- hierarchy -------------------------------------------------------
     Level l0;
-    l0.dev.nx = p.nW; l0.dev.ny = p.nH;
+    l0.dev.nx = p.nW; l0.dev.gny = p.nH;
     l0.hx_host.assign(p.nW - 1, hx0);
     l0.hy_host.assign(p.nH - 1, hy0);
+    l0.g0 = 0; l0.g1 = p.nH;
+    if (s->slab) {  // contiguous row slabs with even boundaries
+        auto cut = [&](int r) { return r >= s->slab_world ? p.nH : (int)(((long long)p.nH * r / s->slab_world) & ~1LL); };
+        l0.g0 = cut(s->slab_rank); l0.g1 = cut(s->slab_rank + 1);
+        if (l0.g1 - l0.g0 < 8) { s->set_error("slab too thin: fewer than 8 rows per rank"); return EQGPU_EINVAL; }
+        s->fused = false;
+    }
     s->levels.clear();
     s->levels.push_back(l0);
     const int maxl = p.max_levels > 0 ? p.max_levels : 12;
     const double tau = p.dt * p.D;
     while ((int)s->levels.size() < maxl) {
         const Level &f = s->levels.back();
-        if (std::min(f.dev.nx, f.dev.ny) < 5) break;
+        if (std::min(f.dev.nx, f.dev.gny) < 5) break;
+        if (s->slab && (f.dev.gny / 2) / s->slab_world < 4) break;  // keep >= ~4 rows per rank
         // stop once the mass term dominates: Jacobi alone converges fast there
         if (tau / (f.hx_host[0] * f.hy_host[0]) < 0.6) break;
         Level c;
         c.hx_host = coarsen_cells(f.hx_host);
         c.hy_host = coarsen_cells(f.hy_host);
         c.dev.nx = (int)c.hx_host.size() + 1;
-        c.dev.ny = (int)c.hy_host.size() + 1;
+        c.dev.gny = (int)c.hy_host.size() + 1;
+        // coarse row I belongs to whoever owns its coincident fine row min(2I, nf-1)
+        c.g0 = c.dev.gny; c.g1 = 0;
+        for (int I = 0; I < c.dev.gny; ++I) {
+            const int fi = std::min(2 * I, f.dev.gny - 1);
+            if (fi >= f.g0 && fi < f.g1) { c.g0 = std::min(c.g0, I); c.g1 = std::max(c.g1, I + 1); }
+        }
+        if (c.g1 <= c.g0) break;
         s->levels.push_back(c);
+    }
+    for (auto &lv : s->levels) {  // local window: owned rows plus one halo row towards each neighbour
+        LevelDev &L = lv.dev;
+        const int hb = lv.g0 > 0 ? 1 : 0, ht = lv.g1 < L.gny ? 1 : 0;
+        L.row0 = lv.g0 - hb;
+        L.ny = (lv.g1 + ht) - L.row0;
+        L.own0 = hb;
+        L.own1 = L.ny - ht;
     }
     for (size_t l = 0; l < s->levels.size(); ++l) {
         Level &lv = s->levels[l];
         if (upload_padded(s, lv.hx_host, &lv.d_hx, &lv.d_ihx)) return EQGPU_ECUDA;
-        if (upload_padded(s, lv.hy_host, &lv.d_hy, &lv.d_ihy)) return EQGPU_ECUDA;
+        if (upload_padded(s, lv.hy_host, &lv.d_hy, &lv.d_ihy, lv.dev.row0, lv.dev.ny)) return EQGPU_ECUDA;
         const size_t bytes = sizeof(double) * lv.n();
         EQ_CUDA(cudaMalloc(&lv.t, bytes));
         if (l > 0) {
@@ -457,6 +529,7 @@ int solver_setup(eqgpu_solver *s)
         fill_level_consts(s, lv);
     }
     // ---- fine vectors ----------------------------------------------------
+    s->N = s->levels[0].n();  // local nodes (owned rows + halo rows); == nW*nH on a single GPU
     const size_t bytes = sizeof(double) * s->N;
     EQ_CUDA(cudaMalloc(&s->u, bytes));
     EQ_CUDA(cudaMalloc(&s->r, bytes));
@@ -467,6 +540,13 @@ int solver_setup(eqgpu_solver *s)
     EQ_CUDA(cudaMalloc(&s->z, bytes));
     EQ_CUDA(cudaMemset(s->u, 0, bytes));
     EQ_CUDA(cudaMemset(s->pv, 0, bytes));
+    EQ_CUDA(cudaMemset(s->r, 0, bytes));
+    EQ_CUDA(cudaMemset(s->Ap, 0, bytes));
+    EQ_CUDA(cudaMemset(s->z, 0, bytes));
+    for (auto &lv : s->levels) {
+        EQ_CUDA(cudaMemset(lv.t, 0, sizeof(double) * lv.n()));
+        if (&lv != &s->levels[0]) { EQ_CUDA(cudaMemset(lv.x, 0, sizeof(double) * lv.n())); EQ_CUDA(cudaMemset(lv.b, 0, sizeof(double) * lv.n())); }
+    }
     s->levels[0].x = s->z;
     s->levels[0].b = s->r;
     // ---- reductions ------------------------------------------------------
@@ -623,52 +703,66 @@ static DirData make_dirdata(eqgpu_solver *s)
     return d;
 }
 
+static SmoothW smooth_weights(eqgpu_solver *s);
+static CoarseW coarse_weights(eqgpu_solver *s);
+
+// Unfused V-cycle: one kernel per sweep / transfer.  Serves the variable-tensor operator and the
+// row-slab mode, where a one-row halo exchange (slab_exchange) precedes every kernel that reads
+// neighbours.  Same Chebyshev-weighted smoother and coarse solve as the fused cycle.
 template <bool T>
 static void vcycle(eqgpu_solver *s)
 {
     const dim3 blk(BX, BY);
     cudaStream_t st = s->stream;
     const int nl = (int)s->levels.size();
-    const double om = s->omega;
-    // sweeps sweeps from a zero guess, result left in lv.x (uses lv.t as ping-pong)
-    auto smooth_from_zero = [&](Level &lv, int sweeps) {
+    const SmoothW sw = smooth_weights(s);
+    const CoarseW cw = coarse_weights(s);
+    auto xch = [&](Level &lv, double *v) { if (s->slab) slab_exchange(s, lv.dev, v); };
+    // sweeps from a zero guess, result left in lv.x (uses lv.t as ping-pong)
+    auto smooth_from_zero = [&](Level &lv, int sweeps, const double *w) {
         const dim3 g = grid2d(lv.dev);
         double *cur = (sweeps & 1) ? lv.x : lv.t;  // so that the last write lands in lv.x
-        k_jacobi0<T><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, om, s->sc);
+        k_jacobi0<T><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, w[0], s->sc);
         s->launches++;
         for (int k = 1; k < sweeps; ++k) {
             double *nxt = (cur == lv.x) ? lv.t : lv.x;
-            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, om, s->sc);
+            xch(lv, cur);
+            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
             s->launches++;
             cur = nxt;
         }
     };
-    auto smooth = [&](Level &lv, int sweeps) {  // in: lv.x, out: lv.x
+    auto smooth = [&](Level &lv, int sweeps, const double *w) {  // in: lv.x, out: lv.x
         const dim3 g = grid2d(lv.dev);
         double *cur = lv.x;
+        if (sweeps & 1) {  // odd count: start from a copy in lv.t so the last write lands in lv.x
+            cudaMemcpyAsync(lv.t, lv.x, sizeof(double) * lv.n(), cudaMemcpyDeviceToDevice, st);
+            cur = lv.t;
+        }
         for (int k = 0; k < sweeps; ++k) {
             double *nxt = (cur == lv.x) ? lv.t : lv.x;
-            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, om, s->sc);
+            xch(lv, cur);
+            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
             s->launches++;
             cur = nxt;
-        }
-        if (cur != lv.x) {  // odd sweep count: one more would break symmetry, so copy
-            cudaMemcpyAsync(lv.x, lv.t, sizeof(double) * lv.n(), cudaMemcpyDeviceToDevice, st);
         }
     };
     for (int l = 0; l < nl - 1; ++l) {
         Level &lv = s->levels[l], &cv = s->levels[l + 1];
-        smooth_from_zero(lv, s->nu);
-        k_jacobi<T, true><<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, lv.b, lv.x, lv.t, om, s->sc);
+        smooth_from_zero(lv, s->nu, sw.w);
+        xch(lv, lv.x);
+        k_jacobi<T, true><<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, lv.b, lv.x, lv.t, 0.0, s->sc);
+        xch(lv, lv.t);
         k_restrict<<<grid2d(cv.dev), blk, 0, st>>>(lv.dev, cv.dev, lv.t, cv.b, s->sc);
         s->launches += 2;
     }
-    smooth_from_zero(s->levels[nl - 1], nl > 1 ? s->ncoarse : std::max(s->ncoarse, 2 * s->nu));
+    smooth_from_zero(s->levels[nl - 1], cw.n, cw.w);
     for (int l = nl - 2; l >= 0; --l) {
         Level &lv = s->levels[l], &cv = s->levels[l + 1];
+        xch(cv, cv.x);
         k_prolong_add<<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, cv.dev, cv.x, lv.x, s->sc);
         s->launches++;
-        smooth(lv, s->nu);
+        smooth(lv, s->nu, sw.w);
     }
 }
 
@@ -809,13 +903,13 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     default: vcycle_fused<4>(s, st); break;
     }
     if ((s->use_cluster ? s->ctail_first : s->tail_first) == 0) {
-        k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
+        k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1, &s->sc->rz_new);
         s->launches++;
     }
     const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
     k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
     std::swap(s->pv, s->pv2);
-    k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials, s->counters + 3);
+    k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials, s->counters + 3, 1, &s->sc->rr);
     s->launches += 2;
 }
 
@@ -862,8 +956,17 @@ static int pcg(eqgpu_solver *s)
         if (rc) return rc;
     }
 
-    k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, s->sc, s->partials,
-                                  s->counters + 0);
+    // owned rows are contiguous in memory: flat kernels run on [own0*nx, own1*nx)
+    const size_t ooff = (size_t)L.own0 * L.nx, on = (size_t)(L.own1 - L.own0) * L.nx;
+    if (s->slab) slab_exchange(s, L, s->u);
+    CGScalars *sc = s->sc;
+    const bool sl = s->slab;
+    k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
+                                  sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
+    if (sl) {  // rank-sum the two start residuals
+        slab_allreduce(s, &sc->part_rr0, &sc->rr0, 1);
+        slab_allreduce(s, &sc->part_b2, &sc->bnorm2, 1);
+    }
     k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->sc, rtol, max_iters);
     s->launches += 2;
 
@@ -878,11 +981,21 @@ static int pcg(eqgpu_solver *s)
         } else {
             for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
                 vcycle<T>(s);
-                k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1);
-                k_update_p<<<nb1, 256, 0, st>>>(s->N, s->z, s->pv, s->sc);
-                k_apply<T, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, s->sc, s->partials, s->counters + 2);
-                k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials,
-                                                 s->counters + 3);
+                k_dot<<<nb1, 256, 0, st>>>(on, s->r + ooff, s->z + ooff, sc, s->partials, s->counters + 1,
+                                           sl ? &sc->part_rz : &sc->rz_new);
+                if (sl) slab_allreduce(s, &sc->part_rz, &sc->rz_new, 1);
+                k_update_p<<<nb1, 256, 0, st>>>(on, s->z + ooff, s->pv + ooff, sc);
+                if (sl) slab_exchange(s, L, s->pv);
+                k_apply<T, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, sc, s->partials, s->counters + 2,
+                                                     sl ? &sc->part_pAp : &sc->pAp);
+                if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
+                k_update_xr<<<nb1, 256, 0, st>>>(on, s->u + ooff, s->r + ooff, s->pv + ooff, s->Ap + ooff, sc,
+                                                 s->partials, s->counters + 3, sl ? 0 : 1,
+                                                 sl ? &sc->part_rr : &sc->rr);
+                if (sl) {
+                    slab_allreduce(s, &sc->part_rr, &sc->rr, 1);
+                    k_book<<<1, 1, 0, st>>>(sc);
+                }
                 s->launches += 4;
             }
         }
@@ -956,7 +1069,7 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
     EQ_CUDA(cudaMemsetAsync(&s->sc->done, 0, sizeof(int), st));
     auto launch = [&](int k) -> bool {
         if (nm == "apply") {  // read p, write Ap (+ p.Ap): 16 B/DOF
-            k_apply<false, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, s->sc, s->partials, s->counters + 2);
+            k_apply<false, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, s->sc, s->partials, s->counters + 2, &s->sc->pAp);
             *alg_bytes = 16.0 * s->N;
         } else if (nm == "jacobi") {  // read x, b, write x': 24 B/DOF
             double *a = (k & 1) ? l0.t : s->z, *b = (k & 1) ? s->z : l0.t;
@@ -964,7 +1077,8 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
             *alg_bytes = 24.0 * s->N;
         } else if (nm == "update_xr") {  // read x,r,p,Ap write x,r: 48 B/DOF
             const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
-            k_update_xr<<<nb1, 256, 0, st>>>(s->N, l0.t, s->z, s->pv, s->Ap, s->sc, s->partials, s->counters + 3);
+            k_update_xr<<<nb1, 256, 0, st>>>(s->N, l0.t, s->z, s->pv, s->Ap, s->sc, s->partials, s->counters + 3, 1,
+                                             &s->sc->rr);
             *alg_bytes = 48.0 * s->N;
         } else if (nm == "apply_p") {  // read z,p write p',Ap: 32 B/DOF
             const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));

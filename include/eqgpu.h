@@ -96,6 +96,18 @@ EQGPU_API void eqgpu_default_params(eqgpu_params *p);
 
 /* ctor + initDiffusion (src/fHSL.cpp:17-24,37-53,195-328). */
 EQGPU_API int eqgpu_create(const eqgpu_params *p, eqgpu_solver **out);
+/* Row-slab variant for meshes split over the GPUs of one box (BASELINE configs[4]; the reference's
+ * precedent is the DMDA decomposition of diffuclass.cpp:364-370 and the per-layer sub-communicator of
+ * src/simulation.cpp:657-666).  One process per GPU calls this with its rank; rank r owns a contiguous
+ * block of rows, keeps one halo row per neighbour, exchanges halos and sums the CG scalars over NCCL
+ * (loaded at run time from the calling process).  nccl_unique_id: 128 bytes from eqgpu_nccl_unique_id
+ * on rank 0, distributed by the caller.  Host field pointers always address the WHOLE nW x nH field;
+ * a slab reads its window and writes back its owned rows (eqgpu_slab_rows).  Per-cell calls take the
+ * full cell list on every rank and return rank-summed samples. */
+EQGPU_API int eqgpu_create_slab(const eqgpu_params *p, int rank, int world, const void *nccl_unique_id,
+                                eqgpu_solver **out);
+EQGPU_API int eqgpu_nccl_unique_id(void *out128);
+EQGPU_API int eqgpu_slab_rows(eqgpu_solver *s, int32_t *g0, int32_t *g1);
 /* dtor / finalize (src/fHSL.cpp:655-661). */
 EQGPU_API void eqgpu_destroy(eqgpu_solver *s);
 /* Message of the last failure on this solver (s == NULL: last create failure). */

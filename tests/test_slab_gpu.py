@@ -1,0 +1,88 @@
+"""Row-slab decomposition over 2 GPUs (eqgpu_create_slab): halo exchange + CG all-reduce over NCCL.
+The decomposed solve must equal the single-GPU solve and the oracle.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NW, NH, NPM = 384, 256, 2.0
+BC = dict(bc_type=(2, 1, 0, 1), bc_value=(120.0, 2.0, 0.0, 0.5))
+
+
+def problem():
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    p = O.Problem(nW=NW, nH=NH, **BC)
+    cells = O.synthetic_colony(300, p.W, p.H, seed=11)
+    return O, p, cells
+
+
+def worker(rank, world, q_id, q_out):
+    sys.path.insert(0, ROOT)
+    import torch
+    torch.cuda.set_device(rank)
+    import eq_b200 as E
+    O, p, cells = problem()
+    if rank == 0:
+        uid = E.nccl_unique_id()
+        for _ in range(world - 1):
+            q_id.put(uid)
+    else:
+        uid = q_id.get(timeout=120)
+    g = E.GpuHSL(NW, NH, device=rank, slab=(rank, world, uid), **BC)
+    g0, g1 = g.slab_rows()
+    g.upload_cells(cells, NPM)
+    rng = np.random.default_rng(3)
+    u = rng.uniform(0, 5, NW * NH)
+    g.set_field(u)
+    hist = []
+    for _ in range(3):
+        s = g.gather()
+        g.scatter(100.0 + 0.5 * s)
+        g.step()
+        hist.append((s, g.totalBoundaryFlux, g.stats().iterations))
+    out = np.zeros(NW * NH)
+    g.get_field(out)
+    q_out.put((rank, g0, g1, out[g0 * NW:g1 * NW].copy(), hist))
+    g.close()
+
+
+def test_two_gpu_slab_equals_single_gpu_and_oracle():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import eq_b200 as E
+    O, p, cells = problem()
+    ctx = mp.get_context("spawn")
+    q_id, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, 2, q_id, q_out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q_out.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == NH   # contiguous partition
+    field = np.concatenate([res[0][3], res[1][3]])
+    # oracle with the same coupling
+    rng = np.random.default_rng(3)
+    s = O.new_state(p)
+    s.u = rng.uniform(0, 5, NW * NH)
+    hist = []
+    for _ in range(3):
+        smp = O.gather(cells, NPM, NH, NW, s.u)
+        s.u = O.scatter(cells, NPM, NH, NW, 100.0 + 0.5 * smp, s.u)
+        s = O.step(p, s)
+        hist.append((smp, s.total_boundary_flux))
+    rel = np.linalg.norm(field - s.u) / np.linalg.norm(s.u)
+    assert rel < 1e-8, rel
+    for r in range(2):
+        for (smp, flux, it), (smp0, flux0) in zip(res[r][4], hist):
+            assert np.allclose(smp, smp0, rtol=1e-9, atol=1e-12)        # rank-summed samples, same on both ranks
+            assert abs(flux - flux0) <= 1e-7 * max(abs(flux0), 1.0)
+            assert 0 < it < 40
