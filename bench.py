@@ -140,6 +140,59 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_slab(args, rank, local_rank, world):
+    """--mode slab: BASELINE configs[4] style -- one mesh split into row slabs over the GPUs of the box,
+    one-row halo exchange + CG all-reduce over NCCL.  16384 columns, 2048 rows and 25k rods per GPU
+    (= the 16384^2 / 200k-rod configuration at 8 GPUs)."""
+    import torch
+    import torch.distributed as dist
+    import eq_b200 as E
+    from oracle import oracle as O
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nW, nH, ncells = args.slab_cols, 2048 * world, 25000 * world
+    ids = [E.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    stream = torch.cuda.current_stream()
+    g = E.GpuHSL(nW, nH, h=H, dt=DT, D=D, device=local_rank, stream=stream.cuda_stream, slab=(rank, world, ids[0]))
+    cells = O.synthetic_colony(ncells, (nW - 1) * H, (nH - 1) * H, seed=777)
+    g.upload_cells(cells, NPM)
+    g.set_amounts(np.full(len(cells), 100.0))
+
+    def step():
+        g.gather_resident()
+        g.scatter_resident()
+        g.step()
+
+    for _ in range(args.warmup):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = g.stats().kernel_launches
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        N = nW * nH
+        print(json.dumps({
+            "metric": f"hsl_diffusion_steps_per_sec_{nW}x{nH}_row_slab", "value": args.steps / (ms / 1e3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[4] style: {nW}x{nH} mesh in {world} row slabs of 2048 rows, {len(cells)} rods, "
+                                   "one-row NCCL halo exchange + CG all-reduce (unfused kernels)",
+                       "pcg_iterations": int(g.stats().iterations), "relres": g.stats().relres,
+                       "mg_levels": int(g.stats().levels), "dof_updates_per_sec": N * args.steps / (ms / 1e3)},
+            "gpu_launches": int(g.stats().kernel_launches - l0)}), flush=True)
+    g.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +200,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="eq_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="layers", choices=["layers", "slab"])
+    ap.add_argument("--slab-cols", type=int, default=16384)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -155,6 +210,11 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.mode == "slab":
+        if world < 2:
+            raise SystemExit("--mode slab needs torchrun with >= 2 ranks")
+        run_slab(args, rank, local_rank, world)
         return
 
     import torch

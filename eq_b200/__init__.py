@@ -32,6 +32,7 @@ API_SYMBOLS = [
     "eqgpu_field_device_ptr", "eqgpu_sync", "eqgpu_cells_set_amounts",
     "eqgpu_cells_gather_resident", "eqgpu_cells_scatter_resident", "eqgpu_cells_get_gathered",
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
+    "eqgpu_slab_plan",
 ]
 
 
@@ -104,6 +105,17 @@ def nccl_unique_id() -> bytes:
     if rc != 0:
         raise EqGpuError("eqgpu_nccl_unique_id failed (is libnccl.so.2 loadable?)")
     return buf.raw
+
+
+def slab_plan(nH: int, world: int, rank: int, max_levels: int = 16):
+    """Owned rows per multigrid level for one rank (host arithmetic only): [(g0, g1, rows), ...]."""
+    a = (C.c_int32 * max_levels)()
+    b = (C.c_int32 * max_levels)()
+    n = (C.c_int32 * max_levels)()
+    k = lib().eqgpu_slab_plan(C.c_int32(nH), C.c_int32(world), C.c_int32(rank), C.c_int32(max_levels), a, b, n)
+    if k < 0:
+        raise EqGpuError("bad slab plan arguments")
+    return [(a[i], b[i], n[i]) for i in range(k)]
 
 
 def default_params() -> Params:

@@ -44,6 +44,31 @@ int eqgpu_create_slab(const eqgpu_params *p, int rank, int world, const void *nc
 
 int eqgpu_nccl_unique_id(void *out128) { return out128 ? slab_unique_id(out128) : EQGPU_EINVAL; }
 
+// Pure host arithmetic (no device): the owned row range [g0, g1) of `rank` on every multigrid level of an
+// nH-row mesh split over `world` ranks -- the same rule solver_setup applies (even cuts on level 0; a
+// coarse row belongs to the owner of its coincident fine row).  Returns the number of levels written.
+int eqgpu_slab_plan(int32_t nH, int32_t world, int32_t rank, int32_t max_levels, int32_t *g0, int32_t *g1,
+                    int32_t *rows)
+{
+    if (nH < 3 || world < 1 || rank < 0 || rank >= world || max_levels < 1 || !g0 || !g1 || !rows) return EQGPU_EINVAL;
+    auto cut = [&](int r) { return r >= world ? nH : (int)(((long long)nH * r / world) & ~1LL); };
+    int n = nH, a = cut(rank), b = cut(rank + 1), l = 0;
+    while (true) {
+        g0[l] = a; g1[l] = b; rows[l] = n;
+        ++l;
+        if (l >= max_levels || n < 5 || (world > 1 && (n / 2) / world < 4)) break;
+        const int nc = n / 2 + 1;
+        int ca = nc, cb = 0;
+        for (int I = 0; I < nc; ++I) {
+            const int fi = 2 * I < n - 1 ? 2 * I : n - 1;
+            if (fi >= a && fi < b) { if (I < ca) ca = I; if (I + 1 > cb) cb = I + 1; }
+        }
+        if (cb <= ca) break;
+        n = nc; a = ca; b = cb;
+    }
+    return l;
+}
+
 int eqgpu_slab_rows(eqgpu_solver *s, int32_t *g0, int32_t *g1)
 {
     if (!s || !g0 || !g1) return EQGPU_EINVAL;

@@ -108,6 +108,9 @@ EQGPU_API int eqgpu_create_slab(const eqgpu_params *p, int rank, int world, cons
                                 eqgpu_solver **out);
 EQGPU_API int eqgpu_nccl_unique_id(void *out128);
 EQGPU_API int eqgpu_slab_rows(eqgpu_solver *s, int32_t *g0, int32_t *g1);
+/* Host-only: owned rows [g0[l], g1[l]) of `rank` and the row count rows[l] on each multigrid level. */
+EQGPU_API int eqgpu_slab_plan(int32_t nH, int32_t world, int32_t rank, int32_t max_levels, int32_t *g0, int32_t *g1,
+                              int32_t *rows);
 /* dtor / finalize (src/fHSL.cpp:655-661). */
 EQGPU_API void eqgpu_destroy(eqgpu_solver *s);
 /* Message of the last failure on this solver (s == NULL: last create failure). */

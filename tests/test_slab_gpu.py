@@ -35,6 +35,7 @@ def worker(rank, world, q_id, q_out):
         uid = q_id.get(timeout=120)
     g = E.GpuHSL(NW, NH, device=rank, slab=(rank, world, uid), **BC)
     g0, g1 = g.slab_rows()
+    assert (g0, g1) == E.slab_plan(NH, world, rank)[0][:2]
     g.upload_cells(cells, NPM)
     rng = np.random.default_rng(3)
     u = rng.uniform(0, 5, NW * NH)
