@@ -81,7 +81,8 @@ struct eqgpu_solver {
     bool use_cluster = false;      // deepest levels on a 16-CTA cluster (k_ctail) instead of one CTA (k_tail)
     int ctail_first = 0, ctail_ncta = 0;
     size_t ctail_smem = 0;
-    cudaGraphExec_t graph_exec = nullptr;  // two fused PCG iterations
+    cudaGraphExec_t graph_exec = nullptr, graph_exec2 = nullptr;  // one fused PCG iteration each (p ping / pong)
+    int graph_phase = 0;
     int graph_launches = 0;
     double *d11 = nullptr, *d22 = nullptr, *d12 = nullptr;
     // Dirichlet data
@@ -108,7 +109,7 @@ struct eqgpu_solver {
     // stats
     eqgpu_stats st{};
     int64_t launches = 0;
-    int nu = 2, ncoarse = 24;
+    int nu = 3, nuc = 3, ncoarse = 24;  // smoothing sweeps on level 0 / on the coarser levels
     double omega = 0.8;
     bool tensor = false;
 

@@ -88,7 +88,10 @@ __device__ __forceinline__ double load_row(const LevelDev &L, int i, int j,
                                            const double *__restrict__ u0, double rs_l, double rs_r)
 {
     double c[NBAND];
-    stencil_mass(L, i, j, c);
+    if (i >= 1 && i <= L.ireg_hi && j >= 1 && j <= L.jreg_hi) {  // regular node: constant consistent-mass row
+        const double m = L.cD;  // hx*hy/12
+        c[B_C] = 6.0 * m; c[B_E] = m; c[B_W] = m; c[B_N] = m; c[B_S] = m; c[B_NE] = m; c[B_SW] = m;
+    } else stencil_mass(L, i, j, c);
     double b = stencil_dot(L, i, j, c, u0);
     if (j == 0) b += rs_l * 0.5 * (L.hy[i] + L.hy[i + 1]);
     if (j == L.nx - 1) b += rs_r * 0.5 * (L.hy[i] + L.hy[i + 1]);
@@ -472,6 +475,9 @@ int solver_setup(eqgpu_solver *s)
     s->N = (size_t)p.nW * p.nH;  // replaced by the local size once the slab window is known
     const double hx0 = p.hx, hy0 = p.hy > 0 ? p.hy : p.hx;
     s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 3;
+    s->nuc = s->nu;
+    if (const char *e = getenv("EQGPU_NU0")) s->nu = std::max(1, std::min(atoi(e), 4));   // tuning knobs
+    if (const char *e = getenv("EQGPU_NUC")) s->nuc = std::max(1, std::min(atoi(e), 4));
     // ---- hierarchy -------------------------------------------------------
     Level l0;
     l0.dev.nx = p.nW; l0.dev.gny = p.nH;
@@ -632,7 +638,7 @@ int solver_setup(eqgpu_solver *s)
         EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));  \
         EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
         break;
-        switch (nu) { SET_SMEM(1) SET_SMEM(2) SET_SMEM(3) SET_SMEM(4) }
+        for (int q = 1; q <= 4; ++q) switch (q) { SET_SMEM(1) SET_SMEM(2) SET_SMEM(3) SET_SMEM(4) }
 #undef SET_SMEM
     }
     return 0;
@@ -648,6 +654,7 @@ void solver_teardown(eqgpu_solver *s)
     }
     s->levels.clear();
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    if (s->graph_exec2) { cudaGraphExecDestroy(s->graph_exec2); s->graph_exec2 = nullptr; }
     cudaFree(s->d_levels); cudaFree(s->pv2);
     cudaFree(s->u); cudaFree(s->r); cudaFree(s->pv); cudaFree(s->Ap); cudaFree(s->z);
     cudaFree(s->d11); cudaFree(s->d22); cudaFree(s->d12);
@@ -824,25 +831,62 @@ static CoarseW coarse_weights(eqgpu_solver *s)
     return cw;
 }
 
-// Fused V-cycle (isotropic): two kernels per large level + one tail CTA.
-// Leaves z = B r in levels[0].x and (when the fine level is tiled) r.z in sc->rz_new.
+static SmoothW smooth_weights_n(int n)
+{
+    SmoothW sw{};
+    cheb_weights(n, 0.5, 2.0, sw.w);
+    return sw;
+}
+
 template <int NU>
+static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
+{
+    Level &lv = s->levels[l], &cv = s->levels[l + 1];
+    constexpr int TO = TS - 2 * (NU + 1);
+    const size_t tsm = 2 * TN * sizeof(double);
+    const SmoothW sw = smooth_weights_n(NU);
+    const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
+    if ((int)(g.x * g.y) >= 2 * s->num_sms)
+        k_presmooth<NU, 8><<<g, 512, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
+    else
+        k_presmooth<NU, 4><<<g, 1024, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
+    s->launches++;
+}
+
+template <int NU>
+static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
+{
+    Level &lv = s->levels[l], &cv = s->levels[l + 1];
+    constexpr int TO = TS - 2 * NU;
+    const size_t tsm = 2 * TN * sizeof(double);
+    const SmoothW sw = smooth_weights_n(NU);
+    const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
+    const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
+#define POST(DOT, R, NT)                                                                                          \
+    k_postsmooth<NU, DOT, R><<<g, NT, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, lv.x, cv.x, sw, s->sc, s->partials, \
+                                                 s->counters + 1)
+    if (l == 0) { if (big) POST(true, 8, 512); else POST(true, 4, 1024); }
+    else { if (big) POST(false, 8, 512); else POST(false, 4, 1024); }
+#undef POST
+    s->launches++;
+}
+
+static int nu_of(const eqgpu_solver *s, int l) { return l == 0 ? s->nu : s->nuc; }
+
+// Fused V-cycle (isotropic): two kernels per large level + one tail kernel.
+// Leaves z = B r in levels[0].x and (when the fine level is tiled) r.z in sc->rz_new.
 static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
 {
     const int lt = s->use_cluster ? s->ctail_first : s->tail_first, nl = (int)s->levels.size();
-    const size_t tsm = 2 * TN * sizeof(double);
-    const SmoothW sw = smooth_weights(s);
+    const SmoothW sw = smooth_weights_n(s->nuc);
     const CoarseW cw = coarse_weights(s);
-    auto tgrid = [](const LevelDev &L, int to) { return dim3((L.nx + to - 1) / to, (L.ny + to - 1) / to); };
-    constexpr int TO_PRE = TS - 2 * (NU + 1), TO_POST = TS - 2 * NU;
     for (int l = 0; l < lt; ++l) {
-        Level &lv = s->levels[l], &cv = s->levels[l + 1];
-        const dim3 g = tgrid(lv.dev, TO_PRE);
-        if ((int)(g.x * g.y) >= 2 * s->num_sms)
-            k_presmooth<NU, 8><<<g, 512, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
-        else
-            k_presmooth<NU, 4><<<g, 1024, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
-        s->launches++;
+        switch (nu_of(s, l)) {
+        case 1: launch_pre<1>(s, st, l); break;
+        case 2: launch_pre<2>(s, st, l); break;
+        case 3: launch_pre<3>(s, st, l); break;
+        default: launch_pre<4>(s, st, l); break;
+        }
     }
     if (s->use_cluster) {
         const CTailDesc ctd = make_ctail_desc(s, lt, s->ctail_ncta);
@@ -856,38 +900,34 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
         const LevelDev *dl = s->d_levels;
         const double *bin = s->levels[lt].b;
         double *xout = s->levels[lt].x;
-        int nu = s->nu;
+        int nu = s->nuc;
         const CGScalars *scp = s->sc;
         cudaLaunchKernelEx(&cfg, k_ctail, dl, ctd, bin, xout, nu, sw, cw, scp);
         s->launches++;
     } else {
-    TailDesc td;
-    td.first = lt; td.last = nl - 1;
-    int off = 0;
-    for (int l = lt; l < nl; ++l) {
-        td.off[l] = off;
-        off += 3 * (s->levels[l].dev.nx + 2) * (s->levels[l].dev.ny + 2);
-    }
-    for (int l = lt; l < nl; ++l) {
-        td.soff[l] = off;
-        off += 2 * (s->levels[l].dev.nx + 1) + 2 * (s->levels[l].dev.ny + 1);
-    }
-    td.total = off;
-    k_tail<<<1, TAIL_THREADS, s->tail_smem, st>>>(s->d_levels, td, s->levels[lt].b, s->levels[lt].x, s->nu, sw, cw,
-                                                  s->sc);
-    s->launches++;
+        TailDesc td;
+        td.first = lt; td.last = nl - 1;
+        int off = 0;
+        for (int l = lt; l < nl; ++l) {
+            td.off[l] = off;
+            off += 3 * (s->levels[l].dev.nx + 2) * (s->levels[l].dev.ny + 2);
+        }
+        for (int l = lt; l < nl; ++l) {
+            td.soff[l] = off;
+            off += 2 * (s->levels[l].dev.nx + 1) + 2 * (s->levels[l].dev.ny + 1);
+        }
+        td.total = off;
+        k_tail<<<1, TAIL_THREADS, s->tail_smem, st>>>(s->d_levels, td, s->levels[lt].b, s->levels[lt].x, s->nuc, sw,
+                                                      cw, s->sc);
+        s->launches++;
     }
     for (int l = lt - 1; l >= 0; --l) {
-        Level &lv = s->levels[l], &cv = s->levels[l + 1];
-        const dim3 g = tgrid(lv.dev, TO_POST);
-        const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
-#define POST(DOT, R, NT)                                                                                          \
-    k_postsmooth<NU, DOT, R><<<g, NT, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, lv.x, cv.x, sw, s->sc, s->partials, \
-                                                 s->counters + 1)
-        if (l == 0) { if (big) POST(true, 8, 512); else POST(true, 4, 1024); }
-        else { if (big) POST(false, 8, 512); else POST(false, 4, 1024); }
-#undef POST
-        s->launches++;
+        switch (nu_of(s, l)) {
+        case 1: launch_post<1>(s, st, l); break;
+        case 2: launch_post<2>(s, st, l); break;
+        case 3: launch_post<3>(s, st, l); break;
+        default: launch_post<4>(s, st, l); break;
+        }
     }
 }
 
@@ -896,12 +936,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
 {
     const LevelDev &L = s->levels[0].dev;
     const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
-    switch (s->nu) {
-    case 1: vcycle_fused<1>(s, st); break;
-    case 2: vcycle_fused<2>(s, st); break;
-    case 3: vcycle_fused<3>(s, st); break;
-    default: vcycle_fused<4>(s, st); break;
-    }
+    vcycle_fused(s, st);
     if ((s->use_cluster ? s->ctail_first : s->tail_first) == 0) {
         k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1, &s->sc->rz_new);
         s->launches++;
@@ -922,18 +957,21 @@ static int build_iteration_graph(eqgpu_solver *s)
     if (s->graph_exec) return 0;
     cudaStream_t cap;
     EQ_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-    const int64_t l0 = s->launches;
-    EQ_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    enqueue_fused_iteration(s, cap);
-    enqueue_fused_iteration(s, cap);
-    cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamEndCapture(cap, &graph);
-    s->graph_launches = (int)(s->launches - l0);
-    s->launches = l0;
-    if (e != cudaSuccess) { s->set_error(std::string("graph capture: ") + cudaGetErrorString(e)); return EQGPU_ECUDA; }
-    EQ_CUDA(cudaGraphInstantiate(&s->graph_exec, graph, 0));
-    cudaGraphDestroy(graph);
+    // graph 0: p in pv -> p' in pv2 ; graph 1: the other way round.  Replayed alternately.
+    for (int k = 0; k < 2; ++k) {
+        const int64_t l0 = s->launches;
+        EQ_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        enqueue_fused_iteration(s, cap);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(cap, &graph);
+        s->graph_launches = (int)(s->launches - l0);
+        s->launches = l0;
+        if (e != cudaSuccess) { s->set_error(std::string("graph capture: ") + cudaGetErrorString(e)); return EQGPU_ECUDA; }
+        EQ_CUDA(cudaGraphInstantiate(k == 0 ? &s->graph_exec : &s->graph_exec2, graph, 0));
+        cudaGraphDestroy(graph);
+    }
     cudaStreamDestroy(cap);
+    s->graph_phase = 0;
     return 0;
 }
 
@@ -974,8 +1012,9 @@ static int pcg(eqgpu_solver *s)
     int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
     while (true) {
         if (fused) {
-            for (int k = 0; k < chunk && issued < max_iters; k += 2, issued += 2) {
-                EQ_CUDA(cudaGraphLaunch(s->graph_exec, st));
+            for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
+                EQ_CUDA(cudaGraphLaunch(s->graph_phase == 0 ? s->graph_exec : s->graph_exec2, st));
+                s->graph_phase ^= 1;
                 s->launches += s->graph_launches;
             }
         } else {
@@ -1002,7 +1041,7 @@ static int pcg(eqgpu_solver *s)
         EQ_CUDA(cudaMemcpyAsync(s->sc_host, s->sc, sizeof(CGScalars), cudaMemcpyDeviceToHost, st));
         EQ_CUDA(cudaStreamSynchronize(st));
         if (s->sc_host->done || issued >= max_iters) break;
-        chunk = 2;
+        chunk = 1;
     }
     s->st.iterations = s->sc_host->iters;
     const double ref = s->sc_host->bnorm2;
