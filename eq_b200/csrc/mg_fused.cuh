@@ -286,6 +286,60 @@ k_presmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, double *__res
     }
 }
 
+// ---------------------------------------------------------------------------
+// coarsest level: all NC Chebyshev-Jacobi sweeps of the coarse solve on one tile
+// pass (halo NC-1), x = p_NC(D^-1 A) b from a zero guess.  Replaces a chain of
+// NC latency-bound whole-level sweeps by a single wave of a few CTAs.
+// ---------------------------------------------------------------------------
+template <int NC, int R, bool REG>
+__device__ __forceinline__ void coarsest_body(const LevelDev &F, const Spacing &S, int ox, int oy,
+                                              const double *__restrict__ b, double *__restrict__ x,
+                                              const CoarseW &cw, double *xa, double *xb)
+{
+    constexpr int H = NC - 1;
+    const int lx = threadIdx.x & (TS - 1), ly0 = (threadIdx.x >> 6) * R;
+    double bv[R];
+    column_load<R, REG>(F, ox, oy, b, bv);
+    tile_pass<0, R, REG>(F, S, ox, oy, bv, b, xa, xa, cw.w[0]);
+    double *cur = xa, *oth = xb;
+#pragma unroll 1
+    for (int k = 1; k < NC; ++k) {
+        tile_pass<1, R, REG>(F, S, ox, oy, bv, b, cur, oth, cw.w[k]);
+        double *t = cur; cur = oth; oth = t;
+    }
+    const int gj = ox + lx;
+    if (lx >= H && lx < TS - H && gj >= 0 && gj < F.nx) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int ly = ly0 + k, gi = oy + ly;
+            if (ly >= H && ly < TS - H && gi >= 0 && gi < F.ny) x[(size_t)gi * F.nx + gj] = cur[tidx(ly, lx)];
+        }
+    }
+}
+
+template <int NC, int R>
+__global__ void __launch_bounds__(TS *(TS / R), 1)
+k_coarsest(LevelDev F, const double *__restrict__ b, double *__restrict__ x, CoarseW cw, const CGScalars *sc)
+{
+    if (sc->done) return;
+    constexpr int H = NC - 1, TO = TS - 2 * H;
+    extern __shared__ double sm[];
+    double *xa = sm, *xb = sm + TN;
+    __shared__ double spc[4 * (TS + 2)];
+    const int ox = blockIdx.x * TO - H, oy = blockIdx.y * TO - H;
+    const bool regular = tile_regular(F, ox, oy);
+    tile_zero_pads(xa);
+    tile_zero_pads(xb);
+    if (regular) {
+        __syncthreads();
+        coarsest_body<NC, R, true>(F, Spacing{}, ox, oy, b, x, cw, xa, xb);
+    } else {
+        const Spacing S = tile_spacing(F, ox, oy, spc);
+        __syncthreads();
+        coarsest_body<NC, R, false>(F, S, ox, oy, b, x, cw, xa, xb);
+    }
+}
+
 // value of P*xc at fine node (gi,gj), coarse values read from global memory
 __device__ __forceinline__ double prolong_at(const LevelDev &F, const LevelDev &Cc,
                                              const double *__restrict__ xc, int gi, int gj)

@@ -639,6 +639,10 @@ int solver_setup(eqgpu_solver *s)
         EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
         break;
         for (int q = 1; q <= 4; ++q) switch (q) { SET_SMEM(1) SET_SMEM(2) SET_SMEM(3) SET_SMEM(4) }
+#define SET_C(NC) EQ_CUDA(cudaFuncSetAttribute((k_coarsest<NC, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+        SET_C(2) SET_C(3) SET_C(4) SET_C(5) SET_C(6) SET_C(7) SET_C(8)
+#undef SET_C
+        if (const char *e = getenv("EQGPU_TILE_COARSEST")) s->tile_coarsest = atoi(e) != 0;
 #undef SET_SMEM
     }
     return 0;
@@ -834,7 +838,10 @@ static CoarseW coarse_weights(eqgpu_solver *s)
 static SmoothW smooth_weights_n(int n)
 {
     SmoothW sw{};
-    cheb_weights(n, 0.5, 2.0, sw.w);
+    double lo = 0.25, hi = 2.0;  // smoothing interval of D^-1 A: [0.5,2] is the high-frequency range; 0.25 measured best
+    if (const char *e = getenv("EQGPU_CHEB_LO")) lo = atof(e);  // tuning knobs
+    if (const char *e = getenv("EQGPU_CHEB_HI")) hi = atof(e);
+    cheb_weights(n, lo, hi, sw.w);
     return sw;
 }
 
@@ -871,15 +878,28 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
     s->launches++;
 }
 
+template <int NC>
+static void launch_coarsest(eqgpu_solver *s, cudaStream_t st, const CoarseW &cw)
+{
+    Level &lv = s->levels.back();
+    constexpr int TO = TS - 2 * (NC - 1);
+    const size_t tsm = 2 * TN * sizeof(double);
+    const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
+    k_coarsest<NC, 4><<<g, 1024, tsm, st>>>(lv.dev, lv.b, lv.x, cw, s->sc);
+    s->launches++;
+}
+
 static int nu_of(const eqgpu_solver *s, int l) { return l == 0 ? s->nu : s->nuc; }
 
 // Fused V-cycle (isotropic): two kernels per large level + one tail kernel.
 // Leaves z = B r in levels[0].x and (when the fine level is tiled) r.z in sc->rz_new.
 static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
 {
-    const int lt = s->use_cluster ? s->ctail_first : s->tail_first, nl = (int)s->levels.size();
-    const SmoothW sw = smooth_weights_n(s->nuc);
+    const int nl = (int)s->levels.size();
     const CoarseW cw = coarse_weights(s);
+    const bool tiled_coarsest = s->tile_coarsest && cw.n >= 2 && cw.n <= 8 && nl >= 2;
+    const int lt = tiled_coarsest ? nl - 1 : (s->use_cluster ? s->ctail_first : s->tail_first);
+    const SmoothW sw = smooth_weights_n(s->nuc);
     for (int l = 0; l < lt; ++l) {
         switch (nu_of(s, l)) {
         case 1: launch_pre<1>(s, st, l); break;
@@ -888,7 +908,17 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
         default: launch_pre<4>(s, st, l); break;
         }
     }
-    if (s->use_cluster) {
+    if (tiled_coarsest) {
+        switch (cw.n) {
+        case 2: launch_coarsest<2>(s, st, cw); break;
+        case 3: launch_coarsest<3>(s, st, cw); break;
+        case 4: launch_coarsest<4>(s, st, cw); break;
+        case 5: launch_coarsest<5>(s, st, cw); break;
+        case 6: launch_coarsest<6>(s, st, cw); break;
+        case 7: launch_coarsest<7>(s, st, cw); break;
+        default: launch_coarsest<8>(s, st, cw); break;
+        }
+    } else if (s->use_cluster) {
         const CTailDesc ctd = make_ctail_desc(s, lt, s->ctail_ncta);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(s->ctail_ncta); cfg.blockDim = dim3(CT_THREADS); cfg.dynamicSmemBytes = s->ctail_smem;
@@ -937,7 +967,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     const LevelDev &L = s->levels[0].dev;
     const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
     vcycle_fused(s, st);
-    if ((s->use_cluster ? s->ctail_first : s->tail_first) == 0) {
+    if (s->levels.size() < 2 || (!s->tile_coarsest && (s->use_cluster ? s->ctail_first : s->tail_first) == 0)) {
         k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1, &s->sc->rz_new);
         s->launches++;
     }
