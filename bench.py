@@ -201,6 +201,9 @@ def main():
     ap.add_argument("--impl", default="eq_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="layers", choices=["layers", "slab"])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4],
+                    help="BASELINE.json configs index+1: 3 = the headline 2048^2 workload (default); 2 = dual layers "
+                         "with Robin walls (C4/C14 on alternating GPUs); 4 = channel-flow trap at 4096^2")
     ap.add_argument("--slab-cols", type=int, default=16384)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -226,8 +229,23 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream()
-    g = E.GpuHSL(NW, NH, h=H, dt=DT, D=D, device=local_rank, stream=stream.cuda_stream,
-                 smooth_sweeps=int(os.environ.get("EQ_NU", "0")))
+    global NW, NH, WORKLOAD, METRIC
+    kw = {}
+    Dl = D
+    if args.config == 2:    # H_TRAP: Robin left/right at the flow rate, Neumann top/bottom (src/fHSL.cpp:448-453)
+        Dl = D if rank % 2 == 0 else 640.0     # C4HSL / C14HSL (src/eQinit.h:12-13)
+        kw = dict(bc_type=(2, 2, 0, 0), bc_value=(120.0, 120.0, 0.0, 0.0))
+        WORKLOAD = "configs[1]: dual QS layers (C4 D=1200 / C14 D=640 on alternating GPUs), Robin left/right r=120, 2048x2048, 20k rods"
+        METRIC = "hsl_diffusion_steps_per_sec_2048x2048_robin"
+    elif args.config == 4:  # MICROFLUIDIC_TRAP: Robin left/right, channel Dirichlet top/bottom, 48 CN sub-steps
+        NW = NH = 4096
+        rl, rr = O.robin_rates(120.0, D, 20.0, 20.0)
+        kw = dict(bc_type=(2, 2, 3, 3), bc_value=(rl, rr, 0.0, 0.0), channels=True, channel_v=120.0,
+                  channel_r=(rl, rr), channel_iters=48, well_scaling=10.0 * (25.0 / 5.0) * 0.5)
+        WORKLOAD = "configs[3]: channel-flow trap (1-D advection-diffusion channels, 48 CN sub-steps) at 4096x4096, 20k rods"
+        METRIC = "hsl_diffusion_steps_per_sec_4096x4096_channels"
+    g = E.GpuHSL(NW, NH, h=H, dt=DT, D=Dl, device=local_rank, stream=stream.cuda_stream,
+                 smooth_sweeps=int(os.environ.get("EQ_NU", "0")), **kw)
     W = (NW - 1) * H
     cells = O.synthetic_colony(NCELLS, W, W, seed=12345 + rank)
     ncells = len(cells)

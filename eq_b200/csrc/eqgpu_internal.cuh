@@ -73,6 +73,7 @@ struct eqgpu_solver {
     int tail_first = 0;            // first level handled by the single-CTA tail kernel
     size_t tail_smem = 0;
     bool fused = true;
+    bool tail_fits = true;         // the deepest levels fit one CTA's shared memory (k_tail / k_ctail usable)
     bool tile_coarsest = true;     // coarsest level solved by the deep-halo tile kernel instead of a tail kernel
     // row-slab mode (eqgpu_create_slab): this rank owns rows [levels[l].g0, levels[l].g1) of every level
     bool slab = false;

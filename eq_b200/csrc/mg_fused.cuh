@@ -56,7 +56,7 @@ __device__ __forceinline__ bool tile_regular(const LevelDev &L, int ox, int oy)
 // tiles lie strictly inside the grid (no clamping, no masking).
 template <int R, bool REG>
 __device__ __forceinline__ void column_load(const LevelDev &L, int ox, int oy, const double *__restrict__ g,
-                                            double (&v)[R])
+                                            double (&v)[R], double *mirror = nullptr)
 {
     const int lx = threadIdx.x & (TS - 1), ly0 = (threadIdx.x >> 6) * R;
     const int gj = ox + lx;
@@ -73,6 +73,7 @@ __device__ __forceinline__ void column_load(const LevelDev &L, int ox, int oy, c
         for (int k = 0; k < R; ++k) {
             const int gi = oy + ly0 + k;
             if (!(okx && gi >= 0 && gi < L.ny)) v[k] = 0.0;
+            if (mirror) mirror[tidx(ly0 + k, lx)] = v[k];
         }
     }
 }
@@ -126,7 +127,7 @@ __device__ __forceinline__ double node_generic(const LevelDev &L, const Spacing 
 template <int MODE, int R, bool REG>
 __device__ __forceinline__ void tile_pass(const LevelDev &L, const Spacing &S, int ox, int oy,
                                           const double (&bv)[R], const double *__restrict__ bglob,
-                                          const double *src, double *dst, double w)
+                                          const double *src, double *dst, double w, const double *sbm = nullptr)
 {
     constexpr int NT = TS * (TS / R);
     const int lx = threadIdx.x & (TS - 1), ly0 = (threadIdx.x >> 6) * R;
@@ -182,8 +183,8 @@ __device__ __forceinline__ void tile_pass(const LevelDev &L, const Spacing &S, i
             if (ly < 0 || ly >= TS || lxx < 0 || lxx >= TS) continue;
             const int gi = oy + ly, gjj = ox + lxx;
             const bool in = gi >= 0 && gi < L.ny && gjj >= 0 && gjj < L.nx;
-            const double bval = in ? __ldg(bglob + (size_t)gi * L.nx + gjj) : 0.0;
             const int cc2 = tidx(ly, lxx);
+            const double bval = sbm ? sbm[cc2] : (in ? __ldg(bglob + (size_t)gi * L.nx + gjj) : 0.0);
             dst[cc2] = node_generic<MODE>(L, S, gi, gjj, cc2, bval, src, w);
         }
     }
@@ -196,20 +197,22 @@ __device__ __forceinline__ void tile_pass(const LevelDev &L, const Spacing &S, i
 template <int NU, int R, bool REG>
 __device__ __forceinline__ void presmooth_body(const LevelDev &F, const LevelDev &Cc, const Spacing &S, int ox,
                                                int oy, const double *__restrict__ b, double *__restrict__ x,
-                                               double *__restrict__ bc, const SmoothW &sw, double *xa, double *xb)
+                                               double *__restrict__ bc, const SmoothW &sw, double *xa, double *xb,
+                                               double *sb)
 {
     constexpr int H = NU + 1, TO = TS - 2 * H, NT = TS * (TS / R);
     const int lx = threadIdx.x & (TS - 1), ly0 = (threadIdx.x >> 6) * R;
     double bv[R];
-    column_load<R, REG>(F, ox, oy, b, bv);
-    tile_pass<0, R, REG>(F, S, ox, oy, bv, b, xa, xa, sw.w[0]);
+    column_load<R, REG>(F, ox, oy, b, bv, sb);
+    if (sb) __syncthreads();
+    tile_pass<0, R, REG>(F, S, ox, oy, bv, b, xa, xa, sw.w[0], sb);
     double *cur = xa, *oth = xb;
 #pragma unroll
     for (int k = 1; k < NU; ++k) {
-        tile_pass<1, R, REG>(F, S, ox, oy, bv, b, cur, oth, sw.w[k]);
+        tile_pass<1, R, REG>(F, S, ox, oy, bv, b, cur, oth, sw.w[k], sb);
         double *t = cur; cur = oth; oth = t;
     }
-    tile_pass<2, R, REG>(F, S, ox, oy, bv, b, cur, oth, 0.0);  // residual, valid on T+1
+    tile_pass<2, R, REG>(F, S, ox, oy, bv, b, cur, oth, 0.0, sb);  // residual, valid on T+1
     const int gj = ox + lx;
     if (REG) {
         // x on T -> global
@@ -278,11 +281,11 @@ k_presmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, double *__res
     tile_zero_pads(xb);
     if (regular) {
         __syncthreads();
-        presmooth_body<NU, R, true>(F, Cc, Spacing{}, ox, oy, b, x, bc, sw, xa, xb);
+        presmooth_body<NU, R, true>(F, Cc, Spacing{}, ox, oy, b, x, bc, sw, xa, xb, nullptr);
     } else {
         const Spacing S = tile_spacing(F, ox, oy, spc);
         __syncthreads();
-        presmooth_body<NU, R, false>(F, Cc, S, ox, oy, b, x, bc, sw, xa, xb);
+        presmooth_body<NU, R, false>(F, Cc, S, ox, oy, b, x, bc, sw, xa, xb, R == 4 ? sm + 2 * TN : nullptr);
     }
 }
 
@@ -294,17 +297,18 @@ k_presmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, double *__res
 template <int NC, int R, bool REG>
 __device__ __forceinline__ void coarsest_body(const LevelDev &F, const Spacing &S, int ox, int oy,
                                               const double *__restrict__ b, double *__restrict__ x,
-                                              const CoarseW &cw, double *xa, double *xb)
+                                              const CoarseW &cw, double *xa, double *xb, double *sb)
 {
     constexpr int H = NC - 1;
     const int lx = threadIdx.x & (TS - 1), ly0 = (threadIdx.x >> 6) * R;
     double bv[R];
-    column_load<R, REG>(F, ox, oy, b, bv);
-    tile_pass<0, R, REG>(F, S, ox, oy, bv, b, xa, xa, cw.w[0]);
+    column_load<R, REG>(F, ox, oy, b, bv, sb);
+    if (sb) __syncthreads();
+    tile_pass<0, R, REG>(F, S, ox, oy, bv, b, xa, xa, cw.w[0], sb);
     double *cur = xa, *oth = xb;
 #pragma unroll 1
     for (int k = 1; k < NC; ++k) {
-        tile_pass<1, R, REG>(F, S, ox, oy, bv, b, cur, oth, cw.w[k]);
+        tile_pass<1, R, REG>(F, S, ox, oy, bv, b, cur, oth, cw.w[k], sb);
         double *t = cur; cur = oth; oth = t;
     }
     const int gj = ox + lx;
@@ -332,11 +336,11 @@ k_coarsest(LevelDev F, const double *__restrict__ b, double *__restrict__ x, Coa
     tile_zero_pads(xb);
     if (regular) {
         __syncthreads();
-        coarsest_body<NC, R, true>(F, Spacing{}, ox, oy, b, x, cw, xa, xb);
+        coarsest_body<NC, R, true>(F, Spacing{}, ox, oy, b, x, cw, xa, xb, nullptr);
     } else {
         const Spacing S = tile_spacing(F, ox, oy, spc);
         __syncthreads();
-        coarsest_body<NC, R, false>(F, S, ox, oy, b, x, cw, xa, xb);
+        coarsest_body<NC, R, false>(F, S, ox, oy, b, x, cw, xa, xb, R == 4 ? sm + 2 * TN : nullptr);
     }
 }
 
@@ -360,13 +364,13 @@ __device__ __forceinline__ double postsmooth_body(const LevelDev &F, const Level
                                                   int oy, const double *__restrict__ b,
                                                   const double *__restrict__ xin, double *__restrict__ x,
                                                   const double *__restrict__ xc, const SmoothW &sw, double *xa,
-                                                  double *xb)
+                                                  double *xb, double *sb)
 {
     constexpr int H = NU, CP = TS / 2 + 2;
     const int lx = threadIdx.x & (TS - 1), ly0 = (threadIdx.x >> 6) * R;
     const int gj = ox + lx;
     double bv[R], xv[R];
-    column_load<R, REG>(F, ox, oy, b, bv);
+    column_load<R, REG>(F, ox, oy, b, bv, sb);
     column_load<R, REG>(F, ox, oy, xin, xv);
     // coarse patch covering the tile -> xb (as scratch): coarse nodes [J0, J0+CP) x [I0, I0+CP)
     const int J0 = coarse_lo(min(max(ox, 0), F.nx - 1), F.nx, Cc.nx);
@@ -414,7 +418,7 @@ __device__ __forceinline__ double postsmooth_body(const LevelDev &F, const Level
     double *cur = xa, *oth = xb;
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-        tile_pass<1, R, REG>(F, S, ox, oy, bv, b, cur, oth, sw.w[k]);
+        tile_pass<1, R, REG>(F, S, ox, oy, bv, b, cur, oth, sw.w[k], sb);
         double *t = cur; cur = oth; oth = t;
     }
     double acc = 0.0;
@@ -448,10 +452,11 @@ k_postsmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, const double
     tile_zero_pads(xa);
     double v[1];
     if (regular) {
-        v[0] = postsmooth_body<NU, DOT, R, true>(F, Cc, Spacing{}, ox, oy, b, xin, x, xc, sw, xa, xb);
+        v[0] = postsmooth_body<NU, DOT, R, true>(F, Cc, Spacing{}, ox, oy, b, xin, x, xc, sw, xa, xb, nullptr);
     } else {
         const Spacing S = tile_spacing(F, ox, oy, spc);
-        v[0] = postsmooth_body<NU, DOT, R, false>(F, Cc, S, ox, oy, b, xin, x, xc, sw, xa, xb);
+        v[0] = postsmooth_body<NU, DOT, R, false>(F, Cc, S, ox, oy, b, xin, x, xc, sw, xa, xb,
+                                                   R == 4 ? sm + 2 * TN : nullptr);
     }
     if (DOT) {
         double tot[1];

@@ -468,6 +468,7 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
 }
 
 static CTailDesc make_ctail_desc(eqgpu_solver *s, int first, int ncta);
+static CoarseW coarse_weights(eqgpu_solver *s);
 
 int solver_setup(eqgpu_solver *s)
 {
@@ -592,9 +593,14 @@ int solver_setup(eqgpu_solver *s)
             --first;
             used += need(first);
         }
-        if (used > budget) { s->fused = false; }  // coarsest level alone too big: unfused path
         s->tail_first = first;
         s->tail_smem = used;
+        // the tile kernel solves the coarsest level whatever its size when the coarse Chebyshev degree is
+        // <= 8; otherwise the coarsest level has to fit the single-CTA tail, else the unfused path runs
+        const int cn = coarse_weights(s).n;
+        s->tail_fits = used <= budget;
+        if (!(cn >= 2 && cn <= 8 && nl >= 2) && !s->tail_fits) s->fused = false;
+        if (!s->tail_fits) { s->tail_smem = 0; s->tile_coarsest = true; }
     }
     if (s->fused) {
         // Cluster tail.  Measured at 2048^2 (profiles/r01_cluster_tail.md): the ~1.5 us cluster barrier per
@@ -609,7 +615,7 @@ int solver_setup(eqgpu_solver *s)
         const CTailDesc td = make_ctail_desc(s, cf, CT_MAX_CTAS);
         const size_t csm = (size_t)td.total * sizeof(double);
         s->use_cluster = false;
-        if (csm <= 200 * 1024 &&
+        if (s->tail_fits && csm <= 200 * 1024 &&
             cudaFuncSetAttribute(k_ctail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
             cudaFuncSetAttribute(k_ctail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm) == cudaSuccess) {
             cudaLaunchConfig_t cfg{};
@@ -625,24 +631,26 @@ int solver_setup(eqgpu_solver *s)
             }
         }
         cudaGetLastError();  // a refused attribute is not an error of the solver
-        EQ_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tail_smem));
+        if (s->tail_fits)
+            EQ_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tail_smem));
         const int nu = s->nu;
         if (nu > 4) { s->set_error("smooth_sweeps must be <= 4"); return EQGPU_EINVAL; }
-        const int tsm = 2 * TN * (int)sizeof(double);
+        const int tsm = 2 * TN * (int)sizeof(double), tsm3 = 3 * TN * (int)sizeof(double);
 #define SET_SMEM(NU)                                                                                         \
     case NU:                                                                                                 \
         EQ_CUDA(cudaFuncSetAttribute((k_presmooth<NU, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));       \
-        EQ_CUDA(cudaFuncSetAttribute((k_presmooth<NU, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));        \
+        EQ_CUDA(cudaFuncSetAttribute((k_presmooth<NU, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));       \
         EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
         EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
-        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));  \
-        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
+        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3)); \
+        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3)); \
         break;
         for (int q = 1; q <= 4; ++q) switch (q) { SET_SMEM(1) SET_SMEM(2) SET_SMEM(3) SET_SMEM(4) }
-#define SET_C(NC) EQ_CUDA(cudaFuncSetAttribute((k_coarsest<NC, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+#define SET_C(NC) EQ_CUDA(cudaFuncSetAttribute((k_coarsest<NC, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));
         SET_C(2) SET_C(3) SET_C(4) SET_C(5) SET_C(6) SET_C(7) SET_C(8)
 #undef SET_C
-        if (const char *e = getenv("EQGPU_TILE_COARSEST")) s->tile_coarsest = atoi(e) != 0;
+        if (const char *e = getenv("EQGPU_TILE_COARSEST")) s->tile_coarsest = atoi(e) != 0 || !s->tail_fits;
+
 #undef SET_SMEM
     }
     return 0;
@@ -835,6 +843,16 @@ static CoarseW coarse_weights(eqgpu_solver *s)
     return cw;
 }
 
+static std::vector<cudaEvent_t> *g_trace = nullptr;  // debugging aid (EQGPU_TRACE): event after each launch
+static void trace_mark(cudaStream_t st)
+{
+    if (!g_trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_trace->push_back(e);
+}
+
 static SmoothW smooth_weights_n(int n)
 {
     SmoothW sw{};
@@ -856,8 +874,9 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
     if ((int)(g.x * g.y) >= 2 * s->num_sms)
         k_presmooth<NU, 8><<<g, 512, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
     else
-        k_presmooth<NU, 4><<<g, 1024, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
+        k_presmooth<NU, 4><<<g, 1024, tsm + tsm / 2, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
     s->launches++;
+    trace_mark(st);
 }
 
 template <int NU>
@@ -869,13 +888,14 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
     const SmoothW sw = smooth_weights_n(NU);
     const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
     const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
-#define POST(DOT, R, NT)                                                                                          \
-    k_postsmooth<NU, DOT, R><<<g, NT, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, lv.x, cv.x, sw, s->sc, s->partials, \
-                                                 s->counters + 1)
+#define POST(DOT, R, NT)                                                                                     \
+    k_postsmooth<NU, DOT, R><<<g, NT, (R == 4 ? tsm + tsm / 2 : tsm), st>>>(lv.dev, cv.dev, lv.b, lv.t, lv.x, cv.x, \
+                                                                            sw, s->sc, s->partials, s->counters + 1)
     if (l == 0) { if (big) POST(true, 8, 512); else POST(true, 4, 1024); }
     else { if (big) POST(false, 8, 512); else POST(false, 4, 1024); }
 #undef POST
     s->launches++;
+    trace_mark(st);
 }
 
 template <int NC>
@@ -885,8 +905,9 @@ static void launch_coarsest(eqgpu_solver *s, cudaStream_t st, const CoarseW &cw)
     constexpr int TO = TS - 2 * (NC - 1);
     const size_t tsm = 2 * TN * sizeof(double);
     const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
-    k_coarsest<NC, 4><<<g, 1024, tsm, st>>>(lv.dev, lv.b, lv.x, cw, s->sc);
+    k_coarsest<NC, 4><<<g, 1024, tsm + tsm / 2, st>>>(lv.dev, lv.b, lv.x, cw, s->sc);
     s->launches++;
+    trace_mark(st);
 }
 
 static int nu_of(const eqgpu_solver *s, int l) { return l == 0 ? s->nu : s->nuc; }
@@ -973,8 +994,10 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     }
     const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
     k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
+    trace_mark(st);
     std::swap(s->pv, s->pv2);
     k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials, s->counters + 3, 1, &s->sc->rr);
+    trace_mark(st);
     s->launches += 2;
 }
 
@@ -1040,6 +1063,21 @@ static int pcg(eqgpu_solver *s)
 
     int issued = 0;
     int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
+    if (fused && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
+        std::vector<cudaEvent_t> ev;
+        g_trace = &ev;
+        trace_mark(st);
+        for (int k = 0; k < 2; ++k, ++issued) { enqueue_fused_iteration(s, st); }
+        g_trace = nullptr;
+        s->graph_phase = 0;
+        cudaStreamSynchronize(st);
+        for (size_t k = 1; k < ev.size(); ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+            fprintf(stderr, "trace kernel %2zu: %7.1f us\n", k, ms * 1e3);
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+    }
     while (true) {
         if (fused) {
             for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {

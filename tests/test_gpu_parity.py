@@ -238,3 +238,60 @@ def test_full_size_2048_properties(oracle):
     assert it > 0
     assert rel(out, ref) < TOL
     g.close(); g2.close()
+
+
+def test_config4_channels_midsize(oracle):
+    """BASELINE configs[3] (channel-flow trap) at a size the LU oracle still handles: 769x385 nodes,
+    4 steps, Robin left/right + channel Dirichlet top/bottom + 48 CN channel sub-steps per step."""
+    rl, rr = oracle.robin_rates(120.0, 1200.0, 20.0, 20.0)
+    kw = dict(bc_type=(2, 2, 3, 3), bc_value=(rl, rr, 0, 0), channels=True, channel_v=120.0,
+              channel_r=(rl, rr), channel_iters=48, well_scaling=10.0 * (25.0 / 5.0) * 0.5)
+    p, g = make(oracle, 769, 385, **kw)
+    cells = oracle.synthetic_colony(800, p.W, p.H, seed=4)
+    g.upload_cells(cells, 2.0)
+    s = oracle.new_state(p)
+    for k in range(4):
+        amount = 100.0 + 2.0 * oracle.gather(cells, 2.0, p.nH, p.nW, s.u)
+        s.u = oracle.scatter(cells, 2.0, p.nH, p.nW, amount, s.u)
+        s = oracle.step(p, s)
+        g.scatter(100.0 + 2.0 * g.gather())
+        g.step()
+    t, b = g.channels()
+    assert rel(g.get_field(), s.u) < TOL
+    assert rel(t, s.top) < TOL and rel(b, s.bottom) < TOL
+    g.close()
+
+
+def test_config4_channels_4096_properties(oracle):
+    """configs[3] at the full 4096^2: no direct solve fits, so check the step against the oracle's assembled
+    operator (residual), the channel recurrence against the oracle's channel solver fed with the GPU's own
+    wall flux, and the one-step lag of the channel Dirichlet rows."""
+    n = 4096
+    rl, rr = oracle.robin_rates(120.0, 1200.0, 20.0, 20.0)
+    kw = dict(bc_type=(2, 2, 3, 3), bc_value=(rl, rr, 0, 0), channels=True, channel_v=120.0,
+              channel_r=(rl, rr), channel_iters=48, well_scaling=10.0 * (25.0 / 5.0) * 0.5)
+    p, g = make(oracle, n, n, **kw)
+    cells = oracle.synthetic_colony(20000, p.W, p.H, seed=6)
+    g.upload_cells(cells, 2.0)
+    g.scatter(np.full(len(cells), 100.0))
+    g.step()
+    t1, b1 = g.channels()
+    g.scatter(np.full(len(cells), 100.0))
+    u_in = g.get_field()
+    g.step()
+    u_out = g.get_field()
+    t2, b2 = g.channels()
+    ft, fb = g.channel_flux()
+    # (a) the solve: residual of u_out in the oracle's operator with the lagged channel values as Dirichlet data
+    bands, b = oracle.assemble(p, u_in)
+    r = b - oracle.band_matvec(p, bands, u_out)
+    U = u_out.reshape(n, n)
+    assert np.array_equal(U[0], b1) and np.array_equal(U[-1], t1)          # rows = previous step's channels
+    interior = np.zeros((n, n), bool); interior[1:-1, :] = True
+    assert np.linalg.norm(r.reshape(n, n)[interior]) < 1e-10 * np.linalg.norm(b)
+    # (b) wall flux (src/fHSL.cpp:54-96) and the 48 CN sub-steps of both channels
+    fb_ref, ft_ref = oracle.compute_boundary_flux(p, u_out)
+    assert np.allclose(ft, ft_ref, rtol=1e-12, atol=0) and np.allclose(fb, fb_ref, rtol=1e-12, atol=0)
+    assert rel(t2, oracle.channel_substeps(p, ft, t1)) < 1e-10
+    assert rel(b2, oracle.channel_substeps(p, fb, b1)) < 1e-10
+    g.close()
