@@ -32,7 +32,7 @@ API_SYMBOLS = [
     "eqgpu_field_device_ptr", "eqgpu_sync", "eqgpu_cells_set_amounts",
     "eqgpu_cells_gather_resident", "eqgpu_cells_scatter_resident", "eqgpu_cells_get_gathered",
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
-    "eqgpu_slab_plan",
+    "eqgpu_slab_plan", "eqgpu_set_scatter_mode",
 ]
 
 
@@ -288,6 +288,10 @@ class GpuHSL:
         out = np.empty(self.ncells)
         self._ck(lib().eqgpu_cells_gather(self._h, _dp(out)))
         return out
+
+    def set_scatter_mode(self, mode: int):
+        """0 = direct global atomics, 1 = shared-memory-binned (dense colonies)."""
+        self._ck(lib().eqgpu_set_scatter_mode(self._h, C.c_int(mode)))
 
     def scatter(self, amount_nM):
         a = _f64(amount_nM)

@@ -151,7 +151,7 @@ void eqgpu_destroy(eqgpu_solver *s)
     cudaStreamSynchronize(s->stream);
     slab_destroy_comm(s);
     solver_teardown(s);
-    cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt);
+    cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt); cudaFree(s->bin_ints);
     if (s->own_stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -338,6 +338,14 @@ int eqgpu_cells_scatter(eqgpu_solver *s, const double *amount)
     int rc = cells_scatter(s, s->cell_amt);
     if (rc) return rc;
     EQ_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int eqgpu_set_scatter_mode(eqgpu_solver *s, int mode)
+{
+    CHECK_S(s);
+    if (mode != 0 && mode != 1) { s->set_error("scatter mode must be 0 (direct) or 1 (binned)"); return EQGPU_EINVAL; }
+    s->scatter_mode = mode;
     return 0;
 }
 

@@ -184,6 +184,149 @@ k_cells_scatter(const double *__restrict__ cells, long long ncells, double npm, 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Binned scatter (dense colonies): rods are bucketed by the 64x64-node tile that holds the
+// origin of their search box; one CTA per non-empty tile rasterises its rods into a
+// shared-memory window (tile + BIN_EXT nodes, which covers every search box that starts
+// in the tile) with shared-memory atomics, then flushes the touched nodes to the field
+// with one global atomic each.  Overlapping rods thus collide in shared memory instead
+// of at the L2 atomic units.  Rods whose box is larger than BIN_EXT fall back to direct
+// global atomics.
+// ---------------------------------------------------------------------------
+#define BIN_T 64
+#define BIN_EXT 32
+#define BIN_W (BIN_T + BIN_EXT)
+
+__global__ void k_bin_count(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
+                            int ntx, int *__restrict__ tile_of, int *__restrict__ tile_count)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncells) return;
+    const CellBox b = cell_box(cells + k * EQGPU_CELL_STRIDE, npm, nH, nW, nte);
+    int t = -1;  // -1: direct path (box too large for the window, or degenerate)
+    if (b.i2 >= b.i1 && b.j2 >= b.j1 && b.i2 - (b.i1 / BIN_T) * BIN_T < BIN_W && b.j2 - (b.j1 / BIN_T) * BIN_T < BIN_W) {
+        t = (b.i1 / BIN_T) * ntx + b.j1 / BIN_T;
+        atomicAdd(tile_count + t, 1);
+    }
+    tile_of[k] = t;
+}
+
+// exclusive scan of the tile counts (single block) -> tile_start[0..ntiles]; resets the fill cursors
+__global__ void k_bin_scan(int ntiles, const int *__restrict__ tile_count, int *__restrict__ tile_start,
+                           int *__restrict__ tile_fill)
+{
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        const int t = base + threadIdx.x;
+        const int v = t < ntiles ? tile_count[t] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += n; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int excl = carry + (warp > 0 ? wsum[warp - 1] : 0) + inc - v;
+        if (t < ntiles) { tile_start[t] = excl; tile_fill[t] = 0; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_start[ntiles] = carry;
+}
+
+__global__ void k_bin_fill(long long ncells, const int *__restrict__ tile_of, const int *__restrict__ tile_start,
+                           int *__restrict__ tile_fill, int *__restrict__ list)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncells) return;
+    const int t = tile_of[k];
+    if (t < 0) return;
+    list[tile_start[t] + atomicAdd(tile_fill + t, 1)] = (int)k;
+}
+
+__device__ __forceinline__ double deposit_of(const double *c, double amount, double npm, int n)
+{
+    const double L = c[13];
+    const double vol = cell_volume(L);
+    const double nanoMolarPerMoleculePerCubicMicron = 1.0 / 0.602;
+    const double numberHSL = mul(__ddiv_rn(amount, nanoMolarPerMoleculePerCubicMicron), vol);
+    const double extra = sub(1.0, __ddiv_rn(vol, mul(mul(L, 1.0), 1.0)));
+    const double perSquareMicron = __ddiv_rn(numberHSL, extra);
+    const double onePoint = mul(mul(perSquareMicron, npm), npm);
+    return __ddiv_rn(onePoint, (double)n);
+}
+
+__global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
+k_cells_scatter_binned(const double *__restrict__ cells, double npm, int nH, int nW, int nte, int ntx,
+                       const double *__restrict__ amount, const int *__restrict__ counts,
+                       const int *__restrict__ tile_start, const int *__restrict__ list, double *__restrict__ u,
+                       int row0, int g0, int g1)
+{
+    extern __shared__ double acc[];  // BIN_W x BIN_W window
+    const int t = blockIdx.x, n0 = tile_start[t], n1 = tile_start[t + 1];
+    if (n1 == n0) return;
+    const int oi = (t / ntx) * BIN_T, oj = (t % ntx) * BIN_T;
+    for (int q = threadIdx.x; q < BIN_W * BIN_W; q += blockDim.x) acc[q] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = n0 + warp; e < n1; e += CELLS_PER_BLOCK) {
+        const int k = list[e];
+        const double *c = cells + (long long)k * EQGPU_CELL_STRIDE;
+        const double dHSL = deposit_of(c, amount[k], npm, counts[k]);
+        int found = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned, bool in, int) {
+            if (in) {
+                const int gi = (int)(node / nW), gj = (int)(node - (long long)gi * nW);
+                atomicAdd(acc + (gi - oi) * BIN_W + (gj - oj), dHSL);
+            }
+        });
+        if (found == 0 && lane == 0) {
+            const long long cn = centre_node(c, npm, nW);
+            const int gi = (int)(cn / nW), gj = (int)(cn - (long long)gi * nW);
+            if (gi - oi >= 0 && gi - oi < BIN_W && gj - oj >= 0 && gj - oj < BIN_W)
+                atomicAdd(acc + (gi - oi) * BIN_W + (gj - oj), dHSL);
+            else if (gi >= g0 && gi < g1)
+                atomicAdd(u + cn - (long long)row0 * nW, dHSL);
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < BIN_W * BIN_W; q += blockDim.x) {
+        const double v = acc[q];
+        if (v != 0.0) {
+            const int gi = oi + q / BIN_W, gj = oj + q % BIN_W;
+            if (gi >= g0 && gi < g1 && gj < nW) atomicAdd(u + (size_t)(gi - row0) * nW + gj, v);
+        }
+    }
+}
+
+// rods that did not fit a window: direct global atomics
+__global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
+k_cells_scatter_rest(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
+                     const double *__restrict__ amount, const int *__restrict__ counts,
+                     const int *__restrict__ tile_of, double *__restrict__ u, int row0, int g0, int g1)
+{
+    const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
+    if (k >= ncells || tile_of[k] >= 0) return;
+    const int lane = threadIdx.x & 31;
+    const double *c = cells + k * EQGPU_CELL_STRIDE;
+    const double dHSL = deposit_of(c, amount[k], npm, counts[k]);
+    auto owned = [&](long long node) { const int gi = (int)(node / nW); return gi >= g0 && gi < g1; };
+    int found = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned, bool in, int) {
+        if (in && owned(node)) atomicAdd(u + node - (long long)row0 * nW, dHSL);
+    });
+    if (found == 0 && lane == 0) {
+        const long long cn = centre_node(c, npm, nW);
+        if (owned(cn)) atomicAdd(u + cn - (long long)row0 * nW, dHSL);
+    }
+}
+
 static int nte_of(double npm) { return (int)llround(npm * 1.0 / 2.0); }  // src/abm/eQabm.cpp:75
 
 int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap)
@@ -213,9 +356,48 @@ int cells_gather(eqgpu_solver *s, double *d_out)
     return 0;
 }
 
+static int cells_scatter_binned(eqgpu_solver *s, const double *d_amount)
+{
+    const int nW = s->p.nW, nH = s->p.nH, nte = nte_of(s->npm);
+    const int ntx = (nW + BIN_T - 1) / BIN_T, nty = (nH + BIN_T - 1) / BIN_T, ntiles = ntx * nty;
+    const long long n = s->ncells;
+    if (s->bin_cap_cells < n || s->bin_cap_tiles < ntiles) {
+        cudaFree(s->bin_ints);
+        s->bin_ints = nullptr;
+        const size_t ints = (size_t)2 * (n + 64) + (size_t)3 * (ntiles + 1);
+        EQ_CUDA(cudaMalloc(&s->bin_ints, sizeof(int) * ints));
+        s->bin_cap_cells = n + 64;
+        s->bin_cap_tiles = ntiles;
+    }
+    int *tile_of = s->bin_ints, *list = tile_of + s->bin_cap_cells, *tile_count = list + s->bin_cap_cells;
+    int *tile_start = tile_count + (ntiles + 1), *tile_fill = tile_start + (ntiles + 1);
+    const int blocks = (int)((n + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK), tb = (int)((n + 255) / 256);
+    const Level &l0 = s->levels[0];
+    const size_t smem = sizeof(double) * BIN_W * BIN_W;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EQ_CUDA(cudaFuncSetAttribute(k_cells_scatter_binned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    EQ_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int) * (ntiles + 1), s->stream));
+    k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(s->cells, n, s->npm, nH, nW, nte, s->cell_counts,
+                                                                   nullptr, 0);
+    k_bin_count<<<tb, 256, 0, s->stream>>>(s->cells, n, s->npm, nH, nW, nte, ntx, tile_of, tile_count);
+    k_bin_scan<<<1, 1024, 0, s->stream>>>(ntiles, tile_count, tile_start, tile_fill);
+    k_bin_fill<<<tb, 256, 0, s->stream>>>(n, tile_of, tile_start, tile_fill, list);
+    k_cells_scatter_binned<<<ntiles, 32 * CELLS_PER_BLOCK, smem, s->stream>>>(
+        s->cells, s->npm, nH, nW, nte, ntx, d_amount, s->cell_counts, tile_start, list, s->u, l0.dev.row0, l0.g0, l0.g1);
+    k_cells_scatter_rest<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
+        s->cells, n, s->npm, nH, nW, nte, d_amount, s->cell_counts, tile_of, s->u, l0.dev.row0, l0.g0, l0.g1);
+    s->launches += 6;
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int cells_scatter(eqgpu_solver *s, const double *d_amount)
 {
     if (s->ncells == 0) return 0;
+    if (s->scatter_mode == 1) return cells_scatter_binned(s, d_amount);
     const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
     // point counts first (the per-node amount divides by them)
     k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(

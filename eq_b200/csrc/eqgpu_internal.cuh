@@ -79,7 +79,10 @@ struct eqgpu_solver {
     bool slab = false;
     int slab_rank = 0, slab_world = 1;
     void *nccl_comm = nullptr;
-    double *cell_cnt = nullptr;    // per-cell owned-point counts (slab gather)
+    int scatter_mode = 0;          // 0 direct global atomics, 1 shared-memory-binned
+    int *bin_ints = nullptr;       // binned scatter scratch
+    long long bin_cap_cells = 0;
+    int bin_cap_tiles = 0;
     bool use_cluster = false;      // deepest levels on a 16-CTA cluster (k_ctail) instead of one CTA (k_tail)
     int ctail_first = 0, ctail_ncta = 0;
     size_t ctail_smem = 0;

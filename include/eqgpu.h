@@ -160,6 +160,11 @@ EQGPU_API int eqgpu_cells_gather(eqgpu_solver *s, double *out);
 /* writeHSL for every cell: amount_nM[k] is Strain's deltaHSL for this layer. */
 EQGPU_API int eqgpu_cells_scatter(eqgpu_solver *s, const double *amount_nM);
 
+/* writeHSL strategy: 0 = one global fp64 atomic per (rod, node) (default; exact for non-overlapping rods),
+ * 1 = rods binned by 64x64-node tile and accumulated with shared-memory atomics before one global atomic
+ * per touched node (dense / overlapping colonies). */
+EQGPU_API int eqgpu_set_scatter_mode(eqgpu_solver *s, int mode);
+
 /* Device-resident variants (no host copy inside): gather into the solver's
  * per-cell buffer / scatter the amounts last given to eqgpu_cells_set_amounts.
  * eqgpu_cells_get_gathered copies the last gather result to the host. */

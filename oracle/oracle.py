@@ -86,6 +86,7 @@ class Problem:
     nW: int
     nH: int
     h: float = 0.5
+    hy: float | None = None   # row spacing when it differs from h (W/ceil(W*npm) != H/ceil(H*npm) upstream)
     dt: float = 0.1
     D: float = 1200.0
     # per wall (left,right,top,bottom): type and value (Dirichlet value / Robin rate)
@@ -112,7 +113,7 @@ class Problem:
 
     @property
     def H(self):
-        return (self.nH - 1) * self.h
+        return (self.nH - 1) * (self.hy if self.hy else self.h)
 
     @property
     def use_robin(self):

@@ -29,7 +29,7 @@ def field(p, seed=0, smooth=True):
 
 def make(oracle, nW, nH, **kw):
     p = oracle.Problem(nW=nW, nH=nH, **kw)
-    g = E.GpuHSL(nW, nH, h=p.h, dt=p.dt, D=p.D, bc_type=p.bc_type, bc_value=p.bc_value,
+    g = E.GpuHSL(nW, nH, h=p.h, hy=p.hy, dt=p.dt, D=p.D, bc_type=p.bc_type, bc_value=p.bc_value,
                  robin_s=p.robin_s, channels=p.channels, channel_v=p.channel_v,
                  channel_r=p.channel_r, channel_iters=p.channel_iters, well_scaling=p.well_scaling)
     return p, g
@@ -294,4 +294,56 @@ def test_config4_channels_4096_properties(oracle):
     assert np.allclose(ft, ft_ref, rtol=1e-12, atol=0) and np.allclose(fb, fb_ref, rtol=1e-12, atol=0)
     assert rel(t2, oracle.channel_substeps(p, ft, t1)) < 1e-10
     assert rel(b2, oracle.channel_substeps(p, fb, b1)) < 1e-10
+    g.close()
+
+
+@pytest.mark.parametrize("npm,n", [(2.0, 512), (4.0, 640)])
+def test_binned_scatter_matches_direct_and_oracle(oracle, npm, n):
+    """writeHSL through shared-memory bins (eqgpu_set_scatter_mode 1): bit-exact for separated rods, and equal
+    to the oracle's sequential sum to rounding for a dense overlapping colony; oversize rods take the direct path."""
+    h = 1.0 / npm
+    W = (n - 1) * h
+    rng = np.random.default_rng(31)
+    sep = oracle.synthetic_colony(1500, W, W, seed=13)
+    g = E.GpuHSL(n, n, h=h)
+    g.set_scatter_mode(1)
+    u0 = rng.uniform(0, 5, n * n)
+    amount = rng.uniform(10, 200, len(sep))
+    g.upload_cells(sep, npm)
+    g.set_field(u0)
+    g.scatter(amount)
+    assert np.array_equal(g.get_field(), oracle.scatter(sep, npm, n, n, amount, u0))
+    # dense: 6000 overlapping rods in a corner, plus a few rods far longer than a bin window
+    m = 6000
+    centers = np.c_[rng.uniform(2, W / 4, m), rng.uniform(2, W / 4, m)]
+    dense = oracle.make_cells(centers, rng.uniform(0, 2 * np.pi, m), (1 + rng.uniform(size=m)) * 2.1, W, W)
+    big = oracle.make_cells([(W / 2, W / 2), (W / 3, W / 2)], [0.3, 1.2], [60.0, 45.0], W, W)
+    cells = np.vstack([dense, big])
+    amount = rng.uniform(10, 200, len(cells))
+    g.upload_cells(cells, npm)
+    g.set_field(u0)
+    g.scatter(amount)
+    ref = oracle.scatter(cells, npm, n, n, amount, u0)
+    out = g.get_field()
+    assert np.allclose(out, ref, rtol=1e-12, atol=0)
+    g.set_scatter_mode(0)
+    g.set_field(u0)
+    g.scatter(amount)
+    assert np.allclose(g.get_field(), ref, rtol=1e-12, atol=0)
+    g.close()
+
+
+@pytest.mark.parametrize("bc", ["robin_lr_dir_tb", "neumann"])
+def test_unequal_spacing(oracle, bc):
+    """hx != hy (fenicsClassInit rounds the cell counts up separately, src/fHSL.cpp:242-243, so the two mesh
+    spacings differ whenever W*npm or H*npm is not an integer)."""
+    p, g = make(oracle, 151, 97, h=0.5, hy=0.4, **BCS[bc])
+    bands, _ = oracle.assemble(p, None)
+    x = field(p, 1, smooth=False)
+    assert rel(g.apply_operator(x), oracle.band_matvec(p, bands, x)) < 1e-13
+    u0 = field(p, 2)
+    g.solution_vector[:] = u0
+    assert rel(g.stepDiffusion(), oracle.solve_lu(p, u0)) < TOL
+    want = p.D * p.dt * oracle.boundary_functional(p, oracle.solve_lu(p, u0))
+    assert abs(g.totalBoundaryFlux - want) <= 1e-7 * max(abs(want), 1.0)
     g.close()
