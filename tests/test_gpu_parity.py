@@ -347,3 +347,18 @@ def test_unequal_spacing(oracle, bc):
     want = p.D * p.dt * oracle.boundary_functional(p, oracle.solve_lu(p, u0))
     assert abs(g.totalBoundaryFlux - want) <= 1e-7 * max(abs(want), 1.0)
     g.close()
+
+
+@pytest.mark.parametrize("D,dt", [(1.0, 0.1), (10.0, 0.01), (640.0, 0.1), (1.0e5, 0.1), (3.0e4, 1.0)])
+@pytest.mark.parametrize("bc", ["dirichlet0", "neumann", "robin_lr"])
+def test_parameter_extremes(oracle, D, dt, bc):
+    """Fourier numbers from 0.04 (mass-dominated, single level) to 4e5 (deep hierarchy, high-degree coarse
+    solve): the hierarchy depth, the coarse Chebyshev degree and the tail/tile choice all change."""
+    p, g = make(oracle, 321, 193, D=D, dt=dt, **BCS[bc])
+    u0 = field(p, 5)
+    g.solution_vector[:] = u0
+    out = g.stepDiffusion()
+    st = g.stats()
+    assert rel(out, oracle.solve_lu(p, u0)) < TOL, (st.iterations, st.relres, st.levels)
+    assert st.iterations <= 40
+    g.close()
