@@ -32,7 +32,7 @@ API_SYMBOLS = [
     "eqgpu_field_device_ptr", "eqgpu_sync", "eqgpu_cells_set_amounts",
     "eqgpu_cells_gather_resident", "eqgpu_cells_scatter_resident", "eqgpu_cells_get_gathered",
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
-    "eqgpu_slab_plan", "eqgpu_set_scatter_mode",
+    "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path",
 ]
 
 
@@ -200,6 +200,11 @@ class GpuHSL:
         u = _f64(u)
         assert u.size == self.N
         self._ck(lib().eqgpu_set_field(self._h, _dp(u)))
+
+    def path(self) -> dict:
+        b = lib().eqgpu_solver_path(self._h)
+        return {"fused": bool(b & 1), "slab": bool(b & 2), "slab_fused": bool(b & 4), "cluster_tail": bool(b & 8),
+                "tiled_coarsest": bool(b & 16), "tensor": bool(b & 32)}
 
     def slab_rows(self):
         a, b = C.c_int32(), C.c_int32()

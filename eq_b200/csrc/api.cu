@@ -56,7 +56,7 @@ int eqgpu_slab_plan(int32_t nH, int32_t world, int32_t rank, int32_t max_levels,
     while (true) {
         g0[l] = a; g1[l] = b; rows[l] = n;
         ++l;
-        if (l >= max_levels || n < 5 || (world > 1 && (n / 2) / world < 4)) break;
+        if (l >= max_levels || n < 5 || (world > 1 && (n / 2) / world < 12)) break;
         const int nc = n / 2 + 1;
         int ca = nc, cb = 0;
         for (int I = 0; I < nc; ++I) {
@@ -67,6 +67,13 @@ int eqgpu_slab_plan(int32_t nH, int32_t world, int32_t rank, int32_t max_levels,
         n = nc; a = ca; b = cb;
     }
     return l;
+}
+
+int eqgpu_solver_path(eqgpu_solver *s)
+{
+    if (!s) return EQGPU_EINVAL;
+    return (s->fused ? 1 : 0) | (s->slab ? 2 : 0) | (s->slab_fused ? 4 : 0) | (s->use_cluster ? 8 : 0) |
+           (s->tile_coarsest ? 16 : 0) | (s->tensor ? 32 : 0);
 }
 
 int eqgpu_slab_rows(eqgpu_solver *s, int32_t *g0, int32_t *g1)

@@ -38,6 +38,10 @@ struct LevelDev {
     // row-slab decomposition: the arrays hold global rows [row0, row0+ny) of a gny-row grid, of
     // which local rows [own0, own1) are owned (the others are halo copies).  Single GPU: 0, ny, 0, ny.
     int row0, gny, own0, own1;
+    // tile kernels (global row indices): rows [slo, shi) are present in storage (pointers are passed
+    // pre-offset so that row gi lives at ptr[gi*nx]), rows [wlo, whi) may be written by this rank, and
+    // tile rows start at the even row tbase.  Single GPU: 0, ny, 0, ny, 0.
+    int slo, shi, wlo, whi, tbase;
 };
 
 struct CGScalars {
@@ -49,7 +53,9 @@ struct CGScalars {
 };
 
 struct Level {
-    LevelDev dev;
+    LevelDev dev;    // local view (row 0 = first stored row): unfused kernels
+    LevelDev gdev;   // global view for the tile kernels (== dev on a single GPU)
+    double *d_hy_g = nullptr, *d_ihy_g = nullptr;  // slab mode: padded row sizes of the whole grid
     std::vector<double> hx_host, hy_host;  // unpadded cell sizes (global grid)
     int g0 = 0, g1 = 0;                    // owned global rows [g0, g1)
     double *d_hx = nullptr, *d_ihx = nullptr, *d_hy = nullptr, *d_ihy = nullptr;
@@ -79,6 +85,8 @@ struct eqgpu_solver {
     bool slab = false;
     int slab_rank = 0, slab_world = 1;
     void *nccl_comm = nullptr;
+    int halo = 1;                  // halo rows kept per neighbour (1 unfused, 6 for the tile kernels)
+    bool slab_fused = false;
     int scatter_mode = 0;          // 0 direct global atomics, 1 shared-memory-binned
     int *bin_ints = nullptr;       // binned scatter scratch
     long long bin_cap_cells = 0;
@@ -132,7 +140,7 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
 // ---- slab.cu ----
 int slab_init_comm(eqgpu_solver *s, const void *unique_id);
 void slab_destroy_comm(eqgpu_solver *s);
-int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v);          // one-row halos of a level vector
+int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth = 1);  // halo rows of a level vector (local view)
 int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count);  // sum over ranks, stream-ordered
 int slab_unique_id(void *out128);
 // ---- cells.cu ----

@@ -49,7 +49,8 @@ __device__ __forceinline__ int tidx(int ly, int lx) { return (ly + 1) * TP + lx 
 // does the whole shared tile [ox, ox+TS) x [oy, oy+TS) consist of regular nodes?
 __device__ __forceinline__ bool tile_regular(const LevelDev &L, int ox, int oy)
 {
-    return ox >= 1 && ox + TS - 1 <= L.jreg_hi && oy >= 1 && oy + TS - 1 <= L.ireg_hi;
+    return ox >= 1 && ox + TS - 1 <= L.jreg_hi && oy >= 1 && oy + TS - 1 <= L.ireg_hi && oy >= L.slo &&
+           oy + TS <= L.shi;
 }
 
 // Per-thread slice of a global field: the thread's column, its R rows.  REG
@@ -68,7 +69,7 @@ __device__ __forceinline__ void column_load(const LevelDev &L, int ox, int oy, c
         const bool okx = gj >= 0 && gj < L.nx;
         const int gjc = min(max(gj, 0), L.nx - 1);
 #pragma unroll
-        for (int k = 0; k < R; ++k) v[k] = __ldg(g + (size_t)min(max(oy + ly0 + k, 0), L.ny - 1) * L.nx + gjc);
+        for (int k = 0; k < R; ++k) v[k] = __ldg(g + (size_t)min(max(oy + ly0 + k, L.slo), L.shi - 1) * L.nx + gjc);
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int gi = oy + ly0 + k;
@@ -182,7 +183,7 @@ __device__ __forceinline__ void tile_pass(const LevelDev &L, const Spacing &S, i
             else { const int kk = k - nr; const int gjj = kk == 0 ? 0 : L.jreg_hi + kk; lxx = gjj - ox; ly = e; }
             if (ly < 0 || ly >= TS || lxx < 0 || lxx >= TS) continue;
             const int gi = oy + ly, gjj = ox + lxx;
-            const bool in = gi >= 0 && gi < L.ny && gjj >= 0 && gjj < L.nx;
+            const bool in = gi >= L.slo && gi < L.shi && gjj >= 0 && gjj < L.nx;
             const int cc2 = tidx(ly, lxx);
             const double bval = sbm ? sbm[cc2] : (in ? __ldg(bglob + (size_t)gi * L.nx + gjj) : 0.0);
             dst[cc2] = node_generic<MODE>(L, S, gi, gjj, cc2, bval, src, w);
@@ -220,8 +221,8 @@ __device__ __forceinline__ void presmooth_body(const LevelDev &F, const LevelDev
             double *q = x + (size_t)(oy + ly0) * F.nx + gj;
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const int ly = ly0 + k;
-                if (ly >= H && ly < TS - H) q[(size_t)k * F.nx] = cur[tidx(ly, lx)];
+                const int ly = ly0 + k, gi = oy + ly;
+                if (ly >= H && ly < TS - H && gi >= F.wlo && gi < F.whi) q[(size_t)k * F.nx] = cur[tidx(ly, lx)];
             }
         }
         // restriction: coarse nodes = even fine nodes of T (tile origin is even)
@@ -229,6 +230,8 @@ __device__ __forceinline__ void presmooth_body(const LevelDev &F, const LevelDev
         const int I0 = (oy + H) >> 1, J0 = (ox + H) >> 1;
         for (int q = threadIdx.x; q < CT * CT; q += NT) {
             const int cy = q / CT, cx = q - cy * CT;
+            const int gfi = oy + H + 2 * cy;
+            if (gfi < F.wlo || gfi >= F.whi) continue;
             const int c = tidx(H + 2 * cy, H + 2 * cx);
             const double h = oth[c + 1] + oth[c - 1] + oth[c + TP] + oth[c - TP] + oth[c + TP + 1] + oth[c - TP - 1];
             bc[(size_t)(I0 + cy) * Cc.nx + J0 + cx] = oth[c] + 0.5 * h;
@@ -239,7 +242,7 @@ __device__ __forceinline__ void presmooth_body(const LevelDev &F, const LevelDev
 #pragma unroll 2
             for (int k = 0; k < R; ++k) {
                 const int ly = ly0 + k, gi = oy + ly;
-                if (ly < H || ly >= TS - H || gi >= F.ny) continue;
+                if (ly < H || ly >= TS - H || gi < F.wlo || gi >= F.whi) continue;
                 const int c = tidx(ly, lx);
                 x[(size_t)gi * F.nx + gj] = cur[c];
                 const bool ci = !(gi & 1) || gi == F.ny - 1;
@@ -275,7 +278,7 @@ k_presmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, double *__res
     extern __shared__ double sm[];
     double *xa = sm, *xb = sm + TN;
     __shared__ double spc[4 * (TS + 2)];
-    const int ox = blockIdx.x * TO - H, oy = blockIdx.y * TO - H;
+    const int ox = blockIdx.x * TO - H, oy = F.tbase + blockIdx.y * TO - H;
     const bool regular = tile_regular(F, ox, oy);
     tile_zero_pads(xa);
     tile_zero_pads(xb);
@@ -316,7 +319,7 @@ __device__ __forceinline__ void coarsest_body(const LevelDev &F, const Spacing &
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int ly = ly0 + k, gi = oy + ly;
-            if (ly >= H && ly < TS - H && gi >= 0 && gi < F.ny) x[(size_t)gi * F.nx + gj] = cur[tidx(ly, lx)];
+            if (ly >= H && ly < TS - H && gi >= F.wlo && gi < F.whi) x[(size_t)gi * F.nx + gj] = cur[tidx(ly, lx)];
         }
     }
 }
@@ -330,7 +333,7 @@ k_coarsest(LevelDev F, const double *__restrict__ b, double *__restrict__ x, Coa
     extern __shared__ double sm[];
     double *xa = sm, *xb = sm + TN;
     __shared__ double spc[4 * (TS + 2)];
-    const int ox = blockIdx.x * TO - H, oy = blockIdx.y * TO - H;
+    const int ox = blockIdx.x * TO - H, oy = F.tbase + blockIdx.y * TO - H;
     const bool regular = tile_regular(F, ox, oy);
     tile_zero_pads(xa);
     tile_zero_pads(xb);
@@ -377,7 +380,7 @@ __device__ __forceinline__ double postsmooth_body(const LevelDev &F, const Level
     const int I0 = coarse_lo(min(max(oy, 0), F.ny - 1), F.ny, Cc.ny);
     for (int k = threadIdx.x; k < CP * CP; k += blockDim.x) {
         const int ci = k / CP, cj = k - ci * CP;
-        xb[k] = __ldg(xc + (size_t)min(I0 + ci, Cc.ny - 1) * Cc.nx + min(J0 + cj, Cc.nx - 1));
+        xb[k] = __ldg(xc + (size_t)min(max(I0 + ci, Cc.slo), Cc.shi - 1) * Cc.nx + min(J0 + cj, Cc.nx - 1));
     }
     __syncthreads();
     if (REG) {   // interior tile: midpoint <=> odd index, nothing is Dirichlet
@@ -426,7 +429,7 @@ __device__ __forceinline__ double postsmooth_body(const LevelDev &F, const Level
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int ly = ly0 + k, gi = oy + ly;
-            if (ly >= H && ly < TS - H && (REG || gi < F.ny)) {
+            if (ly >= H && ly < TS - H && gi >= F.wlo && gi < F.whi) {
                 const double v = cur[tidx(ly, lx)];
                 x[(size_t)gi * F.nx + gj] = v;
                 if (DOT) acc += v * bv[k];
@@ -440,14 +443,14 @@ template <int NU, bool DOT, int R>
 __global__ void __launch_bounds__(TS *(TS / R), R == 8 ? 2 : 1)
 k_postsmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, const double *__restrict__ xin,
              double *__restrict__ x, const double *__restrict__ xc, SmoothW sw, CGScalars *sc,
-             double *partials, unsigned *counter)
+             double *partials, unsigned *counter, double *out_dot)
 {
     if (sc->done) return;
     constexpr int H = NU, TO = TS - 2 * H;
     extern __shared__ double sm[];
     double *xa = sm, *xb = sm + TN;
     __shared__ double spc[4 * (TS + 2)];
-    const int ox = blockIdx.x * TO - H, oy = blockIdx.y * TO - H;
+    const int ox = blockIdx.x * TO - H, oy = F.tbase + blockIdx.y * TO - H;
     const bool regular = tile_regular(F, ox, oy);
     tile_zero_pads(xa);
     double v[1];
@@ -460,7 +463,7 @@ k_postsmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, const double
     }
     if (DOT) {
         double tot[1];
-        if (grid_reduce<1>(v, partials, counter, tot)) sc->rz_new = tot[0];
+        if (grid_reduce<1>(v, partials, counter, tot)) *out_dot = tot[0];
     }
 }
 
@@ -469,13 +472,13 @@ k_postsmooth(LevelDev F, LevelDev Cc, const double *__restrict__ b, const double
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_apply_p(LevelDev L, const double *__restrict__ z, const double *__restrict__ pin, double *__restrict__ p,
-          double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter)
+          double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter, double *out_pAp)
 {
     if (sc->done) return;
     constexpr int TO = TS - 2, TROWS = 16;
     __shared__ double sp[TN];
     const double beta = sc->iters == 0 ? 0.0 : sc->rz_new / sc->rz_old;
-    const int ox = blockIdx.x * TO - 1, oy = blockIdx.y * TO - 1;
+    const int ox = blockIdx.x * TO - 1, oy = L.tbase + blockIdx.y * TO - 1;
     const int lx = threadIdx.x & (TS - 1), ly0 = (threadIdx.x >> 6) * TROWS;
     const int gj = ox + lx;
     const bool regular = tile_regular(L, ox, oy);
@@ -488,7 +491,7 @@ k_apply_p(LevelDev L, const double *__restrict__ z, const double *__restrict__ p
         double vz[TROWS], vp[TROWS];
 #pragma unroll
         for (int k = 0; k < TROWS; ++k) {
-            const size_t g = (size_t)min(max(oy + ly0 + k, 0), L.ny - 1) * L.nx + gjc;
+            const size_t g = (size_t)min(max(oy + ly0 + k, L.slo), L.shi - 1) * L.nx + gjc;
             vz[k] = __ldg(z + g);
             vp[k] = __ldg(pin + g);
         }
@@ -510,7 +513,7 @@ k_apply_p(LevelDev L, const double *__restrict__ z, const double *__restrict__ p
         for (int k = 0; k < TROWS; ++k, c += TP) {
             const double nw = sp[c + TP - 1], nc = sp[c + TP], ne = sp[c + TP + 1];
             const int ly = ly0 + k, gi = oy + ly;
-            if (ly >= 1 && ly < TS - 1 && gi < L.ny) {
+            if (ly >= 1 && ly < TS - 1 && gi >= L.wlo && gi < L.whi) {
                 const size_t g = (size_t)gi * L.nx + gj;
                 p[g] = cc;
                 if (regx && (regular || (gi >= 1 && gi <= L.ireg_hi))) {
@@ -534,7 +537,7 @@ k_apply_p(LevelDev L, const double *__restrict__ z, const double *__restrict__ p
             else { const int kk = k - nr; const int gjj = kk == 0 ? 0 : L.jreg_hi + kk; lxx = gjj - ox; ly = e; }
             if (ly < 1 || ly >= TS - 1 || lxx < 1 || lxx >= TS - 1) continue;
             const int gi = oy + ly, gjj = ox + lxx;
-            if (gi >= L.ny || gjj >= L.nx) continue;
+            if (gi < L.wlo || gi >= L.whi || gjj >= L.nx) continue;
             // a node on an irregular row AND an irregular column is handled by its row item only
             if (!rowitem && !(gi >= 1 && gi <= L.ireg_hi)) continue;
             const int c = tidx(ly, lxx);
@@ -551,7 +554,7 @@ k_apply_p(LevelDev L, const double *__restrict__ z, const double *__restrict__ p
         }
     }
     double tot[1];
-    if (grid_reduce<1>(v, partials, counter, tot)) sc->pAp = tot[0];
+    if (grid_reduce<1>(v, partials, counter, tot)) *out_pAp = tot[0];
 }
 
 // ---------------------------------------------------------------------------

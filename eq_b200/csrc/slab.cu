@@ -93,22 +93,22 @@ void slab_destroy_comm(eqgpu_solver *s)
     s->nccl_comm = nullptr;
 }
 
-// Refresh the halo rows of a level vector: my first/last owned rows go to the neighbours below/above,
-// theirs arrive in my halo rows.  Stream-ordered; every rank issues the same sequence.
-int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v)
+// Refresh `depth` halo rows of a level vector (local view L): my first/last `depth` owned rows go to the
+// neighbours below/above, theirs arrive in my halo rows.  Stream-ordered; every rank issues the same sequence.
+int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth)
 {
     ncclComm_t comm = (ncclComm_t)s->nccl_comm;
     const bool below = L.own0 > 0, above = L.own1 < L.ny;
     if (!below && !above) return 0;
-    const size_t nx = (size_t)L.nx;
+    const size_t nx = (size_t)L.nx, cnt = nx * depth;
     EQ_NCCL(g_nccl.GroupStart());
     if (below) {
-        EQ_NCCL(g_nccl.Send(v + (size_t)L.own0 * nx, nx, ncclFloat64, s->slab_rank - 1, comm, s->stream));
-        EQ_NCCL(g_nccl.Recv(v, nx, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+        EQ_NCCL(g_nccl.Send(v + (size_t)L.own0 * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+        EQ_NCCL(g_nccl.Recv(v + (size_t)(L.own0 - depth) * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
     }
     if (above) {
-        EQ_NCCL(g_nccl.Send(v + (size_t)(L.own1 - 1) * nx, nx, ncclFloat64, s->slab_rank + 1, comm, s->stream));
-        EQ_NCCL(g_nccl.Recv(v + (size_t)L.own1 * nx, nx, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+        EQ_NCCL(g_nccl.Send(v + (size_t)(L.own1 - depth) * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+        EQ_NCCL(g_nccl.Recv(v + (size_t)L.own1 * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
     }
     EQ_NCCL(g_nccl.GroupEnd());
     return 0;

@@ -450,6 +450,7 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
     for (int w = 0; w < 4; ++w)
         if (p.bc_type[w] == EQGPU_BC_DIRICHLET || p.bc_type[w] == EQGPU_BC_DIRICHLET_CHANNEL)
             m |= 1u << w;
+    const unsigned mglob = m;
     // a slab sees the top/bottom walls only if its local first/last row IS the global wall row
     if (L.row0 > 0) m &= ~8u;
     if (L.row0 + L.ny < L.gny) m &= ~4u;
@@ -465,6 +466,20 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
     L.icC = 1.0 / L.cC;
     L.hx = lv.d_hx; L.ihx = lv.d_ihx; L.hy = lv.d_hy; L.ihy = lv.d_ihy;
     L.d11 = lv.t11; L.d22 = lv.t22; L.d12 = lv.t12;
+    // global view for the tile kernels: whole-grid index logic, windows saying which rows are stored / owned
+    LevelDev &G = lv.gdev;
+    G = L;
+    if (s->slab_fused) {
+        G.ny = L.gny;
+        G.row0 = 0;
+        G.own0 = 0; G.own1 = L.gny;
+        G.dirmask = mglob;
+        G.ireg_hi = L.ireg_hi + L.row0;
+        G.hy = lv.d_hy_g; G.ihy = lv.d_ihy_g;
+        G.slo = L.row0; G.shi = L.row0 + L.ny;
+        G.wlo = lv.g0; G.whi = lv.g1;
+        G.tbase = lv.g0 & ~1;
+    }
 }
 
 static CTailDesc make_ctail_desc(eqgpu_solver *s, int first, int ncta);
@@ -488,8 +503,10 @@ int solver_setup(eqgpu_solver *s)
     if (s->slab) {  // contiguous row slabs with even boundaries
         auto cut = [&](int r) { return r >= s->slab_world ? p.nH : (int)(((long long)p.nH * r / s->slab_world) & ~1LL); };
         l0.g0 = cut(s->slab_rank); l0.g1 = cut(s->slab_rank + 1);
-        if (l0.g1 - l0.g0 < 8) { s->set_error("slab too thin: fewer than 8 rows per rank"); return EQGPU_EINVAL; }
-        s->fused = false;
+        if (l0.g1 - l0.g0 < 16) { s->set_error("slab too thin: fewer than 16 rows per rank"); return EQGPU_EINVAL; }
+        s->slab_fused = getenv("EQGPU_SLAB_UNFUSED") == nullptr;
+        s->halo = s->slab_fused ? 6 : 1;
+        if (!s->slab_fused) s->fused = false;
     }
     s->levels.clear();
     s->levels.push_back(l0);
@@ -498,7 +515,7 @@ int solver_setup(eqgpu_solver *s)
     while ((int)s->levels.size() < maxl) {
         const Level &f = s->levels.back();
         if (std::min(f.dev.nx, f.dev.gny) < 5) break;
-        if (s->slab && (f.dev.gny / 2) / s->slab_world < 4) break;  // keep >= ~4 rows per rank
+        if (s->slab && (f.dev.gny / 2) / s->slab_world < (s->slab_fused ? 12 : 4)) break;  // keep enough rows per rank
         // stop once the mass term dominates: Jacobi alone converges fast there
         if (tau / (f.hx_host[0] * f.hy_host[0]) < 0.6) break;
         Level c;
@@ -517,11 +534,13 @@ int solver_setup(eqgpu_solver *s)
     }
     for (auto &lv : s->levels) {  // local window: owned rows plus one halo row towards each neighbour
         LevelDev &L = lv.dev;
-        const int hb = lv.g0 > 0 ? 1 : 0, ht = lv.g1 < L.gny ? 1 : 0;
+        const int hb = lv.g0 > 0 ? s->halo : 0, ht = lv.g1 < L.gny ? s->halo : 0;
+        if (s->slab && lv.g1 - lv.g0 < s->halo) { s->set_error("slab level thinner than its halo"); return EQGPU_EINVAL; }
         L.row0 = lv.g0 - hb;
         L.ny = (lv.g1 + ht) - L.row0;
         L.own0 = hb;
         L.own1 = L.ny - ht;
+        L.slo = 0; L.shi = L.ny; L.wlo = 0; L.whi = L.ny; L.tbase = 0;
     }
     for (size_t l = 0; l < s->levels.size(); ++l) {
         Level &lv = s->levels[l];
@@ -533,6 +552,7 @@ int solver_setup(eqgpu_solver *s)
             EQ_CUDA(cudaMalloc(&lv.x, bytes));
             EQ_CUDA(cudaMalloc(&lv.b, bytes));
         }
+        if (s->slab_fused && upload_padded(s, lv.hy_host, &lv.d_hy_g, &lv.d_ihy_g)) return EQGPU_ECUDA;
         fill_level_consts(s, lv);
     }
     // ---- fine vectors ----------------------------------------------------
@@ -600,6 +620,10 @@ int solver_setup(eqgpu_solver *s)
         const int cn = coarse_weights(s).n;
         s->tail_fits = used <= budget;
         if (!(cn >= 2 && cn <= 8 && nl >= 2) && !s->tail_fits) s->fused = false;
+        if (s->slab_fused) {  // the tail kernels see one rank's rows only: slabs need the tiled coarsest solve
+            if (cn >= 2 && cn <= 8 && nl >= 2) s->tile_coarsest = true;
+            else { s->slab_fused = false; s->fused = false; }
+        }
         if (!s->tail_fits) { s->tail_smem = 0; s->tile_coarsest = true; }
     }
     if (s->fused) {
@@ -615,7 +639,7 @@ int solver_setup(eqgpu_solver *s)
         const CTailDesc td = make_ctail_desc(s, cf, CT_MAX_CTAS);
         const size_t csm = (size_t)td.total * sizeof(double);
         s->use_cluster = false;
-        if (s->tail_fits && csm <= 200 * 1024 &&
+        if (!s->slab && s->tail_fits && csm <= 200 * 1024 &&
             cudaFuncSetAttribute(k_ctail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
             cudaFuncSetAttribute(k_ctail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm) == cudaSuccess) {
             cudaLaunchConfig_t cfg{};
@@ -649,7 +673,7 @@ int solver_setup(eqgpu_solver *s)
 #define SET_C(NC) EQ_CUDA(cudaFuncSetAttribute((k_coarsest<NC, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));
         SET_C(2) SET_C(3) SET_C(4) SET_C(5) SET_C(6) SET_C(7) SET_C(8)
 #undef SET_C
-        if (const char *e = getenv("EQGPU_TILE_COARSEST")) s->tile_coarsest = atoi(e) != 0 || !s->tail_fits;
+        if (const char *e = getenv("EQGPU_TILE_COARSEST")) s->tile_coarsest = atoi(e) != 0 || !s->tail_fits || s->slab;
 
 #undef SET_SMEM
     }
@@ -660,6 +684,7 @@ void solver_teardown(eqgpu_solver *s)
 {
     for (auto &lv : s->levels) {
         cudaFree(lv.d_hx); cudaFree(lv.d_ihx); cudaFree(lv.d_hy); cudaFree(lv.d_ihy);
+        cudaFree(lv.d_hy_g); cudaFree(lv.d_ihy_g);
         cudaFree(lv.t);
         if (&lv != &s->levels[0]) { cudaFree(lv.x); cudaFree(lv.b); }
         if (&lv != &s->levels[0]) { cudaFree(lv.t11); cudaFree(lv.t22); cudaFree(lv.t12); }
@@ -863,6 +888,22 @@ static SmoothW smooth_weights_n(int n)
     return sw;
 }
 
+// The LevelDev the tile kernels see (global row indices) and the matching pre-offset pointers.
+static inline const LevelDev &TV(const eqgpu_solver *s, const Level &lv) { return s->slab_fused ? lv.gdev : lv.dev; }
+template <class P>
+static inline P *VP(const eqgpu_solver *s, const Level &lv, P *ptr)
+{
+    return s->slab_fused ? ptr - (ptrdiff_t)lv.dev.row0 * lv.dev.nx : ptr;
+}
+static inline dim3 tile_grid(const LevelDev &L, int to)
+{
+    return dim3((L.nx + to - 1) / to, (L.whi - L.tbase + to - 1) / to);
+}
+static inline void xch(eqgpu_solver *s, Level &lv, double *v, int depth)
+{
+    if (s->slab) slab_exchange(s, lv.dev, v, depth);
+}
+
 template <int NU>
 static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
 {
@@ -870,11 +911,14 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
     constexpr int TO = TS - 2 * (NU + 1);
     const size_t tsm = 2 * TN * sizeof(double);
     const SmoothW sw = smooth_weights_n(NU);
-    const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
+    const LevelDev &F = TV(s, lv), &Cc = TV(s, cv);
+    const dim3 g = tile_grid(F, TO);
+    xch(s, lv, lv.b, NU + 1);
     if ((int)(g.x * g.y) >= 2 * s->num_sms)
-        k_presmooth<NU, 8><<<g, 512, tsm, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
+        k_presmooth<NU, 8><<<g, 512, tsm, st>>>(F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, cv, cv.b), sw, s->sc);
     else
-        k_presmooth<NU, 4><<<g, 1024, tsm + tsm / 2, st>>>(lv.dev, cv.dev, lv.b, lv.t, cv.b, sw, s->sc);
+        k_presmooth<NU, 4><<<g, 1024, tsm + tsm / 2, st>>>(F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, cv, cv.b), sw,
+                                                           s->sc);
     s->launches++;
     trace_mark(st);
 }
@@ -886,11 +930,16 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
     constexpr int TO = TS - 2 * NU;
     const size_t tsm = 2 * TN * sizeof(double);
     const SmoothW sw = smooth_weights_n(NU);
-    const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
+    const LevelDev &F = TV(s, lv), &Cc = TV(s, cv);
+    const dim3 g = tile_grid(F, TO);
     const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
-#define POST(DOT, R, NT)                                                                                     \
-    k_postsmooth<NU, DOT, R><<<g, NT, (R == 4 ? tsm + tsm / 2 : tsm), st>>>(lv.dev, cv.dev, lv.b, lv.t, lv.x, cv.x, \
-                                                                            sw, s->sc, s->partials, s->counters + 1)
+    xch(s, cv, cv.x, NU + 1);   // coarse correction rows reached by the prolongation of my halo
+    xch(s, lv, lv.t, NU);       // pre-smoothed iterate; lv.b halos are still valid from the pre-smoothing exchange
+    double *out_dot = s->slab ? &s->sc->part_rz : &s->sc->rz_new;
+#define POST(DOT, R, NT)                                                                                          \
+    k_postsmooth<NU, DOT, R><<<g, NT, (R == 4 ? tsm + tsm / 2 : tsm), st>>>(                                      \
+        F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, lv, lv.x), VP(s, cv, cv.x), sw, s->sc, s->partials,        \
+        s->counters + 1, out_dot)
     if (l == 0) { if (big) POST(true, 8, 512); else POST(true, 4, 1024); }
     else { if (big) POST(false, 8, 512); else POST(false, 4, 1024); }
 #undef POST
@@ -904,8 +953,10 @@ static void launch_coarsest(eqgpu_solver *s, cudaStream_t st, const CoarseW &cw)
     Level &lv = s->levels.back();
     constexpr int TO = TS - 2 * (NC - 1);
     const size_t tsm = 2 * TN * sizeof(double);
-    const dim3 g((lv.dev.nx + TO - 1) / TO, (lv.dev.ny + TO - 1) / TO);
-    k_coarsest<NC, 4><<<g, 1024, tsm + tsm / 2, st>>>(lv.dev, lv.b, lv.x, cw, s->sc);
+    const LevelDev &F = TV(s, lv);
+    const dim3 g = tile_grid(F, TO);
+    xch(s, lv, lv.b, NC - 1);
+    k_coarsest<NC, 4><<<g, 1024, tsm + tsm / 2, st>>>(F, VP(s, lv, lv.b), VP(s, lv, lv.x), cw, s->sc);
     s->launches++;
     trace_mark(st);
 }
@@ -985,19 +1036,36 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
 // One PCG iteration of the fused (isotropic) path, enqueued on `st`.
 static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
 {
-    const LevelDev &L = s->levels[0].dev;
+    Level &l0 = s->levels[0];
+    const LevelDev &L = TV(s, l0), &Ll = l0.dev;
+    CGScalars *sc = s->sc;
+    const bool sl = s->slab;
     const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+    const size_t ooff = (size_t)Ll.own0 * Ll.nx, on = (size_t)(Ll.own1 - Ll.own0) * Ll.nx;
     vcycle_fused(s, st);
     if (s->levels.size() < 2 || (!s->tile_coarsest && (s->use_cluster ? s->ctail_first : s->tail_first) == 0)) {
-        k_dot<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->sc, s->partials, s->counters + 1, &s->sc->rz_new);
+        k_dot<<<nb1, 256, 0, st>>>(on, s->r + ooff, s->z + ooff, sc, s->partials, s->counters + 1,
+                                   sl ? &sc->part_rz : &sc->rz_new);
         s->launches++;
     }
-    const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
-    k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
+    if (sl) {
+        slab_allreduce(s, &sc->part_rz, &sc->rz_new, 1);
+        slab_exchange(s, Ll, s->z, 1);
+        slab_exchange(s, Ll, s->pv, 1);
+    }
+    const dim3 tg = tile_grid(L, TS - 2);
+    k_apply_p<<<tg, 256, 0, st>>>(L, VP(s, l0, s->z), VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc,
+                                  s->partials, s->counters + 2, sl ? &sc->part_pAp : &sc->pAp);
     trace_mark(st);
     std::swap(s->pv, s->pv2);
-    k_update_xr<<<nb1, 256, 0, st>>>(s->N, s->u, s->r, s->pv, s->Ap, s->sc, s->partials, s->counters + 3, 1, &s->sc->rr);
+    if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
+    k_update_xr<<<nb1, 256, 0, st>>>(on, s->u + ooff, s->r + ooff, s->pv + ooff, s->Ap + ooff, sc, s->partials,
+                                     s->counters + 3, sl ? 0 : 1, sl ? &sc->part_rr : &sc->rr);
     trace_mark(st);
+    if (sl) {
+        slab_allreduce(s, &sc->part_rr, &sc->rr, 1);
+        k_book<<<1, 1, 0, st>>>(sc);
+    }
     s->launches += 2;
 }
 
@@ -1042,7 +1110,7 @@ static int pcg(eqgpu_solver *s)
     DirData dd = make_dirdata(s);
     const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
     const bool fused = !T && s->fused;
-    if (fused) {
+    if (fused && !s->slab) {
         int rc = build_iteration_graph(s);
         if (rc) return rc;
     }
@@ -1063,7 +1131,7 @@ static int pcg(eqgpu_solver *s)
 
     int issued = 0;
     int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
-    if (fused && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
+    if (fused && !s->slab && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
         std::vector<cudaEvent_t> ev;
         g_trace = &ev;
         trace_mark(st);
@@ -1081,6 +1149,7 @@ static int pcg(eqgpu_solver *s)
     while (true) {
         if (fused) {
             for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
+                if (s->slab) { enqueue_fused_iteration(s, st); continue; }  // NCCL calls in between: no graph
                 EQ_CUDA(cudaGraphLaunch(s->graph_phase == 0 ? s->graph_exec : s->graph_exec2, st));
                 s->graph_phase ^= 1;
                 s->launches += s->graph_launches;
@@ -1189,7 +1258,7 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
             *alg_bytes = 48.0 * s->N;
         } else if (nm == "apply_p") {  // read z,p write p',Ap: 32 B/DOF
             const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
-            k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2);
+            k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2, &s->sc->pAp);
             *alg_bytes = 32.0 * s->N;
         } else if (nm == "presmooth" || nm == "postsmooth") {
             if (!s->fused || (s->use_cluster ? s->ctail_first : s->tail_first) == 0 || s->nu != 3) return false;
@@ -1205,7 +1274,7 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
                 const int to = TS - 6;
                 const dim3 tg((L.nx + to - 1) / to, (L.ny + to - 1) / to);
                 k_postsmooth<3, true, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, s->z, cv.x, sw, s->sc,
-                                                                    s->partials, s->counters + 1);
+                                                                    s->partials, s->counters + 1, &s->sc->rz_new);
                 *alg_bytes = 26.0 * s->N;
             }
         } else return false;

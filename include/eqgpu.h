@@ -183,6 +183,9 @@ EQGPU_API int eqgpu_build_rhs(eqgpu_solver *s, const double *host_u0, double *ho
 /* Device pointer to the resident field (for benchmarks that stage inputs in HBM). */
 EQGPU_API int eqgpu_field_device_ptr(eqgpu_solver *s, void **dev_ptr);
 EQGPU_API int eqgpu_sync(eqgpu_solver *s);
+/* Which code path the solver selected (diagnostics / tests): bit 0 fused tile kernels, 1 row-slab mode,
+ * 2 fused kernels in slab mode, 3 cluster tail, 4 tiled coarsest solve, 5 variable tensor active. */
+EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
 /* Times `reps` back-to-back launches of one named kernel on the solver's
  * stream with CUDA events (for bench.py's roofline line).  Returns the average
  * milliseconds per launch and the algorithmic bytes one launch must move

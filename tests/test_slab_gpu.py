@@ -11,29 +11,33 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NW, NH, NPM = 384, 256, 2.0
 BC = dict(bc_type=(2, 1, 0, 1), bc_value=(120.0, 2.0, 0.0, 0.5))
+# D = 50: the hierarchy ends mass-dominated while every rank still has >= 12 rows -> fused tile kernels on
+# slabs (6-row halos).  D = 1200: the coarse solve needs a high Chebyshev degree -> unfused fallback (1-row halos).
+CASES = {"fused": 50.0, "unfused": 1200.0}
 
 
-def problem():
+def problem(D):
     sys.path.insert(0, ROOT)
     from oracle import oracle as O
-    p = O.Problem(nW=NW, nH=NH, **BC)
+    p = O.Problem(nW=NW, nH=NH, D=D, **BC)
     cells = O.synthetic_colony(300, p.W, p.H, seed=11)
     return O, p, cells
 
 
-def worker(rank, world, q_id, q_out):
+def worker(rank, world, q_id, q_out, kase):
     sys.path.insert(0, ROOT)
     import torch
     torch.cuda.set_device(rank)
     import eq_b200 as E
-    O, p, cells = problem()
+    O, p, cells = problem(CASES[kase])
     if rank == 0:
         uid = E.nccl_unique_id()
         for _ in range(world - 1):
             q_id.put(uid)
     else:
         uid = q_id.get(timeout=120)
-    g = E.GpuHSL(NW, NH, device=rank, slab=(rank, world, uid), **BC)
+    g = E.GpuHSL(NW, NH, D=CASES[kase], device=rank, slab=(rank, world, uid), **BC)
+    assert g.path()["slab"] and g.path()["slab_fused"] == (kase == "fused"), g.path()
     g0, g1 = g.slab_rows()
     assert (g0, g1) == E.slab_plan(NH, world, rank)[0][:2]
     g.upload_cells(cells, NPM)
@@ -52,19 +56,20 @@ def worker(rank, world, q_id, q_out):
     g.close()
 
 
-def test_two_gpu_slab_equals_single_gpu_and_oracle():
+@pytest.mark.parametrize("kase", list(CASES))
+def test_two_gpu_slab_equals_single_gpu_and_oracle(kase):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     import eq_b200 as E
-    O, p, cells = problem()
+    O, p, cells = problem(CASES[kase])
     ctx = mp.get_context("spawn")
     q_id, q_out = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, 2, q_id, q_out)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, q_id, q_out, kase)) for r in range(2)]
     for pr in procs:
         pr.start()
-    res = sorted([q_out.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    res = sorted([q_out.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
