@@ -15,6 +15,13 @@
 
 #define BX 32
 #define BY 8
+constexpr int TN64 = 66 * 66, TN32 = 34 * 34;  // doubles per shared tile array (mg_tile.inc TN)
+// Can the deep-halo tile kernel do an n-sweep coarsest solve?  (64-node tile, halo n-1, owned region >= 8;
+// row slabs carry 6 halo rows.)
+static inline bool coarsest_tileable(const eqgpu_solver *s, int n)
+{
+    return n >= 2 && n <= MAX_CHEB && 64 - 2 * (n - 1) >= 8 && (!s->slab || n <= 7);
+}
 
 struct DirData {
     double val[4];
@@ -221,6 +228,8 @@ k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const doub
             const double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter, int book,
             double *out_rr)
 {
+    pdl_trigger();
+    pdl_wait();
     if (sc->done) return;
     const double alpha = sc->rz_new / sc->pAp;
     double v[1] = {0.0};
@@ -510,7 +519,8 @@ int solver_setup(eqgpu_solver *s)
     }
     s->levels.clear();
     s->levels.push_back(l0);
-    const int maxl = p.max_levels > 0 ? p.max_levels : 12;
+    int maxl = p.max_levels > 0 ? p.max_levels : 12;
+    if (const char *e = getenv("EQGPU_MAX_LEVELS")) maxl = std::max(1, atoi(e));   // tuning knob
     const double tau = p.dt * p.D;
     while ((int)s->levels.size() < maxl) {
         const Level &f = s->levels.back();
@@ -619,9 +629,9 @@ int solver_setup(eqgpu_solver *s)
         // <= 8; otherwise the coarsest level has to fit the single-CTA tail, else the unfused path runs
         const int cn = coarse_weights(s).n;
         s->tail_fits = used <= budget;
-        if (!(cn >= 2 && cn <= 8 && nl >= 2) && !s->tail_fits) s->fused = false;
+        if (!(coarsest_tileable(s, cn) && nl >= 2) && !s->tail_fits) s->fused = false;
         if (s->slab_fused) {  // the tail kernels see one rank's rows only: slabs need the tiled coarsest solve
-            if (cn >= 2 && cn <= 8 && nl >= 2) s->tile_coarsest = true;
+            if (coarsest_tileable(s, cn) && nl >= 2) s->tile_coarsest = true;
             else { s->slab_fused = false; s->fused = false; }
         }
         if (!s->tail_fits) { s->tail_smem = 0; s->tile_coarsest = true; }
@@ -659,21 +669,25 @@ int solver_setup(eqgpu_solver *s)
             EQ_CUDA(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tail_smem));
         const int nu = s->nu;
         if (nu > 4) { s->set_error("smooth_sweeps must be <= 4"); return EQGPU_EINVAL; }
-        const int tsm = 2 * TN * (int)sizeof(double), tsm3 = 3 * TN * (int)sizeof(double);
+        // 64-node tiles need more than the default 48 KB of dynamic shared memory (32-node tiles: 27.7 KB)
+        const int tsm = 2 * TN64 * (int)sizeof(double), tsm3 = 3 * TN64 * (int)sizeof(double);
 #define SET_SMEM(NU)                                                                                         \
     case NU:                                                                                                 \
-        EQ_CUDA(cudaFuncSetAttribute((k_presmooth<NU, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));       \
-        EQ_CUDA(cudaFuncSetAttribute((k_presmooth<NU, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));       \
-        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
-        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
-        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3)); \
-        EQ_CUDA(cudaFuncSetAttribute((k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3)); \
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_presmooth<NU, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));       \
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_presmooth<NU, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));       \
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_postsmooth<NU, true, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_postsmooth<NU, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm)); \
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_postsmooth<NU, true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3)); \
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3)); \
         break;
         for (int q = 1; q <= 4; ++q) switch (q) { SET_SMEM(1) SET_SMEM(2) SET_SMEM(3) SET_SMEM(4) }
-#define SET_C(NC) EQ_CUDA(cudaFuncSetAttribute((k_coarsest<NC, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));
-        SET_C(2) SET_C(3) SET_C(4) SET_C(5) SET_C(6) SET_C(7) SET_C(8)
-#undef SET_C
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_coarsest<4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));
         if (const char *e = getenv("EQGPU_TILE_COARSEST")) s->tile_coarsest = atoi(e) != 0 || !s->tail_fits || s->slab;
+        // Levels whose 64-node tiling gives fewer than t32_below CTAs are latency-bound (one big tile per
+        // SM, most SMs idle): they run on 32-node tiles, 256 threads, several CTAs per SM.
+        if (const char *e = getenv("EQGPU_T32_BELOW")) s->t32_below = atoi(e);
+        s->pdl = !s->slab;   // slab mode has NCCL calls between the kernels
+        if (const char *e = getenv("EQGPU_PDL")) s->pdl = atoi(e) != 0 && !s->slab;
 
 #undef SET_SMEM
     }
@@ -861,7 +875,9 @@ static CoarseW coarse_weights(eqgpu_solver *s)
     // smallest eigenvalue of D^-1 A >= (mass row sum)/(diagonal) = 1/(0.5 + 4F) on square cells
     const double lo = 0.8 / (0.5 + 4.0 * F), hi = 2.0;
     const double sigma = (hi + lo) / (hi - lo);
-    int n = (int)std::ceil(std::acosh(50.0) / std::acosh(sigma));
+    double target = 50.0;   // worst-case error reduction of the coarsest solve over [lo, hi]
+    if (const char *e = getenv("EQGPU_COARSE_TARGET")) target = std::max(2.0, atof(e));   // tuning knob
+    int n = (int)std::ceil(std::acosh(target) / std::acosh(sigma));
     n = std::max(2, std::min(n, MAX_CHEB));
     cw.n = n;
     cheb_weights(n, lo, hi, cw.w);
@@ -904,21 +920,54 @@ static inline void xch(eqgpu_solver *s, Level &lv, double *v, int depth)
     if (s->slab) slab_exchange(s, lv.dev, v, depth);
 }
 
+// Launch on `st`; with s->pdl and PDL_OK the launch carries the programmatic-serialization attribute, so
+// the kernel's prologue overlaps the tail of its predecessor (every such kernel calls pdl_wait() before it
+// touches data).  The first kernel of an iteration is launched plainly: it has no predecessor in the graph.
+#define LAUNCH_K(PDL_OK, KERN, G, B, SM, ST, ...)                                                         \
+    do {                                                                                                  \
+        cudaLaunchConfig_t cfg_{};                                                                        \
+        cfg_.gridDim = (G); cfg_.blockDim = (B); cfg_.dynamicSmemBytes = (SM); cfg_.stream = (ST);        \
+        cudaLaunchAttribute at_[1];                                                                       \
+        if (s->pdl && (PDL_OK)) {                                                                         \
+            at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                               \
+            at_[0].val.programmaticStreamSerializationAllowed = 1;                                        \
+            cfg_.attrs = at_; cfg_.numAttrs = 1;                                                          \
+        }                                                                                                 \
+        cudaLaunchKernelEx(&cfg_, KERN, __VA_ARGS__);                                                     \
+    } while (0)
+
+// Tile edge for a level: 32-node tiles (256 threads, ~28 KB) when the 64-node tiling would leave the GPU
+// mostly idle -- those levels are bound by the latency of one tile, not by bandwidth.
+static inline bool use_t32(const eqgpu_solver *s, const LevelDev &L, int to64)
+{
+    const dim3 g = tile_grid(L, to64);
+    return (int)(g.x * g.y) < s->t32_below;
+}
+
 template <int NU>
 static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
 {
     Level &lv = s->levels[l], &cv = s->levels[l + 1];
-    constexpr int TO = TS - 2 * (NU + 1);
-    const size_t tsm = 2 * TN * sizeof(double);
+    constexpr int H2 = 2 * (NU + 1);
     const SmoothW sw = smooth_weights_n(NU);
     const LevelDev &F = TV(s, lv), &Cc = TV(s, cv);
-    const dim3 g = tile_grid(F, TO);
+    const CGScalars *scc = s->sc;
+    const bool pdl_ok = l > 0;   // level 0 opens the iteration
     xch(s, lv, lv.b, NU + 1);
-    if ((int)(g.x * g.y) >= 2 * s->num_sms)
-        k_presmooth<NU, 8><<<g, 512, tsm, st>>>(F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, cv, cv.b), sw, s->sc);
-    else
-        k_presmooth<NU, 4><<<g, 1024, tsm + tsm / 2, st>>>(F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, cv, cv.b), sw,
-                                                           s->sc);
+    if (use_t32(s, F, 64 - H2)) {
+        const size_t tsm = 3 * TN32 * sizeof(double);
+        LAUNCH_K(pdl_ok, (T32::k_presmooth<NU, 4>), tile_grid(F, 32 - H2), dim3(256), tsm, st, F, Cc, VP(s, lv, lv.b),
+                 VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
+    } else {
+        const size_t tsm = 2 * TN64 * sizeof(double);
+        const dim3 g = tile_grid(F, 64 - H2);
+        if ((int)(g.x * g.y) >= 2 * s->num_sms)
+            LAUNCH_K(pdl_ok, (T64::k_presmooth<NU, 8>), g, dim3(512), tsm, st, F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t),
+                     VP(s, cv, cv.b), sw, scc);
+        else
+            LAUNCH_K(pdl_ok, (T64::k_presmooth<NU, 4>), g, dim3(1024), tsm + tsm / 2, st, F, Cc, VP(s, lv, lv.b),
+                     VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
+    }
     s->launches++;
     trace_mark(st);
 }
@@ -927,36 +976,55 @@ template <int NU>
 static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
 {
     Level &lv = s->levels[l], &cv = s->levels[l + 1];
-    constexpr int TO = TS - 2 * NU;
-    const size_t tsm = 2 * TN * sizeof(double);
     const SmoothW sw = smooth_weights_n(NU);
     const LevelDev &F = TV(s, lv), &Cc = TV(s, cv);
-    const dim3 g = tile_grid(F, TO);
-    const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
     xch(s, cv, cv.x, NU + 1);   // coarse correction rows reached by the prolongation of my halo
     xch(s, lv, lv.t, NU);       // pre-smoothed iterate; lv.b halos are still valid from the pre-smoothing exchange
     double *out_dot = s->slab ? &s->sc->part_rz : &s->sc->rz_new;
-#define POST(DOT, R, NT)                                                                                          \
-    k_postsmooth<NU, DOT, R><<<g, NT, (R == 4 ? tsm + tsm / 2 : tsm), st>>>(                                      \
-        F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, lv, lv.x), VP(s, cv, cv.x), sw, s->sc, s->partials,        \
-        s->counters + 1, out_dot)
-    if (l == 0) { if (big) POST(true, 8, 512); else POST(true, 4, 1024); }
-    else { if (big) POST(false, 8, 512); else POST(false, 4, 1024); }
+#define POST(NS, DOT, R, NT, G, SM)                                                                               \
+    LAUNCH_K(true, (NS::k_postsmooth<NU, DOT, R>), G, dim3(NT), SM, st, F, Cc, (const double *)VP(s, lv, lv.b),   \
+             (const double *)VP(s, lv, lv.t), VP(s, lv, lv.x), (const double *)VP(s, cv, cv.x), sw, s->sc,        \
+             s->partials, s->counters + 1, out_dot)
+    if (use_t32(s, F, 64 - 2 * NU)) {
+        const size_t tsm = 3 * TN32 * sizeof(double);
+        const dim3 g = tile_grid(F, 32 - 2 * NU);
+        if (l == 0) POST(T32, true, 4, 256, g, tsm); else POST(T32, false, 4, 256, g, tsm);
+    } else {
+        const size_t tsm = 2 * TN64 * sizeof(double);
+        const dim3 g = tile_grid(F, 64 - 2 * NU);
+        const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
+        if (l == 0) { if (big) POST(T64, true, 8, 512, g, tsm); else POST(T64, true, 4, 1024, g, tsm + tsm / 2); }
+        else { if (big) POST(T64, false, 8, 512, g, tsm); else POST(T64, false, 4, 1024, g, tsm + tsm / 2); }
+    }
 #undef POST
     s->launches++;
     trace_mark(st);
 }
 
-template <int NC>
+// Coarsest level: cw.n Chebyshev-Jacobi sweeps in one tile pass (halo cw.n-1).  32-node tiles while they
+// keep an owned region of >= 8 nodes and the level is small (latency-bound), else 64-node tiles.
+static inline bool coarsest_t32(const eqgpu_solver *s, const LevelDev &F, int n)
+{
+    const int to32 = 32 - 2 * (n - 1), to64 = 64 - 2 * (n - 1);
+    if (to32 < 8) return false;
+    if (to64 < 8) return true;
+    const dim3 g32 = tile_grid(F, to32);
+    return use_t32(s, F, to64) && (int)(g32.x * g32.y) <= 4 * s->num_sms;
+}
+
 static void launch_coarsest(eqgpu_solver *s, cudaStream_t st, const CoarseW &cw)
 {
     Level &lv = s->levels.back();
-    constexpr int TO = TS - 2 * (NC - 1);
-    const size_t tsm = 2 * TN * sizeof(double);
     const LevelDev &F = TV(s, lv);
-    const dim3 g = tile_grid(F, TO);
-    xch(s, lv, lv.b, NC - 1);
-    k_coarsest<NC, 4><<<g, 1024, tsm + tsm / 2, st>>>(F, VP(s, lv, lv.b), VP(s, lv, lv.x), cw, s->sc);
+    const CGScalars *scc = s->sc;
+    const int H2 = 2 * (cw.n - 1);
+    xch(s, lv, lv.b, cw.n - 1);
+    if (coarsest_t32(s, F, cw.n))
+        LAUNCH_K(true, (T32::k_coarsest<4>), tile_grid(F, 32 - H2), dim3(256), 3 * TN32 * sizeof(double), st, F,
+                 (const double *)VP(s, lv, lv.b), VP(s, lv, lv.x), cw, scc);
+    else
+        LAUNCH_K(true, (T64::k_coarsest<4>), tile_grid(F, 64 - H2), dim3(1024), 3 * TN64 * sizeof(double), st, F,
+                 (const double *)VP(s, lv, lv.b), VP(s, lv, lv.x), cw, scc);
     s->launches++;
     trace_mark(st);
 }
@@ -969,7 +1037,7 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
 {
     const int nl = (int)s->levels.size();
     const CoarseW cw = coarse_weights(s);
-    const bool tiled_coarsest = s->tile_coarsest && cw.n >= 2 && cw.n <= 8 && nl >= 2;
+    const bool tiled_coarsest = s->tile_coarsest && coarsest_tileable(s, cw.n) && nl >= 2;
     const int lt = tiled_coarsest ? nl - 1 : (s->use_cluster ? s->ctail_first : s->tail_first);
     const SmoothW sw = smooth_weights_n(s->nuc);
     for (int l = 0; l < lt; ++l) {
@@ -981,15 +1049,7 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
         }
     }
     if (tiled_coarsest) {
-        switch (cw.n) {
-        case 2: launch_coarsest<2>(s, st, cw); break;
-        case 3: launch_coarsest<3>(s, st, cw); break;
-        case 4: launch_coarsest<4>(s, st, cw); break;
-        case 5: launch_coarsest<5>(s, st, cw); break;
-        case 6: launch_coarsest<6>(s, st, cw); break;
-        case 7: launch_coarsest<7>(s, st, cw); break;
-        default: launch_coarsest<8>(s, st, cw); break;
-        }
+        launch_coarsest(s, st, cw);
     } else if (s->use_cluster) {
         const CTailDesc ctd = make_ctail_desc(s, lt, s->ctail_ncta);
         cudaLaunchConfig_t cfg{};
@@ -1053,14 +1113,16 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
         slab_exchange(s, Ll, s->z, 1);
         slab_exchange(s, Ll, s->pv, 1);
     }
-    const dim3 tg = tile_grid(L, TS - 2);
-    k_apply_p<<<tg, 256, 0, st>>>(L, VP(s, l0, s->z), VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc,
-                                  s->partials, s->counters + 2, sl ? &sc->part_pAp : &sc->pAp);
+    const dim3 tg = tile_grid(L, 64 - 2);
+    LAUNCH_K(!sl, T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
+             (const double *)VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc, s->partials, s->counters + 2,
+             sl ? &sc->part_pAp : &sc->pAp);
     trace_mark(st);
     std::swap(s->pv, s->pv2);
     if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
-    k_update_xr<<<nb1, 256, 0, st>>>(on, s->u + ooff, s->r + ooff, s->pv + ooff, s->Ap + ooff, sc, s->partials,
-                                     s->counters + 3, sl ? 0 : 1, sl ? &sc->part_rr : &sc->rr);
+    LAUNCH_K(!sl, k_update_xr, dim3(nb1), dim3(256), 0, st, on, s->u + ooff, s->r + ooff,
+             (const double *)(s->pv + ooff), (const double *)(s->Ap + ooff), sc, s->partials, s->counters + 3,
+             sl ? 0 : 1, sl ? &sc->part_rr : &sc->rr);
     trace_mark(st);
     if (sl) {
         slab_allreduce(s, &sc->part_rr, &sc->rr, 1);
@@ -1257,23 +1319,23 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
                                              &s->sc->rr);
             *alg_bytes = 48.0 * s->N;
         } else if (nm == "apply_p") {  // read z,p write p',Ap: 32 B/DOF
-            const dim3 tg((L.nx + TS - 3) / (TS - 2), (L.ny + TS - 3) / (TS - 2));
-            k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2, &s->sc->pAp);
+            const dim3 tg((L.nx + 61) / 62, (L.ny + 61) / 62);
+            T64::k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2, &s->sc->pAp);
             *alg_bytes = 32.0 * s->N;
         } else if (nm == "presmooth" || nm == "postsmooth") {
             if (!s->fused || (s->use_cluster ? s->ctail_first : s->tail_first) == 0 || s->nu != 3) return false;
             Level &cv = s->levels[1];
-            const size_t tsm = 2 * TN * sizeof(double);
+            const size_t tsm = 2 * TN64 * sizeof(double);
             const SmoothW sw = smooth_weights(s);
             if (nm == "presmooth") {  // read b, write x and b_coarse: 16 + 2 B/DOF
-                const int to = TS - 8;
+                const int to = 64 - 8;
                 const dim3 tg((L.nx + to - 1) / to, (L.ny + to - 1) / to);
-                k_presmooth<3, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, cv.b, sw, s->sc);
+                T64::k_presmooth<3, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, cv.b, sw, s->sc);
                 *alg_bytes = 18.0 * s->N;
             } else {  // read x, b, x_coarse, write x: 24 + 2 B/DOF
-                const int to = TS - 6;
+                const int to = 64 - 6;
                 const dim3 tg((L.nx + to - 1) / to, (L.ny + to - 1) / to);
-                k_postsmooth<3, true, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, s->z, cv.x, sw, s->sc,
+                T64::k_postsmooth<3, true, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, s->z, cv.x, sw, s->sc,
                                                                     s->partials, s->counters + 1, &s->sc->rz_new);
                 *alg_bytes = 26.0 * s->N;
             }
