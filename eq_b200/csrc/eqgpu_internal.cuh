@@ -81,6 +81,7 @@ struct eqgpu_solver {
     bool fused = true;
     bool tail_fits = true;         // the deepest levels fit one CTA's shared memory (k_tail / k_ctail usable)
     bool tile_coarsest = true;     // coarsest level solved by the deep-halo tile kernel instead of a tail kernel
+    bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration
     int t32_below = 148;           // levels with fewer 64-node tiles than this run on 32-node tiles
     // row-slab mode (eqgpu_create_slab): this rank owns rows [levels[l].g0, levels[l].g1) of every level
@@ -164,16 +165,6 @@ int boundary_functional(eqgpu_solver *s);
 // Both are no-ops for ordinary launches.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// Asynchronous global -> shared copies (LDGSTS): a persistent tile kernel stages the inputs of its next
-// tile while it sweeps the current one.  8-byte granularity, because tile origins are odd node offsets.
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ bool is_dirichlet(const LevelDev &L, int i, int j)
 {

@@ -168,6 +168,100 @@ k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict_
     }
 }
 
+// Tile version of k_init for the isotropic operator on one GPU: u0 goes through a shared 64x64 tile
+// (1-node halo, 62x62 owned), so that the consistent-mass row and the operator row -- both 7-point sums
+// over the same neighbourhood -- cost one global load per node instead of fourteen.  Tiles that touch the
+// irregular frame (wall rows/columns, their Dirichlet-adjacent neighbours, the narrower last cell) take
+// the general per-node path of k_init.
+__global__ void __launch_bounds__(256)
+k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict__ rA,
+            double *__restrict__ rB, double rs_l, double rs_r, double *partials, unsigned *counter,
+            double *out_rr0, double *out_b2)
+{
+    constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = 16;
+    __shared__ double sp[TPI * TPI];
+    const int ox = blockIdx.x * TOI - 1, oy = blockIdx.y * TOI - 1;
+    const int lx = threadIdx.x & (TSI - 1), ly0 = (threadIdx.x >> 6) * TROWS;
+    const int gj = ox + lx;
+    // owned nodes [ox+1, ox+62] x [oy+1, oy+62] all regular and at least two nodes away from every wall
+    const bool deep = ox + 1 >= 2 && ox + TOI <= min(L.jreg_hi, L.nx - 3) && oy + 1 >= 2 &&
+                      oy + TOI <= min(L.ireg_hi, L.ny - 3);
+    double v[2] = {0.0, 0.0};
+    if (deep) {
+        {
+            double vu[TROWS];
+            const double *q = u + (size_t)(oy + ly0) * L.nx + gj;
+#pragma unroll
+            for (int k = 0; k < TROWS; ++k) vu[k] = __ldg(q + (size_t)k * L.nx);
+#pragma unroll
+            for (int k = 0; k < TROWS; ++k) sp[(ly0 + k + 1) * TPI + lx + 1] = vu[k];
+        }
+        __syncthreads();
+        if (lx >= 1 && lx < TSI - 1) {
+            const double cC = L.cC, cEW = L.cEW, cNS = L.cNS, cD = L.cD, m = L.cD;   // mass row: 6m centre, m else
+            int c = (ly0 + 1) * TPI + lx + 1;
+            double sw = 0.0, s0 = 0.0, ww = 0.0, cc = 0.0, ee = 0.0;
+            if (ly0 > 0) { sw = sp[c - TPI - 1]; s0 = sp[c - TPI]; }
+            ww = sp[c - 1]; cc = sp[c]; ee = sp[c + 1];
+#pragma unroll
+            for (int k = 0; k < TROWS; ++k, c += TPI) {
+                const int ly = ly0 + k;
+                double nw = 0.0, nc = 0.0, ne = 0.0;
+                if (ly < TSI - 1) { nw = sp[c + TPI - 1]; nc = sp[c + TPI]; ne = sp[c + TPI + 1]; }
+                if (ly >= 1 && ly < TSI - 1) {
+                    const double h6 = (ee + ww) + (nc + s0) + (ne + sw);
+                    const double b = m * (6.0 * cc + h6);
+                    const double ax = cC * cc + cEW * (ee + ww) + cNS * (nc + s0) + cD * (ne + sw);
+                    const double resA = b - ax;
+                    const size_t g = (size_t)(oy + ly) * L.nx + gj;
+                    rA[g] = resA;
+                    rB[g] = b;
+                    v[0] += resA * resA;
+                    v[1] += b * b;
+                }
+                sw = ww; s0 = cc; ww = nw; cc = nc; ee = ne;
+            }
+        }
+    } else if (lx >= 1 && lx < TSI - 1 && gj < L.nx) {
+        for (int k = 0; k < TROWS; ++k) {
+            const int ly = ly0 + k, i = oy + ly, j = gj;
+            if (ly < 1 || ly >= TSI - 1 || i >= L.ny) continue;
+            const size_t g = (size_t)i * L.nx + j;
+            double resA = 0.0, resB = 0.0;
+            if (!is_dirichlet(L, i, j)) {
+                const double b = load_row(L, i, j, u, rs_l, rs_r);
+                double c[NBAND];
+                stencil_iso(L, i, j, c);
+                const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
+                double ax = c[B_C] * __ldg(u + g), ag = 0.0;
+                auto acc = [&](int ii, int jj, double ck) {
+                    if (is_dirichlet(L, ii, jj)) {
+                        const double t = ck * dir_value(L, dd, ii, jj);
+                        ax += t; ag += t;
+                    } else ax += ck * __ldg(u + (size_t)ii * L.nx + jj);
+                };
+                if (hasE) acc(i, j + 1, c[B_E]);
+                if (hasW) acc(i, j - 1, c[B_W]);
+                if (hasN) acc(i + 1, j, c[B_N]);
+                if (hasS) acc(i - 1, j, c[B_S]);
+                if (hasN && hasE) acc(i + 1, j + 1, c[B_NE]);
+                if (hasS && hasW) acc(i - 1, j - 1, c[B_SW]);
+                resA = b - ax;
+                resB = b - ag;
+                v[0] += resA * resA;
+                v[1] += resB * resB;
+            }
+            rA[g] = resA;
+            rB[g] = resB;
+        }
+    }
+    double tot[2];
+    if (grid_reduce<2>(v, partials, counter, tot)) {
+        *out_rr0 = tot[0];
+        *out_b2 = tot[1];
+    }
+}
+
 // Pick the starting guess, impose u_d = g_d, set up the PCG scalars.
 __global__ void __launch_bounds__(BX *BY)
 k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
@@ -686,6 +780,7 @@ int solver_setup(eqgpu_solver *s)
         // Levels whose 64-node tiling gives fewer than t32_below CTAs are latency-bound (one big tile per
         // SM, most SMs idle): they run on 32-node tiles, 256 threads, several CTAs per SM.
         if (const char *e = getenv("EQGPU_T32_BELOW")) s->t32_below = atoi(e);
+        if (const char *e = getenv("EQGPU_INIT_TILE")) s->init_tile = atoi(e) != 0;
         s->pdl = !s->slab;   // slab mode has NCCL calls between the kernels
         if (const char *e = getenv("EQGPU_PDL")) s->pdl = atoi(e) != 0 && !s->slab;
 
@@ -1182,8 +1277,13 @@ static int pcg(eqgpu_solver *s)
     if (s->slab) slab_exchange(s, L, s->u);
     CGScalars *sc = s->sc;
     const bool sl = s->slab;
-    k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
-                                  sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
+    if (!T && !sl && s->init_tile) {
+        const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
+        k_init_tile<<<gi, 256, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, s->partials, s->counters + 0, &sc->rr0,
+                                        &sc->bnorm2);
+    } else
+        k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
+                                      sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
     if (sl) {  // rank-sum the two start residuals
         slab_allreduce(s, &sc->part_rr0, &sc->rr0, 1);
         slab_allreduce(s, &sc->part_b2, &sc->bnorm2, 1);
