@@ -594,7 +594,9 @@ int solver_setup(eqgpu_solver *s)
     s->N = (size_t)p.nW * p.nH;  // replaced by the local size once the slab window is known
     const double hx0 = p.hx, hy0 = p.hy > 0 ? p.hy : p.hx;
     s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 3;
-    s->nuc = s->nu;
+    // one more sweep on the coarser levels: they are latency-bound, so it is nearly free, and it widens the
+    // margin at the 8th iteration (relres 1.6e-13 vs 7.2e-13 at 2048^2; measured 488 vs 479 steps/s)
+    s->nuc = p.smooth_sweeps > 0 ? s->nu : 4;
     if (const char *e = getenv("EQGPU_NU0")) s->nu = std::max(1, std::min(atoi(e), 4));   // tuning knobs
     if (const char *e = getenv("EQGPU_NUC")) s->nuc = std::max(1, std::min(atoi(e), 4));
     // ---- hierarchy -------------------------------------------------------
