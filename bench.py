@@ -36,6 +36,16 @@ WORKLOAD = ("configs[2]: synthetic 2048x2048-node trap mesh (h=0.5, dt=0.1, D=12
             "20k rod cells secreting/sampling, one HSL layer per GPU")
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a level-0 kernel from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by profiles/ncu_summary.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return float(json.load(f)["kernels"][kernel]["dram_bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -184,7 +194,7 @@ def run_slab(args, rank, local_rank, world):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"configs[4] style: {nW}x{nH} mesh in {world} row slabs of 2048 rows, {len(cells)} rods, "
-                                   "one-row NCCL halo exchange + CG all-reduce (unfused kernels)",
+                                   "fused tile kernels with 6-row NCCL halo exchange + CG all-reduce",
                        "pcg_iterations": int(g.stats().iterations), "relres": g.stats().relres,
                        "mg_levels": int(g.stats().levels), "dof_updates_per_sec": N * args.steps / (ms / 1e3)},
             "gpu_launches": int(g.stats().kernel_launches - l0)}), flush=True)
@@ -339,7 +349,7 @@ def main():
         peak, peak_src = peaks()
         # dominant kernel, timed alone with CUDA events on the launching stream
         roof = {}
-        for name in ("presmooth", "postsmooth", "apply_p", "update_xr"):
+        for name in ("presmooth", "postsmooth", "apply_p", "update_r", "update_xr"):
             try:
                 kms, kbytes = g.bench_kernel(name, 50)
             except E.EqGpuError:
@@ -366,7 +376,11 @@ def main():
                            "path": "eqgpu_step_host: fenicsInterface::stepDiffusion contract, full solution_vector in/out"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": f"k_{dom} (level 0, 2048^2)", "achieved": roof[dom]["gbs"],
-                         "peak": peak, "unit": "GB/s", "frac": roof[dom]["gbs"] / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": roof[dom]["gbs"] / peak,
+                         "traffic": ncu_traffic(dom) if (NW, NH) == (2048, 2048) else None,
+                         "traffic_note": "bytes/launch, dram__bytes_read.sum + dram__bytes_write.sum from the ncu "
+                                         "--set full capture in profiles/ (below the algorithmic bytes where "
+                                         "freshly written vectors are still in the 126 MB L2)",
                          "peak_source": peak_src, "kernels": roof,
                          "step_ideal_frac": (16.0 * N / (ms_step * 1e-3) / 1e9) / peak},
         }

@@ -50,6 +50,10 @@ struct CGScalars {
     // global value into the field above (idempotent when replayed after convergence)
     double part_rz, part_pAp, part_rr, part_b2, part_rr0;
     int iters, done, max_iters, pad;
+    // deferred x update (single-GPU fused path): k_update_r leaves the step length and the iteration number
+    // here, k_update_x applies x += alpha_x * p later, off the critical path; x_applied == x_stamp: nothing pending
+    double alpha_x;
+    int x_stamp, x_applied;
 };
 
 struct Level {
@@ -81,6 +85,10 @@ struct eqgpu_solver {
     bool fused = true;
     bool tail_fits = true;         // the deepest levels fit one CTA's shared memory (k_tail / k_ctail usable)
     bool tile_coarsest = true;     // coarsest level solved by the deep-halo tile kernel instead of a tail kernel
+    bool defer_x = false;          // x += alpha p runs beside the coarse levels of the next iteration (k_update_x)
+    cudaStream_t side_stream = nullptr;
+    bool x_forked = false;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration
     int t32_below = 148;           // levels with fewer 64-node tiles than this run on 32-node tiles

@@ -287,6 +287,8 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
         sc->done = (rr <= stop2) ? 1 : 0;
         sc->rz_old = 1.0;
         sc->rz_new = 0.0;
+        sc->x_stamp = 0;
+        sc->x_applied = 0;
     }
 }
 
@@ -375,6 +377,87 @@ k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const doub
     }
 }
 
+// Split form of k_update_xr for the single-GPU fused path.  Only r is on the critical path of the next
+// iteration (the V-cycle smooths r), so k_update_r updates r alone (24 B/DOF) and leaves the step length for
+// k_update_x, which adds alpha*p to x while the next iteration works through its latency-bound coarse
+// levels -- that window leaves most of the HBM bandwidth idle.
+__global__ void __launch_bounds__(256)
+k_update_r(size_t n, double *__restrict__ r, const double *__restrict__ Ap, CGScalars *sc, double *partials,
+           unsigned *counter)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (sc->done) return;
+    const double alpha = sc->rz_new / sc->pAp;
+    double v[1] = {0.0};
+    const size_t n2 = n >> 1, stride = (size_t)gridDim.x * blockDim.x;
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *A2 = reinterpret_cast<const double2 *>(Ap);
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + stride < n2; g += 2 * stride) {
+        const size_t h = g + stride;
+        double2 ra = r2[g], rb = r2[h];
+        const double2 aa = __ldg(A2 + g), ab = __ldg(A2 + h);
+        ra.x -= alpha * aa.x; ra.y -= alpha * aa.y; rb.x -= alpha * ab.x; rb.y -= alpha * ab.y;
+        r2[g] = ra; r2[h] = rb;
+        v[0] += ra.x * ra.x + ra.y * ra.y + rb.x * rb.x + rb.y * rb.y;
+    }
+    for (; g < n2; g += stride) {
+        double2 ra = r2[g];
+        const double2 aa = __ldg(A2 + g);
+        ra.x -= alpha * aa.x; ra.y -= alpha * aa.y;
+        r2[g] = ra;
+        v[0] += ra.x * ra.x + ra.y * ra.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t t = n - 1;
+        const double rn = r[t] - alpha * Ap[t];
+        r[t] = rn;
+        v[0] += rn * rn;
+    }
+    double tot[1];
+    if (grid_reduce<1>(v, partials, counter, tot)) {
+        sc->rr = tot[0];
+        sc->rz_old = sc->rz_new;
+        sc->iters += 1;
+        sc->alpha_x = alpha;
+        sc->x_stamp = sc->iters;
+        if (tot[0] <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
+    }
+}
+
+// x += alpha_x * p for the pending iteration, p being the search direction of that iteration: odd iterations
+// leave it in p_odd, even ones in p_even (the p ping-pong).  Does nothing when no update is pending; the
+// pending mark is cleared by the next kernel on the main path (k_apply_p or k_mark_x), after this one completed.
+__global__ void __launch_bounds__(256)
+k_update_x(size_t n, double *__restrict__ x, const double *__restrict__ p_odd, const double *__restrict__ p_even,
+           const CGScalars *sc)
+{
+    if (sc->x_applied == sc->x_stamp) return;
+    const double alpha = sc->alpha_x;
+    const double *p = (sc->x_stamp & 1) ? p_odd : p_even;
+    const size_t n2 = n >> 1, stride = (size_t)gridDim.x * blockDim.x;
+    double2 *x2 = reinterpret_cast<double2 *>(x);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + stride < n2; g += 2 * stride) {
+        const size_t h = g + stride;
+        double2 xa = x2[g], xb = x2[h];
+        const double2 pa = __ldg(p2 + g), pb = __ldg(p2 + h);
+        xa.x += alpha * pa.x; xa.y += alpha * pa.y; xb.x += alpha * pb.x; xb.y += alpha * pb.y;
+        x2[g] = xa; x2[h] = xb;
+    }
+    for (; g < n2; g += stride) {
+        double2 xa = x2[g];
+        const double2 pa = __ldg(p2 + g);
+        xa.x += alpha * pa.x; xa.y += alpha * pa.y;
+        x2[g] = xa;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) x[n - 1] += alpha * p[n - 1];
+}
+
+__global__ void k_mark_x(CGScalars *sc) { sc->x_applied = sc->x_stamp; }
+
 // iteration bookkeeping when ||r||^2 had to be summed over ranks first (slab mode)
 __global__ void k_book(CGScalars *sc)
 {
@@ -396,6 +479,8 @@ __global__ void k_cg_setup(CGScalars *sc, double rtol, int max_iters)
     sc->done = (rr <= sc->stop2) ? 1 : 0;
     sc->rz_old = 1.0;
     sc->rz_new = 0.0;
+    sc->x_stamp = 0;
+    sc->x_applied = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -783,6 +868,13 @@ int solver_setup(eqgpu_solver *s)
         // SM, most SMs idle): they run on 32-node tiles, 256 threads, several CTAs per SM.
         if (const char *e = getenv("EQGPU_T32_BELOW")) s->t32_below = atoi(e);
         if (const char *e = getenv("EQGPU_INIT_TILE")) s->init_tile = atoi(e) != 0;
+        s->defer_x = !s->slab;
+        if (const char *e = getenv("EQGPU_DEFER_X")) s->defer_x = atoi(e) != 0 && !s->slab;
+        if (s->defer_x) {
+            EQ_CUDA(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+            EQ_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            EQ_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        }
         s->pdl = !s->slab;   // slab mode has NCCL calls between the kernels
         if (const char *e = getenv("EQGPU_PDL")) s->pdl = atoi(e) != 0 && !s->slab;
 
@@ -803,6 +895,9 @@ void solver_teardown(eqgpu_solver *s)
     s->levels.clear();
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->graph_exec2) { cudaGraphExecDestroy(s->graph_exec2); s->graph_exec2 = nullptr; }
+    if (s->ev_fork) { cudaEventDestroy(s->ev_fork); s->ev_fork = nullptr; }
+    if (s->ev_join) { cudaEventDestroy(s->ev_join); s->ev_join = nullptr; }
+    if (s->side_stream) { cudaStreamDestroy(s->side_stream); s->side_stream = nullptr; }
     cudaFree(s->d_levels); cudaFree(s->pv2);
     cudaFree(s->u); cudaFree(s->r); cudaFree(s->pv); cudaFree(s->Ap); cudaFree(s->z);
     cudaFree(s->d11); cudaFree(s->d22); cudaFree(s->d12);
@@ -1144,6 +1239,18 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
         case 3: launch_pre<3>(s, st, l); break;
         default: launch_pre<4>(s, st, l); break;
         }
+        if (l == 0 && s->defer_x) {
+            // side branch: the previous iteration's x += alpha p, beside the latency-bound coarse levels
+            // (its p is this iteration's input direction s->pv, whatever the parity); joined before k_apply_p
+            const Level &l0 = s->levels[0];
+            const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+            cudaEventRecord(s->ev_fork, st);
+            cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
+            k_update_x<<<nb1, 256, 0, s->side_stream>>>(l0.n(), s->u, s->pv, s->pv, s->sc);
+            cudaEventRecord(s->ev_join, s->side_stream);
+            s->x_forked = true;
+            s->launches++;
+        }
     }
     if (tiled_coarsest) {
         launch_coarsest(s, st, cw);
@@ -1199,6 +1306,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     const bool sl = s->slab;
     const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
     const size_t ooff = (size_t)Ll.own0 * Ll.nx, on = (size_t)(Ll.own1 - Ll.own0) * Ll.nx;
+    s->x_forked = false;
     vcycle_fused(s, st);
     if (s->levels.size() < 2 || (!s->tile_coarsest && (s->use_cluster ? s->ctail_first : s->tail_first) == 0)) {
         k_dot<<<nb1, 256, 0, st>>>(on, s->r + ooff, s->z + ooff, sc, s->partials, s->counters + 1,
@@ -1211,15 +1319,26 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
         slab_exchange(s, Ll, s->pv, 1);
     }
     const dim3 tg = tile_grid(L, 64 - 2);
-    LAUNCH_K(!sl, T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
+    if (s->defer_x) {
+        if (s->x_forked) cudaStreamWaitEvent(st, s->ev_join, 0);
+        else {   // no tiled level ran (tiny grid): nothing to hide behind, update x in line
+            k_update_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, s->pv, s->pv, sc);
+            s->launches++;
+        }
+    }
+    LAUNCH_K(!sl && !s->defer_x, T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
              (const double *)VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc, s->partials, s->counters + 2,
              sl ? &sc->part_pAp : &sc->pAp);
     trace_mark(st);
     std::swap(s->pv, s->pv2);
     if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
-    LAUNCH_K(!sl, k_update_xr, dim3(nb1), dim3(256), 0, st, on, s->u + ooff, s->r + ooff,
-             (const double *)(s->pv + ooff), (const double *)(s->Ap + ooff), sc, s->partials, s->counters + 3,
-             sl ? 0 : 1, sl ? &sc->part_rr : &sc->rr);
+    if (s->defer_x)
+        LAUNCH_K(true, k_update_r, dim3(nb1), dim3(256), 0, st, on, s->r + ooff, (const double *)(s->Ap + ooff), sc,
+                 s->partials, s->counters + 3);
+    else
+        LAUNCH_K(!sl, k_update_xr, dim3(nb1), dim3(256), 0, st, on, s->u + ooff, s->r + ooff,
+                 (const double *)(s->pv + ooff), (const double *)(s->Ap + ooff), sc, s->partials, s->counters + 3,
+                 sl ? 0 : 1, sl ? &sc->part_rr : &sc->rr);
     trace_mark(st);
     if (sl) {
         slab_allreduce(s, &sc->part_rr, &sc->rr, 1);
@@ -1295,6 +1414,8 @@ static int pcg(eqgpu_solver *s)
 
     int issued = 0;
     int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
+    s->graph_phase = 0;   // odd iterations leave their search direction in pv2, even ones in pv (k_update_x flush)
+    double *const p_odd = s->pv2, *const p_even = s->pv;
     if (fused && !s->slab && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
         std::vector<cudaEvent_t> ev;
         g_trace = &ev;
@@ -1343,6 +1464,11 @@ static int pcg(eqgpu_solver *s)
         EQ_CUDA(cudaStreamSynchronize(st));
         if (s->sc_host->done || issued >= max_iters) break;
         chunk = 1;
+    }
+    if (fused && s->defer_x && s->sc_host->x_applied != s->sc_host->x_stamp) {  // the last iteration's x update
+        k_update_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc);
+        k_mark_x<<<1, 1, 0, st>>>(sc);
+        s->launches += 2;
     }
     s->st.iterations = s->sc_host->iters;
     const double ref = s->sc_host->bnorm2;
@@ -1420,6 +1546,10 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
             k_update_xr<<<nb1, 256, 0, st>>>(s->N, l0.t, s->z, s->pv, s->Ap, s->sc, s->partials, s->counters + 3, 1,
                                              &s->sc->rr);
             *alg_bytes = 48.0 * s->N;
+        } else if (nm == "update_r") {  // read r,Ap write r: 24 B/DOF (split update, r on the critical path)
+            const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+            k_update_r<<<nb1, 256, 0, st>>>(s->N, s->z, s->Ap, s->sc, s->partials, s->counters + 3);
+            *alg_bytes = 24.0 * s->N;
         } else if (nm == "apply_p") {  // read z,p write p',Ap: 32 B/DOF
             const dim3 tg((L.nx + 61) / 62, (L.ny + 61) / 62);
             T64::k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2, &s->sc->pAp);

@@ -55,7 +55,44 @@ def sass(path):
     print("stall samples:", ", ".join(f"{k[6:]} {v / ts * 100:.0f}%" for k, v in st.most_common(8)))
 
 
+def traffic(path, out_json):
+    """Write {kernels: {presmooth|postsmooth|apply_p|update_xr: {dram_bytes, time_us, grid}}} for the level-0
+    launches (largest grid of each kernel) of a capture; bench.py reads it for roofline.traffic."""
+    import json
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def num(v, unit):
+        x = float(v.replace(',', ''))
+        return x * {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'byte': 1.0, 'us': 1.0, 'ms': 1e3, 'ns': 1e-3}.get(unit, 1.0)
+
+    best = {}
+    for r in rows[2:]:
+        name = r[col['Kernel Name']]
+        key = next((k for k in ('presmooth', 'postsmooth', 'apply_p', 'update_xr') if 'k_' + k in name), None)
+        if not key:
+            continue
+        g = r[col['Grid Size']]
+        gsz = 1
+        for t in g.strip('()').split(','):
+            gsz *= int(t)
+        rd, wr = col['dram__bytes_read.sum'], col['dram__bytes_write.sum']
+        rec = {'dram_bytes': num(r[rd], units[rd]) + num(r[wr], units[wr]),
+               'dram_read': num(r[rd], units[rd]), 'dram_write': num(r[wr], units[wr]),
+               'time_us': num(r[col['gpu__time_duration.sum']], units[col['gpu__time_duration.sum']]),
+               'grid': g, 'kernel': name.split('(')[0]}
+        if key not in best or gsz > best[key][0]:
+            best[key] = (gsz, rec)
+    json.dump({'source': path, 'kernels': {k: v[1] for k, v in best.items()}}, open(out_json, 'w'), indent=1)
+    print(json.dumps({k: v[1] for k, v in best.items()}, indent=1))
+
+
 if __name__ == "__main__":
-    raw(sys.argv[1])
-    if len(sys.argv) > 2:
-        sass(sys.argv[1])
+    if len(sys.argv) > 3 and sys.argv[2] == '--traffic':
+        traffic(sys.argv[1], sys.argv[3])
+    else:
+        raw(sys.argv[1])
+        if len(sys.argv) > 2:
+            sass(sys.argv[1])
