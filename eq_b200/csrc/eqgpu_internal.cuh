@@ -88,6 +88,8 @@ struct eqgpu_solver {
     bool defer_x = false;          // x += alpha p runs beside the coarse levels of the next iteration (k_update_x)
     cudaStream_t side_stream = nullptr;
     bool x_forked = false;
+    int xupd_blocks = 296;         // CTAs of the deferred k_update_x (few: it runs beside the coarse levels)
+    bool join_pdl = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration

@@ -871,7 +871,13 @@ int solver_setup(eqgpu_solver *s)
         s->defer_x = !s->slab;
         if (const char *e = getenv("EQGPU_DEFER_X")) s->defer_x = atoi(e) != 0 && !s->slab;
         if (s->defer_x) {
-            EQ_CUDA(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+            int prio_lo = 0, prio_hi = 0;   // lowest priority: the critical path's CTAs are scheduled first
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            EQ_CUDA(cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, prio_lo));
+            s->xupd_blocks = std::max(1, s->num_sms / 2);   // measured: 74 CTAs 522 steps/s, 148: 518, 296: 512, 592: 511
+            if (const char *e = getenv("EQGPU_XUPD_BLOCKS")) s->xupd_blocks = std::max(1, atoi(e));
+            s->join_pdl = true;   // k_apply_p keeps its programmatic edge from k_postsmooth beside the full edge from k_update_x
+            if (const char *e = getenv("EQGPU_JOIN_PDL")) s->join_pdl = atoi(e) != 0;
             EQ_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
             EQ_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
         }
@@ -1243,10 +1249,10 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
             // side branch: the previous iteration's x += alpha p, beside the latency-bound coarse levels
             // (its p is this iteration's input direction s->pv, whatever the parity); joined before k_apply_p
             const Level &l0 = s->levels[0];
-            const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
+            // few CTAs: it must not crowd the coarse-level kernels out of the SMs, and has ~70 us to finish
             cudaEventRecord(s->ev_fork, st);
             cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
-            k_update_x<<<nb1, 256, 0, s->side_stream>>>(l0.n(), s->u, s->pv, s->pv, s->sc);
+            k_update_x<<<s->xupd_blocks, 256, 0, s->side_stream>>>(l0.n(), s->u, s->pv, s->pv, s->sc);
             cudaEventRecord(s->ev_join, s->side_stream);
             s->x_forked = true;
             s->launches++;
@@ -1326,7 +1332,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
             s->launches++;
         }
     }
-    LAUNCH_K(!sl && !s->defer_x, T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
+    LAUNCH_K(!sl && (!s->defer_x || s->join_pdl), T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
              (const double *)VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc, s->partials, s->counters + 2,
              sl ? &sc->part_pAp : &sc->pAp);
     trace_mark(st);
