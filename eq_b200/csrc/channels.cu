@@ -218,7 +218,8 @@ int channels_step(eqgpu_solver *s)
     return 0;
 }
 
-int boundary_functional(eqgpu_solver *s)
+// Functional kernel + copy of the scalar to pinned memory, stream-ordered, no host synchronisation.
+int boundary_functional_enqueue(eqgpu_solver *s)
 {
     const eqgpu_params &p = s->p;
     const double hy = p.hy > 0 ? p.hy : p.hx;
@@ -231,8 +232,17 @@ int boundary_functional(eqgpu_solver *s)
         if (rc) return rc;
     }
     EQ_CUDA(cudaMemcpyAsync(s->flux_host, s->flux_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+// After the stream has been synchronised: src/fHSL.cpp:160
+void boundary_functional_finish(eqgpu_solver *s) { s->st.total_boundary_flux = s->p.D * s->p.dt * (*s->flux_host); }
+
+int boundary_functional(eqgpu_solver *s)
+{
+    int rc = boundary_functional_enqueue(s);
+    if (rc) return rc;
     EQ_CUDA(cudaStreamSynchronize(s->stream));
-    // src/fHSL.cpp:160
-    s->st.total_boundary_flux = p.D * p.dt * (*s->flux_host);
+    boundary_functional_finish(s);
     return 0;
 }

@@ -88,6 +88,7 @@ struct eqgpu_solver {
     bool defer_x = false;          // x += alpha p runs beside the coarse levels of the next iteration (k_update_x)
     cudaStream_t side_stream = nullptr;
     bool x_forked = false;
+    bool functional_enqueued = false;  // pcg() already ran the flux functional in its speculative step tail
     int xupd_blocks = 296;         // CTAs of the deferred k_update_x (few: it runs beside the coarse levels)
     bool join_pdl = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -164,6 +165,8 @@ int cells_scatter(eqgpu_solver *s, const double *d_amount);
 int channels_setup(eqgpu_solver *s);
 int channels_step(eqgpu_solver *s);
 int boundary_functional(eqgpu_solver *s);
+int boundary_functional_enqueue(eqgpu_solver *s);   // kernel + scalar copy, no host sync
+void boundary_functional_finish(eqgpu_solver *s);   // after the stream was synchronised
 
 #ifdef __CUDACC__
 // --------------------------------------------------------------------------

@@ -1467,14 +1467,25 @@ static int pcg(eqgpu_solver *s)
             }
         }
         EQ_CUDA(cudaMemcpyAsync(s->sc_host, s->sc, sizeof(CGScalars), cudaMemcpyDeviceToHost, st));
+        // Speculative step tail, so that a converged step costs one host round trip instead of two: flush
+        // the pending x update (the kernel checks the stamp on the device) and run the boundary-flux
+        // functional before the host knows whether this was the last iteration.  If it was not, the loop
+        // goes on (the in-graph k_update_x then finds nothing pending) and the tail is redone.  Not with
+        // channels: their sub-steps advance state and must see the converged field only.
+        const bool spec = fused && s->defer_x && !s->p.channels;
+        if (fused && s->defer_x) {
+            k_update_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc);
+            k_mark_x<<<1, 1, 0, st>>>(sc);
+            s->launches += 2;
+        }
+        if (spec) {
+            int rc = boundary_functional_enqueue(s);
+            if (rc) return rc;
+        }
         EQ_CUDA(cudaStreamSynchronize(st));
+        s->functional_enqueued = spec;
         if (s->sc_host->done || issued >= max_iters) break;
         chunk = 1;
-    }
-    if (fused && s->defer_x && s->sc_host->x_applied != s->sc_host->x_stamp) {  // the last iteration's x update
-        k_update_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc);
-        k_mark_x<<<1, 1, 0, st>>>(sc);
-        s->launches += 2;
     }
     s->st.iterations = s->sc_host->iters;
     const double ref = s->sc_host->bnorm2;
@@ -1497,8 +1508,12 @@ int solver_step(eqgpu_solver *s)
         rc = channels_step(s);
         if (rc) return rc;
     }
-    rc = boundary_functional(s);
-    if (rc) return rc;
+    if (s->functional_enqueued && !s->p.channels) boundary_functional_finish(s);   // already computed in pcg()'s tail
+    else {
+        rc = boundary_functional(s);
+        if (rc) return rc;
+    }
+    s->functional_enqueued = false;
     s->st.steps++;
     s->st.kernel_launches = s->launches;
     return 0;
