@@ -268,10 +268,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    it_hist = []
+
     def step_resident():
         g.gather_resident()
         g.scatter_resident()
         g.step()
+        it_hist.append(g.stats().iterations)   # host-side read of the last step's count (the step has synchronised)
 
     # pinned host buffers for the end-to-end legs
     rec_pin = torch.from_numpy(cells.copy()).pin_memory()
@@ -318,6 +321,7 @@ def main():
     ms = timed(step_resident, args.steps)
     launches = g.stats().kernel_launches - l0
     iters = g.stats().iterations
+    iters_mean = float(np.mean(it_hist[-args.steps:]))
     relres = g.stats().relres
     clocks = sampler.stop()
     ms_step = ms / args.steps
@@ -326,13 +330,16 @@ def main():
     for _ in range(3):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
-    # compat leg: every step starts from the same host field (steady field + this step's deposits)
-    g.gather_resident(); g.scatter_resident()
-    fld_src = torch.from_numpy(g.get_field())
+    # compat leg: the run goes on, but the field now lives on the host as in the reference: each step the host
+    # adds the deposits to solution_vector (writeHSL on the CPU, outside the timed region) and hands it in;
+    # the solution comes back in the same buffer.  (Restarting every step from one fixed field would let the
+    # warm start return the previous, identical answer in zero iterations.)
+    fld_pin.copy_(torch.from_numpy(g.get_field()))
+    dep_t = torch.from_numpy(O.scatter(cells, NPM, NH, NW, amount, np.zeros(NW * NH)))
     kc = max(3, args.steps // 5)
     ms_compat = 0.0
     for it in range(3 + kc):
-        fld_pin.copy_(fld_src)
+        fld_pin.add_(dep_t)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         step_compat()
@@ -362,9 +369,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rods": ncells, "pcg_iterations": int(iters),
+                       "pcg_iterations_mean": iters_mean,
                        "relres": relres, "rtol": 1e-12, "mg_levels": int(g.stats().levels),
                        "parallelism": f"layer-per-gpu x{world}",
                        "l2": "working set (6 fine fp64 vectors = 201 MB + MG hierarchy) exceeds the 126 MB L2; no explicit flush",
+                       "initial_guess": "best of {zero, previous solution, linear extrapolation of the two previous "
+                                        "solutions}, picked on the device by residual norm; stop test relative to the "
+                                        "right-hand side (rtol 1e-12) whatever the guess",
+                       "last_guess": int(g.last_guess()),
                        "dof_updates_per_sec": value * N},
             "clocks": clocks,
             "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT,

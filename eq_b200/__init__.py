@@ -32,7 +32,8 @@ API_SYMBOLS = [
     "eqgpu_field_device_ptr", "eqgpu_sync", "eqgpu_cells_set_amounts",
     "eqgpu_cells_gather_resident", "eqgpu_cells_scatter_resident", "eqgpu_cells_get_gathered",
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
-    "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path",
+    "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
+    "eqgpu_last_guess",
 ]
 
 
@@ -293,6 +294,15 @@ class GpuHSL:
         out = np.empty(self.ncells)
         self._ck(lib().eqgpu_cells_gather(self._h, _dp(out)))
         return out
+
+    def set_warm_start(self, mode: int):
+        """Starting guess of the PCG solve: 0 = field as given or zero, 1 = also the previous solution,
+        2 (default) = also the linear extrapolation of the two previous solutions."""
+        self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
+
+    def last_guess(self) -> int:
+        """0 field as given, 1 zero, 2 previous solution, 3 extrapolation (what the last step started from)."""
+        return int(lib().eqgpu_last_guess(self._h))
 
     def set_scatter_mode(self, mode: int):
         """0 = direct global atomics, 1 = shared-memory-binned (dense colonies)."""

@@ -76,6 +76,16 @@ int eqgpu_solver_path(eqgpu_solver *s)
            (s->tile_coarsest ? 16 : 0) | (s->tensor ? 32 : 0);
 }
 
+int eqgpu_set_warm_start(eqgpu_solver *s, int mode)
+{
+    if (!s) return EQGPU_EINVAL;
+    if (mode < 0 || mode > 2) { s->set_error("warm-start mode must be 0, 1 or 2"); return EQGPU_EINVAL; }
+    s->warm = mode;
+    return 0;
+}
+
+int eqgpu_last_guess(eqgpu_solver *s) { return s ? s->last_guess : EQGPU_EINVAL; }
+
 int eqgpu_slab_rows(eqgpu_solver *s, int32_t *g0, int32_t *g1)
 {
     if (!s || !g0 || !g1) return EQGPU_EINVAL;

@@ -168,15 +168,45 @@ k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict_
     }
 }
 
-// Tile version of k_init for the isotropic operator on one GPU: u0 goes through a shared 64x64 tile
-// (1-node halo, 62x62 owned), so that the consistent-mass row and the operator row -- both 7-point sums
-// over the same neighbourhood -- cost one global load per node instead of fourteen.  Tiles that touch the
-// irregular frame (wall rows/columns, their Dirichlet-adjacent neighbours, the narrower last cell) take
-// the general per-node path of k_init.
+// A x at a free node for the per-node (irregular frame) path of k_init_tile; Dirichlet neighbours
+// contribute their boundary value (ag collects those terms: A_fd g_d).
+__device__ __forceinline__ void frame_apply(const LevelDev &L, const DirData &dd, const double c[NBAND],
+                                            const double *__restrict__ x, int i, int j, double &ax, double &ag)
+{
+    const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
+    ax = c[B_C] * __ldg(x + (size_t)i * L.nx + j);
+    ag = 0.0;
+    auto acc = [&](int ii, int jj, double ck) {
+        if (is_dirichlet(L, ii, jj)) {
+            const double t = ck * dir_value(L, dd, ii, jj);
+            ax += t; ag += t;
+        } else ax += ck * __ldg(x + (size_t)ii * L.nx + jj);
+    };
+    if (hasE) acc(i, j + 1, c[B_E]);
+    if (hasW) acc(i, j - 1, c[B_W]);
+    if (hasN) acc(i + 1, j, c[B_N]);
+    if (hasS) acc(i - 1, j, c[B_S]);
+    if (hasN && hasE) acc(i + 1, j + 1, c[B_NE]);
+    if (hasS && hasW) acc(i - 1, j - 1, c[B_SW]);
+}
+
+// Tile version of k_init for the isotropic operator on one GPU, with warm starts.  Every field goes
+// through a shared 64x64 tile (1-node halo, 62x62 owned), so that a 7-point row costs one global load per
+// node.  Candidate starting guesses, all evaluated in this one pass (k_impose keeps the best):
+//   (1) g1 = h0, the previous step's solution (nh >= 1), or u0 itself, the field as given (nh == 0);
+//   (B) zero;
+//   (D) 2*h0 - h1, the linear extrapolation of the two previous solutions (nh == 2).
+// The previous solution does NOT contain this step's point deposits, whose huge A*d makes u0 a terrible
+// guess (1500x the residual of zero on the bench colony); in quasi-steady state its residual is the change of
+// the sources, and the extrapolation removes the linear drift as well (measured 1e-3 of the zero guess).
+// Outputs: r1 = b - A g1, rB = b - A_fd g_d, dA = A h0 - A h1 (nh == 2), and the three squared norms.
+// Tiles that touch the irregular frame (wall rows/columns, their Dirichlet-adjacent neighbours, the
+// narrower last cell) take the general per-node path.
 __global__ void __launch_bounds__(256)
-k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict__ rA,
-            double *__restrict__ rB, double rs_l, double rs_r, double *partials, unsigned *counter,
-            double *out_rr0, double *out_b2)
+k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *__restrict__ h0,
+            const double *__restrict__ h1, int nh, double *__restrict__ r1, double *__restrict__ rB,
+            double *__restrict__ dA, double rs_l, double rs_r, double *partials, unsigned *counter,
+            CGScalars *sc)
 {
     constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = 16;
     __shared__ double sp[TPI * TPI];
@@ -186,99 +216,122 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, double *__rest
     // owned nodes [ox+1, ox+62] x [oy+1, oy+62] all regular and at least two nodes away from every wall
     const bool deep = ox + 1 >= 2 && ox + TOI <= min(L.jreg_hi, L.nx - 3) && oy + 1 >= 2 &&
                       oy + TOI <= min(L.ireg_hi, L.ny - 3);
-    double v[2] = {0.0, 0.0};
+    double v[3] = {0.0, 0.0, 0.0};
     if (deep) {
-        {
+        // one pass of the 7-point walk over the tile currently in shared memory: out[k] = cc*x + cn*(sum of 6)
+        // (mass row) or the operator row
+        auto stage = [&](const double *__restrict__ src) {
             double vu[TROWS];
-            const double *q = u + (size_t)(oy + ly0) * L.nx + gj;
+            const double *q = src + (size_t)(oy + ly0) * L.nx + gj;
 #pragma unroll
             for (int k = 0; k < TROWS; ++k) vu[k] = __ldg(q + (size_t)k * L.nx);
+            __syncthreads();   // the previous walk has finished with the tile
 #pragma unroll
             for (int k = 0; k < TROWS; ++k) sp[(ly0 + k + 1) * TPI + lx + 1] = vu[k];
-        }
-        __syncthreads();
-        if (lx >= 1 && lx < TSI - 1) {
-            const double cC = L.cC, cEW = L.cEW, cNS = L.cNS, cD = L.cD, m = L.cD;   // mass row: 6m centre, m else
+            __syncthreads();
+        };
+        auto walk = [&](bool mass, double (&out)[TROWS]) {
+            const double cC = mass ? 6.0 * L.cD : L.cC, cEW = mass ? L.cD : L.cEW, cNS = mass ? L.cD : L.cNS, cD = L.cD;
             int c = (ly0 + 1) * TPI + lx + 1;
-            double sw = 0.0, s0 = 0.0, ww = 0.0, cc = 0.0, ee = 0.0;
+            double sw = 0.0, s0 = 0.0;
             if (ly0 > 0) { sw = sp[c - TPI - 1]; s0 = sp[c - TPI]; }
-            ww = sp[c - 1]; cc = sp[c]; ee = sp[c + 1];
+            double ww = sp[c - 1], cc = sp[c], ee = sp[c + 1];
 #pragma unroll
             for (int k = 0; k < TROWS; ++k, c += TPI) {
-                const int ly = ly0 + k;
                 double nw = 0.0, nc = 0.0, ne = 0.0;
-                if (ly < TSI - 1) { nw = sp[c + TPI - 1]; nc = sp[c + TPI]; ne = sp[c + TPI + 1]; }
-                if (ly >= 1 && ly < TSI - 1) {
-                    const double h6 = (ee + ww) + (nc + s0) + (ne + sw);
-                    const double b = m * (6.0 * cc + h6);
-                    const double ax = cC * cc + cEW * (ee + ww) + cNS * (nc + s0) + cD * (ne + sw);
-                    const double resA = b - ax;
-                    const size_t g = (size_t)(oy + ly) * L.nx + gj;
-                    rA[g] = resA;
-                    rB[g] = b;
-                    v[0] += resA * resA;
-                    v[1] += b * b;
-                }
+                if (ly0 + k < TSI - 1) { nw = sp[c + TPI - 1]; nc = sp[c + TPI]; ne = sp[c + TPI + 1]; }
+                out[k] = cC * cc + cEW * (ee + ww) + cNS * (nc + s0) + cD * (ne + sw);
                 sw = ww; s0 = cc; ww = nw; cc = nc; ee = ne;
+            }
+        };
+        const bool col = lx >= 1 && lx < TSI - 1;
+        double b[TROWS], a0[TROWS], a1[TROWS];
+        stage(u);
+        if (col) walk(true, b);                       // b = M u0
+        if (nh >= 1) stage(h0);
+        if (col) walk(false, a0);                     // A g1 (g1 = u0 when there is no history)
+        if (nh == 2) {
+            stage(h1);
+            if (col) walk(false, a1);
+        }
+        if (col) {
+#pragma unroll
+            for (int k = 0; k < TROWS; ++k) {
+                const int ly = ly0 + k;
+                if (ly < 1 || ly >= TSI - 1) continue;
+                const size_t g = (size_t)(oy + ly) * L.nx + gj;
+                const double res1 = b[k] - a0[k];
+                r1[g] = res1;
+                rB[g] = b[k];
+                v[0] += res1 * res1;
+                v[1] += b[k] * b[k];
+                if (nh == 2) {
+                    const double d = a0[k] - a1[k];
+                    dA[g] = d;
+                    v[2] += (res1 - d) * (res1 - d);
+                }
             }
         }
     } else if (lx >= 1 && lx < TSI - 1 && gj < L.nx) {
+        const double *g1 = nh >= 1 ? h0 : u;
         for (int k = 0; k < TROWS; ++k) {
             const int ly = ly0 + k, i = oy + ly, j = gj;
             if (ly < 1 || ly >= TSI - 1 || i >= L.ny) continue;
             const size_t g = (size_t)i * L.nx + j;
-            double resA = 0.0, resB = 0.0;
+            double res1 = 0.0, resB = 0.0, d = 0.0;
             if (!is_dirichlet(L, i, j)) {
                 const double b = load_row(L, i, j, u, rs_l, rs_r);
                 double c[NBAND];
                 stencil_iso(L, i, j, c);
-                const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
-                double ax = c[B_C] * __ldg(u + g), ag = 0.0;
-                auto acc = [&](int ii, int jj, double ck) {
-                    if (is_dirichlet(L, ii, jj)) {
-                        const double t = ck * dir_value(L, dd, ii, jj);
-                        ax += t; ag += t;
-                    } else ax += ck * __ldg(u + (size_t)ii * L.nx + jj);
-                };
-                if (hasE) acc(i, j + 1, c[B_E]);
-                if (hasW) acc(i, j - 1, c[B_W]);
-                if (hasN) acc(i + 1, j, c[B_N]);
-                if (hasS) acc(i - 1, j, c[B_S]);
-                if (hasN && hasE) acc(i + 1, j + 1, c[B_NE]);
-                if (hasS && hasW) acc(i - 1, j - 1, c[B_SW]);
-                resA = b - ax;
+                double ax, ag;
+                frame_apply(L, dd, c, g1, i, j, ax, ag);
+                res1 = b - ax;
                 resB = b - ag;
-                v[0] += resA * resA;
+                v[0] += res1 * res1;
                 v[1] += resB * resB;
+                if (nh == 2) {
+                    double ax1, ag1;
+                    frame_apply(L, dd, c, h1, i, j, ax1, ag1);
+                    d = ax - ax1;
+                    v[2] += (res1 - d) * (res1 - d);
+                }
             }
-            rA[g] = resA;
+            r1[g] = res1;
             rB[g] = resB;
+            if (nh == 2) dA[g] = d;
         }
     }
-    double tot[2];
-    if (grid_reduce<2>(v, partials, counter, tot)) {
-        *out_rr0 = tot[0];
-        *out_b2 = tot[1];
+    double tot[3];
+    if (grid_reduce<3>(v, partials, counter, tot)) {
+        sc->rr0 = tot[0];
+        sc->bnorm2 = tot[1];
+        sc->rrD = tot[2];
     }
 }
 
 // Pick the starting guess, impose u_d = g_d, set up the PCG scalars.
+// Guess codes (sc->guess): 0 the field as given, 1 zero, 2 previous solution, 3 linear extrapolation.
+// Without history (nh == 0: k_init, or k_init_tile's first steps) h0/h1/dA are unused.
 __global__ void __launch_bounds__(BX *BY)
 k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
-         const double *__restrict__ rB, CGScalars *sc, double rtol, int max_iters)
+         const double *__restrict__ rB, const double *__restrict__ dA, const double *__restrict__ h0,
+         const double *__restrict__ h1, int nh, CGScalars *sc, double rtol, int max_iters)
 {
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    const bool useB = sc->bnorm2 < sc->rr0;
+    const double rr1 = sc->rr0, rrB = sc->bnorm2, rrD = nh == 2 ? sc->rrD : 1.0e300;
+    const int pick = (rrD < rr1 && rrD < rrB) ? 3 : (rrB < rr1 ? 1 : (nh >= 1 ? 2 : 0));
     if (i >= L.own0 && i < L.own1 && j < L.nx) {
         const size_t g = (size_t)i * L.nx + j;
         if (is_dirichlet(L, i, j)) u[g] = dir_value(L, dd, i, j);
-        else if (useB) { u[g] = 0.0; r[g] = rB[g]; }
+        else if (pick == 1) { u[g] = 0.0; r[g] = rB[g]; }
+        else if (pick == 2) u[g] = h0[g];
+        else if (pick == 3) { u[g] = 2.0 * h0[g] - h1[g]; r[g] -= dA[g]; }
     }
     __syncthreads();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
-        const double rr = useB ? sc->bnorm2 : sc->rr0;
+        const double rr = pick == 3 ? rrD : (pick == 1 ? rrB : rr1);
         const double stop2 = rtol * rtol * sc->bnorm2;
-        // every block has read bnorm2/rr0 before this block can be the last to
+        // every block has read bnorm2/rr0/rrD before this block can be the last to
         // finish only if we do not overwrite them: keep them, write the rest.
         sc->rr = rr;
         sc->stop2 = stop2;
@@ -289,6 +342,7 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
         sc->rz_new = 0.0;
         sc->x_stamp = 0;
         sc->x_applied = 0;
+        sc->guess = pick;
     }
 }
 
@@ -456,6 +510,35 @@ k_update_x(size_t n, double *__restrict__ x, const double *__restrict__ p_odd, c
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) x[n - 1] += alpha * p[n - 1];
 }
 
+// End of a step: the pending x update, if any, and (hist_out != null) a copy of the solution for the next
+// step's warm start, in one pass.
+__global__ void __launch_bounds__(256)
+k_finish_x(size_t n, double *__restrict__ x, const double *__restrict__ p_odd, const double *__restrict__ p_even,
+           const CGScalars *sc, double *__restrict__ hist_out)
+{
+    const bool pending = sc->x_applied != sc->x_stamp;
+    if (!pending && !hist_out) return;
+    const double alpha = pending ? sc->alpha_x : 0.0;
+    const double *p = (sc->x_stamp & 1) ? p_odd : p_even;
+    const size_t n2 = n >> 1, stride = (size_t)gridDim.x * blockDim.x;
+    double2 *x2 = reinterpret_cast<double2 *>(x), *h2 = reinterpret_cast<double2 *>(hist_out);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n2; g += stride) {
+        double2 xa = x2[g];
+        if (pending) {
+            const double2 pa = __ldg(p2 + g);
+            xa.x += alpha * pa.x; xa.y += alpha * pa.y;
+            x2[g] = xa;
+        }
+        if (hist_out) h2[g] = xa;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double xa = x[n - 1];
+        if (pending) { xa += alpha * p[n - 1]; x[n - 1] = xa; }
+        if (hist_out) hist_out[n - 1] = xa;
+    }
+}
+
 __global__ void k_mark_x(CGScalars *sc) { sc->x_applied = sc->x_stamp; }
 
 // iteration bookkeeping when ||r||^2 had to be summed over ranks first (slab mode)
@@ -465,22 +548,6 @@ __global__ void k_book(CGScalars *sc)
     sc->rz_old = sc->rz_new;
     sc->iters += 1;
     if (sc->rr <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
-}
-
-// PCG setup from the (already rank-summed) start residuals (slab mode; single GPU does this in k_impose)
-__global__ void k_cg_setup(CGScalars *sc, double rtol, int max_iters)
-{
-    const bool useB = sc->bnorm2 < sc->rr0;
-    const double rr = useB ? sc->bnorm2 : sc->rr0;
-    sc->rr = rr;
-    sc->stop2 = rtol * rtol * sc->bnorm2;
-    sc->iters = 0;
-    sc->max_iters = max_iters;
-    sc->done = (rr <= sc->stop2) ? 1 : 0;
-    sc->rz_old = 1.0;
-    sc->rz_new = 0.0;
-    sc->x_stamp = 0;
-    sc->x_applied = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -870,6 +937,14 @@ int solver_setup(eqgpu_solver *s)
         if (const char *e = getenv("EQGPU_INIT_TILE")) s->init_tile = atoi(e) != 0;
         s->defer_x = !s->slab;
         if (const char *e = getenv("EQGPU_DEFER_X")) s->defer_x = atoi(e) != 0 && !s->slab;
+        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 2));
+        if (s->defer_x && s->init_tile && s->warm > 0) {
+            EQ_CUDA(cudaMalloc(&s->uh[0], sizeof(double) * s->N));
+            EQ_CUDA(cudaMalloc(&s->uh[1], sizeof(double) * s->N));
+            EQ_CUDA(cudaMemset(s->uh[0], 0, sizeof(double) * s->N));
+            EQ_CUDA(cudaMemset(s->uh[1], 0, sizeof(double) * s->N));
+            s->hist = 0;
+        }
         if (s->defer_x) {
             int prio_lo = 0, prio_hi = 0;   // lowest priority: the critical path's CTAs are scheduled first
             cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -901,6 +976,7 @@ void solver_teardown(eqgpu_solver *s)
     s->levels.clear();
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->graph_exec2) { cudaGraphExecDestroy(s->graph_exec2); s->graph_exec2 = nullptr; }
+    cudaFree(s->uh[0]); cudaFree(s->uh[1]); s->uh[0] = s->uh[1] = nullptr; s->hist = 0;
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); s->ev_fork = nullptr; }
     if (s->ev_join) { cudaEventDestroy(s->ev_join); s->ev_join = nullptr; }
     if (s->side_stream) { cudaStreamDestroy(s->side_stream); s->side_stream = nullptr; }
@@ -1404,10 +1480,13 @@ static int pcg(eqgpu_solver *s)
     if (s->slab) slab_exchange(s, L, s->u);
     CGScalars *sc = s->sc;
     const bool sl = s->slab;
+    // warm start: history only on the path that maintains it (k_init_tile + the deferred-x step tail)
+    const bool keep_hist = !T && !sl && s->init_tile && s->fused && s->defer_x && s->warm > 0 && s->uh[0] && s->uh[1];
+    const int nh = keep_hist ? std::min(s->hist, s->warm) : 0;
     if (!T && !sl && s->init_tile) {
         const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
-        k_init_tile<<<gi, 256, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, s->partials, s->counters + 0, &sc->rr0,
-                                        &sc->bnorm2);
+        k_init_tile<<<gi, 256, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], nh, s->r, s->z, s->Ap, rs_l, rs_r,
+                                        s->partials, s->counters + 0, sc);
     } else
         k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
                                       sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
@@ -1415,7 +1494,7 @@ static int pcg(eqgpu_solver *s)
         slab_allreduce(s, &sc->part_rr0, &sc->rr0, 1);
         slab_allreduce(s, &sc->part_b2, &sc->bnorm2, 1);
     }
-    k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->sc, rtol, max_iters);
+    k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->uh[0], s->uh[1], nh, s->sc, rtol, max_iters);
     s->launches += 2;
 
     int issued = 0;
@@ -1474,7 +1553,8 @@ static int pcg(eqgpu_solver *s)
         // channels: their sub-steps advance state and must see the converged field only.
         const bool spec = fused && s->defer_x && !s->p.channels;
         if (fused && s->defer_x) {
-            k_update_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc);
+            // ... and, for the next step's warm start, leave a copy of the solution in the older history slot
+            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[1] : nullptr);
             k_mark_x<<<1, 1, 0, st>>>(sc);
             s->launches += 2;
         }
@@ -1488,6 +1568,11 @@ static int pcg(eqgpu_solver *s)
         chunk = 1;
     }
     s->st.iterations = s->sc_host->iters;
+    s->last_guess = s->sc_host->guess;
+    if (keep_hist && s->sc_host->rr <= s->sc_host->stop2) {   // the copy just written is now the newest solution
+        std::swap(s->uh[0], s->uh[1]);
+        s->hist = std::min(s->hist + 1, 2);
+    }
     const double ref = s->sc_host->bnorm2;
     s->st.relres = ref > 0 ? std::sqrt(s->sc_host->rr / ref) : 0.0;
     if (s->sc_host->rr > s->sc_host->stop2) {

@@ -362,3 +362,54 @@ def test_parameter_extremes(oracle, D, dt, bc):
     assert rel(out, oracle.solve_lu(p, u0)) < TOL, (st.iterations, st.relres, st.levels)
     assert st.iterations <= 40
     g.close()
+
+
+@pytest.mark.parametrize("bc", ["dirichlet0", "robin_lr"])
+def test_warm_start_changes_iterations_not_the_answer(oracle, bc):
+    """eqgpu_set_warm_start: previous-solution / extrapolated starting guesses against the direct solve, and
+    against the same run with warm starts off.  The stopping test is relative to the right-hand side in
+    every mode, so the fields must agree far below TOL while the iteration count drops."""
+    nW = nH = 321
+    runs = {}
+    for mode in (0, 2):
+        p, g = make(oracle, nW, nH, **BCS[bc])
+        g.set_warm_start(mode)
+        cells = oracle.synthetic_colony(400, p.W, p.H, seed=21)
+        npm = 1.0 / p.h
+        g.upload_cells(cells, npm)
+        its, guesses = [], []
+        s = oracle.new_state(p)
+        for k in range(14):
+            amount = np.full(len(cells), 100.0 + 3.0 * k)
+            if mode == 0:
+                s.u = oracle.scatter(cells, npm, p.nH, p.nW, amount, s.u)
+                s = oracle.step(p, s)
+            g.scatter(amount)
+            g.step()
+            its.append(g.stats().iterations)
+            guesses.append(g.last_guess())
+        runs[mode] = (g.get_field(), its, guesses)
+        if mode == 0:
+            ref = s.u.copy()
+        g.close()
+    assert rel(runs[0][0], ref) < TOL and rel(runs[2][0], ref) < TOL
+    assert rel(runs[2][0], runs[0][0]) < 1e-10
+    assert set(runs[0][2]) <= {0, 1}                      # no history used when warm starts are off
+    assert runs[2][2][0] in (0, 1) and runs[2][2][1] in (1, 2)
+    assert all(q in (2, 3) for q in runs[2][2][4:]), runs[2][2]
+    assert sum(runs[2][1][4:]) < sum(runs[0][1][4:]), (runs[0][1], runs[2][1])
+
+
+def test_warm_start_survives_a_field_reset(oracle):
+    """A field that has nothing to do with the history (set_field of noise): the zero guess or the stale
+    history is picked on the device by residual norm; the answer still matches the direct solve."""
+    p, g = make(oracle, 257, 129, **BCS["dir_values"])
+    s = oracle.new_state(p)
+    for k in range(3):
+        u = field(p, seed=40 + k, smooth=(k != 1)) * (1.0 + 10.0 * k)
+        g.set_field(u)
+        s.u = u.copy()
+        s = oracle.step(p, s)
+        g.step()
+        assert rel(g.get_field(), s.u) < TOL
+    g.close()
