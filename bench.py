@@ -206,8 +206,8 @@ def run_slab(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)    # 100 steps after 10 warm-up
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="eq_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="layers", choices=["layers", "slab"])
@@ -373,7 +373,7 @@ def main():
                        "relres": relres, "rtol": 1e-12, "mg_levels": int(g.stats().levels),
                        "parallelism": f"layer-per-gpu x{world}",
                        "l2": "working set (6 fine fp64 vectors = 201 MB + MG hierarchy) exceeds the 126 MB L2; no explicit flush",
-                       "initial_guess": "best of {zero, previous solution, linear extrapolation of the two previous "
+                       "initial_guess": "best of {zero, previous solution, linear / quadratic extrapolation of the previous "
                                         "solutions}, picked on the device by residual norm; stop test relative to the "
                                         "right-hand side (rtol 1e-12) whatever the guess",
                        "last_guess": int(g.last_guess()),

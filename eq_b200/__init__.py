@@ -297,11 +297,11 @@ class GpuHSL:
 
     def set_warm_start(self, mode: int):
         """Starting guess of the PCG solve: 0 = field as given or zero, 1 = also the previous solution,
-        2 (default) = also the linear extrapolation of the two previous solutions."""
+        2 = also the linear, 3 (default) = also the quadratic extrapolation of the previous solutions."""
         self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
 
     def last_guess(self) -> int:
-        """0 field as given, 1 zero, 2 previous solution, 3 extrapolation (what the last step started from)."""
+        """0 field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic extrapolation (last step's start)."""
         return int(lib().eqgpu_last_guess(self._h))
 
     def set_scatter_mode(self, mode: int):

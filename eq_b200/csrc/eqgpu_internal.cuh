@@ -55,7 +55,7 @@ struct CGScalars {
     double alpha_x;
     int x_stamp, x_applied;
     // warm start: squared residual of the extrapolated guess (k_init_tile) and the guess k_impose picked
-    double rrD;
+    double rrD, rrE;
     int guess, pad2;
 };
 
@@ -95,11 +95,11 @@ struct eqgpu_solver {
     int xupd_blocks = 296;         // CTAs of the deferred k_update_x (few: it runs beside the coarse levels)
     bool join_pdl = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // warm start (single-GPU isotropic fused path): the last two solutions, newest first; k_init_tile tries
-    // the previous solution and its linear extrapolation as starting guesses
-    double *uh[2] = {nullptr, nullptr};
+    // warm start (single-GPU isotropic fused path): the last three solutions, newest first; k_init_tile tries
+    // the previous solution and its linear / quadratic extrapolation as starting guesses
+    double *uh[3] = {nullptr, nullptr, nullptr};
     int hist = 0;                  // valid entries of uh[]
-    int warm = 2;                  // 0 off, 1 previous solution, 2 + linear extrapolation
+    int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation
     int last_guess = 0;
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration

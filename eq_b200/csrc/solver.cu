@@ -195,20 +195,23 @@ __device__ __forceinline__ void frame_apply(const LevelDev &L, const DirData &dd
 // node.  Candidate starting guesses, all evaluated in this one pass (k_impose keeps the best):
 //   (1) g1 = h0, the previous step's solution (nh >= 1), or u0 itself, the field as given (nh == 0);
 //   (B) zero;
-//   (D) 2*h0 - h1, the linear extrapolation of the two previous solutions (nh == 2).
+//   (D) 2 h0 - h1, the linear extrapolation of the last two solutions (nh >= 2);
+//   (E) 3 h0 - 3 h1 + h2, the quadratic extrapolation of the last three (nh == 3).
 // The previous solution does NOT contain this step's point deposits, whose huge A*d makes u0 a terrible
 // guess (1500x the residual of zero on the bench colony); in quasi-steady state its residual is the change of
-// the sources, and the extrapolation removes the linear drift as well (measured 1e-3 of the zero guess).
-// Outputs: r1 = b - A g1, rB = b - A_fd g_d, dA = A h0 - A h1 (nh == 2), and the three squared norms.
+// the sources, and the extrapolations remove the linear / quadratic drift as well (measured on the bench
+// colony after 30 steps: 2e-2, 7e-4 and 2e-5 of the zero guess's residual).
+// Outputs: r1 = b - A g1, rB = b - A_fd g_d, d1 = A h0 - A h1, d2 = A h1 - A h2 (so that the residuals of
+// (D) and (E) are r1 - d1 and r1 - 2 d1 + d2), and the four squared norms.
 // Tiles that touch the irregular frame (wall rows/columns, their Dirichlet-adjacent neighbours, the
 // narrower last cell) take the general per-node path.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *__restrict__ h0,
-            const double *__restrict__ h1, int nh, double *__restrict__ r1, double *__restrict__ rB,
-            double *__restrict__ dA, double rs_l, double rs_r, double *partials, unsigned *counter,
-            CGScalars *sc)
+            const double *__restrict__ h1, const double *__restrict__ h2, int nh, double *__restrict__ r1,
+            double *__restrict__ rB, double *__restrict__ d1o, double *__restrict__ d2o, double rs_l, double rs_r,
+            double *partials, unsigned *counter, CGScalars *sc)
 {
-    constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = 16;
+    constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = 8;
     __shared__ double sp[TPI * TPI];
     const int ox = blockIdx.x * TOI - 1, oy = blockIdx.y * TOI - 1;
     const int lx = threadIdx.x & (TSI - 1), ly0 = (threadIdx.x >> 6) * TROWS;
@@ -216,10 +219,8 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
     // owned nodes [ox+1, ox+62] x [oy+1, oy+62] all regular and at least two nodes away from every wall
     const bool deep = ox + 1 >= 2 && ox + TOI <= min(L.jreg_hi, L.nx - 3) && oy + 1 >= 2 &&
                       oy + TOI <= min(L.ireg_hi, L.ny - 3);
-    double v[3] = {0.0, 0.0, 0.0};
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (deep) {
-        // one pass of the 7-point walk over the tile currently in shared memory: out[k] = cc*x + cn*(sum of 6)
-        // (mass row) or the operator row
         auto stage = [&](const double *__restrict__ src) {
             double vu[TROWS];
             const double *q = src + (size_t)(oy + ly0) * L.nx + gj;
@@ -230,6 +231,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             for (int k = 0; k < TROWS; ++k) sp[(ly0 + k + 1) * TPI + lx + 1] = vu[k];
             __syncthreads();
         };
+        // 7-point walk up the thread's column over the tile in shared memory: mass row or operator row
         auto walk = [&](bool mass, double (&out)[TROWS]) {
             const double cC = mass ? 6.0 * L.cD : L.cC, cEW = mass ? L.cD : L.cEW, cNS = mass ? L.cD : L.cNS, cD = L.cD;
             int c = (ly0 + 1) * TPI + lx + 1;
@@ -245,14 +247,30 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             }
         };
         const bool col = lx >= 1 && lx < TSI - 1;
-        double b[TROWS], a0[TROWS], a1[TROWS];
+        double b[TROWS], c1[TROWS], d1[TROWS], d2[TROWS], a[TROWS];
         stage(u);
         if (col) walk(true, b);                       // b = M u0
         if (nh >= 1) stage(h0);
-        if (col) walk(false, a0);                     // A g1 (g1 = u0 when there is no history)
-        if (nh == 2) {
+        if (col) {
+            walk(false, a);                           // A g1 (g1 = u0 when there is no history)
+#pragma unroll
+            for (int k = 0; k < TROWS; ++k) { c1[k] = b[k] - a[k]; d1[k] = a[k]; d2[k] = 0.0; }
+        }
+        if (nh >= 2) {
             stage(h1);
-            if (col) walk(false, a1);
+            if (col) {
+                walk(false, a);
+#pragma unroll
+                for (int k = 0; k < TROWS; ++k) { d1[k] -= a[k]; d2[k] = a[k]; }
+            }
+        }
+        if (nh >= 3) {
+            stage(h2);
+            if (col) {
+                walk(false, a);
+#pragma unroll
+                for (int k = 0; k < TROWS; ++k) d2[k] -= a[k];
+            }
         }
         if (col) {
 #pragma unroll
@@ -260,15 +278,19 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 const int ly = ly0 + k;
                 if (ly < 1 || ly >= TSI - 1) continue;
                 const size_t g = (size_t)(oy + ly) * L.nx + gj;
-                const double res1 = b[k] - a0[k];
-                r1[g] = res1;
+                r1[g] = c1[k];
                 rB[g] = b[k];
-                v[0] += res1 * res1;
+                v[0] += c1[k] * c1[k];
                 v[1] += b[k] * b[k];
-                if (nh == 2) {
-                    const double d = a0[k] - a1[k];
-                    dA[g] = d;
-                    v[2] += (res1 - d) * (res1 - d);
+                if (nh >= 2) {
+                    const double rd = c1[k] - d1[k];
+                    d1o[g] = d1[k];
+                    v[2] += rd * rd;
+                }
+                if (nh >= 3) {
+                    const double re = c1[k] - 2.0 * d1[k] + d2[k];
+                    d2o[g] = d2[k];
+                    v[3] += re * re;
                 }
             }
         }
@@ -278,7 +300,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             const int ly = ly0 + k, i = oy + ly, j = gj;
             if (ly < 1 || ly >= TSI - 1 || i >= L.ny) continue;
             const size_t g = (size_t)i * L.nx + j;
-            double res1 = 0.0, resB = 0.0, d = 0.0;
+            double res1 = 0.0, resB = 0.0, e1 = 0.0, e2 = 0.0;
             if (!is_dirichlet(L, i, j)) {
                 const double b = load_row(L, i, j, u, rs_l, rs_r);
                 double c[NBAND];
@@ -289,55 +311,70 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 resB = b - ag;
                 v[0] += res1 * res1;
                 v[1] += resB * resB;
-                if (nh == 2) {
+                if (nh >= 2) {
                     double ax1, ag1;
                     frame_apply(L, dd, c, h1, i, j, ax1, ag1);
-                    d = ax - ax1;
-                    v[2] += (res1 - d) * (res1 - d);
+                    e1 = ax - ax1;
+                    v[2] += (res1 - e1) * (res1 - e1);
+                    if (nh >= 3) {
+                        double ax2, ag2;
+                        frame_apply(L, dd, c, h2, i, j, ax2, ag2);
+                        e2 = ax1 - ax2;
+                        const double re = res1 - 2.0 * e1 + e2;
+                        v[3] += re * re;
+                    }
                 }
             }
             r1[g] = res1;
             rB[g] = resB;
-            if (nh == 2) dA[g] = d;
+            if (nh >= 2) d1o[g] = e1;
+            if (nh >= 3) d2o[g] = e2;
         }
     }
-    double tot[3];
-    if (grid_reduce<3>(v, partials, counter, tot)) {
+    double tot[4];
+    if (grid_reduce<4>(v, partials, counter, tot)) {
         sc->rr0 = tot[0];
         sc->bnorm2 = tot[1];
         sc->rrD = tot[2];
+        sc->rrE = tot[3];
     }
 }
 
 // Pick the starting guess, impose u_d = g_d, set up the PCG scalars.
-// Guess codes (sc->guess): 0 the field as given, 1 zero, 2 previous solution, 3 linear extrapolation.
-// Without history (nh == 0: k_init, or k_init_tile's first steps) h0/h1/dA are unused.
+// Guess codes (sc->guess): 0 the field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic
+// extrapolation.  Without history (nh == 0: k_init, or k_init_tile's first step) h*/d* are unused.
 __global__ void __launch_bounds__(BX *BY)
 k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
-         const double *__restrict__ rB, const double *__restrict__ dA, const double *__restrict__ h0,
-         const double *__restrict__ h1, int nh, CGScalars *sc, double rtol, int max_iters)
+         const double *__restrict__ rB, const double *__restrict__ d1, const double *__restrict__ d2,
+         const double *__restrict__ h0, const double *__restrict__ h1, const double *__restrict__ h2, int nh,
+         CGScalars *sc, double rtol, int max_iters)
 {
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    const double rr1 = sc->rr0, rrB = sc->bnorm2, rrD = nh == 2 ? sc->rrD : 1.0e300;
-    const int pick = (rrD < rr1 && rrD < rrB) ? 3 : (rrB < rr1 ? 1 : (nh >= 1 ? 2 : 0));
+    const double rr1 = sc->rr0, rrB = sc->bnorm2;
+    const double rrD = nh >= 2 ? sc->rrD : 1.0e300, rrE = nh >= 3 ? sc->rrE : 1.0e300;
+    int pick = nh >= 1 ? 2 : 0;
+    double best = rr1;
+    if (rrB < best) { best = rrB; pick = 1; }
+    if (rrD < best) { best = rrD; pick = 3; }
+    if (rrE < best) { best = rrE; pick = 4; }
     if (i >= L.own0 && i < L.own1 && j < L.nx) {
         const size_t g = (size_t)i * L.nx + j;
         if (is_dirichlet(L, i, j)) u[g] = dir_value(L, dd, i, j);
         else if (pick == 1) { u[g] = 0.0; r[g] = rB[g]; }
         else if (pick == 2) u[g] = h0[g];
-        else if (pick == 3) { u[g] = 2.0 * h0[g] - h1[g]; r[g] -= dA[g]; }
+        else if (pick == 3) { u[g] = 2.0 * h0[g] - h1[g]; r[g] -= d1[g]; }
+        else if (pick == 4) { u[g] = 3.0 * (h0[g] - h1[g]) + h2[g]; r[g] += d2[g] - 2.0 * d1[g]; }
     }
     __syncthreads();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
-        const double rr = pick == 3 ? rrD : (pick == 1 ? rrB : rr1);
         const double stop2 = rtol * rtol * sc->bnorm2;
-        // every block has read bnorm2/rr0/rrD before this block can be the last to
+        // every block has read bnorm2/rr0/rrD/rrE before this block can be the last to
         // finish only if we do not overwrite them: keep them, write the rest.
-        sc->rr = rr;
+        sc->rr = best;
         sc->stop2 = stop2;
         sc->iters = 0;
         sc->max_iters = max_iters;
-        sc->done = (rr <= stop2) ? 1 : 0;
+        sc->done = (best <= stop2) ? 1 : 0;
         sc->rz_old = 1.0;
         sc->rz_new = 0.0;
         sc->x_stamp = 0;
@@ -937,12 +974,12 @@ int solver_setup(eqgpu_solver *s)
         if (const char *e = getenv("EQGPU_INIT_TILE")) s->init_tile = atoi(e) != 0;
         s->defer_x = !s->slab;
         if (const char *e = getenv("EQGPU_DEFER_X")) s->defer_x = atoi(e) != 0 && !s->slab;
-        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 2));
+        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 3));
         if (s->defer_x && s->init_tile && s->warm > 0) {
-            EQ_CUDA(cudaMalloc(&s->uh[0], sizeof(double) * s->N));
-            EQ_CUDA(cudaMalloc(&s->uh[1], sizeof(double) * s->N));
-            EQ_CUDA(cudaMemset(s->uh[0], 0, sizeof(double) * s->N));
-            EQ_CUDA(cudaMemset(s->uh[1], 0, sizeof(double) * s->N));
+            for (int k = 0; k < 3; ++k) {
+                EQ_CUDA(cudaMalloc(&s->uh[k], sizeof(double) * s->N));
+                EQ_CUDA(cudaMemset(s->uh[k], 0, sizeof(double) * s->N));
+            }
             s->hist = 0;
         }
         if (s->defer_x) {
@@ -976,7 +1013,8 @@ void solver_teardown(eqgpu_solver *s)
     s->levels.clear();
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->graph_exec2) { cudaGraphExecDestroy(s->graph_exec2); s->graph_exec2 = nullptr; }
-    cudaFree(s->uh[0]); cudaFree(s->uh[1]); s->uh[0] = s->uh[1] = nullptr; s->hist = 0;
+    for (int k = 0; k < 3; ++k) { cudaFree(s->uh[k]); s->uh[k] = nullptr; }
+    s->hist = 0;
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); s->ev_fork = nullptr; }
     if (s->ev_join) { cudaEventDestroy(s->ev_join); s->ev_join = nullptr; }
     if (s->side_stream) { cudaStreamDestroy(s->side_stream); s->side_stream = nullptr; }
@@ -1481,12 +1519,13 @@ static int pcg(eqgpu_solver *s)
     CGScalars *sc = s->sc;
     const bool sl = s->slab;
     // warm start: history only on the path that maintains it (k_init_tile + the deferred-x step tail)
-    const bool keep_hist = !T && !sl && s->init_tile && s->fused && s->defer_x && s->warm > 0 && s->uh[0] && s->uh[1];
+    const bool keep_hist = !T && !sl && s->init_tile && s->fused && s->defer_x && s->warm > 0 && s->uh[0];
     const int nh = keep_hist ? std::min(s->hist, s->warm) : 0;
+    // scratch for the extrapolation terms: Ap and pv2 are free until the first k_apply_p writes them
     if (!T && !sl && s->init_tile) {
         const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
-        k_init_tile<<<gi, 256, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], nh, s->r, s->z, s->Ap, rs_l, rs_r,
-                                        s->partials, s->counters + 0, sc);
+        k_init_tile<<<gi, 512, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2,
+                                        rs_l, rs_r, s->partials, s->counters + 0, sc);
     } else
         k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
                                       sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
@@ -1494,7 +1533,8 @@ static int pcg(eqgpu_solver *s)
         slab_allreduce(s, &sc->part_rr0, &sc->rr0, 1);
         slab_allreduce(s, &sc->part_b2, &sc->bnorm2, 1);
     }
-    k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->uh[0], s->uh[1], nh, s->sc, rtol, max_iters);
+    k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->pv2, s->uh[0], s->uh[1], s->uh[2], nh, s->sc,
+                                 rtol, max_iters);
     s->launches += 2;
 
     int issued = 0;
@@ -1554,7 +1594,7 @@ static int pcg(eqgpu_solver *s)
         const bool spec = fused && s->defer_x && !s->p.channels;
         if (fused && s->defer_x) {
             // ... and, for the next step's warm start, leave a copy of the solution in the older history slot
-            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[1] : nullptr);
+            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[2] : nullptr);
             k_mark_x<<<1, 1, 0, st>>>(sc);
             s->launches += 2;
         }
@@ -1570,8 +1610,9 @@ static int pcg(eqgpu_solver *s)
     s->st.iterations = s->sc_host->iters;
     s->last_guess = s->sc_host->guess;
     if (keep_hist && s->sc_host->rr <= s->sc_host->stop2) {   // the copy just written is now the newest solution
-        std::swap(s->uh[0], s->uh[1]);
-        s->hist = std::min(s->hist + 1, 2);
+        double *newest = s->uh[2];
+        s->uh[2] = s->uh[1]; s->uh[1] = s->uh[0]; s->uh[0] = newest;
+        s->hist = std::min(s->hist + 1, 3);
     }
     const double ref = s->sc_host->bnorm2;
     s->st.relres = ref > 0 ? std::sqrt(s->sc_host->rr / ref) : 0.0;

@@ -188,13 +188,14 @@ EQGPU_API int eqgpu_sync(eqgpu_solver *s);
 EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
 /* Starting guess of the iterative solve that stands in for LinearVariationalSolver::solve()
  * (src/fHSL.cpp:106; the reference's LU has no such notion).  mode 0: the field as given or zero, whichever
- * has the smaller residual; 1: also the previous step's solution; 2 (default): also the linear extrapolation
- * of the two previous solutions.  The stopping test is relative to the right-hand side in every mode, so
+ * has the smaller residual; 1: also the previous step's solution; 2: also the linear extrapolation of the
+ * two previous solutions; 3 (default): also the quadratic extrapolation of the last three.  The stopping test is relative to the right-hand side in every mode, so
  * the mode changes the iteration count, not the accuracy.  History lives on the device, survives
  * eqgpu_set_field, and is kept on the single-GPU isotropic path only (elsewhere the call is accepted and
  * mode 0 is what runs). */
 EQGPU_API int eqgpu_set_warm_start(eqgpu_solver *s, int mode);
-/* Which guess the last step started from: 0 field as given, 1 zero, 2 previous solution, 3 extrapolation. */
+/* Which guess the last step started from: 0 field as given, 1 zero, 2 previous solution, 3 linear,
+ * 4 quadratic extrapolation. */
 EQGPU_API int eqgpu_last_guess(eqgpu_solver *s);
 /* Times `reps` back-to-back launches of one named kernel on the solver's
  * stream with CUDA events (for bench.py's roofline line).  Returns the average

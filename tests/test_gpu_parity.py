@@ -371,7 +371,7 @@ def test_warm_start_changes_iterations_not_the_answer(oracle, bc):
     every mode, so the fields must agree far below TOL while the iteration count drops."""
     nW = nH = 321
     runs = {}
-    for mode in (0, 2):
+    for mode in (0, 3):
         p, g = make(oracle, nW, nH, **BCS[bc])
         g.set_warm_start(mode)
         cells = oracle.synthetic_colony(400, p.W, p.H, seed=21)
@@ -392,12 +392,12 @@ def test_warm_start_changes_iterations_not_the_answer(oracle, bc):
         if mode == 0:
             ref = s.u.copy()
         g.close()
-    assert rel(runs[0][0], ref) < TOL and rel(runs[2][0], ref) < TOL
-    assert rel(runs[2][0], runs[0][0]) < 1e-10
+    assert rel(runs[0][0], ref) < TOL and rel(runs[3][0], ref) < TOL
+    assert rel(runs[3][0], runs[0][0]) < 1e-10
     assert set(runs[0][2]) <= {0, 1}                      # no history used when warm starts are off
-    assert runs[2][2][0] in (0, 1) and runs[2][2][1] in (1, 2)
-    assert all(q in (2, 3) for q in runs[2][2][4:]), runs[2][2]
-    assert sum(runs[2][1][4:]) < sum(runs[0][1][4:]), (runs[0][1], runs[2][1])
+    assert runs[3][2][0] in (0, 1) and runs[3][2][1] in (1, 2)
+    assert all(q in (2, 3, 4) for q in runs[3][2][4:]), runs[3][2]
+    assert sum(runs[3][1][4:]) < sum(runs[0][1][4:]), (runs[0][1], runs[3][1])
 
 
 def test_warm_start_survives_a_field_reset(oracle):
