@@ -48,7 +48,7 @@ struct CGScalars {
     double rz_old, rz_new, pAp, rr, bnorm2, stop2, rr0;
     // slab mode: kernels leave their rank-local sums here; an out-of-place all-reduce then writes the
     // global value into the field above (idempotent when replayed after convergence)
-    double part_rz, part_pAp, part_rr, part_b2, part_rr0;
+    double part_rz, part_pAp, part_rr, part_b2, part_rr0, part_rrD, part_rrE;
     int iters, done, max_iters, pad;
     // deferred x update (single-GPU fused path): k_update_r leaves the step length and the iteration number
     // here, k_update_x applies x += alpha_x * p later, off the critical path; x_applied == x_stamp: nothing pending

@@ -168,6 +168,11 @@ k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict_
     }
 }
 
+// k_init_tile: 64x64 tile, one column per thread, 64*64/INIT_THREADS rows each.  1024 threads (4 rows):
+// the four stage-and-walk phases are exposed to load latency, and 32 warps hide it better than 16 with 8 rows
+// (122 registers, one CTA per SM either way).
+#define INIT_THREADS 1024
+
 // A x at a free node for the per-node (irregular frame) path of k_init_tile; Dirichlet neighbours
 // contribute their boundary value (ag collects those terms: A_fd g_d).
 __device__ __forceinline__ void frame_apply(const LevelDev &L, const DirData &dd, const double c[NBAND],
@@ -205,13 +210,15 @@ __device__ __forceinline__ void frame_apply(const LevelDev &L, const DirData &dd
 // (D) and (E) are r1 - d1 and r1 - 2 d1 + d2), and the four squared norms.
 // Tiles that touch the irregular frame (wall rows/columns, their Dirichlet-adjacent neighbours, the
 // narrower last cell) take the general per-node path.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(INIT_THREADS)
 k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *__restrict__ h0,
             const double *__restrict__ h1, const double *__restrict__ h2, int nh, double *__restrict__ r1,
             double *__restrict__ rB, double *__restrict__ d1o, double *__restrict__ d2o, double rs_l, double rs_r,
-            double *partials, unsigned *counter, CGScalars *sc)
+            double *partials, unsigned *counter, CGScalars *sc, int slab)
 {
-    constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = 8;
+    // Row slabs: L is the rank's local view (halo rows included); only owned rows [own0, own1) are written
+    // and summed, and the sums are rank-local partials (slab != 0) for the host to all-reduce.
+    constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = TSI * TSI / INIT_THREADS;
     __shared__ double sp[TPI * TPI];
     const int ox = blockIdx.x * TOI - 1, oy = blockIdx.y * TOI - 1;
     const int lx = threadIdx.x & (TSI - 1), ly0 = (threadIdx.x >> 6) * TROWS;
@@ -276,7 +283,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
 #pragma unroll
             for (int k = 0; k < TROWS; ++k) {
                 const int ly = ly0 + k;
-                if (ly < 1 || ly >= TSI - 1) continue;
+                if (ly < 1 || ly >= TSI - 1 || oy + ly < L.own0 || oy + ly >= L.own1) continue;
                 const size_t g = (size_t)(oy + ly) * L.nx + gj;
                 r1[g] = c1[k];
                 rB[g] = b[k];
@@ -298,7 +305,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
         const double *g1 = nh >= 1 ? h0 : u;
         for (int k = 0; k < TROWS; ++k) {
             const int ly = ly0 + k, i = oy + ly, j = gj;
-            if (ly < 1 || ly >= TSI - 1 || i >= L.ny) continue;
+            if (ly < 1 || ly >= TSI - 1 || i < L.own0 || i >= L.own1) continue;
             const size_t g = (size_t)i * L.nx + j;
             double res1 = 0.0, resB = 0.0, e1 = 0.0, e2 = 0.0;
             if (!is_dirichlet(L, i, j)) {
@@ -333,10 +340,8 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
     }
     double tot[4];
     if (grid_reduce<4>(v, partials, counter, tot)) {
-        sc->rr0 = tot[0];
-        sc->bnorm2 = tot[1];
-        sc->rrD = tot[2];
-        sc->rrE = tot[3];
+        if (slab) { sc->part_rr0 = tot[0]; sc->part_b2 = tot[1]; sc->part_rrD = tot[2]; sc->part_rrE = tot[3]; }
+        else { sc->rr0 = tot[0]; sc->bnorm2 = tot[1]; sc->rrD = tot[2]; sc->rrE = tot[3]; }
     }
 }
 
@@ -975,7 +980,7 @@ int solver_setup(eqgpu_solver *s)
         s->defer_x = !s->slab;
         if (const char *e = getenv("EQGPU_DEFER_X")) s->defer_x = atoi(e) != 0 && !s->slab;
         if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 3));
-        if (s->defer_x && s->init_tile && s->warm > 0) {
+        if ((s->defer_x || s->slab) && s->init_tile && s->warm > 0) {
             for (int k = 0; k < 3; ++k) {
                 EQ_CUDA(cudaMalloc(&s->uh[k], sizeof(double) * s->N));
                 EQ_CUDA(cudaMemset(s->uh[k], 0, sizeof(double) * s->N));
@@ -1519,13 +1524,18 @@ static int pcg(eqgpu_solver *s)
     CGScalars *sc = s->sc;
     const bool sl = s->slab;
     // warm start: history only on the path that maintains it (k_init_tile + the deferred-x step tail)
-    const bool keep_hist = !T && !sl && s->init_tile && s->fused && s->defer_x && s->warm > 0 && s->uh[0];
+    // (single GPU: the deferred-x step tail stores the history; slabs: a device copy + halo exchange)
+    const bool keep_hist = !T && s->init_tile && s->fused && (sl || s->defer_x) && s->warm > 0 && s->uh[0];
     const int nh = keep_hist ? std::min(s->hist, s->warm) : 0;
     // scratch for the extrapolation terms: Ap and pv2 are free until the first k_apply_p writes them
-    if (!T && !sl && s->init_tile) {
+    if (!T && s->init_tile) {
         const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
-        k_init_tile<<<gi, 512, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2,
-                                        rs_l, rs_r, s->partials, s->counters + 0, sc);
+        k_init_tile<<<gi, INIT_THREADS, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2,
+                                        rs_l, rs_r, s->partials, s->counters + 0, sc, sl ? 1 : 0);
+        if (sl) {
+            slab_allreduce(s, &sc->part_rrD, &sc->rrD, 1);
+            slab_allreduce(s, &sc->part_rrE, &sc->rrE, 1);
+        }
     } else
         k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
                                       sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
@@ -1610,6 +1620,11 @@ static int pcg(eqgpu_solver *s)
     s->st.iterations = s->sc_host->iters;
     s->last_guess = s->sc_host->guess;
     if (keep_hist && s->sc_host->rr <= s->sc_host->stop2) {   // the copy just written is now the newest solution
+        if (sl) {   // slabs: copy now (owned rows are final), then bring the halo rows of the copy up to date
+            EQ_CUDA(cudaMemcpyAsync(s->uh[2], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
+            int rc = slab_exchange(s, L, s->uh[2]);
+            if (rc) return rc;
+        }
         double *newest = s->uh[2];
         s->uh[2] = s->uh[1]; s->uh[1] = s->uh[0]; s->uh[0] = newest;
         s->hist = std::min(s->hist + 1, 3);

@@ -49,7 +49,7 @@ def worker(rank, world, q_id, q_out, kase):
         s = g.gather()
         g.scatter(100.0 + 0.5 * s)
         g.step()
-        hist.append((s, g.totalBoundaryFlux, g.stats().iterations))
+        hist.append((s, g.totalBoundaryFlux, g.stats().iterations, g.last_guess()))
     out = np.zeros(NW * NH)
     g.get_field(out)
     q_out.put((rank, g0, g1, out[g0 * NW:g1 * NW].copy(), hist))
@@ -88,7 +88,14 @@ def test_two_gpu_slab_equals_single_gpu_and_oracle(kase):
     rel = np.linalg.norm(field - s.u) / np.linalg.norm(s.u)
     assert rel < 1e-8, rel
     for r in range(2):
-        for (smp, flux, it), (smp0, flux0) in zip(res[r][4], hist):
+        for (smp, flux, it, guess), (smp0, flux0) in zip(res[r][4], hist):
             assert np.allclose(smp, smp0, rtol=1e-9, atol=1e-12)        # rank-summed samples, same on both ranks
             assert abs(flux - flux0) <= 1e-7 * max(abs(flux0), 1.0)
             assert 0 < it < 40
+        # warm start on slabs (fused path): steps 2 and 3 start from the previous solution or an extrapolation
+        # of it (history copied on the device, halo rows exchanged); both ranks take the same rank-summed decision
+        guesses = [h[3] for h in res[r][4]]
+        assert guesses[0] in (0, 1)
+        if kase == "fused":
+            assert all(q >= 2 for q in guesses[1:]), guesses
+        assert guesses == [h[3] for h in res[0][4]]
