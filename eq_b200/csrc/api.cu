@@ -307,6 +307,7 @@ int eqgpu_cells_upload(eqgpu_solver *s, const double *rec, int64_t n, double npm
         s->cells_cap = cap;
     }
     s->ncells = n;
+    s->counts_valid = false;
     s->npm = npm;
     if (n) EQ_CUDA(cudaMemcpyAsync(s->cells, rec, sizeof(double) * EQGPU_CELL_STRIDE * n, cudaMemcpyHostToDevice, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));

@@ -119,7 +119,8 @@ k_cells_raster(const double *__restrict__ cells, long long ncells, double npm, i
 // the reference's order (every lane carries the same running sum).
 __global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
 k_cells_gather(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
-               const double *__restrict__ u, double *__restrict__ out, int row0, int g0, int g1)
+               const double *__restrict__ u, double *__restrict__ out, int *__restrict__ counts, int row0, int g0,
+               int g1)
 {
     const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
     if (k >= ncells) return;
@@ -141,7 +142,10 @@ k_cells_gather(const double *__restrict__ cells, long long ncells, double npm, i
         HSL = owned(cn) ? __ldg(u + cn - (long long)row0 * nW) : 0.0;
         n = 1;
     }
-    if (lane == 0) out[k] = __ddiv_rn(HSL, (double)n);
+    if (lane == 0) {
+        out[k] = __ddiv_rn(HSL, (double)n);
+        counts[k] = n;   // the point count writeHSL divides by: the scatter that follows needs no raster pass
+    }
 }
 
 // src/eQcell.h:40-93 (poleRadius = 1/2)
@@ -345,9 +349,10 @@ int cells_gather(eqgpu_solver *s, double *d_out)
     if (s->ncells == 0) return 0;
     const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
     k_cells_gather<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
-        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->u, d_out, s->levels[0].dev.row0,
-        s->levels[0].g0, s->levels[0].g1);
+        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->u, d_out, s->cell_counts,
+        s->levels[0].dev.row0, s->levels[0].g0, s->levels[0].g1);
     s->launches++;
+    s->counts_valid = true;   // until the next eqgpu_cells_upload
     EQ_CUDA(cudaGetLastError());
     if (s->slab) {
         int rc = slab_allreduce(s, d_out, d_out, (int)s->ncells);
@@ -399,13 +404,17 @@ int cells_scatter(eqgpu_solver *s, const double *d_amount)
     if (s->ncells == 0) return 0;
     if (s->scatter_mode == 1) return cells_scatter_binned(s, d_amount);
     const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
-    // point counts first (the per-node amount divides by them)
-    k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
-        s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->cell_counts, nullptr, 0);
+    // point counts first (the per-node amount divides by them), unless a gather of the same cell set left them
+    if (!s->counts_valid) {
+        k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
+            s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), s->cell_counts, nullptr, 0);
+        s->launches++;
+        s->counts_valid = true;
+    }
     k_cells_scatter<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(
         s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), d_amount, s->cell_counts, s->u,
         s->levels[0].dev.row0, s->levels[0].g0, s->levels[0].g1);
-    s->launches += 2;
+    s->launches++;
     EQ_CUDA(cudaGetLastError());
     return 0;
 }

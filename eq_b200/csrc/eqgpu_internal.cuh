@@ -141,6 +141,7 @@ struct eqgpu_solver {
     double *cell_vals = nullptr;   // device per-cell gather result
     double *cell_amt = nullptr;    // device per-cell deposit amounts (nM)
     int32_t *cell_counts = nullptr;
+    bool counts_valid = false;     // cell_counts match the uploaded cell set (left by the last gather/raster)
     double *stage_host = nullptr;  // pinned staging for field copies
     // stats
     eqgpu_stats st{};
@@ -187,6 +188,17 @@ void boundary_functional_finish(eqgpu_solver *s);   // after the stream was sync
 // Both are no-ops for ordinary launches.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Asynchronous global -> shared copies (LDGSTS), 8-byte granularity because tile origins are odd node
+// offsets; completion by commit groups.  k_init_tile uses them to have all its input tiles in flight at once.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ bool is_dirichlet(const LevelDev &L, int i, int j)
 {

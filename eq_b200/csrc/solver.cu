@@ -172,6 +172,7 @@ k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict_
 // the four stage-and-walk phases are exposed to load latency, and 32 warps hide it better than 16 with 8 rows
 // (122 registers, one CTA per SM either way).
 #define INIT_THREADS 1024
+constexpr int INIT_SMEM = 4 * 66 * 66 * (int)sizeof(double);   // four 64x64 tiles with a pad ring: 139 KB
 
 // A x at a free node for the per-node (irregular frame) path of k_init_tile; Dirichlet neighbours
 // contribute their boundary value (ag collects those terms: A_fd g_d).
@@ -219,7 +220,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
     // Row slabs: L is the rank's local view (halo rows included); only owned rows [own0, own1) are written
     // and summed, and the sums are rank-local partials (slab != 0) for the host to all-reduce.
     constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = TSI * TSI / INIT_THREADS;
-    __shared__ double sp[TPI * TPI];
+    extern __shared__ double sm_init[];   // four tiles: u0, h0, h1, h2
     const int ox = blockIdx.x * TOI - 1, oy = blockIdx.y * TOI - 1;
     const int lx = threadIdx.x & (TSI - 1), ly0 = (threadIdx.x >> 6) * TROWS;
     const int gj = ox + lx;
@@ -228,18 +229,24 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                       oy + TOI <= min(L.ireg_hi, L.ny - 3);
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (deep) {
-        auto stage = [&](const double *__restrict__ src) {
-            double vu[TROWS];
-            const double *q = src + (size_t)(oy + ly0) * L.nx + gj;
+        // all input tiles in flight at once: one cp.async commit group per field (an empty group where the
+        // history is shorter), waited for one by one below -- no registers held, no load phase per stage
+        auto stage = [&](const double *__restrict__ src, int q, bool on) {
+            if (on) {
+                const double *g = src + (size_t)(oy + ly0) * L.nx + gj;
+                double *t = sm_init + q * (TPI * TPI) + (ly0 + 1) * TPI + lx + 1;
 #pragma unroll
-            for (int k = 0; k < TROWS; ++k) vu[k] = __ldg(q + (size_t)k * L.nx);
-            __syncthreads();   // the previous walk has finished with the tile
-#pragma unroll
-            for (int k = 0; k < TROWS; ++k) sp[(ly0 + k + 1) * TPI + lx + 1] = vu[k];
-            __syncthreads();
+                for (int k = 0; k < TROWS; ++k) cp_async8(t + k * TPI, g + (size_t)k * L.nx);
+            }
+            cp_async_commit();
         };
-        // 7-point walk up the thread's column over the tile in shared memory: mass row or operator row
-        auto walk = [&](bool mass, double (&out)[TROWS]) {
+        stage(u, 0, true);
+        stage(h0, 1, nh >= 1);
+        stage(h1, 2, nh >= 2);
+        stage(h2, 3, nh >= 3);
+        // 7-point walk up the thread's column over tile q: mass row or operator row
+        auto walk = [&](int q, bool mass, double (&out)[TROWS]) {
+            const double *sp = sm_init + q * (TPI * TPI);
             const double cC = mass ? 6.0 * L.cD : L.cC, cEW = mass ? L.cD : L.cEW, cNS = mass ? L.cD : L.cNS, cD = L.cD;
             int c = (ly0 + 1) * TPI + lx + 1;
             double sw = 0.0, s0 = 0.0;
@@ -255,26 +262,30 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
         };
         const bool col = lx >= 1 && lx < TSI - 1;
         double b[TROWS], c1[TROWS], d1[TROWS], d2[TROWS], a[TROWS];
-        stage(u);
-        if (col) walk(true, b);                       // b = M u0
-        if (nh >= 1) stage(h0);
+        cp_async_wait<3>();
+        __syncthreads();
+        if (col) walk(0, true, b);                    // b = M u0
+        cp_async_wait<2>();
+        __syncthreads();
         if (col) {
-            walk(false, a);                           // A g1 (g1 = u0 when there is no history)
+            walk(nh >= 1 ? 1 : 0, false, a);          // A g1 (g1 = u0 when there is no history)
 #pragma unroll
             for (int k = 0; k < TROWS; ++k) { c1[k] = b[k] - a[k]; d1[k] = a[k]; d2[k] = 0.0; }
         }
         if (nh >= 2) {
-            stage(h1);
+            cp_async_wait<1>();
+            __syncthreads();
             if (col) {
-                walk(false, a);
+                walk(2, false, a);
 #pragma unroll
                 for (int k = 0; k < TROWS; ++k) { d1[k] -= a[k]; d2[k] = a[k]; }
             }
         }
         if (nh >= 3) {
-            stage(h2);
+            cp_async_wait<0>();
+            __syncthreads();
             if (col) {
-                walk(false, a);
+                walk(3, false, a);
 #pragma unroll
                 for (int k = 0; k < TROWS; ++k) d2[k] -= a[k];
             }
@@ -787,6 +798,7 @@ int solver_setup(eqgpu_solver *s)
     const eqgpu_params &p = s->p;
     s->N = (size_t)p.nW * p.nH;  // replaced by the local size once the slab window is known
     const double hx0 = p.hx, hy0 = p.hy > 0 ? p.hy : p.hx;
+    EQ_CUDA(cudaFuncSetAttribute(k_init_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, INIT_SMEM));
     s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 3;
     // one more sweep on the coarser levels: they are latency-bound, so it is nearly free, and it widens the
     // margin at the 8th iteration (relres 1.6e-13 vs 7.2e-13 at 2048^2; measured 488 vs 479 steps/s)
@@ -1530,7 +1542,7 @@ static int pcg(eqgpu_solver *s)
     // scratch for the extrapolation terms: Ap and pv2 are free until the first k_apply_p writes them
     if (!T && s->init_tile) {
         const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
-        k_init_tile<<<gi, INIT_THREADS, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2,
+        k_init_tile<<<gi, INIT_THREADS, INIT_SMEM, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2,
                                         rs_l, rs_r, s->partials, s->counters + 0, sc, sl ? 1 : 0);
         if (sl) {
             slab_allreduce(s, &sc->part_rrD, &sc->rrD, 1);
