@@ -33,7 +33,7 @@ API_SYMBOLS = [
     "eqgpu_cells_gather_resident", "eqgpu_cells_scatter_resident", "eqgpu_cells_get_gathered",
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
     "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
-    "eqgpu_last_guess",
+    "eqgpu_last_guess", "eqgpu_cells_tensor", "eqgpu_get_tensor",
 ]
 
 
@@ -312,6 +312,15 @@ class GpuHSL:
         a = _f64(amount_nM)
         assert a.size == self.ncells
         self._ck(lib().eqgpu_cells_scatter(self._h, _dp(a)))
+
+    def cells_tensor(self, Dx: float, Dy: float):
+        """setDiffusionTensor for every uploaded rod (src/abm/eQabm.cpp:306-325); becomes the solver's tensor."""
+        self._ck(lib().eqgpu_cells_tensor(self._h, C.c_double(Dx), C.c_double(Dy)))
+
+    def get_tensor(self):
+        a, b, c = np.empty(self.N), np.empty(self.N), np.empty(self.N)
+        self._ck(lib().eqgpu_get_tensor(self._h, _dp(a), _dp(b), _dp(c)))
+        return a, b, c
 
     # -- device-resident cell ops (no host copies inside) ---------------------
     def set_amounts(self, amount_nM):

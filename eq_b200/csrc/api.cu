@@ -168,7 +168,7 @@ void eqgpu_destroy(eqgpu_solver *s)
     cudaStreamSynchronize(s->stream);
     slab_destroy_comm(s);
     solver_teardown(s);
-    cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt); cudaFree(s->bin_ints);
+    cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt); cudaFree(s->bin_ints); cudaFree(s->tensor_owner);
     if (s->own_stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -219,6 +219,36 @@ int eqgpu_set_tensor(eqgpu_solver *s, const double *d11, const double *d22, cons
     s->tensor = true;
     int rc = solver_refresh_levels(s);
     if (rc) return rc;
+    EQ_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int eqgpu_cells_tensor(eqgpu_solver *s, double Dx, double Dy)
+{
+    CHECK_S(s);
+    if (s->slab) { s->set_error("variable tensor is single-GPU only for now"); return EQGPU_ESTATE; }
+    if (!(Dx > 0) || !(Dy > 0)) { s->set_error("axial / transverse scalings must be positive"); return EQGPU_EINVAL; }
+    int rc = cells_tensor(s, Dx, Dy);
+    if (rc) return rc;
+    // Dx == Dy == 1 (the shipped values, src/eQinit.h:64-65): the grids differ from 1,1,0 only by the
+    // rounding of c^2 + s^2 (<= 1 ulp), so the solve stays on the constant-coefficient kernels.
+    s->tensor = !(Dx == 1.0 && Dy == 1.0);
+    return solver_refresh_levels(s);
+}
+
+int eqgpu_get_tensor(eqgpu_solver *s, double *d11, double *d22, double *d12)
+{
+    CHECK_S(s);
+    if (!d11 || !d22 || !d12) { s->set_error("null tensor output"); return EQGPU_EINVAL; }
+    if (s->slab) { s->set_error("variable tensor is single-GPU only for now"); return EQGPU_ESTATE; }
+    const size_t n = s->N, bytes = sizeof(double) * n;
+    if (!s->d11) {   // never set: the isotropic default of src/fHSL.cpp:313-323
+        for (size_t g = 0; g < n; ++g) { d11[g] = 1.0; d22[g] = 1.0; d12[g] = 0.0; }
+        return 0;
+    }
+    EQ_CUDA(cudaMemcpyAsync(d11, s->d11, bytes, cudaMemcpyDeviceToHost, s->stream));
+    EQ_CUDA(cudaMemcpyAsync(d22, s->d22, bytes, cudaMemcpyDeviceToHost, s->stream));
+    EQ_CUDA(cudaMemcpyAsync(d12, s->d12, bytes, cudaMemcpyDeviceToHost, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }

@@ -331,6 +331,66 @@ k_cells_scatter_rest(const double *__restrict__ cells, long long ncells, double 
     }
 }
 
+// ---------------------------------------------------------------------------
+// setDiffusionTensor (src/abm/eQabm.cpp:246-248,306-325,407): the D11/D22/D12 grids are reset to 1,1,0
+// and every cell writes the rotated tensor on its interior points; cells are visited in list order, so on
+// a node shared by two rods the LATER record wins.  Two passes reproduce that without ordering the rods:
+// k_tensor_owner leaves the highest record index per node (atomicMax), k_tensor_write lets exactly that
+// rod store.  cos/sin of cpmCell->angle come in record slots 14,15 from the host's libm (as upstream), and
+// the three products are explicit round-to-nearest mul/add, so the grids equal the CPU's bit for bit.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tensor_reset(size_t n, double *__restrict__ d11, double *__restrict__ d22, double *__restrict__ d12,
+               int *__restrict__ owner)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        d11[g] = 1.0; d22[g] = 1.0; d12[g] = 0.0; owner[g] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
+k_tensor_owner(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
+               int *__restrict__ owner)
+{
+    const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
+    if (k >= ncells) return;
+    const int lane = threadIdx.x & 31;
+    const double *c = cells + k * EQGPU_CELL_STRIDE;
+    const long long N = (long long)nH * nW;
+    int found = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned, bool in, int) {
+        if (in) atomicMax(owner + node, (int)k);
+    });
+    if (found == 0 && lane == 0) {
+        const long long cn = centre_node(c, npm, nW);
+        if (cn >= 0 && cn < N) atomicMax(owner + cn, (int)k);   // gridFunction::isValidIndex (src/eQ.h:66-69)
+    }
+}
+
+__global__ void __launch_bounds__(32 * CELLS_PER_BLOCK)
+k_tensor_write(const double *__restrict__ cells, long long ncells, double npm, int nH, int nW, int nte,
+               double Dx, double Dy, const int *__restrict__ owner, double *__restrict__ d11,
+               double *__restrict__ d22, double *__restrict__ d12)
+{
+    const long long k = (long long)blockIdx.x * CELLS_PER_BLOCK + (threadIdx.x >> 5);
+    if (k >= ncells) return;
+    const int lane = threadIdx.x & 31;
+    const double *c = cells + k * EQGPU_CELL_STRIDE;
+    const long long N = (long long)nH * nW;
+    const double ct = c[14], st = c[15];
+    const double cos2t = mul(ct, ct), sin2t = mul(st, st), sincost = mul(st, ct);
+    const double v11 = add(mul(Dx, cos2t), mul(Dy, sin2t));
+    const double v22 = add(mul(Dx, sin2t), mul(Dy, cos2t));
+    const double v12 = mul(sub(Dx, Dy), sincost);
+    int found = raster_walk(c, npm, nH, nW, nte, [&](long long node, unsigned, bool in, int) {
+        if (in && owner[node] == (int)k) { d11[node] = v11; d22[node] = v22; d12[node] = v12; }
+    });
+    if (found == 0 && lane == 0) {
+        const long long cn = centre_node(c, npm, nW);
+        if (cn >= 0 && cn < N && owner[cn] == (int)k) { d11[cn] = v11; d22[cn] = v22; d12[cn] = v12; }
+    }
+}
+
 static int nte_of(double npm) { return (int)llround(npm * 1.0 / 2.0); }  // src/abm/eQabm.cpp:75
 
 int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap)
@@ -415,6 +475,31 @@ int cells_scatter(eqgpu_solver *s, const double *d_amount)
         s->cells, s->ncells, s->npm, s->p.nH, s->p.nW, nte_of(s->npm), d_amount, s->cell_counts, s->u,
         s->levels[0].dev.row0, s->levels[0].g0, s->levels[0].g1);
     s->launches++;
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// D11/D22/D12 from the uploaded rods into the solver's tensor fields (allocated on first use).
+int cells_tensor(eqgpu_solver *s, double Dx, double Dy)
+{
+    const size_t n = s->N;
+    if (!s->d11) {
+        EQ_CUDA(cudaMalloc(&s->d11, sizeof(double) * n));
+        EQ_CUDA(cudaMalloc(&s->d22, sizeof(double) * n));
+        EQ_CUDA(cudaMalloc(&s->d12, sizeof(double) * n));
+    }
+    if (!s->tensor_owner) EQ_CUDA(cudaMalloc(&s->tensor_owner, sizeof(int) * n));
+    k_tensor_reset<<<4 * s->num_sms, 256, 0, s->stream>>>(n, s->d11, s->d22, s->d12, s->tensor_owner);
+    s->launches++;
+    if (s->ncells > 0) {
+        const int blocks = (int)((s->ncells + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK);
+        k_tensor_owner<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(s->cells, s->ncells, s->npm, s->p.nH, s->p.nW,
+                                                                       nte_of(s->npm), s->tensor_owner);
+        k_tensor_write<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(s->cells, s->ncells, s->npm, s->p.nH, s->p.nW,
+                                                                       nte_of(s->npm), Dx, Dy, s->tensor_owner, s->d11,
+                                                                       s->d22, s->d12);
+        s->launches += 2;
+    }
     EQ_CUDA(cudaGetLastError());
     return 0;
 }

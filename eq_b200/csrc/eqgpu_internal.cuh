@@ -121,6 +121,7 @@ struct eqgpu_solver {
     int graph_phase = 0;
     int graph_launches = 0;
     double *d11 = nullptr, *d22 = nullptr, *d12 = nullptr;
+    int *tensor_owner = nullptr;   // per node: highest record index of the rods covering it (cells_tensor)
     // Dirichlet data
     double dir_val[4] = {0, 0, 0, 0};
     double *chan_top = nullptr, *chan_bot = nullptr;       // channel u (nW)
@@ -171,6 +172,7 @@ int slab_unique_id(void *out128);
 int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap);
 int cells_gather(eqgpu_solver *s, double *d_out);
 int cells_scatter(eqgpu_solver *s, const double *d_amount);
+int cells_tensor(eqgpu_solver *s, double Dx, double Dy);
 // ---- channels.cu ----
 int channels_setup(eqgpu_solver *s);
 int channels_step(eqgpu_solver *s);

@@ -160,6 +160,15 @@ EQGPU_API int eqgpu_cells_gather(eqgpu_solver *s, double *out);
 /* writeHSL for every cell: amount_nM[k] is Strain's deltaHSL for this layer. */
 EQGPU_API int eqgpu_cells_scatter(eqgpu_solver *s, const double *amount_nM);
 
+/* setDiffusionTensor for every cell (src/abm/eQabm.cpp:246-248,306-325,407): the D11/D22/D12 fields are
+ * reset to 1,1,0 and each rod writes Dx c^2 + Dy s^2, Dx s^2 + Dy c^2, (Dx - Dy) s c on its points (Dx, Dy =
+ * parameters["AnisotropicDiffusion_Axial" / "_Transverse"]); a later record wins a shared node, as the
+ * reference's list order does.  The result becomes the solver's tensor, as after eqgpu_set_tensor (with
+ * Dx == Dy == 1, the shipped values, the solve stays on the constant-coefficient kernels: the fields
+ * then differ from 1,1,0 by rounding only).  eqgpu_get_tensor copies the three fields to the host. */
+EQGPU_API int eqgpu_cells_tensor(eqgpu_solver *s, double Dx, double Dy);
+EQGPU_API int eqgpu_get_tensor(eqgpu_solver *s, double *d11, double *d22, double *d12);
+
 /* writeHSL strategy: 0 = one global fp64 atomic per (rod, node) (default; exact for non-overlapping rods),
  * 1 = rods binned by 64x64-node tile and accumulated with shared-memory atomics before one global atomic
  * per touched node (dense / overlapping colonies). */

@@ -770,7 +770,9 @@ EQO_API void eqo_robin_rates(double v, double D, double L_left, double L_right,
  *  4    offset  (vertsA[0].x = -offset)         5    newOffset (vertsA[1].x)
  *  6    radius                                  7,8  polePositionA (x,y)
  *  9,10 polePositionB                           11,12 centre (x,y)
- *  13   length                                  14,15 unused */
+ *  13   length                                  14,15 cos, sin of cpmCell->angle
+ *       (the mean body angle setDiffusionTensor receives, src/abm/Ecoli.h:42,
+ *        src/abm/cpmEcoli.cpp:387-389; evaluated by the HOST's libm, as upstream) */
 #define CELL_STRIDE 16
 
 /* src/eQ.h:119-130 ij_from_xy: size_t(round(x*n)); C round = half away from 0. */
@@ -956,5 +958,39 @@ EQO_API void eqo_make_cell(double cx, double cy, double angle, double length,
         if (py > trapH) py = trapH;
         rec[7 + 2 * k] = px; rec[8 + 2 * k] = py;
     }
-    rec[11] = cx; rec[12] = cy; rec[13] = length; rec[14] = 0; rec[15] = 0;
+    rec[11] = cx; rec[12] = cy; rec[13] = length;
+    rec[14] = ca; rec[15] = sa;  /* fresh cell: angle == both body angles (cpmEcoli.cpp:107,155-158) */
+}
+
+/* src/abm/eQabm.cpp:246-248 (D11/D22/D12 grids reset to 1,1,0 every step) and
+ * :306-325,407 setDiffusionTensor for every cell in list order: on the cell's
+ * interior points D11 = Dx c^2 + Dy s^2, D22 = Dx s^2 + Dy c^2,
+ * D12 = (Dx - Dy) s c with c = cos(theta), s = sin(theta) (record slots 14,15);
+ * a later cell overwrites an earlier one on a shared node; points outside the
+ * grid are skipped (gridFunction::isValidIndex, src/eQ.h:66-69). */
+EQO_API void eqo_cells_tensor(const double *cells, long ncells, double npm,
+                              long nH, long nW, long nodesToEdge, double Dx,
+                              double Dy, double *d11, double *d22, double *d12)
+{
+    const long N = nH * nW;
+    for (long g = 0; g < N; ++g) { d11[g] = 1.0; d22[g] = 1.0; d12[g] = 0.0; }
+    long cap = 4096;
+    long *nodes = malloc(sizeof(long) * cap);
+    for (long k = 0; k < ncells; ++k) {
+        const double *c = cells + k * CELL_STRIDE;
+        long n = eqo_raster_cell(c, npm, nH, nW, nodesToEdge, nodes, cap);
+        const double ct = c[14], st = c[15];
+        double cos2t = ct * ct;
+        double sin2t = st * st;
+        double sincost = st * ct;
+        for (long p = 0; p < n; ++p) {
+            const long i = nodes[p] / nW, j = nodes[p] - i * nW;
+            if (nodes[p] >= 0 && i < nH && j < nW) {
+                d11[nodes[p]] = Dx * cos2t + Dy * sin2t;
+                d22[nodes[p]] = Dx * sin2t + Dy * cos2t;
+                d12[nodes[p]] = (Dx - Dy) * sincost;
+            }
+        }
+    }
+    free(nodes);
 }

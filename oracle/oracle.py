@@ -321,6 +321,14 @@ def scatter(cells, npm, nH, nW, amount_nM, u):
     return u
 
 
+def cells_tensor(cells, npm, nH, nW, Dx, Dy):
+    """eQabm::updateCells' D11/D22/D12 grids (src/abm/eQabm.cpp:246-248,306-325,407)."""
+    d11, d22, d12 = np.empty(nH * nW), np.empty(nH * nW), np.empty(nH * nW)
+    lib().eqo_cells_tensor(_dp(cells), C.c_long(cells.shape[0]), C.c_double(npm), C.c_long(nH), C.c_long(nW),
+                           C.c_long(nodes_to_edge(npm)), C.c_double(Dx), C.c_double(Dy), _dp(d11), _dp(d22), _dp(d12))
+    return d11, d22, d12
+
+
 def update_cells_sequential(cells, npm, nH, nW, a0, a1, u):
     u = np.array(u, dtype=np.float64, copy=True)
     g = np.zeros(cells.shape[0])

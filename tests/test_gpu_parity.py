@@ -156,6 +156,48 @@ def test_tensor_operator_and_step(oracle):
     g.close()
 
 
+@pytest.mark.parametrize("npm,shape", [(2.0, (201, 41)), (4.0, (401, 81))])
+def test_cells_tensor_feed_bit_exact_and_step(oracle, npm, shape):
+    """eqgpu_cells_tensor == eQabm::updateCells' setDiffusionTensor (src/abm/eQabm.cpp:246-248,306-325,407):
+    the three grids bit-exact (overlapping rods included: the later record wins), and a step with the fed
+    tensor against the direct solve of the system assembled with the oracle's grids."""
+    nW, nH = shape
+    p, g = make(oracle, nW, nH, **BCS["robin_lr_dir_tb"], h=1.0 / npm)
+    rng = np.random.default_rng(17)
+    n = 160
+    centers = np.c_[rng.uniform(1, p.W - 1, n), rng.uniform(0.5, p.H - 0.5, n)]
+    cells = oracle.make_cells(centers, rng.uniform(0, 2 * np.pi, n), (1 + rng.uniform(size=n)) * 2.1, p.W, p.H)
+    # the heading setDiffusionTensor sees is the mean body angle, not bodyA's: give some rods another one
+    th = rng.uniform(0, 2 * np.pi, n)
+    cells[::3, 14], cells[::3, 15] = np.cos(th[::3]), np.sin(th[::3])
+    cells = np.vstack([cells, cells[:20]])          # duplicates: full overlap, later record must win
+    cells[-20:, 14], cells[-20:, 15] = np.cos(th[:20] + 1.0), np.sin(th[:20] + 1.0)
+    Dx, Dy = 1.5, 0.6
+    g.upload_cells(cells, npm)
+    g.cells_tensor(Dx, Dy)
+    ref = oracle.cells_tensor(cells, npm, nH, nW, Dx, Dy)
+    got = g.get_tensor()
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    assert g.path()["tensor"]
+    p.d11, p.d22, p.d12 = ref
+    bands, _ = oracle.assemble(p, None)
+    x = field(p, 1, smooth=False)
+    assert rel(g.apply_operator(x), oracle.band_matvec(p, bands, x)) < 1e-12
+    u0 = field(p, 4)
+    g.solution_vector[:] = u0
+    assert rel(g.stepDiffusion(), oracle.solve_lu(p, u0)) < TOL
+    # the shipped scalings Dx = Dy = 1: grids still written (bit-exact), solve stays on the isotropic kernels
+    g.cells_tensor(1.0, 1.0)
+    for a, b in zip(g.get_tensor(), oracle.cells_tensor(cells, npm, nH, nW, 1.0, 1.0)):
+        assert np.array_equal(a, b)
+    assert not g.path()["tensor"]
+    p.d11 = p.d22 = p.d12 = None
+    g.solution_vector[:] = u0
+    assert rel(g.stepDiffusion(), oracle.solve_lu(p, u0)) < TOL
+    g.close()
+
+
 @pytest.mark.parametrize("npm,shape", [(2.0, (201, 41)), (1.0, (101, 21)), (4.0, (401, 81))])
 def test_raster_bit_exact(oracle, npm, shape):
     """Cell -> node lookup must be bit-exact (north_star): identical node lists, order included."""

@@ -238,3 +238,35 @@ def test_full_step_with_channels_runs_and_feeds_back(oracle):
     u = s.u.reshape(p.nH, p.nW)
     assert s.total_boundary_flux > 0  # -oint grad(u).n > 0: net outflow
     assert np.allclose(u[0], prev_bottom, rtol=1e-12) and np.allclose(u[-1], prev_top, rtol=1e-12)
+
+
+def test_cells_tensor_known_answers(oracle):
+    """setDiffusionTensor (src/abm/eQabm.cpp:246-248,306-325): isotropic away from rods; on a horizontal rod
+    (theta = 0) D11 = Dx, D22 = Dy, D12 = 0; on a vertical one the roles swap; trace and determinant of the
+    nodal tensor are rotation invariants (Dx + Dy, Dx * Dy); a later rod overwrites an earlier one."""
+    nW, nH, npm = 81, 61, 2.0
+    W, H = (nW - 1) / npm, (nH - 1) / npm
+    Dx, Dy = 1.5, 0.6
+    cells = oracle.make_cells([(10.0, 10.0), (25.0, 12.0), (30.0, 22.0)], [0.0, np.pi / 2, 0.7], [4.0, 3.5, 4.2], W, H)
+    d11, d22, d12 = oracle.cells_tensor(cells, npm, nH, nW, Dx, Dy)
+    cnt, nodes = oracle.raster(cells, npm, nH, nW, cap=256)
+    touched = np.zeros(nW * nH, dtype=bool)
+    for k in range(3):
+        touched[nodes[k, :cnt[k]]] = True
+    assert np.all(d11[~touched] == 1.0) and np.all(d22[~touched] == 1.0) and np.all(d12[~touched] == 0.0)
+    a = nodes[0, :cnt[0]]
+    assert np.all(d11[a] == Dx) and np.all(d22[a] == Dy) and np.all(d12[a] == 0.0)
+    b = nodes[1, :cnt[1]]
+    assert np.allclose(d11[b], Dy, rtol=1e-15) and np.allclose(d22[b], Dx, rtol=1e-15) and np.all(np.abs(d12[b]) < 1e-16)
+    c = nodes[2, :cnt[2]]
+    assert np.allclose(d11[c] + d22[c], Dx + Dy, rtol=1e-14)
+    assert np.allclose(d11[c] * d22[c] - d12[c] ** 2, Dx * Dy, rtol=1e-14)
+    # list order: the same rod twice with different angles -> the later record's tensor stays
+    two = oracle.make_cells([(10.0, 10.0), (10.0, 10.0)], [0.0, np.pi / 2], [4.0, 4.0], W, H)
+    e11, _, _ = oracle.cells_tensor(two, npm, nH, nW, Dx, Dy)
+    cnt2, nodes2 = oracle.raster(two, npm, nH, nW, cap=256)
+    both = np.intersect1d(nodes2[0, :cnt2[0]], nodes2[1, :cnt2[1]])
+    assert len(both) > 0 and np.allclose(e11[both], Dy, rtol=1e-15)
+    # Dx = Dy = 1 (the shipped values, src/eQinit.h:64-65): identity up to the rounding of c^2 + s^2
+    i11, i22, i12 = oracle.cells_tensor(cells, npm, nH, nW, 1.0, 1.0)
+    assert np.abs(i11 - 1).max() < 3e-16 and np.abs(i22 - 1).max() < 3e-16 and np.all(i12 == 0.0)
