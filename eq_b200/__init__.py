@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libeqgpu.so")
 
 NEUMANN, DIRICHLET, ROBIN, DIRICHLET_CHANNEL = 0, 1, 2, 3
+DISC_P1, DISC_FD = 0, 1   # fenicsInterface's P1 finite elements / diffusionPETSc's 5-point finite differences
 LEFT, RIGHT, TOP, BOTTOM = 0, 1, 2, 3
 CELL_STRIDE = 16
 
@@ -45,7 +46,8 @@ class Params(C.Structure):
         ("channels", C.c_int32), ("channel_iters", C.c_int32), ("channel_v", C.c_double),
         ("channel_r", C.c_double * 2), ("well_scaling", C.c_double), ("rtol", C.c_double),
         ("max_iters", C.c_int32), ("device", C.c_int32), ("stream", C.c_void_p),
-        ("smooth_sweeps", C.c_int32), ("max_levels", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("smooth_sweeps", C.c_int32), ("max_levels", C.c_int32), ("discretisation", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -133,7 +135,7 @@ class GpuHSL:
                  bc_type=(DIRICHLET,) * 4, bc_value=(0.0,) * 4, robin_s=(0.0, 0.0),
                  channels=False, channel_v=120.0, channel_r=(0.0, 0.0), channel_iters=48,
                  well_scaling=25.0, rtol=1e-12, max_iters=200, device=0, stream=None,
-                 smooth_sweeps=0, max_levels=0, hy=None, slab=None):
+                 smooth_sweeps=0, max_levels=0, hy=None, slab=None, discretisation=DISC_P1):
         """slab = (rank, world, nccl_id_bytes) selects the row-slab decomposition (eqgpu_create_slab)."""
         L = lib()
         p = default_params()
@@ -150,6 +152,7 @@ class GpuHSL:
         p.rtol, p.max_iters, p.device = rtol, max_iters, device
         p.stream = stream
         p.smooth_sweeps, p.max_levels = smooth_sweeps, max_levels
+        p.discretisation = int(discretisation)
         self.params = p
         self.nW, self.nH, self.N = nW, nH, nW * nH
         self._h = C.c_void_p()

@@ -110,6 +110,14 @@ static int create_common(const eqgpu_params *p, int rank, int world, const void 
             return EQGPU_EINVAL;
         }
     }
+    if (p->discretisation != EQGPU_DISC_P1 && p->discretisation != EQGPU_DISC_FD) {
+        g_create_error = "unknown discretisation";
+        return EQGPU_EINVAL;
+    }
+    if (p->discretisation == EQGPU_DISC_FD && (p->channels || world > 1)) {
+        g_create_error = "the finite-difference discretisation (diffusionPETSc) has no flow channels and no row slabs";
+        return EQGPU_EINVAL;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -206,6 +214,7 @@ int eqgpu_set_tensor(eqgpu_solver *s, const double *d11, const double *d22, cons
         return solver_refresh_levels(s);
     }
     if (!d11 || !d22 || !d12) { s->set_error("give all three tensor components or none"); return EQGPU_EINVAL; }
+    if (s->p.discretisation == EQGPU_DISC_FD) { s->set_error("the variable tensor belongs to the P1 discretisation"); return EQGPU_ESTATE; }
     if (s->slab) { s->set_error("variable tensor is single-GPU only for now"); return EQGPU_ESTATE; }
     const size_t bytes = sizeof(double) * s->N;
     if (!s->d11) {
@@ -228,6 +237,10 @@ int eqgpu_cells_tensor(eqgpu_solver *s, double Dx, double Dy)
     CHECK_S(s);
     if (s->slab) { s->set_error("variable tensor is single-GPU only for now"); return EQGPU_ESTATE; }
     if (!(Dx > 0) || !(Dy > 0)) { s->set_error("axial / transverse scalings must be positive"); return EQGPU_EINVAL; }
+    if (s->p.discretisation == EQGPU_DISC_FD && !(Dx == 1.0 && Dy == 1.0)) {
+        s->set_error("the variable tensor belongs to the P1 discretisation");
+        return EQGPU_ESTATE;
+    }
     int rc = cells_tensor(s, Dx, Dy);
     if (rc) return rc;
     // Dx == Dy == 1 (the shipped values, src/eQinit.h:64-65): the grids differ from 1,1,0 only by the

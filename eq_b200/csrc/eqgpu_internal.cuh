@@ -33,6 +33,12 @@ struct LevelDev {
     // uniform fast path: nodes 1<=j<=jreg_hi, 1<=i<=ireg_hi see four regular cells
     int jreg_hi, ireg_hi;
     double cC, cEW, cNS, cD, icC;
+    // mass row on regular nodes (load vector b = M u0): centre and each of the six neighbours
+    double mC, mO;
+    // 1: diffusionPETSc's discretisation (diffuclass.cpp:786-862) -- 5-point finite differences with unit
+    // (lumped) mass and ghost-node Robin rows, i.e. lumped nodal mass (aw+ae)(bs+bn)/4 and lumped Robin edge
+    // mass on the same tensor-product grid; 0: the consistent P1 mass of fenics/hslD.ufl
+    int lumped;
     // optional nodal tensor fields (level-local, injected); null = isotropic
     const double *d11, *d22, *d12;
     // row-slab decomposition: the arrays hold global rows [row0, row0+ny) of a gny-row grid, of
@@ -235,6 +241,18 @@ __device__ __forceinline__ void stencil_iso(const LevelDev &L, const Spacing &S,
     const double aw = S.hx[jj], ae = S.hx[jj + 1], bs = S.hy[ii], bn = S.hy[ii + 1];
     const double iaw = S.ihx[jj], iae = S.ihx[jj + 1], ibs = S.ihy[ii], ibn = S.ihy[ii + 1];
     const double sy = 0.5 * L.tau * (bs + bn), sx = 0.5 * L.tau * (aw + ae);
+    if (L.lumped) {
+        // MyMatMult's row (diffuclass.cpp:786-862) times the node's cell share w*h^2 (w = 1, 1/2 on a wall,
+        // 1/4 in a corner), which makes the ghost-node rows symmetric: interior (1+4F)u - F(uE+uW+uN+uS);
+        // wall rows -2F to the inner neighbour, -F along the wall, Robin term 2hF(Dc/Nc) on the diagonal
+        c[B_E] = -sy * iae; c[B_W] = -sy * iaw; c[B_N] = -sx * ibn; c[B_S] = -sx * ibs;
+        c[B_NE] = 0.0; c[B_SW] = 0.0;
+        double cl = sy * (iae + iaw) + sx * (ibn + ibs) + 0.25 * (aw + ae) * (bs + bn);
+        if (j == 0) cl += L.rob_l * 0.5 * (bs + bn);
+        if (j == L.nx - 1) cl += L.rob_r * 0.5 * (bs + bn);
+        c[B_C] = cl;
+        return;
+    }
     const double my = (bs + bn) * (1.0 / 24.0), mx = (aw + ae) * (1.0 / 24.0);
     c[B_E] = ae * my - sy * iae;
     c[B_W] = aw * my - sy * iaw;
@@ -267,6 +285,11 @@ __device__ __forceinline__ void stencil_iso(const LevelDev &L, int i, int j, dou
 __device__ __forceinline__ void stencil_mass(const LevelDev &L, int i, int j, double c[NBAND])
 {
     const double aw = L.hx[j], ae = L.hx[j + 1], bs = L.hy[i], bn = L.hy[i + 1];
+    if (L.lumped) {   // b_i = u0_i of diffuclass.cpp (TimeStep: KSPSolve(b = globalVector)), times the cell share
+        c[B_E] = 0.0; c[B_W] = 0.0; c[B_N] = 0.0; c[B_S] = 0.0; c[B_NE] = 0.0; c[B_SW] = 0.0;
+        c[B_C] = 0.25 * (aw + ae) * (bs + bn);
+        return;
+    }
     const double my = (bs + bn) * (1.0 / 24.0), mx = (aw + ae) * (1.0 / 24.0);
     c[B_E] = ae * my; c[B_W] = aw * my; c[B_N] = bn * mx; c[B_S] = bs * mx;
     c[B_NE] = ae * bn * (1.0 / 12.0);

@@ -33,6 +33,10 @@ __device__ __forceinline__ double dir_value(const LevelDev &L, const DirData &d,
     // DirichletBC objects are applied in the order left,right,top,bottom
     // (src/fHSL.cpp:468-539); the last one applied wins at a corner.
     const unsigned m = L.dirmask;
+    if (L.lumped) {   // ApplyBoundaryConditions writes top/bottom first, then right/left (diffuclass.cpp:218-272)
+        if ((m & 2u) && j == L.nx - 1) return d.val[1];
+        if ((m & 1u) && j == 0) return d.val[0];
+    }
     if ((m & 8u) && i == 0) return d.bot ? d.bot[j] : d.val[3];
     if ((m & 4u) && i == L.ny - 1) return d.top ? d.top[j] : d.val[2];
     if ((m & 2u) && j == L.nx - 1) return d.val[1];
@@ -96,8 +100,8 @@ __device__ __forceinline__ double load_row(const LevelDev &L, int i, int j,
 {
     double c[NBAND];
     if (i >= 1 && i <= L.ireg_hi && j >= 1 && j <= L.jreg_hi) {  // regular node: constant consistent-mass row
-        const double m = L.cD;  // hx*hy/12
-        c[B_C] = 6.0 * m; c[B_E] = m; c[B_W] = m; c[B_N] = m; c[B_S] = m; c[B_NE] = m; c[B_SW] = m;
+        const double m = L.mO;  // hx*hy/12 (0 with the lumped mass)
+        c[B_C] = L.mC; c[B_E] = m; c[B_W] = m; c[B_N] = m; c[B_S] = m; c[B_NE] = m; c[B_SW] = m;
     } else stencil_mass(L, i, j, c);
     double b = stencil_dot(L, i, j, c, u0);
     if (j == 0) b += rs_l * 0.5 * (L.hy[i] + L.hy[i + 1]);
@@ -247,7 +251,8 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
         // 7-point walk up the thread's column over tile q: mass row or operator row
         auto walk = [&](int q, bool mass, double (&out)[TROWS]) {
             const double *sp = sm_init + q * (TPI * TPI);
-            const double cC = mass ? 6.0 * L.cD : L.cC, cEW = mass ? L.cD : L.cEW, cNS = mass ? L.cD : L.cNS, cD = L.cD;
+            const double cC = mass ? L.mC : L.cC, cEW = mass ? L.mO : L.cEW, cNS = mass ? L.mO : L.cNS;
+            const double cD = mass ? L.mO : L.cD;
             int c = (ly0 + 1) * TPI + lx + 1;
             double sw = 0.0, s0 = 0.0;
             if (ly0 > 0) { sw = sp[c - TPI - 1]; s0 = sp[c - TPI]; }
@@ -767,10 +772,20 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
     // node j (1 <= j) is regular when cells j-1 and j are: j <= leading_regular-1
     L.jreg_hi = std::min(leading_regular(lv.hx_host) - 1, L.nx - 2);
     L.ireg_hi = std::min(leading_regular(lv.hy_host) - 1, L.gny - 2) - L.row0;  // local index
-    L.cC = 2.0 * L.tau * (b / a + a / b) + a * b * 0.5;
-    L.cEW = a * b / 12.0 - L.tau * b / a;
-    L.cNS = a * b / 12.0 - L.tau * a / b;
-    L.cD = a * b / 12.0;
+    L.lumped = p.discretisation == EQGPU_DISC_FD ? 1 : 0;
+    if (L.lumped) {   // 5-point row times h^2: (1 + 4F) and -F of diffuclass.cpp:857-860
+        L.mC = a * b; L.mO = 0.0;
+        L.cC = 2.0 * L.tau * (b / a + a / b) + a * b;
+        L.cEW = -L.tau * b / a;
+        L.cNS = -L.tau * a / b;
+        L.cD = 0.0;
+    } else {
+        L.mC = a * b * 0.5; L.mO = a * b / 12.0;
+        L.cC = 2.0 * L.tau * (b / a + a / b) + a * b * 0.5;
+        L.cEW = a * b / 12.0 - L.tau * b / a;
+        L.cNS = a * b / 12.0 - L.tau * a / b;
+        L.cD = a * b / 12.0;
+    }
     L.icC = 1.0 / L.cC;
     L.hx = lv.d_hx; L.ihx = lv.d_ihx; L.hy = lv.d_hy; L.ihy = lv.d_ihy;
     L.d11 = lv.t11; L.d22 = lv.t22; L.d12 = lv.t12;
@@ -1202,7 +1217,8 @@ static CoarseW coarse_weights(eqgpu_solver *s)
     const Level &c = s->levels.back();
     const double F = s->p.dt * s->p.D / (c.hx_host[0] * c.hy_host[0]);
     // smallest eigenvalue of D^-1 A >= (mass row sum)/(diagonal) = 1/(0.5 + 4F) on square cells
-    const double lo = 0.8 / (0.5 + 4.0 * F), hi = 2.0;
+    // (1/(1 + 4F) with the lumped mass of the finite-difference discretisation)
+    const double lo = 0.8 / ((s->p.discretisation == EQGPU_DISC_FD ? 1.0 : 0.5) + 4.0 * F), hi = 2.0;
     const double sigma = (hi + lo) / (hi - lo);
     double target = 50.0;   // worst-case error reduction of the coarsest solve over [lo, hi]
     if (const char *e = getenv("EQGPU_COARSE_TARGET")) target = std::max(2.0, atof(e));   // tuning knob

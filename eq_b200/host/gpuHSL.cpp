@@ -122,6 +122,7 @@ void gpuHSL::pushTensorIfChanged()
 {
     // The controller sends D11/D22/D12 every step (src/simulation.cpp:503-505) but as shipped they
     // stay 1,1,0 (SURVEY.md finding 5): only a non-trivial tensor switches the variable-tensor operator on.
+    if (tensorFromCells) return;   // the tensor was rasterised on the device (setDiffusionTensorFromCells)
     bool iso = true;
     const size_t N = solution_vector.size();
     for (size_t k = 0; k < N && iso; ++k)
@@ -177,6 +178,12 @@ void gpuHSL::setBoundaryValues(const double v) { check(eqgpu_set_boundary_value(
 void gpuHSL::uploadCells(const double *records, size_t n)
 {
     check(eqgpu_cells_upload(h, records, (int64_t)n, myParams.nodesPerMicron), "eqgpu_cells_upload");
+}
+void gpuHSL::setDiffusionTensorFromCells(double Dx, double Dy, bool fetch)
+{
+    check(eqgpu_cells_tensor(h, Dx, Dy), "eqgpu_cells_tensor");
+    tensorFromCells = true;
+    if (fetch) check(eqgpu_get_tensor(h, D11->data(), D22->data(), D12->data()), "eqgpu_get_tensor");
 }
 void gpuHSL::readHSL(double *out) { check(eqgpu_cells_gather(h, out), "eqgpu_cells_gather"); }
 void gpuHSL::writeHSL(const double *amount) { check(eqgpu_cells_scatter(h, amount), "eqgpu_cells_scatter"); }

@@ -78,6 +78,10 @@ public:
     void uploadCells(const double *records, size_t ncells);  // EQGPU_CELL_STRIDE doubles each
     void readHSL(double *out);                               // src/abm/eQabm.cpp:326-337, all cells
     void writeHSL(const double *amount_nM);                  // src/abm/eQabm.cpp:338-359, all cells
+    // setDiffusionTensor for all uploaded cells (src/abm/eQabm.cpp:246-248,306-325,407) straight into the
+    // solver's tensor; Dx, Dy = parameters["AnisotropicDiffusion_Axial" / "_Transverse"].  fetch = also copy
+    // the three grids into D11/D22/D12 (what the controller would have sent, src/simulation.cpp:503-505)
+    void setDiffusionTensorFromCells(double Dx, double Dy, bool fetch = false);
     void stepDiffusionResident();                            // stepDiffusion without the host round trip
     void fetchSolution();                                    // device field -> solution_vector
 
@@ -86,8 +90,42 @@ public:
 
 private:
     eqgpu_solver *h = nullptr;
+    bool tensorFromCells = false;
     double leftRate = 0.0, rightRate = 0.0, channelFlowVelocity = 0.0;
     bool tensorDirty = false;
     void check(int rc, const char *what);
     void pushTensorIfChanged();
+};
+
+// The boundary-well model Simulation keeps next to a DIRICHLET_UPDATE layer (src/simulation.cpp:581-627):
+// the HSL that leaves the trap accumulates in the flow channels' volume, decays with the flow, and comes
+// back as the Dirichlet value of every wall.  Same members and arithmetic as Simulation's; `solver` is any
+// class with totalBoundaryFlux and setBoundaryValues(double) (gpuHSL, fenicsInterface).
+struct boundaryWell {
+    double boundaryWellConcentration = 0.0, boundaryDecayRate = 0.0, wellScaling = 0.0, dt = 0.0;
+    long boundaryUnderFlow = 0;
+    bool dirichletUpdate = true;   // "DIRICHLET_UPDATE" == parameters["boundaryType"]
+    // initBoundaryWell + setBoundaryRate (src/simulation.cpp:607-627)
+    void init(double dt_, double lengthScaling, double simulationTrapWidthMicrons, double simulationTrapHeightMicrons,
+              double simulationFlowRate)
+    {
+        dt = dt_;
+        boundaryWellConcentration = 0.0;
+        boundaryUnderFlow = 0;
+        wellScaling = 2.0 * 10.0 * (15.0 / lengthScaling) * (simulationTrapWidthMicrons + simulationTrapHeightMicrons);
+        boundaryDecayRate = simulationFlowRate / simulationTrapWidthMicrons;
+    }
+    // computeBoundaryWell (src/simulation.cpp:581-605)
+    template <class Solver>
+    void compute(Solver &solver)
+    {
+        const double flux = solver.totalBoundaryFlux;
+        boundaryWellConcentration += flux / wellScaling;
+        boundaryWellConcentration -= dt * boundaryDecayRate * boundaryWellConcentration;
+        if (boundaryWellConcentration < 0.0) {
+            boundaryWellConcentration = 0.0;
+            boundaryUnderFlow++;
+        }
+        if (dirichletUpdate) solver.setBoundaryValues(boundaryWellConcentration);
+    }
 };

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#include "gpuFD.h"
 #include "gpuHSL.h"
 
 static std::vector<double> read_all(const char *path)
@@ -34,8 +35,51 @@ int main(int argc, char **argv)
     const double *cells = in.data() + 7;
     const double *deposit = cells + ncells * EQGPU_CELL_STRIDE;
 
+    eQ::diffusionSolver::params p{};
+    p.dt = dt; p.D_HSL = D; p.trapHeightMicrons = H; p.trapWidthMicrons = W; p.nodesPerMicron = npm;
+    p.uniqueID = 0; p.comm = 0;
+
+    if (kase == "fd" || kase == "fd_robin") {
+        // diffusionPETSc driven through eQ::diffusionSolver the way src/simulation.cpp:211,244,475 would
+        // (the PETSC_SIMULATION branch): initDiffusion, then deposits arrive and stepDiffusion runs
+        try {
+            std::shared_ptr<gpuFD> solver = std::make_shared<gpuFD>();
+            solver->initDiffusion(p);
+            if (kase == "fd_robin") {   // "set boundaries explicitly by writing the data structures" (diffuclass.cpp:123)
+                solver->initData.leftNeumannCoefficient = 1.0; solver->initData.leftDirichletCoefficient = 0.1;
+                solver->initData.leftBoundaryValue = 0.03;
+                solver->initData.rightNeumannCoefficient = 1.0; solver->initData.rightDirichletCoefficient = 0.02;
+                solver->initData.rightBoundaryValue = 0.0;
+                solver->initData.topBoundaryValue = 2.0; solver->initData.bottomBoundaryValue = 0.5;
+                solver->applyBoundaryCoefficients();
+            }
+            const size_t N = solver->solution_vector.size();
+            std::vector<double> flux;
+            for (int s = 0; s < nsteps; ++s) {
+                for (size_t k = 0; k < N; ++k) solver->solution_vector[k] += deposit[k];
+                solver->stepDiffusion();
+                flux.push_back(solver->getBoundaryFlux()["totalFlux"]);
+            }
+            FILE *f = fopen(argv[3], "wb");
+            double hdr[3] = {double(solver->gridNodesX), double(solver->gridNodesY), double(solver->lastIterations())};
+            fwrite(hdr, sizeof(double), 3, f);
+            fwrite(solver->solution_vector.data(), sizeof(double), N, f);
+            std::vector<double> zero(2 * solver->gridNodesX, 0.0);
+            fwrite(zero.data(), sizeof(double), zero.size(), f);
+            fwrite(flux.data(), sizeof(double), flux.size(), f);
+            fclose(f);
+            solver->finalize();
+        } catch (const std::exception &e) {
+            fprintf(stderr, "%s\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
+
     gpuHSL::config cfg;
-    if (kase == "default") { cfg.boundaryType = "DIRICHLET_0"; cfg.trapType = "NOWALLED"; }
+    bool well = false;
+    if (kase == "well") { cfg.boundaryType = "DIRICHLET_UPDATE"; cfg.trapType = "NOWALLED"; well = true; }
+    else if (kase == "default") { cfg.boundaryType = "DIRICHLET_0"; cfg.trapType = "NOWALLED"; }
     else if (kase == "threewall") { cfg.boundaryType = "DIRICHLET_0"; cfg.trapType = "THREEWALLED"; }
     else if (kase == "htrap") {  // MICROFLUIDIC_TRAP + H_TRAP: Robin left/right = flow rate, top/bottom Neumann
         cfg.boundaryType = "MICROFLUIDIC_TRAP"; cfg.trapType = "H_TRAP";
@@ -49,20 +93,22 @@ int main(int argc, char **argv)
         memcpy(cfg.boundaries[2], chan, sizeof chan); memcpy(cfg.boundaries[3], chan, sizeof chan);
     } else { fprintf(stderr, "unknown case\n"); return 2; }
 
-    eQ::diffusionSolver::params p{};
-    p.dt = dt; p.D_HSL = D; p.trapHeightMicrons = H; p.trapWidthMicrons = W; p.nodesPerMicron = npm;
-    p.uniqueID = 0; p.comm = 0;
-
     std::shared_ptr<gpuHSL> solver = std::make_shared<gpuHSL>(cfg);  // simulation.cpp:207
     try {
         solver->initDiffusion(p);                                    // simulation.cpp:244
         const size_t N = solver->solution_vector.size();
         if (solver->shell->mesh->num_vertices() != N) return 3;      // simulation.cpp:298-301
         std::vector<double> flux;
+        boundaryWell bw;
+        if (well) bw.init(dt, cfg.lengthScaling, W, H, cfg.simulationFlowRate);   // simulation.cpp:607-627
         for (int s = 0; s < nsteps; ++s) {
             for (size_t k = 0; k < N; ++k) solver->solution_vector[k] += deposit[k];  // controller's writeHSL result arrives
             solver->stepDiffusion();                                 // simulation.cpp:475
-            flux.push_back(solver->getBoundaryFlux()["totalFlux"]);
+            if (well) {                                              // simulation.cpp:581-605 (after every HSL step)
+                bw.compute(*solver);
+                flux.push_back(bw.boundaryWellConcentration);
+            } else
+                flux.push_back(solver->getBoundaryFlux()["totalFlux"]);
         }
         FILE *f = fopen(argv[3], "wb");
         double hdr[3] = {double(solver->nodesW), double(solver->nodesH), double(solver->lastIterations())};

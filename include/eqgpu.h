@@ -55,6 +55,15 @@ enum {
     EQGPU_BC_DIRICHLET_CHANNEL = 3   /* top/bottom only: value = channel u   */
 };
 
+/* Discretisation = which of the reference's two eQ::diffusionSolver implementations the solver stands in for:
+ * fenicsInterface (P1 finite elements, fenics/hslD.ufl) or diffusionPETSc (diffuclass.cpp: 5-point finite
+ * differences, unit mass, ghost-node Neumann/Robin rows `-2F u_inner ... + (1 + (4 + 2h Dc/Nc) F) u`,
+ * :786-862, right-hand side u0 + 2Fh BV/Nc, :191-275).  With EQGPU_DISC_FD a wall's coefficients map as
+ * Dirichlet (Nc = 0): bc_value = BV/Dc; Neumann: Dc = 0, BV = 0; Robin (left/right): bc_value = r = D*Dc/Nc,
+ * robin_s = BV/Dc.  At a corner a Dirichlet wall wins, and left/right values win over top/bottom ones
+ * (the write order of ApplyBoundaryConditions).  The variable tensor and row slabs are P1-only. */
+enum { EQGPU_DISC_P1 = 0, EQGPU_DISC_FD = 1 };
+
 /* What fenicsInterface::initDiffusion reads from eQ::diffusionSolver::params
  * (src/eQ.h:305-321) and from eQ::data::parameters (SURVEY.md 8b "globals"). */
 typedef struct eqgpu_params {
@@ -77,7 +86,8 @@ typedef struct eqgpu_params {
     void *stream;             /* cudaStream_t to run on, or NULL for an own stream */
     int32_t smooth_sweeps;    /* multigrid pre/post sweeps; <=0 -> default   */
     int32_t max_levels;       /* <=0 -> automatic                            */
-    int32_t reserved[8];
+    int32_t discretisation;   /* EQGPU_DISC_P1 (default) or EQGPU_DISC_FD          */
+    int32_t reserved[7];
 } eqgpu_params;
 
 typedef struct eqgpu_stats {

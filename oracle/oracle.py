@@ -374,3 +374,154 @@ def synthetic_colony(n, trapW, trapH, seed=12345, min_clear=1.2, margin=3.0):
         angles.append(a)
         lengths.append(L)
     return make_cells(centers, angles, lengths, trapW, trapH)
+
+
+# --------------------------------------------------------------------------
+# diffusionPETSc (diffuclass.cpp): the reference's second eQ::diffusionSolver,
+# 5-point finite differences with ghost-node Neumann/Robin rows.  PETSc's
+# matrix-free FBCGSR solve at its default rtol 1e-5 [ext] is replaced here by a
+# sparse direct solve of the same matrix (scipy SuperLU), so the oracle is the
+# exact solution of the system the reference iterates on.
+# --------------------------------------------------------------------------
+@dataclass
+class FDWalls:
+    """DiffusionData's boundary coefficients (diffuclass.h:16-32), wall order left,right,top,bottom:
+    Dc*u + Nc*du/dn = BV.  Nc == 0 is a Dirichlet wall ("if N==0, then D must be 1", diffuclass.cpp:232)."""
+    Dc: tuple = (1.0, 1.0, 1.0, 1.0)
+    Nc: tuple = (0.0, 0.0, 0.0, 0.0)
+    BV: tuple = (0.0, 0.0, 0.0, 0.0)
+
+
+def fd_walls_from_problem(p: Problem) -> FDWalls:
+    """The FD coefficients that describe the same walls as a Problem's (type, value, s): Dirichlet value v ->
+    (Dc 1, Nc 0, BV v); Neumann -> (0, 1, 0); Robin rate r, s -> Nc 1, Dc = r/D, BV = Dc*s."""
+    Dc, Nc, BV = [], [], []
+    for w in range(4):
+        t = p.bc_type[w]
+        if t == DIRICHLET:
+            Dc.append(1.0); Nc.append(0.0); BV.append(float(p.bc_value[w]))
+        elif t == ROBIN:
+            d = float(p.bc_value[w]) / p.D
+            Dc.append(d); Nc.append(1.0); BV.append(d * float(p.robin_s[w]))
+        elif t == NEUMANN:
+            Dc.append(0.0); Nc.append(1.0); BV.append(0.0)
+        else:
+            raise ValueError("diffusionPETSc has no channel-coupled walls")
+    return FDWalls(tuple(Dc), tuple(Nc), tuple(BV))
+
+
+def fd_assemble(p: Problem, walls: FDWalls):
+    """The matrix MyMatMult applies (diffuclass.cpp:786-862, the active loop), natural order i + j*gridNodesX.
+    One deviation: at a corner between a Neumann/Robin top/bottom wall and a Dirichlet side wall the
+    reference falls into its generic top/bottom-wall row and reads xarray[j][i-1] outside the grid, while
+    ApplyBoundaryConditions writes the side wall's Dirichlet value there (:251-271); the row is the identity
+    here, i.e. the Dirichlet wall wins."""
+    import scipy.sparse as sp
+    nX, nY = p.nW, p.nH
+    h = p.h
+    assert p.hy is None or p.hy == p.h, "diffusionPETSc has one grid spacing h"
+    F = (p.D * p.dt) / (h * h)                 # diffuclass.cpp:361
+    lD, rD, tD, bD = walls.Dc
+    lN, rN, tN, bN = walls.Nc
+    top = nY - 1
+    idx = lambda i, j: i + j * nX
+    rows, cols, vals = [], [], []
+    irows, icols, ivals = [], [], []
+
+    def put(r, entries):
+        for (c, v) in entries:
+            rows.append(r); cols.append(c); vals.append(v)
+
+    # interior: -F on the four neighbours, 1 + 4F on the diagonal (:857-860)
+    I, J = np.meshgrid(np.arange(1, nX - 1), np.arange(1, nY - 1))
+    g = (I + J * nX).ravel()
+    for off, v in ((0, 1.0 + 4.0 * F), (1, -F), (-1, -F), (nX, -F), (-nX, -F)):
+        irows.append(g); icols.append(g + off); ivals.append(np.full(g.size, v))
+    for j in range(nY):
+        for i in range(nX):
+            if not (i == 0 or j == 0 or i == nX - 1 or j == top):
+                continue
+            r = idx(i, j)
+            if (tN != 0 and j == top) or (bN != 0 and j == 0 and not (tN != 0 and j == top)):
+                is_top = (tN != 0 and j == top)
+                wD, wN = (tD, tN) if is_top else (bD, bN)
+                jin = j - 1 if is_top else j + 1
+                if i == 0 and lN != 0:
+                    put(r, [(idx(i + 1, j), -2 * F), (idx(i, jin), -2 * F),
+                            (r, 1 + (4 + (2 * h * wD / wN) + (2 * h * lD / lN)) * F)])
+                elif i == nX - 1 and rN != 0:
+                    put(r, [(idx(i - 1, j), -2 * F), (idx(i, jin), -2 * F),
+                            (r, 1 + (4 + (2 * h * wD / wN) + (2 * h * rD / rN)) * F)])
+                elif i == 0 or i == nX - 1:
+                    put(r, [(r, 1.0)])          # Dirichlet side wall wins the corner (see docstring)
+                else:
+                    put(r, [(idx(i, jin), -2 * F), (idx(i - 1, j), -F), (idx(i + 1, j), -F),
+                            (r, 1 + (4 + 2 * h * wD / wN) * F)])
+            elif lN != 0 and i == 0 and j != 0 and j != top:
+                put(r, [(idx(i, j - 1), -F), (idx(i, j + 1), -F), (idx(i + 1, j), -2 * F),
+                        (r, 1 + (4 + (2 * h * lD / lN)) * F)])
+            elif rN != 0 and i == nX - 1 and j != 0 and j != top:
+                put(r, [(idx(i, j - 1), -F), (idx(i, j + 1), -F), (idx(i - 1, j), -2 * F),
+                        (r, 1 + (4 + (2 * h * rD / rN)) * F)])
+            else:
+                put(r, [(r, 1.0)])              # Dirichlet: yarray = xarray (:850-852)
+    rows = np.concatenate(irows + [np.asarray(rows, dtype=np.int64)])
+    cols = np.concatenate(icols + [np.asarray(cols, dtype=np.int64)])
+    vals = np.concatenate(ivals + [np.asarray(vals, dtype=np.float64)])
+    return sp.csc_matrix((vals, (rows, cols)), shape=(p.N, p.N))
+
+
+def fd_rhs(p: Problem, walls: FDWalls, u0):
+    """ApplyBoundaryConditions on b = u0 (diffuclass.cpp:191-275, TimeStep :405-413)."""
+    nX, nY = p.nW, p.nH
+    h = p.h
+    F = (p.D * p.dt) / (h * h)
+    twoFh = 2 * F * h
+    lN, rN, tN, bN = walls.Nc
+    lBV, rBV, tBV, bBV = walls.BV
+    top = nY - 1
+    b = np.array(u0, dtype=np.float64, copy=True).reshape(nY, nX)
+    tBVa = np.broadcast_to(np.asarray(tBV, dtype=np.float64), (nX,))
+    bBVa = np.broadcast_to(np.asarray(bBV, dtype=np.float64), (nX,))
+    for j in range(nY):
+        for i in range(nX):
+            if j == top:
+                if tN != 0:
+                    if (i != 0 or lN != 0) and (i != nX - 1 or rN != 0):
+                        b[j, i] += (twoFh * tBVa[i]) / tN
+                else:
+                    b[j, i] = tBVa[i]
+            elif j == 0:
+                if bN != 0:
+                    if (i != 0 or lN != 0) and (i != nX - 1 or rN != 0):
+                        b[j, i] += (twoFh * bBVa[i]) / bN
+                else:
+                    b[j, i] = bBVa[i]
+            if i == nX - 1:
+                if rN != 0:
+                    if (j != 0 or bN != 0) and (j != top or tN != 0):
+                        b[j, i] += (twoFh * rBV) / rN
+                else:
+                    b[j, i] = rBV
+            elif i == 0:
+                if lN != 0:
+                    if (j != 0 or bN != 0) and (j != top or tN != 0):
+                        b[j, i] += (twoFh * lBV) / lN
+                else:
+                    b[j, i] = lBV
+    return b.ravel()
+
+
+def fd_solve(p: Problem, u0, walls: FDWalls | None = None):
+    """One diffusionPETSc::stepDiffusion (diffuclass.cpp:108-118): KSPSolve(A, b) -- solved exactly."""
+    import scipy.sparse.linalg as spla
+    walls = walls or fd_walls_from_problem(p)
+    return spla.splu(fd_assemble(p, walls)).solve(fd_rhs(p, walls, u0))
+
+
+def fd_node_weights(p: Problem):
+    """w*h^2: the cell share of a node (h^2 inside, h^2/2 on a wall, h^2/4 in a corner).  Multiplying the
+    ghost-node rows by it makes MyMatMult's matrix symmetric -- the form the GPU solver's PCG works on."""
+    wx = np.ones(p.nW); wx[0] = wx[-1] = 0.5
+    wy = np.ones(p.nH); wy[0] = wy[-1] = 0.5
+    return (np.outer(wy, wx) * p.h * p.h).ravel()

@@ -88,3 +88,50 @@ def test_gpuHSL_microfluidic_trap_with_channels(oracle, tmp_path):
         s = oracle.step(p, s)
     assert rel(got["u"], s.u) < 1e-8
     assert rel(got["top"], s.top) < 1e-8 and rel(got["bottom"], s.bottom) < 1e-8
+
+
+@pytest.mark.parametrize("kase", ["fd", "fd_robin"])
+def test_gpuFD_matches_fd_oracle(oracle, tmp_path, kase):
+    """gpuFD, the drop-in for diffusionPETSc (diffuclass.h:34-97): DIRICHLET_0 as initDiffusion wires it
+    (diffuclass.cpp:68-86), and walls rewritten through initData the way upstream intends (:123-124)."""
+    W, H, npm, dt, D, nsteps = 100.0, 20.0, 2.0, 0.1, 1200.0, 4
+    p = oracle.Problem(nW=201, nH=41, h=0.5, dt=dt, D=D)
+    walls = oracle.FDWalls() if kase == "fd" else oracle.FDWalls(Dc=(0.1, 0.02, 1.0, 1.0), Nc=(1.0, 1.0, 0.0, 0.0),
+                                                                 BV=(0.03, 0.0, 2.0, 0.5))
+    rng = np.random.default_rng(12)
+    deposit = np.zeros(p.N)
+    deposit[rng.integers(0, p.N, 80)] = rng.uniform(10, 100, 80)
+    got = run_case(oracle, tmp_path, kase, W, H, npm, dt, D, nsteps, np.zeros((0, 16)), deposit)
+    assert (got["nW"], got["nH"]) == (201, 41)      # gridNodes = length/h + 1 (diffuclass.cpp:358-359)
+    u = np.zeros(p.N)
+    for _ in range(nsteps):
+        u = oracle.fd_solve(p, u + deposit, walls)
+    assert rel(got["u"], u) < 1e-8
+
+
+def test_boundary_well_loop(oracle, tmp_path):
+    """DIRICHLET_UPDATE with Simulation's boundary-well model (src/simulation.cpp:581-627): after every step
+    the well takes flux/wellScaling, decays by dt*rate, is clipped at zero, and becomes the value of all
+    four walls for the next step (setBoundaryValues, src/fHSL.cpp:601-604)."""
+    W, H, npm, dt, D, nsteps = 100.0, 20.0, 2.0, 0.1, 1200.0, 6
+    rng = np.random.default_rng(14)
+    N = 201 * 41
+    deposit = np.zeros(N)
+    deposit[rng.integers(0, N, 200)] = rng.uniform(100, 1000, 200)
+    got = run_case(oracle, tmp_path, "well", W, H, npm, dt, D, nsteps, np.zeros((0, 16)), deposit)
+    well_scaling = 2.0 * 10.0 * (15.0 / 5.0) * (W + H)       # :617-618
+    rate = 120.0 / W                                          # :609-611
+    conc, u, trace = 0.0, np.zeros(N), []
+    for _ in range(nsteps):
+        p = oracle.Problem(nW=201, nH=41, h=0.5, dt=dt, D=D, bc_type=(1, 1, 1, 1), bc_value=(conc,) * 4)
+        s = oracle.State(u=u + deposit, top=np.zeros(201), bottom=np.zeros(201))
+        s = oracle.step(p, s)
+        u = s.u
+        conc += s.total_boundary_flux / well_scaling          # :585-587
+        conc -= dt * rate * conc                              # :588-589
+        if conc < 0.0:                                        # :591-595
+            conc = 0.0
+        trace.append(conc)
+    assert rel(got["u"], u) < 1e-8
+    assert np.allclose(got["flux"], trace, rtol=1e-6, atol=1e-12)
+    assert trace[-1] > 0.0

@@ -270,3 +270,48 @@ def test_cells_tensor_known_answers(oracle):
     # Dx = Dy = 1 (the shipped values, src/eQinit.h:64-65): identity up to the rounding of c^2 + s^2
     i11, i22, i12 = oracle.cells_tensor(cells, npm, nH, nW, 1.0, 1.0)
     assert np.abs(i11 - 1).max() < 3e-16 and np.abs(i22 - 1).max() < 3e-16 and np.all(i12 == 0.0)
+
+
+def test_fd_oracle_known_answers(oracle):
+    """diffusionPETSc restatement (diffuclass.cpp:191-275,786-862): under all-Neumann walls the ghost-node
+    rows make cos(k pi x/W) cos(l pi y/H) an exact eigenvector with factor 1/(1 + F(4 - 2cos tx - 2cos ty));
+    rows sum to one (a constant stays constant, sum of w*u is conserved); times the node's cell share the
+    matrix is symmetric; Dirichlet walls hold their values with left/right winning the corners."""
+    import scipy.sparse as sp
+    nW, nH, k, l = 33, 25, 3, 2
+    p = oracle.Problem(nW=nW, nH=nH, bc_type=(0, 0, 0, 0))
+    y, x = np.mgrid[0:nH, 0:nW]
+    tx, ty = k * np.pi / (nW - 1), l * np.pi / (nH - 1)
+    u0 = (np.cos(tx * x) * np.cos(ty * y)).ravel()
+    F = p.D * p.dt / p.h ** 2
+    u1 = oracle.fd_solve(p, u0)
+    assert np.allclose(u1, u0 / (1 + F * (4 - 2 * np.cos(tx) - 2 * np.cos(ty))), rtol=0, atol=1e-13)
+    w = oracle.fd_node_weights(p)
+    rng = np.random.default_rng(3)
+    v0 = rng.uniform(0, 5, p.N)
+    assert np.isclose(w @ oracle.fd_solve(p, v0), w @ v0, rtol=1e-12)
+    pr = oracle.Problem(nW=19, nH=11, bc_type=(2, 2, 0, 0), bc_value=(138.78, 18.78, 0, 0), robin_s=(0.3, 0.1))
+    S = sp.diags(oracle.fd_node_weights(pr)) @ oracle.fd_assemble(pr, oracle.fd_walls_from_problem(pr))
+    assert abs(S - S.T).max() < 1e-12
+    pd = oracle.Problem(nW=21, nH=15, bc_type=(1, 1, 1, 1), bc_value=(1.0, 2.0, 3.0, 4.0))
+    u = oracle.fd_solve(pd, v0[:pd.N]).reshape(pd.nH, pd.nW)
+    eq = lambda a, v: np.allclose(a, v, rtol=1e-10, atol=0)   # identity rows with kept columns: LU rounding
+    assert eq(u[:, 0], 1.0) and eq(u[:, -1], 2.0)                      # corners included: left/right win
+    assert eq(u[-1, 1:-1], 3.0) and eq(u[0, 1:-1], 4.0)
+    # mixed: Dirichlet top/bottom, Robin sides (the consistent mixed case upstream): Dirichlet rows at the corners
+    pm = oracle.Problem(nW=21, nH=15, bc_type=(2, 2, 1, 1), bc_value=(138.78, 18.78, 2.0, 0.5), robin_s=(0.3, 0.1))
+    um = oracle.fd_solve(pm, v0[:pm.N]).reshape(pm.nH, pm.nW)
+    assert eq(um[-1, :], 2.0) and eq(um[0, :], 0.5)
+
+
+def test_fd_robin_steady_profile(oracle):
+    """1-D steady state between a Dirichlet-like source and a Robin wall: with Neumann top/bottom and
+    u0 == u the FD solution is constant in y and its left-wall ghost-node relation holds to rounding."""
+    p = oracle.Problem(nW=41, nH=7, bc_type=(2, 1, 0, 0), bc_value=(60.0, 5.0, 0, 0), robin_s=(0.0, 0.0), dt=1e6)
+    u = oracle.fd_solve(p, np.zeros(p.N)).reshape(p.nH, p.nW)   # dt -> infinity: the steady profile
+    assert np.allclose(u, u[0], rtol=1e-10)
+    # steady 1-D: linear profile with D u'(0) = r u(0)  (ghost node: (u1 - u_-1)/(2h) = (r/D) u0)
+    r, D, h = 60.0, p.D, p.h
+    slope = (u[0, 2] - u[0, 1]) / h
+    assert np.isclose(slope, (r / D) * u[0, 0], rtol=1e-5)
+    assert np.isclose(u[0, -1], 5.0)
