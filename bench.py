@@ -116,6 +116,30 @@ def cpu_baseline(sample_n=512, threads=1):
             "seconds": dt}
 
 
+def cpu_baseline_fd():
+    """diffusionPETSc's own CPU path restated (oracle/eq_oracle.c: ApplyBoundaryConditions + matrix-free
+    MyMatMult + unpreconditioned BiCGStab to PETSc's default rtol 1e-5, diffuclass.cpp:386-413) on the FULL
+    2048^2 workload, OpenMP over all host cores (upstream: one DMDA decomposition over MPI ranks)."""
+    from oracle import oracle as O
+    p = O.Problem(nW=NW, nH=NH, h=H, dt=DT, D=D)
+    cells = O.synthetic_colony(NCELLS, p.W, p.H)
+    u = np.zeros(p.N)
+    steps, iters = 3, []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        amount = 100.0 + 0.0 * O.gather(cells, NPM, p.nH, p.nW, u)
+        u = O.scatter(cells, NPM, p.nH, p.nW, amount, u)
+        u, it, _ = O.fd_step_krylov(p, u)
+        iters.append(int(it))
+    dt = (time.perf_counter() - t0) / steps
+    cores = int(O.lib().eqo_num_threads())
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": (f"{steps} full steps at 2048x2048 with {len(cells)} rods (gather + scatter + ApplyBoundaryConditions "
+                       f"+ matrix-free BiCGStab to rtol 1e-5, {iters} iterations; the GPU solves to 1e-12), "
+                       f"{dt:.2f} s per step on {cores} OpenMP threads"),
+            "seconds": dt * steps}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (oracle port; the Fenics/PETSc original cannot be
     built here) timed on the host cores."""
@@ -211,9 +235,11 @@ def main():
     ap.add_argument("--impl", default="eq_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="layers", choices=["layers", "slab"])
-    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 6, 7],
                     help="BASELINE.json configs index+1: 3 = the headline 2048^2 workload (default); 2 = dual layers "
-                         "with Robin walls (C4/C14 on alternating GPUs); 4 = channel-flow trap at 4096^2")
+                         "with Robin walls (C4/C14 on alternating GPUs); 4 = channel-flow trap at 4096^2.  Widened "
+                         "rows (SURVEY 8f): 6 = the headline workload on diffusionPETSc's finite-difference "
+                         "discretisation; 7 = with the anisotropic tensor rasterised from the rods every step")
     ap.add_argument("--slab-cols", type=int, default=16384)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -254,6 +280,14 @@ def main():
                   channel_r=(rl, rr), channel_iters=48, well_scaling=10.0 * (25.0 / 5.0) * 0.5)
         WORKLOAD = "configs[3]: channel-flow trap (1-D advection-diffusion channels, 48 CN sub-steps) at 4096x4096, 20k rods"
         METRIC = "hsl_diffusion_steps_per_sec_4096x4096_channels"
+    elif args.config == 6:  # diffusionPETSc (diffuclass.cpp): 5-point FD, DIRICHLET_0 as its initDiffusion wires it
+        kw = dict(discretisation=E.DISC_FD)
+        WORKLOAD = "SURVEY 8(f)4: configs[2] workload on diffusionPETSc's 5-point finite-difference discretisation (DIRICHLET_0), 2048x2048, 20k rods"
+        METRIC = "hsl_diffusion_steps_per_sec_2048x2048_fd"
+    elif args.config == 7:  # setDiffusionTensor from the rods each step (src/abm/eQabm.cpp:306-325), Dx=1.5, Dy=0.6
+        WORKLOAD = "SURVEY 8(f)3: configs[2] workload with D11/D22/D12 rasterised from the 20k rods every step (axial 1.5, transverse 0.6), variable-tensor operator, 2048x2048"
+        METRIC = "hsl_diffusion_steps_per_sec_2048x2048_tensor"
+    tensor_feed = args.config == 7
     g = E.GpuHSL(NW, NH, h=H, dt=DT, D=Dl, device=local_rank, stream=stream.cuda_stream,
                  smooth_sweeps=int(os.environ.get("EQ_NU", "0")), **kw)
     W = (NW - 1) * H
@@ -273,6 +307,8 @@ def main():
     def step_resident():
         g.gather_resident()
         g.scatter_resident()
+        if tensor_feed:
+            g.cells_tensor(1.5, 0.6)
         g.step()
         it_hist.append(g.stats().iterations)   # host-side read of the last step's count (the step has synchronised)
 
@@ -290,6 +326,8 @@ def main():
         g._ck(L.eqgpu_cells_upload(g._h, dpp(rec_pin), C.c_int64(ncells), C.c_double(NPM)))
         g._ck(L.eqgpu_cells_gather(g._h, dpp(out_pin)))
         g._ck(L.eqgpu_cells_scatter(g._h, dpp(amt_pin)))
+        if tensor_feed:
+            g.cells_tensor(1.5, 0.6)
         g.step()
         return g.stats().total_boundary_flux
 
@@ -397,7 +435,7 @@ def main():
                          "step_ideal_frac": (16.0 * N / (ms_step * 1e-3) / 1e9) / peak},
         }
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline_fd() if args.config == 6 else cpu_baseline()
         print(json.dumps(line), flush=True)
     g.close()
     if world > 1:

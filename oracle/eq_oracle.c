@@ -620,6 +620,155 @@ EQO_API void eqo_set_num_threads(int n)
 }
 
 /* ------------------------------------------------------------------------- */
+/* diffusionPETSc (diffuclass.cpp): finite-difference solver, matrix-free       */
+/* ------------------------------------------------------------------------- */
+/* Wall arrays are ordered left, right, top, bottom; a wall obeys
+ * Dc*u + Nc*du/dn = BV and Nc == 0 marks a Dirichlet wall.  Natural order
+ * g = i + j*nX (allXCoordinates/allYCoordinates, diffuclass.cpp:96-99).
+ *
+ * y = A x as MyMatMult computes it (diffuclass.cpp:786-862, the loop that is
+ * compiled; the commented-out twin above it is ignored).  Ghost nodes of a
+ * Neumann/Robin wall are eliminated, which doubles the inner neighbour and
+ * adds 2h(Dc/Nc)F to the diagonal; Dirichlet rows are the identity with the
+ * columns kept.  Deviation, as in oracle.py's fd_assemble: a corner between a
+ * Neumann/Robin top/bottom wall and a Dirichlet side wall is an identity row
+ * (upstream indexes xarray[j][i-1] outside the grid there). */
+EQO_API void eqo_fd_matmult(long nX, long nY, double h, double F,
+                            const double *Dc, const double *Nc,
+                            const double *x, double *y)
+{
+    const double gl = Nc[0] != 0.0 ? 2.0 * h * Dc[0] / Nc[0] : 0.0;
+    const double gr = Nc[1] != 0.0 ? 2.0 * h * Dc[1] / Nc[1] : 0.0;
+    const double gt = Nc[2] != 0.0 ? 2.0 * h * Dc[2] / Nc[2] : 0.0;
+    const double gb = Nc[3] != 0.0 ? 2.0 * h * Dc[3] / Nc[3] : 0.0;
+#pragma omp parallel for schedule(static)
+    for (long j = 0; j < nY; ++j) {
+        const int top = (j == nY - 1), bot = (j == 0);
+        for (long i = 0; i < nX; ++i) {
+            const long g = i + j * nX;
+            const int lef = (i == 0), rig = (i == nX - 1);
+            if (!(top || bot || lef || rig)) {   /* :857-860 */
+                y[g] = -F * x[g - nX] - F * x[g + nX] - F * x[g - 1] - F * x[g + 1] + (1.0 + 4.0 * F) * x[g];
+                continue;
+            }
+            const int ywall = (top && Nc[2] != 0.0) ? 2 : ((bot && Nc[3] != 0.0) ? 3 : -1);
+            if (ywall >= 0) {                    /* :792-846: a non-Dirichlet top or bottom row */
+                const long gin = (ywall == 2) ? g - nX : g + nX;
+                const double gy = (ywall == 2) ? gt : gb;
+                if (lef && Nc[0] != 0.0)
+                    y[g] = -2.0 * F * x[g + 1] - 2.0 * F * x[gin] + (1.0 + (4.0 + gy + gl) * F) * x[g];
+                else if (rig && Nc[1] != 0.0)
+                    y[g] = -2.0 * F * x[g - 1] - 2.0 * F * x[gin] + (1.0 + (4.0 + gy + gr) * F) * x[g];
+                else if (lef || rig)
+                    y[g] = x[g];                 /* Dirichlet side wall wins the corner (see above) */
+                else
+                    y[g] = -2.0 * F * x[gin] - F * x[g - 1] - F * x[g + 1] + (1.0 + (4.0 + gy) * F) * x[g];
+            } else if (lef && Nc[0] != 0.0 && !top && !bot) {   /* :838-842 */
+                y[g] = -F * x[g - nX] - F * x[g + nX] - 2.0 * F * x[g + 1] + (1.0 + (4.0 + gl) * F) * x[g];
+            } else if (rig && Nc[1] != 0.0 && !top && !bot) {   /* :844-848 */
+                y[g] = -F * x[g - nX] - F * x[g + nX] - 2.0 * F * x[g - 1] + (1.0 + (4.0 + gr) * F) * x[g];
+            } else {
+                y[g] = x[g];                     /* :850-852 */
+            }
+        }
+    }
+}
+
+/* ApplyBoundaryConditions on b (= u0 on entry), diffuclass.cpp:191-275.
+ * tBV / bBV are per-node (topBoundaryValue[i], :218,236); left/right scalars. */
+EQO_API void eqo_fd_apply_bc(long nX, long nY, double h, double F,
+                             const double *Nc, const double *tBV,
+                             const double *bBV, double lBV, double rBV,
+                             double *b)
+{
+    const double twoFh = 2 * F * h;
+    const double lN = Nc[0], rN = Nc[1], tN = Nc[2], bN = Nc[3];
+    const long top = nY - 1;
+    for (long j = 0; j < nY; ++j)
+        for (long i = 0; i < nX; ++i) {
+            if (!(i == 0 || i == nX - 1 || j == 0 || j == top)) continue;
+            double *v = b + i + j * nX;
+            if (j == top) {
+                if (tN != 0) {
+                    if ((i != 0 || lN != 0) && (i != nX - 1 || rN != 0)) *v += (twoFh * tBV[i]) / tN;
+                } else *v = tBV[i];
+            } else if (j == 0) {
+                if (bN != 0) {
+                    if ((i != 0 || lN != 0) && (i != nX - 1 || rN != 0)) *v += (twoFh * bBV[i]) / bN;
+                } else *v = bBV[i];
+            }
+            if (i == nX - 1) {
+                if (rN != 0) {
+                    if ((j != 0 || bN != 0) && (j != top || tN != 0)) *v += (twoFh * rBV) / rN;
+                } else *v = rBV;
+            } else if (i == 0) {
+                if (lN != 0) {
+                    if ((j != 0 || bN != 0) && (j != top || tN != 0)) *v += (twoFh * lBV) / lN;
+                } else *v = lBV;
+            }
+        }
+}
+
+/* TimeStep's KSPSolve (diffuclass.cpp:405-413) with the solver InitializeDiffusion
+ * configures (:386-392): no preconditioner, KSPFBCGSR -- flexible BiCGStab, which
+ * without a preconditioner is plain BiCGStab [ext: PETSc] -- zero initial guess,
+ * stop at ||r|| <= rtol*||b|| (PETSc's default rtol is 1e-5).  x must not alias b.
+ * Returns the iteration count (negative if maxit was hit). */
+EQO_API long eqo_fd_bicgstab(long nX, long nY, double h, double F,
+                             const double *Dc, const double *Nc,
+                             const double *b, double *x, double rtol,
+                             long maxit, double *relres_out)
+{
+    const long N = nX * nY;
+    double *r = malloc(sizeof(double) * N), *rh = malloc(sizeof(double) * N),
+           *p = malloc(sizeof(double) * N), *v = malloc(sizeof(double) * N),
+           *sv = malloc(sizeof(double) * N), *t = malloc(sizeof(double) * N);
+    double bb = 0.0;
+#pragma omp parallel for reduction(+ : bb) schedule(static)
+    for (long g = 0; g < N; ++g) {
+        x[g] = 0.0; r[g] = b[g]; rh[g] = b[g]; p[g] = 0.0; v[g] = 0.0;
+        bb += b[g] * b[g];
+    }
+    if (bb == 0.0) bb = 1.0;
+    const double stop = rtol * rtol * bb;
+    double rho = 1.0, alpha = 1.0, omega = 1.0, rr = bb;
+    long it = 0;
+    while (rr > stop && it < maxit) {
+        double rho1 = 0.0;
+#pragma omp parallel for reduction(+ : rho1) schedule(static)
+        for (long g = 0; g < N; ++g) rho1 += rh[g] * r[g];
+        const double beta = (rho1 / rho) * (alpha / omega);
+#pragma omp parallel for schedule(static)
+        for (long g = 0; g < N; ++g) p[g] = r[g] + beta * (p[g] - omega * v[g]);
+        eqo_fd_matmult(nX, nY, h, F, Dc, Nc, p, v);
+        double rv = 0.0;
+#pragma omp parallel for reduction(+ : rv) schedule(static)
+        for (long g = 0; g < N; ++g) rv += rh[g] * v[g];
+        alpha = rho1 / rv;
+#pragma omp parallel for schedule(static)
+        for (long g = 0; g < N; ++g) sv[g] = r[g] - alpha * v[g];
+        eqo_fd_matmult(nX, nY, h, F, Dc, Nc, sv, t);
+        double ts = 0.0, tt = 0.0;
+#pragma omp parallel for reduction(+ : ts, tt) schedule(static)
+        for (long g = 0; g < N; ++g) { ts += t[g] * sv[g]; tt += t[g] * t[g]; }
+        omega = tt > 0.0 ? ts / tt : 0.0;
+        rr = 0.0;
+#pragma omp parallel for reduction(+ : rr) schedule(static)
+        for (long g = 0; g < N; ++g) {
+            x[g] += alpha * p[g] + omega * sv[g];
+            r[g] = sv[g] - omega * t[g];
+            rr += r[g] * r[g];
+        }
+        rho = rho1;
+        ++it;
+        if (omega == 0.0) break;
+    }
+    if (relres_out) *relres_out = sqrt(rr / bb);
+    free(r); free(rh); free(p); free(v); free(sv); free(t);
+    return rr <= stop ? it : -it;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Boundary flux (src/fHSL.cpp:54-96 and :156-160 + fenics/boundary.ufl)      */
 /* ------------------------------------------------------------------------- */
 

@@ -56,6 +56,7 @@ def lib():
         L.eqo_point_in_cell.restype = C.c_int
         L.eqo_num_threads.restype = C.c_int
         L.eqo_assemble.restype = C.c_int
+        L.eqo_fd_bicgstab.restype = C.c_long
         _LIB = L
     return _LIB
 
@@ -525,3 +526,42 @@ def fd_node_weights(p: Problem):
     wx = np.ones(p.nW); wx[0] = wx[-1] = 0.5
     wy = np.ones(p.nH); wy[0] = wy[-1] = 0.5
     return (np.outer(wy, wx) * p.h * p.h).ravel()
+
+
+def _fd_c_args(p: Problem, walls: FDWalls):
+    Dc = (C.c_double * 4)(*[float(v) for v in walls.Dc])
+    Nc = (C.c_double * 4)(*[float(v) for v in walls.Nc])
+    F = (p.D * p.dt) / (p.h * p.h)
+    return Dc, Nc, F
+
+
+def fd_matmult(p: Problem, walls: FDWalls, x):
+    """MyMatMult restated in C (eq_oracle.c: eqo_fd_matmult) -- independent of fd_assemble's sparse matrix."""
+    Dc, Nc, F = _fd_c_args(p, walls)
+    y = np.empty(p.N)
+    lib().eqo_fd_matmult(C.c_long(p.nW), C.c_long(p.nH), C.c_double(p.h), C.c_double(F), Dc, Nc,
+                         _dp(np.ascontiguousarray(x, dtype=np.float64)), _dp(y))
+    return y
+
+
+def fd_rhs_c(p: Problem, walls: FDWalls, u0):
+    Dc, Nc, F = _fd_c_args(p, walls)
+    b = np.array(u0, dtype=np.float64, copy=True)
+    tBV = np.ascontiguousarray(np.broadcast_to(np.asarray(walls.BV[2], dtype=np.float64), (p.nW,)))
+    bBV = np.ascontiguousarray(np.broadcast_to(np.asarray(walls.BV[3], dtype=np.float64), (p.nW,)))
+    lib().eqo_fd_apply_bc(C.c_long(p.nW), C.c_long(p.nH), C.c_double(p.h), C.c_double(F), Nc, _dp(tBV), _dp(bBV),
+                          C.c_double(float(walls.BV[0])), C.c_double(float(walls.BV[1])), _dp(b))
+    return b
+
+
+def fd_step_krylov(p: Problem, u0, walls: FDWalls | None = None, rtol=1e-5, maxit=100000):
+    """diffusionPETSc::stepDiffusion the way the reference runs it: ApplyBoundaryConditions, then the
+    unpreconditioned (F)BiCGStab of diffuclass.cpp:386-392 at PETSc's default rtol.  -> (u, iterations, relres)"""
+    walls = walls or fd_walls_from_problem(p)
+    Dc, Nc, F = _fd_c_args(p, walls)
+    b = fd_rhs_c(p, walls, u0)
+    x = np.empty(p.N)
+    rel = C.c_double(0.0)
+    it = lib().eqo_fd_bicgstab(C.c_long(p.nW), C.c_long(p.nH), C.c_double(p.h), C.c_double(F), Dc, Nc, _dp(b), _dp(x),
+                               C.c_double(rtol), C.c_long(maxit), C.byref(rel))
+    return x, it, rel.value

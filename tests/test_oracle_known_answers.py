@@ -315,3 +315,31 @@ def test_fd_robin_steady_profile(oracle):
     slope = (u[0, 2] - u[0, 1]) / h
     assert np.isclose(slope, (r / D) * u[0, 0], rtol=1e-5)
     assert np.isclose(u[0, -1], 5.0)
+
+
+@pytest.mark.parametrize("bc", [
+    dict(bc_type=(1, 1, 1, 1), bc_value=(1.0, 2.0, 3.0, 4.0)),
+    dict(bc_type=(0, 0, 0, 0)),
+    dict(bc_type=(2, 2, 0, 0), bc_value=(138.78, 18.78, 0, 0), robin_s=(0.3, 0.1)),
+    dict(bc_type=(2, 2, 1, 1), bc_value=(138.78, 18.78, 2.0, 0.5), robin_s=(0.3, 0.1)),
+    dict(bc_type=(1, 1, 0, 0), bc_value=(1.5, 0.5, 0, 0)),
+    dict(bc_type=(0, 2, 1, 0), bc_value=(0, 50.0, 1.0, 0)),
+])
+def test_fd_two_restatements_agree(oracle, bc):
+    """MyMatMult / ApplyBoundaryConditions restated twice, independently: as a sparse matrix in numpy
+    (oracle.fd_assemble / fd_rhs) and as the matrix-free C loops the reference runs (eqo_fd_matmult /
+    eqo_fd_apply_bc); and the reference's own solver -- unpreconditioned BiCGStab to PETSc's default
+    rtol 1e-5 (diffuclass.cpp:386-392) -- lands within that tolerance of the exact solve."""
+    p = oracle.Problem(nW=61, nH=37, **bc)
+    w = oracle.fd_walls_from_problem(p)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 5, p.N)
+    A = oracle.fd_assemble(p, w)
+    assert np.allclose(A @ x, oracle.fd_matmult(p, w, x), rtol=1e-14, atol=1e-11)
+    assert np.array_equal(oracle.fd_rhs(p, w, x), oracle.fd_rhs_c(p, w, x))
+    exact = oracle.fd_solve(p, x)
+    u5, it5, rel5 = oracle.fd_step_krylov(p, x)
+    assert it5 > 0 and rel5 <= 1e-5
+    assert np.linalg.norm(u5 - exact) < 1e-4 * np.linalg.norm(exact)
+    u13, it13, _ = oracle.fd_step_krylov(p, x, rtol=1e-13)
+    assert it13 > it5 and np.linalg.norm(u13 - exact) < 1e-10 * np.linalg.norm(exact)
