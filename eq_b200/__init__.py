@@ -35,6 +35,7 @@ API_SYMBOLS = [
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
     "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
     "eqgpu_last_guess", "eqgpu_cells_tensor", "eqgpu_get_tensor",
+    "eqgpu_ls_solve3",
 ]
 
 
@@ -119,6 +120,17 @@ def slab_plan(nH: int, world: int, rank: int, max_levels: int = 16):
     if k < 0:
         raise EqGpuError("bad slab plan arguments")
     return [(a[i], b[i], n[i]) for i in range(k)]
+
+
+def ls_solve3(G, f, bb):
+    """Host-only hook: the device's 3x3 least-squares solve of warm-start mode 4 -> (c[3], predicted ||r||^2)."""
+    G, f = _f64(G), _f64(f)
+    c = np.zeros(3)
+    pred = C.c_double()
+    rc = lib().eqgpu_ls_solve3(_dp(G), _dp(f), C.c_double(bb), _dp(c), C.byref(pred))
+    if rc != 0:
+        raise EqGpuError("eqgpu_ls_solve3 failed")
+    return c, pred.value
 
 
 def default_params() -> Params:
@@ -300,11 +312,13 @@ class GpuHSL:
 
     def set_warm_start(self, mode: int):
         """Starting guess of the PCG solve: 0 = field as given or zero, 1 = also the previous solution,
-        2 = also the linear, 3 (default) = also the quadratic extrapolation of the previous solutions."""
+        2 = also the linear, 3 = also the quadratic extrapolation of the previous solutions, 4 (default) = the
+        residual-minimising (least-squares) combination of the last three solutions."""
         self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
 
     def last_guess(self) -> int:
-        """0 field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic extrapolation (last step's start)."""
+        """0 field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic extrapolation, 5 least-squares
+        combination (last step's start)."""
         return int(lib().eqgpu_last_guess(self._h))
 
     def set_scatter_mode(self, mode: int):

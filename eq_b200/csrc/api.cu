@@ -79,8 +79,15 @@ int eqgpu_solver_path(eqgpu_solver *s)
 int eqgpu_set_warm_start(eqgpu_solver *s, int mode)
 {
     if (!s) return EQGPU_EINVAL;
-    if (mode < 0 || mode > 3) { s->set_error("warm-start mode must be 0..3"); return EQGPU_EINVAL; }
+    if (mode < 0 || mode > 4) { s->set_error("warm-start mode must be 0..4"); return EQGPU_EINVAL; }
     s->warm = mode;
+    return 0;
+}
+
+int eqgpu_ls_solve3(const double *G, const double *f, double bb, double *c, double *pred)
+{
+    if (!G || !f || !c || !pred) return EQGPU_EINVAL;
+    solver_ls_solve3(G, f, bb, c, pred);
     return 0;
 }
 

@@ -63,6 +63,8 @@ struct CGScalars {
     // warm start: squared residual of the extrapolated guess (k_init_tile) and the guess k_impose picked
     double rrD, rrE;
     int guess, pad2;
+    // least-squares guess (warm mode 4): coefficients of h0, h0-h1, h1-h2 and the predicted squared residual
+    double lsc[3], rrL;
 };
 
 struct Level {
@@ -105,7 +107,8 @@ struct eqgpu_solver {
     // the previous solution and its linear / quadratic extrapolation as starting guesses
     double *uh[3] = {nullptr, nullptr, nullptr};
     int hist = 0;                  // valid entries of uh[]
-    int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation
+    int warm = 4;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation,
+                                   // 4 residual-minimising combination of the last three solutions
     int last_guess = 0;
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration
@@ -168,6 +171,7 @@ int solver_apply(eqgpu_solver *s, const double *dx, double *dy, bool constrained
 int solver_rhs(eqgpu_solver *s, const double *du0, double *db);
 int solver_refresh_levels(eqgpu_solver *s);
 int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes);
+void solver_ls_solve3(const double G[6], const double f[3], double bb, double c[3], double *pred);
 // ---- slab.cu ----
 int slab_init_comm(eqgpu_solver *s, const void *unique_id);
 void slab_destroy_comm(eqgpu_solver *s);

@@ -208,14 +208,20 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
 /* Starting guess of the iterative solve that stands in for LinearVariationalSolver::solve()
  * (src/fHSL.cpp:106; the reference's LU has no such notion).  mode 0: the field as given or zero, whichever
  * has the smaller residual; 1: also the previous step's solution; 2: also the linear extrapolation of the
- * two previous solutions; 3 (default): also the quadratic extrapolation of the last three.  The stopping test is relative to the right-hand side in every mode, so
+ * two previous solutions; 3: also the quadratic extrapolation of the last three; 4 (default): the
+ * residual-minimising combination of the last three solutions (a 3x3 least-squares problem solved on the
+ * device; its span contains the previous solution and both extrapolations).  The stopping test is relative to the right-hand side in every mode, so
  * the mode changes the iteration count, not the accuracy.  History lives on the device, survives
  * eqgpu_set_field, and is kept on the single-GPU isotropic path only (elsewhere the call is accepted and
  * mode 0 is what runs). */
 EQGPU_API int eqgpu_set_warm_start(eqgpu_solver *s, int mode);
 /* Which guess the last step started from: 0 field as given, 1 zero, 2 previous solution, 3 linear,
- * 4 quadratic extrapolation. */
+ * 4 quadratic extrapolation, 5 least-squares combination. */
 EQGPU_API int eqgpu_last_guess(eqgpu_solver *s);
+/* Host-only (no device): the 3x3 least-squares solve warm-start mode 4 runs on the device, for the CPU tests.
+ * G = {a0.a0, a0.a1, a0.a2, a1.a1, a1.a2, a2.a2}, f = {a0.b, a1.b, a2.b}, bb = b.b; c minimises
+ * ||b - c0 a0 - c1 a1 - c2 a2||, *pred is the predicted squared residual (1e300 if the solve failed). */
+EQGPU_API int eqgpu_ls_solve3(const double *G, const double *f, double bb, double *c, double *pred);
 /* Times `reps` back-to-back launches of one named kernel on the solver's
  * stream with CUDA events (for bench.py's roofline line).  Returns the average
  * milliseconds per launch and the algorithmic bytes one launch must move

@@ -413,7 +413,7 @@ def test_warm_start_changes_iterations_not_the_answer(oracle, bc):
     every mode, so the fields must agree far below TOL while the iteration count drops."""
     nW = nH = 321
     runs = {}
-    for mode in (0, 3):
+    for mode in (0, 3, 4):
         p, g = make(oracle, nW, nH, **BCS[bc])
         g.set_warm_start(mode)
         cells = oracle.synthetic_colony(400, p.W, p.H, seed=21)
@@ -440,6 +440,37 @@ def test_warm_start_changes_iterations_not_the_answer(oracle, bc):
     assert runs[3][2][0] in (0, 1) and runs[3][2][1] in (1, 2)
     assert all(q in (2, 3, 4) for q in runs[3][2][4:]), runs[3][2]
     assert sum(runs[3][1][4:]) < sum(runs[0][1][4:]), (runs[0][1], runs[3][1])
+    # mode 4: the least-squares combination of the last three solutions (guess code 5) once two solutions exist;
+    # its span contains every mode-3 candidate, so it needs no more iterations, and the answer is the same
+    assert rel(runs[4][0], ref) < TOL and rel(runs[4][0], runs[0][0]) < 1e-10
+    assert all(q == 5 for q in runs[4][2][4:]), runs[4][2]
+    assert sum(runs[4][1][4:]) <= sum(runs[3][1][4:]), (runs[3][1], runs[4][1])
+
+
+def test_least_squares_guess_in_steady_state_and_after_wall_changes(oracle):
+    """Mode 4 where its Gram matrix degenerates: constant sources until successive solutions coincide to
+    solver tolerance (the difference columns vanish into noise), then a jump of the Dirichlet values
+    (DIRICHLET_UPDATE: the history holds the old wall values).  Every step still matches the direct solve."""
+    p, g = make(oracle, 161, 97, **BCS["dir_values"])
+    g.set_warm_start(4)
+    rng = np.random.default_rng(2)
+    src = np.zeros(p.N)
+    src[rng.integers(0, p.N, 40)] = 50.0
+    s = oracle.new_state(p)
+    its = []
+    for k in range(40):
+        if k == 30:
+            p.bc_value = (4.0, 4.0, 4.0, 4.0)
+            g.setBoundaryValues(4.0)
+        # steady forcing: add the same source to a field that has stopped changing
+        s.u = s.u + src
+        g.set_field(g.get_field() + src)
+        s = oracle.step(p, s)
+        g.step()
+        its.append(g.stats().iterations)
+        assert rel(g.get_field(), s.u) < TOL, (k, its)
+    assert max(its[5:]) <= its[0] + 2, its
+    g.close()
 
 
 def test_warm_start_survives_a_field_reset(oracle):
