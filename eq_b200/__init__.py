@@ -312,7 +312,7 @@ class GpuHSL:
 
     def set_warm_start(self, mode: int):
         """Starting guess of the PCG solve: 0 = field as given or zero, 1 = also the previous solution,
-        2 = also the linear, 3 = also the quadratic extrapolation of the previous solutions, 4 (default) = the
+        2 = also the linear, 3 (default) = also the quadratic extrapolation of the previous solutions, 4 = also the
         residual-minimising (least-squares) combination of the last three solutions."""
         self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
 

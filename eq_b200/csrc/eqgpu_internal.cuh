@@ -65,6 +65,7 @@ struct CGScalars {
     int guess, pad2;
     // least-squares guess (warm mode 4): coefficients of h0, h0-h1, h1-h2 and the predicted squared residual
     double lsc[3], rrL;
+    double rr_init;   // squared residual of the starting guess (measured in k_impose with ls, else the candidate's)
 };
 
 struct Level {
@@ -107,9 +108,10 @@ struct eqgpu_solver {
     // the previous solution and its linear / quadratic extrapolation as starting guesses
     double *uh[3] = {nullptr, nullptr, nullptr};
     int hist = 0;                  // valid entries of uh[]
-    int warm = 4;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation,
-                                   // 4 residual-minimising combination of the last three solutions
+    int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation (default),
+                                   // 4 + residual-minimising combination of the last three solutions (opt-in)
     int last_guess = 0;
+    int ls_form = 1;               // least-squares guess: 1 = correction to h0 fitted to r1 on {A h0, d1, d1-d2}; 0 = first form
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration
     int t32_below = 148;           // levels with fewer 64-node tiles than this run on 32-node tiles
