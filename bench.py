@@ -415,7 +415,7 @@ def main():
                                         "solutions (+ their least-squares combination with EQGPU_WARM=4)}, picked on the "
                                         "device by residual norm; stop test relative to the right-hand side (rtol 1e-12) "
                                         "whatever the guess",
-                       "warm_mode": int(os.environ.get("EQGPU_WARM", "3")),
+                       "warm_mode": int(os.environ.get("EQGPU_WARM", "4" if NW * NH <= 512 * 512 else "3")),
                        "last_guess": int(g.last_guess()),
                        "dof_updates_per_sec": value * N},
             "clocks": clocks,

@@ -312,8 +312,8 @@ class GpuHSL:
 
     def set_warm_start(self, mode: int):
         """Starting guess of the PCG solve: 0 = field as given or zero, 1 = also the previous solution,
-        2 = also the linear, 3 (default) = also the quadratic extrapolation of the previous solutions, 4 = also the
-        residual-minimising (least-squares) combination of the last three solutions."""
+        2 = also the linear, 3 = also the quadratic extrapolation of the previous solutions, 4 = also the residual-minimising
+        (least-squares) combination of the last three solutions.  Default: 4 up to 512^2 nodes, 3 above."""
         self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
 
     def last_guess(self) -> int:

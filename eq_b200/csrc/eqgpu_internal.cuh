@@ -108,8 +108,9 @@ struct eqgpu_solver {
     // the previous solution and its linear / quadratic extrapolation as starting guesses
     double *uh[3] = {nullptr, nullptr, nullptr};
     int hist = 0;                  // valid entries of uh[]
-    int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation (default),
-                                   // 4 + residual-minimising combination of the last three solutions (opt-in)
+    int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation, 4 + the
+                                   // residual-minimising combination of the last three solutions (solver_setup
+                                   // picks 4 up to 512^2 nodes, 3 above)
     int last_guess = 0;
     int ls_form = 1;               // least-squares guess: 1 = correction to h0 fitted to r1 on {A h0, d1, d1-d2}; 0 = first form
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)

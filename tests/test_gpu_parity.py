@@ -198,6 +198,33 @@ def test_cells_tensor_feed_bit_exact_and_step(oracle, npm, shape):
     g.close()
 
 
+def test_tensor_multi_step_with_warm_starts(oracle):
+    """The anisotropic path over several steps (rods secrete, the tensor is re-rasterised every step as
+    eQabm::updateCells does): every field against the direct solve of the oracle's system, and the history
+    candidates (k_init_hist) take over from the cold start."""
+    p, g = make(oracle, 161, 97, **BCS["robin_lr"])
+    npm = 1.0 / p.h
+    cells = oracle.synthetic_colony(120, p.W, p.H, seed=6)
+    g.upload_cells(cells, npm)
+    p.d11, p.d22, p.d12 = oracle.cells_tensor(cells, npm, p.nH, p.nW, 2.0, 0.5)
+    u = np.zeros(p.N)
+    its, guesses = [], []
+    for k in range(10):
+        amount = np.full(len(cells), 100.0 + 2.0 * k)
+        u = oracle.scatter(cells, npm, p.nH, p.nW, amount, u)
+        u = oracle.solve_lu(p, u)
+        g.scatter(amount)
+        g.cells_tensor(2.0, 0.5)
+        g.step()
+        its.append(g.stats().iterations)
+        guesses.append(g.last_guess())
+        assert g.path()["tensor"]
+        assert rel(g.get_field(), u) < TOL, (k, its)
+    assert guesses[0] in (0, 1) and all(q in (2, 3, 4, 5) for q in guesses[4:]), guesses
+    assert max(its[5:]) < its[0], its
+    g.close()
+
+
 @pytest.mark.parametrize("npm,shape", [(2.0, (201, 41)), (1.0, (101, 21)), (4.0, (401, 81))])
 def test_raster_bit_exact(oracle, npm, shape):
     """Cell -> node lookup must be bit-exact (north_star): identical node lists, order included."""
