@@ -66,6 +66,7 @@ struct CGScalars {
     // least-squares guess (warm mode 4): coefficients of h0, h0-h1, h1-h2 and the predicted squared residual
     double lsc[3], rrL;
     double rr_init;   // squared residual of the starting guess (measured in k_impose with ls, else the candidate's)
+    double rrF, part_rrF;   // cubic extrapolation of the last four solutions (warm mode 5)
 };
 
 struct Level {
@@ -106,11 +107,11 @@ struct eqgpu_solver {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // warm start (single-GPU isotropic fused path): the last three solutions, newest first; k_init_tile tries
     // the previous solution and its linear / quadratic extrapolation as starting guesses
-    double *uh[3] = {nullptr, nullptr, nullptr};
+    double *uh[4] = {nullptr, nullptr, nullptr, nullptr};
     int hist = 0;                  // valid entries of uh[]
-    int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation, 4 + the
-                                   // residual-minimising combination of the last three solutions (solver_setup
-                                   // picks 4 up to 512^2 nodes, 3 above)
+    int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation, 4 = 3 + the
+                                   // residual-minimising combination of the last three solutions, 5 = 3 + cubic
+                                   // extrapolation of the last four (solver_setup: 4 up to 512^2 nodes, 5 above)
     int last_guess = 0;
     int ls_form = 1;               // least-squares guess: 1 = correction to h0 fitted to r1 on {A h0, d1, d1-d2}; 0 = first form
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)

@@ -176,7 +176,7 @@ k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict_
 // the four stage-and-walk phases are exposed to load latency, and 32 warps hide it better than 16 with 8 rows
 // (122 registers, one CTA per SM either way).
 #define INIT_THREADS 1024
-constexpr int INIT_SMEM = 4 * 66 * 66 * (int)sizeof(double);   // four 64x64 tiles with a pad ring: 139 KB
+constexpr int INIT_SMEM = 5 * 66 * 66 * (int)sizeof(double);   // five 64x64 tiles with a pad ring: 174 KB
 
 // A x at a free node for the per-node (irregular frame) path of k_init_tile; Dirichlet neighbours
 // contribute their boundary value (ag collects those terms: A_fd g_d).
@@ -217,21 +217,22 @@ __device__ __forceinline__ void frame_apply(const LevelDev &L, const DirData &dd
 // narrower last cell) take the general per-node path.
 __global__ void __launch_bounds__(INIT_THREADS)
 k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *__restrict__ h0,
-            const double *__restrict__ h1, const double *__restrict__ h2, int nh, double *__restrict__ r1,
-            double *__restrict__ rB, double *__restrict__ d1o, double *__restrict__ d2o, double rs_l, double rs_r,
-            double *partials, unsigned *counter, CGScalars *sc, int slab)
+            const double *__restrict__ h1, const double *__restrict__ h2, const double *__restrict__ h3, int nh,
+            double *__restrict__ r1, double *__restrict__ rB, double *__restrict__ d1o, double *__restrict__ d2o,
+            double *__restrict__ d3o, double rs_l, double rs_r, double *partials, unsigned *counter, CGScalars *sc,
+            int slab)
 {
     // Row slabs: L is the rank's local view (halo rows included); only owned rows [own0, own1) are written
     // and summed, and the sums are rank-local partials (slab != 0) for the host to all-reduce.
     constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = TSI * TSI / INIT_THREADS;
-    extern __shared__ double sm_init[];   // four tiles: u0, h0, h1, h2
+    extern __shared__ double sm_init[];   // five tiles: u0, h0, h1, h2, h3
     const int ox = blockIdx.x * TOI - 1, oy = blockIdx.y * TOI - 1;
     const int lx = threadIdx.x & (TSI - 1), ly0 = (threadIdx.x >> 6) * TROWS;
     const int gj = ox + lx;
     // owned nodes [ox+1, ox+62] x [oy+1, oy+62] all regular and at least two nodes away from every wall
     const bool deep = ox + 1 >= 2 && ox + TOI <= min(L.jreg_hi, L.nx - 3) && oy + 1 >= 2 &&
                       oy + TOI <= min(L.ireg_hi, L.ny - 3);
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (deep) {
         // all input tiles in flight at once: one cp.async commit group per field (an empty group where the
         // history is shorter), waited for one by one below -- no registers held, no load phase per stage
@@ -248,6 +249,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
         stage(h0, 1, nh >= 1);
         stage(h1, 2, nh >= 2);
         stage(h2, 3, nh >= 3);
+        stage(h3, 4, nh >= 4);
         // 7-point walk up the thread's column over tile q: mass row or operator row
         auto walk = [&](int q, bool mass, double (&out)[TROWS]) {
             const double *sp = sm_init + q * (TPI * TPI);
@@ -266,19 +268,28 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             }
         };
         const bool col = lx >= 1 && lx < TSI - 1;
-        double b[TROWS], c1[TROWS], d1[TROWS], d2[TROWS], a[TROWS];
-        cp_async_wait<3>();
+        double b[TROWS], c1[TROWS], d1[TROWS], d2[TROWS], d3[TROWS], a[TROWS];
+        cp_async_wait<4>();
         __syncthreads();
         if (col) walk(0, true, b);                    // b = M u0
-        cp_async_wait<2>();
+        cp_async_wait<3>();
         __syncthreads();
         if (col) {
             walk(nh >= 1 ? 1 : 0, false, a);          // A g1 (g1 = u0 when there is no history)
 #pragma unroll
-            for (int k = 0; k < TROWS; ++k) { c1[k] = b[k] - a[k]; d1[k] = a[k]; d2[k] = 0.0; }
+            for (int k = 0; k < TROWS; ++k) {
+                c1[k] = b[k] - a[k]; d1[k] = a[k]; d2[k] = 0.0; d3[k] = 0.0;
+                // the right-hand side is complete: store it now, so that b's registers are free for the
+                // remaining walks (64 registers per thread at 1024 threads)
+                const int ly = ly0 + k;
+                if (ly >= 1 && ly < TSI - 1 && oy + ly >= L.own0 && oy + ly < L.own1) {
+                    rB[(size_t)(oy + ly) * L.nx + gj] = b[k];
+                    v[1] += b[k] * b[k];
+                }
+            }
         }
         if (nh >= 2) {
-            cp_async_wait<1>();
+            cp_async_wait<2>();
             __syncthreads();
             if (col) {
                 walk(2, false, a);
@@ -287,12 +298,21 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             }
         }
         if (nh >= 3) {
-            cp_async_wait<0>();
+            cp_async_wait<1>();
             __syncthreads();
             if (col) {
                 walk(3, false, a);
 #pragma unroll
-                for (int k = 0; k < TROWS; ++k) d2[k] -= a[k];
+                for (int k = 0; k < TROWS; ++k) { d2[k] -= a[k]; d3[k] = a[k]; }
+            }
+        }
+        if (nh >= 4) {
+            cp_async_wait<0>();
+            __syncthreads();
+            if (col) {
+                walk(4, false, a);
+#pragma unroll
+                for (int k = 0; k < TROWS; ++k) d3[k] -= a[k];   // A h2 - A h3
             }
         }
         if (col) {
@@ -302,9 +322,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 if (ly < 1 || ly >= TSI - 1 || oy + ly < L.own0 || oy + ly >= L.own1) continue;
                 const size_t g = (size_t)(oy + ly) * L.nx + gj;
                 r1[g] = c1[k];
-                rB[g] = b[k];
                 v[0] += c1[k] * c1[k];
-                v[1] += b[k] * b[k];
                 if (nh >= 2) {
                     const double rd = c1[k] - d1[k];
                     d1o[g] = d1[k];
@@ -315,6 +333,11 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                     d2o[g] = d2[k];
                     v[3] += re * re;
                 }
+                if (nh >= 4) {   // cubic: b - A (4 h0 - 6 h1 + 4 h2 - h3) = r1 - 3 d1 + 3 d2 - d3
+                    const double rf = c1[k] - 3.0 * (d1[k] - d2[k]) - d3[k];
+                    d3o[g] = d3[k];
+                    v[4] += rf * rf;
+                }
             }
         }
     } else if (lx >= 1 && lx < TSI - 1 && gj < L.nx) {
@@ -323,7 +346,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             const int ly = ly0 + k, i = oy + ly, j = gj;
             if (ly < 1 || ly >= TSI - 1 || i < L.own0 || i >= L.own1) continue;
             const size_t g = (size_t)i * L.nx + j;
-            double res1 = 0.0, resB = 0.0, e1 = 0.0, e2 = 0.0;
+            double res1 = 0.0, resB = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
             if (!is_dirichlet(L, i, j)) {
                 const double b = load_row(L, i, j, u, rs_l, rs_r);
                 double c[NBAND];
@@ -345,6 +368,13 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                         e2 = ax1 - ax2;
                         const double re = res1 - 2.0 * e1 + e2;
                         v[3] += re * re;
+                        if (nh >= 4) {
+                            double ax3, ag3;
+                            frame_apply(L, dd, c, h3, i, j, ax3, ag3);
+                            e3 = ax2 - ax3;
+                            const double rf = res1 - 3.0 * (e1 - e2) - e3;
+                            v[4] += rf * rf;
+                        }
                     }
                 }
             }
@@ -352,12 +382,15 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             rB[g] = resB;
             if (nh >= 2) d1o[g] = e1;
             if (nh >= 3) d2o[g] = e2;
+            if (nh >= 4) d3o[g] = e3;
         }
     }
-    double tot[4];
-    if (grid_reduce<4>(v, partials, counter, tot)) {
-        if (slab) { sc->part_rr0 = tot[0]; sc->part_b2 = tot[1]; sc->part_rrD = tot[2]; sc->part_rrE = tot[3]; }
-        else { sc->rr0 = tot[0]; sc->bnorm2 = tot[1]; sc->rrD = tot[2]; sc->rrE = tot[3]; }
+    double tot[5];
+    if (grid_reduce<5>(v, partials, counter, tot)) {
+        if (slab) {
+            sc->part_rr0 = tot[0]; sc->part_b2 = tot[1]; sc->part_rrD = tot[2]; sc->part_rrE = tot[3];
+            sc->part_rrF = tot[4];
+        } else { sc->rr0 = tot[0]; sc->bnorm2 = tot[1]; sc->rrD = tot[2]; sc->rrE = tot[3]; sc->rrF = tot[4]; }
     }
 }
 
@@ -517,7 +550,7 @@ k_ls_gram(size_t n, const double *__restrict__ r1, const double *__restrict__ rB
 
 // Pick the starting guess, impose u_d = g_d, set up the PCG scalars.
 // Guess codes (sc->guess): 0 the field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic
-// extrapolation, 5 least-squares combination.  Without history (nh == 0: k_init, or k_init_tile's first step)
+// extrapolation, 5 least-squares combination, 6 cubic extrapolation.  Without history (nh == 0: k_init, or k_init_tile's first step)
 // h*/d* are unused.  ls != 0 (k_ls_gram ran, nh >= 2): the least-squares combination joins the candidates, and
 // the squared residual of the guess actually formed is summed here, so that the PCG scalars start from a
 // measured norm, not from the rounding-limited prediction.
@@ -525,17 +558,20 @@ __global__ void __launch_bounds__(BX *BY)
 k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
          const double *__restrict__ rB, const double *__restrict__ d1, const double *__restrict__ d2,
          const double *__restrict__ h0, const double *__restrict__ h1, const double *__restrict__ h2, int nh,
-         CGScalars *sc, double rtol, int max_iters, int ls, double *partials, unsigned *counter)
+         CGScalars *sc, double rtol, int max_iters, int ls, double *partials, unsigned *counter,
+         const double *__restrict__ h3, const double *__restrict__ d3)
 {
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     const double rr1 = sc->rr0, rrB = sc->bnorm2;
     const double rrD = nh >= 2 ? sc->rrD : 1.0e300, rrE = nh >= 3 ? sc->rrE : 1.0e300;
+    const double rrF = nh >= 4 ? sc->rrF : 1.0e300;
     const double rrL = ls ? sc->rrL : 1.0e300;
     int pick = nh >= 1 ? 2 : 0;
     double best = rr1;
     if (rrB < best) { best = rrB; pick = 1; }
     if (rrD < best) { best = rrD; pick = 3; }
     if (rrE < best) { best = rrE; pick = 4; }
+    if (rrF < best) { best = rrF; pick = 6; }
     if (rrL <= best) { best = rrL; pick = 5; }
     double v[1] = {0.0};
     if (i >= L.own0 && i < L.own1 && j < L.nx) {
@@ -546,6 +582,10 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
         else if (pick == 2) u[g] = h0[g];
         else if (pick == 3) { u[g] = 2.0 * h0[g] - h1[g]; r[g] -= d1[g]; }
         else if (pick == 4) { u[g] = 3.0 * (h0[g] - h1[g]) + h2[g]; r[g] += d2[g] - 2.0 * d1[g]; }
+        else if (pick == 6) {   // cubic extrapolation of the last four solutions
+            u[g] = 4.0 * (h0[g] + h2[g]) - 6.0 * h1[g] - h3[g];
+            r[g] += 3.0 * (d2[g] - d1[g]) - d3[g];
+        }
         else if (pick == 5) {
             const double c0 = sc->lsc[0], c1 = sc->lsc[1], c2 = sc->lsc[2];
             const double x0 = h0[g], x1 = h1[g], b = rB[g], rv = r[g];   // r holds r1 = rB - A h0 on entry
@@ -1207,11 +1247,12 @@ int solver_setup(eqgpu_solver *s)
         // iterations per step at 257^2 and 4.5 vs 5.1 at 512^2 over 40 steps of the bench colony, but 4.9 vs 4.5
         // at 2048^2, where the field is far from steady and PCG converges more slowly from the residual-optimal
         // start: on by default up to 512^2 nodes
-        s->warm = (size_t)p.nW * p.nH <= (size_t)512 * 512 ? 4 : 3;
-        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 4));
+        // ... and the cubic extrapolation of the last four solutions above
+        s->warm = (size_t)p.nW * p.nH <= (size_t)512 * 512 ? 4 : 5;
+        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 5));
         if (const char *e = getenv("EQGPU_LS_FORM")) s->ls_form = atoi(e) != 0 ? 1 : 0;   // tuning knob
         if ((s->defer_x || s->slab) && s->init_tile && s->warm > 0) {
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 EQ_CUDA(cudaMalloc(&s->uh[k], sizeof(double) * s->N));
                 EQ_CUDA(cudaMemset(s->uh[k], 0, sizeof(double) * s->N));
             }
@@ -1248,7 +1289,7 @@ void solver_teardown(eqgpu_solver *s)
     s->levels.clear();
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->graph_exec2) { cudaGraphExecDestroy(s->graph_exec2); s->graph_exec2 = nullptr; }
-    for (int k = 0; k < 3; ++k) { cudaFree(s->uh[k]); s->uh[k] = nullptr; }
+    for (int k = 0; k < 4; ++k) { cudaFree(s->uh[k]); s->uh[k] = nullptr; }
     s->hist = 0;
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); s->ev_fork = nullptr; }
     if (s->ev_join) { cudaEventDestroy(s->ev_join); s->ev_join = nullptr; }
@@ -1759,15 +1800,20 @@ static int pcg(eqgpu_solver *s)
     // (variable tensor, one GPU: k_init_hist evaluates the candidates per node, a device copy stores the history)
     const bool hist_tensor = T && !sl && s->warm > 0 && s->uh[0] != nullptr && getenv("EQGPU_TENSOR_COLD") == nullptr;
     const bool keep_hist = hist_tensor || (!T && s->init_tile && s->fused && (sl || s->defer_x) && s->warm > 0 && s->uh[0]);
-    const int nh = keep_hist ? std::min(s->hist, std::min(s->warm, 3)) : 0;
+    // history depth: modes 1-3 use that many solutions, 4 three (+ least squares), 5 four (+ cubic; one GPU,
+    // isotropic path)
+    const int nh_max = (s->warm >= 5 && !sl && !T) ? 4 : std::min(s->warm, 3);
+    const int nh = keep_hist ? std::min(s->hist, nh_max) : 0;
     // least-squares combination of the history beside the fixed extrapolations (single GPU: its nine sums
     // are not rank-reduced)
-    const bool ls = keep_hist && s->warm >= 4 && !sl && nh >= 2;
+    const bool ls = keep_hist && s->warm == 4 && !sl && nh >= 2;
     // scratch for the extrapolation terms: Ap and pv2 are free until the first k_apply_p writes them
     if (!T && s->init_tile) {
         const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
-        k_init_tile<<<gi, INIT_THREADS, INIT_SMEM, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2,
-                                        rs_l, rs_r, s->partials, s->counters + 0, sc, sl ? 1 : 0);
+        // d3 scratch: the level-0 work vector t is free until the first pre-smoothing writes it
+        k_init_tile<<<gi, INIT_THREADS, INIT_SMEM, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], s->uh[3], nh, s->r, s->z,
+                                                        s->Ap, s->pv2, l0.t, rs_l, rs_r, s->partials, s->counters + 0, sc,
+                                                        sl ? 1 : 0);
         if (sl) {
             slab_allreduce(s, &sc->part_rrD, &sc->rrD, 1);
             slab_allreduce(s, &sc->part_rrE, &sc->rrE, 1);
@@ -1783,11 +1829,12 @@ static int pcg(eqgpu_solver *s)
         slab_allreduce(s, &sc->part_b2, &sc->bnorm2, 1);
     }
     if (ls) {
-        k_ls_gram<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->Ap, s->pv2, nh, s->ls_form, s->partials, s->counters + 4, sc);
+        k_ls_gram<<<nb1, 256, 0, st>>>(s->N, s->r, s->z, s->Ap, s->pv2, std::min(nh, 3), s->ls_form, s->partials,
+                                       s->counters + 4, sc);
         s->launches++;
     }
     k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->pv2, s->uh[0], s->uh[1], s->uh[2], nh, s->sc,
-                                 rtol, max_iters, ls ? 1 + s->ls_form : 0, s->partials, s->counters + 5);
+                                 rtol, max_iters, ls ? 1 + s->ls_form : 0, s->partials, s->counters + 5, s->uh[3], l0.t);
     s->launches += 2;
 
     int issued = 0;
@@ -1847,7 +1894,7 @@ static int pcg(eqgpu_solver *s)
         const bool spec = fused && s->defer_x && !s->p.channels;
         if (fused && s->defer_x) {
             // ... and, for the next step's warm start, leave a copy of the solution in the older history slot
-            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[2] : nullptr);
+            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[3] : nullptr);
             k_mark_x<<<1, 1, 0, st>>>(sc);
             s->launches += 2;
         }
@@ -1865,23 +1912,23 @@ static int pcg(eqgpu_solver *s)
     if (getenv("EQGPU_LS_DEBUG")) {   // debugging aid: the candidates' residuals relative to the zero guess's
         const CGScalars &h = *s->sc_host;
         const double b2 = h.bnorm2 > 0 ? h.bnorm2 : 1.0;
-        fprintf(stderr, "guess step %lld nh %d ls %d: prev %.2e lin %.2e quad %.2e ls(pred) %.2e picked %d init(true) %.2e "
-                        "c = (%.6g, %.6g, %.6g) iters %d final %.2e\n",
+        fprintf(stderr, "guess step %lld nh %d ls %d: prev %.2e lin %.2e quad %.2e cubic %.2e ls(pred) %.2e picked %d "
+                        "init(true) %.2e c = (%.6g, %.6g, %.6g) iters %d final %.2e\n",
                 (long long)s->st.steps, nh, ls ? 1 + s->ls_form : 0, sqrt(h.rr0 / b2), sqrt(fabs(h.rrD) / b2),
-                sqrt(fabs(h.rrE) / b2), sqrt(fabs(h.rrL) / b2), h.guess, sqrt(fabs(h.rr_init) / b2), h.lsc[0], h.lsc[1],
-                h.lsc[2], h.iters, sqrt(h.rr / b2));
+                sqrt(fabs(h.rrE) / b2), sqrt(fabs(h.rrF) / b2), sqrt(fabs(h.rrL) / b2), h.guess,
+                sqrt(fabs(h.rr_init) / b2), h.lsc[0], h.lsc[1], h.lsc[2], h.iters, sqrt(h.rr / b2));
     }
     if (keep_hist && s->sc_host->rr <= s->sc_host->stop2) {   // the copy just written is now the newest solution
         if (sl) {   // slabs: copy now (owned rows are final), then bring the halo rows of the copy up to date
-            EQ_CUDA(cudaMemcpyAsync(s->uh[2], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
-            int rc = slab_exchange(s, L, s->uh[2]);
+            EQ_CUDA(cudaMemcpyAsync(s->uh[3], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
+            int rc = slab_exchange(s, L, s->uh[3]);
             if (rc) return rc;
         } else if (hist_tensor) {   // the unfused loop has no k_finish_x: plain device copy
-            EQ_CUDA(cudaMemcpyAsync(s->uh[2], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
+            EQ_CUDA(cudaMemcpyAsync(s->uh[3], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
         }
-        double *newest = s->uh[2];
-        s->uh[2] = s->uh[1]; s->uh[1] = s->uh[0]; s->uh[0] = newest;
-        s->hist = std::min(s->hist + 1, 3);
+        double *newest = s->uh[3];   // the oldest slot received the copy
+        s->uh[3] = s->uh[2]; s->uh[2] = s->uh[1]; s->uh[1] = s->uh[0]; s->uh[0] = newest;
+        s->hist = std::min(s->hist + 1, 4);
     }
     const double ref = s->sc_host->bnorm2;
     s->st.relres = ref > 0 ? std::sqrt(s->sc_host->rr / ref) : 0.0;
