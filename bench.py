@@ -411,11 +411,12 @@ def main():
                        "relres": relres, "rtol": 1e-12, "mg_levels": int(g.stats().levels),
                        "parallelism": f"layer-per-gpu x{world}",
                        "l2": "working set (6 fine fp64 vectors = 201 MB + MG hierarchy) exceeds the 126 MB L2; no explicit flush",
-                       "initial_guess": "best of {zero, previous solution, linear / quadratic / cubic extrapolation of the "
-                                        "previous solutions} (warm mode 5; mode 4, the default up to 512^2 nodes, has their "
-                                        "least-squares combination instead of the cubic), picked on the device by residual "
-                                        "norm; stop test relative to the right-hand side (rtol 1e-12) whatever the guess",
-                       "warm_mode": int(os.environ.get("EQGPU_WARM", "4" if NW * NH <= 512 * 512 else "5")),
+                       "initial_guess": "best of {zero, previous solution, linear / quadratic / cubic / quartic extrapolation "
+                                        "of the previous solutions} (warm mode 6; mode 4, the default up to 512^2 nodes, has "
+                                        "the least-squares combination of the last three instead of cubic and quartic), "
+                                        "picked on the device by residual norm; stop test relative to the right-hand side "
+                                        "(rtol 1e-12) whatever the guess",
+                       "warm_mode": int(os.environ.get("EQGPU_WARM", "4" if NW * NH <= 512 * 512 else "6")),
                        "last_guess": int(g.last_guess()),
                        "dof_updates_per_sec": value * N},
             "clocks": clocks,

@@ -79,7 +79,7 @@ int eqgpu_solver_path(eqgpu_solver *s)
 int eqgpu_set_warm_start(eqgpu_solver *s, int mode)
 {
     if (!s) return EQGPU_EINVAL;
-    if (mode < 0 || mode > 5) { s->set_error("warm-start mode must be 0..5"); return EQGPU_EINVAL; }
+    if (mode < 0 || mode > 6) { s->set_error("warm-start mode must be 0..6"); return EQGPU_EINVAL; }
     s->warm = mode;
     return 0;
 }

@@ -67,6 +67,7 @@ struct CGScalars {
     double lsc[3], rrL;
     double rr_init;   // squared residual of the starting guess (measured in k_impose with ls, else the candidate's)
     double rrF, part_rrF;   // cubic extrapolation of the last four solutions (warm mode 5)
+    double rrG;             // quartic extrapolation of the last five (warm mode 6)
 };
 
 struct Level {
@@ -107,11 +108,18 @@ struct eqgpu_solver {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // warm start (single-GPU isotropic fused path): the last three solutions, newest first; k_init_tile tries
     // the previous solution and its linear / quadratic extrapolation as starting guesses
-    double *uh[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *uh[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // quartic candidate: A (h3 - h4) of this step is A (h2 - h3) of the previous one, so k_init_tile keeps its d3
+    // in dk[dk_cur ^ 1] and reads the previous step's from dk[dk_cur]; valid after a step that wrote it and
+    // rotated the history
+    double *dk[2] = {nullptr, nullptr};
+    int dk_cur = 0;
+    bool dk_valid = false;
     int hist = 0;                  // valid entries of uh[]
     int warm = 3;                  // 0 off, 1 previous solution, 2 + linear, 3 + quadratic extrapolation, 4 = 3 + the
                                    // residual-minimising combination of the last three solutions, 5 = 3 + cubic
-                                   // extrapolation of the last four (solver_setup: 4 up to 512^2 nodes, 5 above)
+                                   // extrapolation of the last four, 6 = 5 + quartic of the last five
+                                   // (solver_setup: 4 up to 512^2 nodes, 6 above)
     int last_guess = 0;
     int ls_form = 1;               // least-squares guess: 1 = correction to h0 fitted to r1 on {A h0, d1, d1-d2}; 0 = first form
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)

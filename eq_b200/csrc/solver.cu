@@ -220,7 +220,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             const double *__restrict__ h1, const double *__restrict__ h2, const double *__restrict__ h3, int nh,
             double *__restrict__ r1, double *__restrict__ rB, double *__restrict__ d1o, double *__restrict__ d2o,
             double *__restrict__ d3o, double rs_l, double rs_r, double *partials, unsigned *counter, CGScalars *sc,
-            int slab)
+            int slab, const double *dk_prev, double *dk_next, int d4ok)
 {
     // Row slabs: L is the rank's local view (halo rows included); only owned rows [own0, own1) are written
     // and summed, and the sums are rank-local partials (slab != 0) for the host to all-reduce.
@@ -232,7 +232,9 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
     // owned nodes [ox+1, ox+62] x [oy+1, oy+62] all regular and at least two nodes away from every wall
     const bool deep = ox + 1 >= 2 && ox + TOI <= min(L.jreg_hi, L.nx - 3) && oy + 1 >= 2 &&
                       oy + TOI <= min(L.ireg_hi, L.ny - 3);
-    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    // dk_next (nh >= 4): this step's d3 = A (h2 - h3), kept for the next step, whose d4 = A (h3 - h4) it is;
+    // dk_prev (d4ok): the one the previous step kept -- the quartic candidate costs no fifth operator walk
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (deep) {
         // all input tiles in flight at once: one cp.async commit group per field (an empty group where the
         // history is shorter), waited for one by one below -- no registers held, no load phase per stage
@@ -337,6 +339,11 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                     const double rf = c1[k] - 3.0 * (d1[k] - d2[k]) - d3[k];
                     d3o[g] = d3[k];
                     v[4] += rf * rf;
+                    if (dk_next) dk_next[g] = d3[k];
+                    if (d4ok) {   // quartic: r1 - 4 d1 + 6 d2 - 4 d3 + d4
+                        const double rg = c1[k] - 4.0 * (d1[k] + d3[k]) + 6.0 * d2[k] + dk_prev[g];
+                        v[5] += rg * rg;
+                    }
                 }
             }
         }
@@ -374,6 +381,10 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                             e3 = ax2 - ax3;
                             const double rf = res1 - 3.0 * (e1 - e2) - e3;
                             v[4] += rf * rf;
+                            if (d4ok) {
+                                const double rg = res1 - 4.0 * (e1 + e3) + 6.0 * e2 + dk_prev[g];
+                                v[5] += rg * rg;
+                            }
                         }
                     }
                 }
@@ -382,15 +393,21 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             rB[g] = resB;
             if (nh >= 2) d1o[g] = e1;
             if (nh >= 3) d2o[g] = e2;
-            if (nh >= 4) d3o[g] = e3;
+            if (nh >= 4) {
+                d3o[g] = e3;
+                if (dk_next) dk_next[g] = e3;   // zero on Dirichlet rows, like every d
+            }
         }
     }
-    double tot[5];
-    if (grid_reduce<5>(v, partials, counter, tot)) {
+    double tot[6];
+    if (grid_reduce<6>(v, partials, counter, tot)) {
         if (slab) {
             sc->part_rr0 = tot[0]; sc->part_b2 = tot[1]; sc->part_rrD = tot[2]; sc->part_rrE = tot[3];
             sc->part_rrF = tot[4];
-        } else { sc->rr0 = tot[0]; sc->bnorm2 = tot[1]; sc->rrD = tot[2]; sc->rrE = tot[3]; sc->rrF = tot[4]; }
+        } else {
+            sc->rr0 = tot[0]; sc->bnorm2 = tot[1]; sc->rrD = tot[2]; sc->rrE = tot[3]; sc->rrF = tot[4];
+            sc->rrG = d4ok ? tot[5] : 1.0e300;
+        }
     }
 }
 
@@ -550,7 +567,7 @@ k_ls_gram(size_t n, const double *__restrict__ r1, const double *__restrict__ rB
 
 // Pick the starting guess, impose u_d = g_d, set up the PCG scalars.
 // Guess codes (sc->guess): 0 the field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic
-// extrapolation, 5 least-squares combination, 6 cubic extrapolation.  Without history (nh == 0: k_init, or k_init_tile's first step)
+// extrapolation, 5 least-squares combination, 6 cubic, 7 quartic extrapolation.  Without history (nh == 0: k_init, or k_init_tile's first step)
 // h*/d* are unused.  ls != 0 (k_ls_gram ran, nh >= 2): the least-squares combination joins the candidates, and
 // the squared residual of the guess actually formed is summed here, so that the PCG scalars start from a
 // measured norm, not from the rounding-limited prediction.
@@ -559,7 +576,8 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
          const double *__restrict__ rB, const double *__restrict__ d1, const double *__restrict__ d2,
          const double *__restrict__ h0, const double *__restrict__ h1, const double *__restrict__ h2, int nh,
          CGScalars *sc, double rtol, int max_iters, int ls, double *partials, unsigned *counter,
-         const double *__restrict__ h3, const double *__restrict__ d3)
+         const double *__restrict__ h3, const double *__restrict__ d3, const double *__restrict__ h4,
+         const double *__restrict__ d4)
 {
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     const double rr1 = sc->rr0, rrB = sc->bnorm2;
@@ -572,6 +590,7 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
     if (rrD < best) { best = rrD; pick = 3; }
     if (rrE < best) { best = rrE; pick = 4; }
     if (rrF < best) { best = rrF; pick = 6; }
+    if (d4 && nh >= 5 && sc->rrG < best) { best = sc->rrG; pick = 7; }
     if (rrL <= best) { best = rrL; pick = 5; }
     double v[1] = {0.0};
     if (i >= L.own0 && i < L.own1 && j < L.nx) {
@@ -582,6 +601,10 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
         else if (pick == 2) u[g] = h0[g];
         else if (pick == 3) { u[g] = 2.0 * h0[g] - h1[g]; r[g] -= d1[g]; }
         else if (pick == 4) { u[g] = 3.0 * (h0[g] - h1[g]) + h2[g]; r[g] += d2[g] - 2.0 * d1[g]; }
+        else if (pick == 7) {   // quartic extrapolation of the last five solutions
+            u[g] = 5.0 * (h0[g] - h3[g]) + 10.0 * (h2[g] - h1[g]) + h4[g];
+            r[g] += 6.0 * d2[g] - 4.0 * (d1[g] + d3[g]) + d4[g];
+        }
         else if (pick == 6) {   // cubic extrapolation of the last four solutions
             u[g] = 4.0 * (h0[g] + h2[g]) - 6.0 * h1[g] - h3[g];
             r[g] += 3.0 * (d2[g] - d1[g]) - d3[g];
@@ -1248,14 +1271,20 @@ int solver_setup(eqgpu_solver *s)
         // at 2048^2, where the field is far from steady and PCG converges more slowly from the residual-optimal
         // start: on by default up to 512^2 nodes
         // ... and the cubic extrapolation of the last four solutions above
-        s->warm = (size_t)p.nW * p.nH <= (size_t)512 * 512 ? 4 : 5;
-        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 5));
+        s->warm = (size_t)p.nW * p.nH <= (size_t)512 * 512 ? 4 : 6;
+        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 6));
         if (const char *e = getenv("EQGPU_LS_FORM")) s->ls_form = atoi(e) != 0 ? 1 : 0;   // tuning knob
         if ((s->defer_x || s->slab) && s->init_tile && s->warm > 0) {
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 5; ++k) {
                 EQ_CUDA(cudaMalloc(&s->uh[k], sizeof(double) * s->N));
                 EQ_CUDA(cudaMemset(s->uh[k], 0, sizeof(double) * s->N));
             }
+            if (!s->slab)
+                for (int k = 0; k < 2; ++k) {
+                    EQ_CUDA(cudaMalloc(&s->dk[k], sizeof(double) * s->N));
+                    EQ_CUDA(cudaMemset(s->dk[k], 0, sizeof(double) * s->N));
+                }
+            s->dk_valid = false;
             s->hist = 0;
         }
         if (s->defer_x) {
@@ -1289,7 +1318,8 @@ void solver_teardown(eqgpu_solver *s)
     s->levels.clear();
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->graph_exec2) { cudaGraphExecDestroy(s->graph_exec2); s->graph_exec2 = nullptr; }
-    for (int k = 0; k < 4; ++k) { cudaFree(s->uh[k]); s->uh[k] = nullptr; }
+    for (int k = 0; k < 5; ++k) { cudaFree(s->uh[k]); s->uh[k] = nullptr; }
+    for (int k = 0; k < 2; ++k) { cudaFree(s->dk[k]); s->dk[k] = nullptr; }
     s->hist = 0;
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); s->ev_fork = nullptr; }
     if (s->ev_join) { cudaEventDestroy(s->ev_join); s->ev_join = nullptr; }
@@ -1802,18 +1832,22 @@ static int pcg(eqgpu_solver *s)
     const bool keep_hist = hist_tensor || (!T && s->init_tile && s->fused && (sl || s->defer_x) && s->warm > 0 && s->uh[0]);
     // history depth: modes 1-3 use that many solutions, 4 three (+ least squares), 5 four (+ cubic; one GPU,
     // isotropic path)
-    const int nh_max = (s->warm >= 5 && !sl && !T) ? 4 : std::min(s->warm, 3);
+    const int nh_max = (s->warm >= 5 && !sl && !T) ? (s->warm >= 6 ? 5 : 4) : std::min(s->warm, 3);
     const int nh = keep_hist ? std::min(s->hist, nh_max) : 0;
     // least-squares combination of the history beside the fixed extrapolations (single GPU: its nine sums
     // are not rank-reduced)
     const bool ls = keep_hist && s->warm == 4 && !sl && nh >= 2;
+    // quartic candidate: this step keeps its d3 when four solutions are in play; the next one may use it as d4
+    const bool wrote_dk = keep_hist && !T && !sl && s->init_tile && nh >= 4 && s->dk[0] != nullptr;
+    const bool d4ok = wrote_dk && nh >= 5 && s->dk_valid;
     // scratch for the extrapolation terms: Ap and pv2 are free until the first k_apply_p writes them
     if (!T && s->init_tile) {
         const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
         // d3 scratch: the level-0 work vector t is free until the first pre-smoothing writes it
         k_init_tile<<<gi, INIT_THREADS, INIT_SMEM, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], s->uh[3], nh, s->r, s->z,
                                                         s->Ap, s->pv2, l0.t, rs_l, rs_r, s->partials, s->counters + 0, sc,
-                                                        sl ? 1 : 0);
+                                                        sl ? 1 : 0, s->dk[s->dk_cur], wrote_dk ? s->dk[s->dk_cur ^ 1] : nullptr,
+                                                        d4ok ? 1 : 0);
         if (sl) {
             slab_allreduce(s, &sc->part_rrD, &sc->rrD, 1);
             slab_allreduce(s, &sc->part_rrE, &sc->rrE, 1);
@@ -1834,7 +1868,8 @@ static int pcg(eqgpu_solver *s)
         s->launches++;
     }
     k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->pv2, s->uh[0], s->uh[1], s->uh[2], nh, s->sc,
-                                 rtol, max_iters, ls ? 1 + s->ls_form : 0, s->partials, s->counters + 5, s->uh[3], l0.t);
+                                 rtol, max_iters, ls ? 1 + s->ls_form : 0, s->partials, s->counters + 5, s->uh[3], l0.t,
+                                 s->uh[4], d4ok ? s->dk[s->dk_cur] : nullptr);
     s->launches += 2;
 
     int issued = 0;
@@ -1894,7 +1929,7 @@ static int pcg(eqgpu_solver *s)
         const bool spec = fused && s->defer_x && !s->p.channels;
         if (fused && s->defer_x) {
             // ... and, for the next step's warm start, leave a copy of the solution in the older history slot
-            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[3] : nullptr);
+            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[4] : nullptr);
             k_mark_x<<<1, 1, 0, st>>>(sc);
             s->launches += 2;
         }
@@ -1912,23 +1947,29 @@ static int pcg(eqgpu_solver *s)
     if (getenv("EQGPU_LS_DEBUG")) {   // debugging aid: the candidates' residuals relative to the zero guess's
         const CGScalars &h = *s->sc_host;
         const double b2 = h.bnorm2 > 0 ? h.bnorm2 : 1.0;
-        fprintf(stderr, "guess step %lld nh %d ls %d: prev %.2e lin %.2e quad %.2e cubic %.2e ls(pred) %.2e picked %d "
+        fprintf(stderr, "guess step %lld nh %d ls %d d4ok %d quartic %.2e: prev %.2e lin %.2e quad %.2e cubic %.2e ls(pred) %.2e picked %d "
                         "init(true) %.2e c = (%.6g, %.6g, %.6g) iters %d final %.2e\n",
-                (long long)s->st.steps, nh, ls ? 1 + s->ls_form : 0, sqrt(h.rr0 / b2), sqrt(fabs(h.rrD) / b2),
+                (long long)s->st.steps, nh, ls ? 1 + s->ls_form : 0, d4ok ? 1 : 0, sqrt(fabs(h.rrG) / b2), sqrt(h.rr0 / b2),
+                sqrt(fabs(h.rrD) / b2),
                 sqrt(fabs(h.rrE) / b2), sqrt(fabs(h.rrF) / b2), sqrt(fabs(h.rrL) / b2), h.guess,
                 sqrt(fabs(h.rr_init) / b2), h.lsc[0], h.lsc[1], h.lsc[2], h.iters, sqrt(h.rr / b2));
     }
     if (keep_hist && s->sc_host->rr <= s->sc_host->stop2) {   // the copy just written is now the newest solution
         if (sl) {   // slabs: copy now (owned rows are final), then bring the halo rows of the copy up to date
-            EQ_CUDA(cudaMemcpyAsync(s->uh[3], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
-            int rc = slab_exchange(s, L, s->uh[3]);
+            EQ_CUDA(cudaMemcpyAsync(s->uh[4], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
+            int rc = slab_exchange(s, L, s->uh[4]);
             if (rc) return rc;
         } else if (hist_tensor) {   // the unfused loop has no k_finish_x: plain device copy
-            EQ_CUDA(cudaMemcpyAsync(s->uh[3], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
+            EQ_CUDA(cudaMemcpyAsync(s->uh[4], s->u, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
         }
-        double *newest = s->uh[3];   // the oldest slot received the copy
-        s->uh[3] = s->uh[2]; s->uh[2] = s->uh[1]; s->uh[1] = s->uh[0]; s->uh[0] = newest;
-        s->hist = std::min(s->hist + 1, 4);
+        double *newest = s->uh[4];   // the oldest slot received the copy
+        s->uh[4] = s->uh[3]; s->uh[3] = s->uh[2]; s->uh[2] = s->uh[1]; s->uh[1] = s->uh[0]; s->uh[0] = newest;
+        s->hist = std::min(s->hist + 1, 5);
+        // the d3 this step kept is the next step's d4 exactly when the history moved on by this one solution
+        s->dk_valid = wrote_dk;
+        if (wrote_dk) s->dk_cur ^= 1;
+    } else {
+        s->dk_valid = false;
     }
     const double ref = s->sc_host->bnorm2;
     s->st.relres = ref > 0 ? std::sqrt(s->sc_host->rr / ref) : 0.0;

@@ -211,7 +211,8 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
  * two previous solutions; 3: also the quadratic extrapolation of the last three; 4: also the
  * residual-minimising combination of the last three solutions (a 3x3 least-squares problem solved on the
  * device; its span contains the previous solution and both extrapolations).  5: mode 3 plus the cubic
- * extrapolation of the last four solutions.  Default: 4 for meshes up to 512^2 nodes, 5 above (measured: the
+ * extrapolation of the last four solutions; 6: mode 5 plus the quartic extrapolation of the last five.
+ * Default: 4 for meshes up to 512^2 nodes, 6 above (measured: the
  * least-squares combination saves up to four iterations per step on small or quasi-steady problems and costs
  * half an iteration at 2048^2).  The stopping test is relative to the right-hand side in every mode, so
  * the mode changes the iteration count, not the accuracy.  History lives on the device, survives
@@ -219,7 +220,7 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
  * mode 0 is what runs). */
 EQGPU_API int eqgpu_set_warm_start(eqgpu_solver *s, int mode);
 /* Which guess the last step started from: 0 field as given, 1 zero, 2 previous solution, 3 linear,
- * 4 quadratic extrapolation, 5 least-squares combination, 6 cubic extrapolation. */
+ * 4 quadratic extrapolation, 5 least-squares combination, 6 cubic, 7 quartic extrapolation. */
 EQGPU_API int eqgpu_last_guess(eqgpu_solver *s);
 /* Host-only (no device): the 3x3 least-squares solve warm-start mode 4 runs on the device, for the CPU tests.
  * G = {a0.a0, a0.a1, a0.a2, a1.a1, a1.a2, a2.a2}, f = {a0.b, a1.b, a2.b}, bb = b.b; c minimises

@@ -440,7 +440,7 @@ def test_warm_start_changes_iterations_not_the_answer(oracle, bc):
     every mode, so the fields must agree far below TOL while the iteration count drops."""
     nW = nH = 321
     runs = {}
-    for mode in (0, 3, 4, 5):
+    for mode in (0, 3, 4, 5, 6):
         p, g = make(oracle, nW, nH, **BCS[bc])
         g.set_warm_start(mode)
         cells = oracle.synthetic_colony(400, p.W, p.H, seed=21)
@@ -476,6 +476,11 @@ def test_warm_start_changes_iterations_not_the_answer(oracle, bc):
     assert rel(runs[5][0], ref) < TOL and rel(runs[5][0], runs[0][0]) < 1e-10
     assert all(q in (2, 3, 4, 6) for q in runs[5][2][4:]) and 6 in runs[5][2], runs[5][2]
     assert sum(runs[5][1][4:]) <= sum(runs[3][1][4:]), (runs[3][1], runs[5][1])
+    # mode 6: plus the quartic extrapolation of the last five (guess code 7; its A (h3 - h4) is the A (h2 - h3)
+    # the previous step kept, so it becomes available one step after the cubic)
+    assert rel(runs[6][0], ref) < TOL and rel(runs[6][0], runs[0][0]) < 1e-10
+    assert all(q in (2, 3, 4, 6, 7) for q in runs[6][2][4:]) and 7 in runs[6][2], runs[6][2]
+    assert sum(runs[6][1][4:]) <= sum(runs[3][1][4:]), (runs[3][1], runs[6][1])
 
 
 def test_least_squares_guess_in_steady_state_and_after_wall_changes(oracle):
