@@ -17,6 +17,14 @@
  * sparse direct solve are DOLFIN 2019.1.0 / PETSc [ext] and are restated from
  * their published algorithms; the rod predicate restates Chipmunk 7.0.1 [ext]
  * (cpBodyWorldToLocal, cpvcross).  Those parts are "parity unpinned".
+ * The finite-difference solver IS pinned end to end: the reference's own class
+ * diffusionPETSc (diffuclass.{h,cpp}) is compiled in place on a one-process
+ * PETSc/MPI/boost interface shim (oracle/shim_petsc/, oracle/petsc_ref.cpp ->
+ * oracle/_ref/libeq_fd_ref.so) and run; eqo_fd_matmult / eqo_fd_apply_bc below
+ * equal its MyMatMult / ApplyBoundaryConditions bit for bit and its
+ * stepDiffusion agrees with the exact solve of the restated system to 1e-13
+ * (tests/test_oracle_golden.py, golden vectors tests/golden/fd_ref.json).  Only
+ * PETSc's Krylov solver [ext] is replaced there (plain BiCGStab).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference root).  All arithmetic is fp64; compile WITHOUT -ffast-math and

@@ -565,3 +565,66 @@ def fd_step_krylov(p: Problem, u0, walls: FDWalls | None = None, rtol=1e-5, maxi
     it = lib().eqo_fd_bicgstab(C.c_long(p.nW), C.c_long(p.nH), C.c_double(p.h), C.c_double(F), Dc, Nc, _dp(b), _dp(x),
                                C.c_double(rtol), C.c_long(maxit), C.byref(rel))
     return x, it, rel.value
+
+
+# --------------------------------------------------------------------------
+# The reference's OWN diffusionPETSc class (oracle/_ref/libeq_fd_ref.so, built by `make -C oracle ref`
+# from /root/reference/diffuclass.{h,cpp} on the interface shim in oracle/shim_petsc/): used to pin the
+# restatements above and to generate tests/golden/fd_ref.json.  None when the library is absent.
+# --------------------------------------------------------------------------
+_FDREF = None
+
+
+def fd_ref_lib():
+    global _FDREF
+    if _FDREF is None:
+        path = os.path.join(_HERE, "_ref", "libeq_fd_ref.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_fd_create.restype = C.c_void_p
+        R.ref_fd_create_dirichlet0.restype = C.c_void_p
+        R.ref_fd_size.restype = C.c_long
+        R.ref_fd_size.argtypes = [C.c_void_p]
+        R.ref_fd_step.argtypes = [C.c_void_p, c_dp, C.c_double, c_dp]
+        R.ref_fd_matmult.argtypes = [C.c_void_p, c_dp, c_dp]
+        R.ref_fd_destroy.argtypes = [C.c_void_p]
+        _FDREF = R
+    return _FDREF
+
+
+class FDReference:
+    """diffusionPETSc itself, driven through its public surface (initData, solution_vector, stepDiffusion).
+    width/height are the integer microns upstream passes; nodes = length*npm + 1 (diffuclass.cpp:358-359)."""
+
+    def __init__(self, width, height, npm, dt, D, walls: FDWalls | None = None):
+        R = fd_ref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libeq_fd_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+        self.R = R
+        if walls is None:
+            self.h = R.ref_fd_create_dirichlet0(C.c_int(width), C.c_int(height), C.c_double(npm), C.c_double(dt), C.c_double(D))
+        else:
+            a = lambda t: (C.c_double * 4)(*[float(v) for v in t])
+            self.h = R.ref_fd_create(C.c_int(width), C.c_int(height), C.c_double(npm), C.c_double(dt), C.c_double(D),
+                                     a(walls.Dc), a(walls.Nc), a(walls.BV))
+        self.N = int(R.ref_fd_size(self.h))
+
+    def step(self, u0, rtol=1e-5):
+        """-> (u1, rhs ApplyBoundaryConditions built, Krylov iterations of the stand-in solve)"""
+        u = np.array(u0, dtype=np.float64, copy=True)
+        rhs = np.empty(self.N)
+        its = self.R.ref_fd_step(self.h, _dp(u), C.c_double(rtol), _dp(rhs))
+        return u, rhs, int(its)
+
+    def matmult(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.N)
+        rc = self.R.ref_fd_matmult(self.h, _dp(x), _dp(y))
+        assert rc == 0, "call step() once first: the shell matrix is created on first use"
+        return y
+
+    def close(self):
+        if self.h:
+            self.R.ref_fd_destroy(self.h)
+            self.h = None

@@ -1,0 +1,1 @@
+#include "petsc_shim.h"

@@ -129,3 +129,33 @@ def test_fd_rejects_what_the_reference_class_does_not_have(oracle):
     with pytest.raises(E.EqGpuError):
         g.set_tensor(np.full(65 * 65, 1.5), np.ones(65 * 65), np.zeros(65 * 65))
     g.close()
+
+
+def test_fd_gpu_against_the_reference_class_itself(oracle):
+    """The GPU path against diffusionPETSc ITSELF (oracle/_ref/libeq_fd_ref.so: the reference's diffuclass.cpp
+    compiled in place on the one-process PETSc shim, Krylov solve run to 1e-13): five steps of the default
+    trap with deposits, as initDiffusion wires it (DIRICHLET_0) and with walls written through initData."""
+    if oracle.fd_ref_lib() is None:
+        pytest.skip("oracle/_ref/libeq_fd_ref.so not built (needs /root/reference at build time)")
+    D = 1200.0
+    cases = [
+        (None, dict(bc_type=(1, 1, 1, 1), bc_value=(0, 0, 0, 0))),
+        (oracle.FDWalls(Dc=(0.1, 0.02, 1, 1), Nc=(1, 1, 0, 0), BV=(0.03, 0.0, 2.0, 0.5)),
+         dict(bc_type=(2, 2, 1, 1), bc_value=(D * 0.1, D * 0.02, 2.0, 0.5), robin_s=(0.3, 0.0))),
+        (oracle.FDWalls(Dc=(0, 0, 0, 0), Nc=(1, 1, 1, 1), BV=(0, 0, 0, 0)), dict(bc_type=(0, 0, 0, 0), bc_value=(0, 0, 0, 0))),
+    ]
+    rng = np.random.default_rng(21)
+    for walls, bc in cases:
+        ref = oracle.FDReference(100, 20, 2.0, 0.1, D, walls)      # 201 x 41 nodes
+        g = E.GpuHSL(201, 41, h=0.5, dt=0.1, D=D, discretisation=E.DISC_FD, **bc)
+        deposit = np.zeros(201 * 41)
+        deposit[rng.integers(0, deposit.size, 60)] = rng.uniform(10, 100, 60)
+        u_ref = np.zeros(deposit.size)
+        g.solution_vector[:] = 0.0
+        for k in range(5):
+            u_ref, _, _ = ref.step(u_ref + deposit, rtol=1e-13)
+            g.solution_vector[:] = g.solution_vector + deposit
+            out = g.stepDiffusion()
+            assert rel(out, u_ref) < TOL, (k, bc["bc_type"])
+        ref.close()
+        g.close()

@@ -73,3 +73,76 @@ def test_against_compiled_reference_when_present(oracle):
         L.eqo_hsld_cell_a(dp(A), dp(d11), dp(d22), dp(d12), cd(D), cd(dt), dp(xy))
         R.ref_hsld_cell_a(dp(B), dp(d11), dp(d22), dp(d12), cd(D), cd(dt), dp(xy))
         assert np.array_equal(A, B)
+
+
+# --------------------------------------------------------------------------
+# diffusionPETSc (diffuclass.cpp): golden vectors produced by the reference's OWN class, compiled in place on the
+# interface shim (tests/golden/make_golden_fd.py).
+# --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def fd_golden():
+    with open(os.path.join(HERE, "golden", "fd_ref.json")) as f:
+        return json.load(f)
+
+
+def _fd_problem(oracle, g, c):
+    nW, nH = int(g["width"] * g["npm"]) + 1, int(g["height"] * g["npm"]) + 1      # diffuclass.cpp:358-359
+    p = oracle.Problem(nW=nW, nH=nH, h=1.0 / g["npm"], dt=c["dt"], D=c["D"])
+    return p, oracle.FDWalls(Dc=tuple(c["Dc"]), Nc=tuple(c["Nc"]), BV=tuple(c["BV"]))
+
+
+def test_fd_golden_file_is_substantial(fd_golden):
+    names = {c["name"] for c in fd_golden["cases"]}
+    assert len(fd_golden["cases"]) >= 12 and {"dirichlet0_as_shipped", "neumann", "robin_lr", "robin_all_walls"} <= names
+
+
+def test_fd_restatements_match_the_reference_class_bit_for_bit(oracle, fd_golden):
+    """MyMatMult (diffuclass.cpp:637-872) and ApplyBoundaryConditions (:191-275): the C restatement equals the
+    reference's compiled code bit for bit; the numpy sparse restatement gives the same right-hand side bit for
+    bit and the same product to rounding (its row sums are ordered differently)."""
+    for c in fd_golden["cases"]:
+        p, w = _fd_problem(oracle, fd_golden, c)
+        x, u0 = np.array(c["x"]), np.array(c["u0"])
+        assert oracle.fd_matmult(p, w, x).tolist() == c["Ax"], c["name"]
+        assert oracle.fd_rhs_c(p, w, u0).tolist() == c["rhs"], c["name"]
+        assert oracle.fd_rhs(p, w, u0).tolist() == c["rhs"], c["name"]
+        assert np.allclose(oracle.fd_assemble(p, w) @ x, np.array(c["Ax"]), rtol=1e-14, atol=1e-12)
+
+
+def test_fd_step_matches_the_reference_class(oracle, fd_golden):
+    """diffusionPETSc::stepDiffusion (diffuclass.cpp:108-118) run by the reference class itself (Krylov solve to
+    1e-13) against the oracle's exact solve of the restated system, two consecutive steps."""
+    for c in fd_golden["cases"]:
+        p, w = _fd_problem(oracle, fd_golden, c)
+        u0, u1, u2 = np.array(c["u0"]), np.array(c["u1"]), np.array(c["u2"])
+        e1 = oracle.fd_solve(p, u0, w)
+        assert np.linalg.norm(e1 - u1) <= 1e-10 * np.linalg.norm(u1), c["name"]
+        e2 = oracle.fd_solve(p, u1 + 0.25 * u0, w)
+        assert np.linalg.norm(e2 - u2) <= 1e-10 * np.linalg.norm(u2), c["name"]
+        # ... and the oracle's own copy of the reference's solver at the reference's tolerance
+        k5, its, rel5 = oracle.fd_step_krylov(p, u0, w)
+        assert rel5 <= 1e-5 and np.linalg.norm(k5 - u1) <= 1e-4 * np.linalg.norm(u1)
+
+
+def test_fd_live_against_the_compiled_reference_class(oracle):
+    """Where oracle/_ref/libeq_fd_ref.so is present (build container; it travels to the GPU box): the default
+    trap (100 x 20 um at 2 nodes/um = 201 x 41 nodes) with fresh random data, every wall set."""
+    if oracle.fd_ref_lib() is None:
+        pytest.skip("oracle/_ref/libeq_fd_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(7)
+    for walls in (None, oracle.FDWalls(Dc=(0.1, 0.02, 1, 1), Nc=(1, 1, 0, 0), BV=(0.03, 0.0, 2.0, 0.5)),
+                  oracle.FDWalls(Dc=(0, 0, 0, 0), Nc=(1, 1, 1, 1), BV=(0, 0, 0, 0))):
+        ref = oracle.FDReference(100, 20, 2.0, 0.1, 1200.0, walls)
+        assert ref.N == 201 * 41
+        p = oracle.Problem(nW=201, nH=41)
+        w = walls or oracle.FDWalls()
+        u0 = rng.uniform(0, 5, p.N)
+        u1, rhs, its = ref.step(u0, rtol=1e-13)
+        x = rng.uniform(-1, 1, p.N)
+        assert np.array_equal(oracle.fd_matmult(p, w, x), ref.matmult(x))
+        assert np.array_equal(oracle.fd_rhs_c(p, w, u0), rhs)
+        ex = oracle.fd_solve(p, u0, w)
+        assert np.linalg.norm(ex - u1) <= 1e-10 * np.linalg.norm(u1)
+        u5, _, its5 = ref.step(u0, rtol=1e-5)             # the tolerance the reference actually runs at
+        assert 0 < its5 < its and np.linalg.norm(u5 - ex) <= 1e-4 * np.linalg.norm(ex)
+        ref.close()
