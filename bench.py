@@ -435,7 +435,15 @@ def main():
                                          "--set full capture in profiles/ (below the algorithmic bytes where "
                                          "freshly written vectors are still in the 126 MB L2)",
                          "peak_source": peak_src, "kernels": roof,
-                         "step_ideal_frac": (16.0 * N / (ms_step * 1e-3) / 1e9) / peak},
+                         "step_ideal_frac": (16.0 * N / (ms_step * 1e-3) / 1e9) / peak,
+                         # whole step, algorithmic bytes of DESIGN.md section 5: per PCG iteration 124 B/DOF on
+                         # level 0 (presmooth 18, postsmooth 26, apply_p 32, update_r 24, update_x 24) + 44/3 on the
+                         # coarser levels; per step 224 B/DOF for the warm start (k_init_tile 96, k_impose 96,
+                         # k_finish_x 32; isotropic one-GPU path with the five-solution history)
+                         "step_algorithmic": (lambda bts: {"bytes": bts, "gbs": bts / (ms_step * 1e-3) / 1e9,
+                                                           "frac": bts / (ms_step * 1e-3) / 1e9 / peak,
+                                                           "formula": "N*(224 + (124 + 44/3)*mean_iterations)"})(
+                             N * (224.0 + (124.0 + 44.0 / 3.0) * iters_mean))},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_fd() if args.config == 6 else cpu_baseline()
