@@ -25,6 +25,14 @@
  * stepDiffusion agrees with the exact solve of the restated system to 1e-13
  * (tests/test_oracle_golden.py, golden vectors tests/golden/fd_ref.json).  Only
  * PETSc's Krylov solver [ext] is replaced there (plain BiCGStab).
+ * The cell <-> mesh coupling IS pinned too: the reference's own eQabm, Ecoli,
+ * cpmEcoli and Strain classes are compiled in place on a Chipmunk 7.0.1
+ * interface shim (oracle/shim_cpm/, oracle/cell_ref.cpp ->
+ * oracle/_ref/libeq_cell_ref.so) and eQabm::updateCells itself is run:
+ * eqo_make_cell, eqo_point_in_cell, eqo_update_cells_sequential and
+ * eqo_cells_tensor equal it bit for bit on fresh, grown, bent and ratcheted
+ * rods (golden vectors tests/golden/cells_ref.json).  What stays restated
+ * there is Chipmunk's rigid-body transform arithmetic [ext], now in the shim.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference root).  All arithmetic is fp64; compile WITHOUT -ffast-math and

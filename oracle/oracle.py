@@ -628,3 +628,76 @@ class FDReference:
         if self.h:
             self.R.ref_fd_destroy(self.h)
             self.h = None
+
+
+# --------------------------------------------------------------------------
+# The reference's OWN agent-based-model classes (oracle/_ref/libeq_cell_ref.so: eQabm, Ecoli, cpmEcoli, Strain
+# compiled in place on the Chipmunk interface shim oracle/shim_cpm/): pins the cell <-> mesh restatements above
+# and generates tests/golden/cells_ref.json.  None when the library is absent.
+# --------------------------------------------------------------------------
+_CELLREF = None
+
+
+def cell_ref_lib():
+    global _CELLREF
+    if _CELLREF is None:
+        path = os.path.join(_HERE, "_ref", "libeq_cell_ref.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_abm_create.restype = C.c_void_p
+        R.ref_abm_count.restype = C.c_long
+        for name in ("ref_abm_add_cell", "ref_abm_count", "ref_abm_move_cell", "ref_abm_record", "ref_abm_point_in_cell",
+                     "ref_abm_update_cells", "ref_abm_destroy"):
+            getattr(R, name)
+        _CELLREF = R
+    return _CELLREF
+
+
+class ABMReference:
+    """eQabm itself on one identity-lookup HSL layer.  Cells are addressed in the reference's list order
+    (newest first: forward_list push_front)."""
+
+    def __init__(self, width, height, npm, Dx=1.0, Dy=1.0):
+        R = cell_ref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libeq_cell_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+        self.R = R
+        self.h = C.c_void_p(R.ref_abm_create(C.c_int(width), C.c_int(height), C.c_double(npm), C.c_double(Dx), C.c_double(Dy)))
+        self.npm = npm
+        self.nW, self.nH = int(width * npm) + 1, int(height * npm) + 1
+
+    def add_cell(self, x, y, angle, length, a0=100.0, a1=0.0):
+        self.R.ref_abm_add_cell(self.h, C.c_double(x), C.c_double(y), C.c_double(angle), C.c_double(length),
+                                C.c_double(a0), C.c_double(a1))
+
+    def count(self):
+        return int(self.R.ref_abm_count(self.h))
+
+    def move_cell(self, k, a, b, calls=1):
+        """a, b = (x, y, angle) of body halves A and B; then `calls` post-step updates (ratchet, poles)."""
+        self.R.ref_abm_move_cell(self.h, C.c_long(k), C.c_double(a[0]), C.c_double(a[1]), C.c_double(a[2]),
+                                 C.c_double(b[0]), C.c_double(b[1]), C.c_double(b[2]), C.c_int(calls))
+
+    def records(self):
+        n = self.count()
+        rec = np.zeros((n, CELL_STRIDE))
+        for k in range(n):
+            self.R.ref_abm_record(self.h, C.c_long(k), rec[k].ctypes.data_as(c_dp))
+        return rec
+
+    def point_in_cell(self, k, x, y):
+        return bool(self.R.ref_abm_point_in_cell(self.h, C.c_long(k), C.c_double(x), C.c_double(y)))
+
+    def update_cells(self, u):
+        u = np.array(u, dtype=np.float64, copy=True)
+        N = self.nW * self.nH
+        g = np.zeros(self.count())
+        d11, d22, d12 = np.empty(N), np.empty(N), np.empty(N)
+        self.R.ref_abm_update_cells(self.h, _dp(u), _dp(g), _dp(d11), _dp(d22), _dp(d12))
+        return u, g, (d11, d22, d12)
+
+    def close(self):
+        if self.h:
+            self.R.ref_abm_destroy(self.h)
+            self.h = None

@@ -146,3 +146,65 @@ def test_fd_live_against_the_compiled_reference_class(oracle):
         u5, _, its5 = ref.step(u0, rtol=1e-5)             # the tolerance the reference actually runs at
         assert 0 < its5 < its and np.linalg.norm(u5 - ex) <= 1e-4 * np.linalg.norm(ex)
         ref.close()
+
+
+# --------------------------------------------------------------------------
+# Cell <-> mesh coupling: golden vectors produced by the reference's OWN eQabm / Ecoli / cpmEcoli classes compiled
+# in place on the Chipmunk interface shim (tests/golden/make_golden_cells.py).
+# --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cells_golden():
+    with open(os.path.join(HERE, "golden", "cells_ref.json")) as f:
+        return json.load(f)
+
+
+def test_cells_restatement_matches_the_reference_classes_bit_for_bit(oracle, cells_golden):
+    """pointIsInCell (src/abm/cpmEcoli.cpp:313-327) on the reference's own rod geometry (fresh, grown, bent and
+    ratcheted rods, poles clamped at the walls), and one eQabm::updateCells pass (src/abm/eQabm.cpp:234-425:
+    findInteriorPoints, readHSL, writeHSL, setDiffusionTensor in list order, overlapping rods included): the
+    oracle's predicate, sequential sample/deposit loop and tensor grids equal the reference's bit for bit."""
+    W, H = cells_golden["width"], cells_golden["height"]
+    L = oracle.lib()
+    assert len(cells_golden["cases"]) >= 3
+    for c in cells_golden["cases"]:
+        npm = c["npm"]
+        nW, nH = int(W * npm) + 1, int(H * npm) + 1
+        rec = np.array(c["records"])
+        assert np.sum(rec[:, 5] > rec[:, 4]) >= 3                    # ratcheted rods are in the set
+        for k, win in enumerate(c["inside"]):
+            for di, row in enumerate(win["mask"]):
+                for dj, want in enumerate(row):
+                    x, y = (win["j0"] + dj) / npm, (win["i0"] + di) / npm
+                    got = L.eqo_point_in_cell(oracle._dp(rec[k]), C.c_double(x), C.c_double(y))
+                    assert got == want, (npm, k, x, y)
+        u1, g = oracle.update_cells_sequential(rec, npm, nH, nW, np.array(c["a0"]), c["a1"], np.array(c["u0"]))
+        assert u1.tolist() == c["u1"] and g.tolist() == c["gathered"]
+        d11, d22, d12 = oracle.cells_tensor(rec, npm, nH, nW, c["Dx"], c["Dy"])
+        assert d11.tolist() == c["d11"] and d22.tolist() == c["d22"] and d12.tolist() == c["d12"]
+
+
+def test_cells_live_against_the_compiled_reference_classes(oracle, capfd):
+    """Where oracle/_ref/libeq_cell_ref.so is present: fresh random colonies through the reference's constructors;
+    the oracle's make_cells record equals the one read from the reference objects bit for bit (pole clamps
+    included), and so does a coupled updateCells pass."""
+    if oracle.cell_ref_lib() is None:
+        pytest.skip("oracle/_ref/libeq_cell_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(11)
+    W, H, npm, n = 40, 20, 2.0, 40
+    ref = oracle.ABMReference(W, H, npm, 1.5, 0.6)
+    xs, ys = rng.uniform(0.5, W - 0.5, n), rng.uniform(0.5, H - 0.5, n)
+    an, Ls = rng.uniform(0, 2 * np.pi, n), (1 + rng.uniform(size=n)) * 2.1
+    a0 = rng.uniform(50, 150, n)
+    for k in range(n):
+        ref.add_cell(xs[k], ys[k], an[k], Ls[k], a0[k], 0.5)
+    order = list(range(n))[::-1]
+    rec = ref.records()
+    mine = oracle.make_cells(np.c_[xs, ys][order], an[order], Ls[order], float(W), float(H))
+    assert np.array_equal(rec, mine)
+    u0 = rng.uniform(0, 5, ref.nW * ref.nH)
+    u1, g, tens = ref.update_cells(u0)
+    mu, mg = oracle.update_cells_sequential(rec, npm, ref.nH, ref.nW, a0[order], 0.5, u0)
+    assert np.array_equal(u1, mu) and np.array_equal(g, mg)
+    for a, b in zip(tens, oracle.cells_tensor(rec, npm, ref.nH, ref.nW, 1.5, 0.6)):
+        assert np.array_equal(a, b)
+    ref.close()
