@@ -701,3 +701,162 @@ class ABMReference:
         if self.h:
             self.R.ref_abm_destroy(self.h)
             self.h = None
+
+
+# --------------------------------------------------------------------------
+# The reference's OWN P1 solver class (oracle/_ref/libeq_fenics_ref.so = /root/reference/src/fHSL.cpp compiled in
+# place on the one-process DOLFIN interface shim of oracle/shim_dolfin/, see oracle/fenics_ref.cpp): fenicsInterface
+# itself runs -- boundary decoding, Robin rates, form wiring, trap solve, wall flux, channel sub-steps, flux
+# functional -- on top of the reference's own generated element kernels.  Pins `step` / `problem_from_parameters`
+# and generates tests/golden/fenics_ref.json.  None when the library is absent.
+# --------------------------------------------------------------------------
+_FENICSREF = None
+
+
+def fenics_ref_lib():
+    global _FENICSREF
+    if _FENICSREF is None:
+        path = os.path.join(_HERE, "_ref", "libeq_fenics_ref.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_fenics_create.restype = C.c_void_p
+        R.ref_fenics_last_error.restype = C.c_char_p
+        R.ref_fenics_total_boundary_flux.restype = C.c_double
+        _FENICSREF = R
+    return _FENICSREF
+
+
+def bc_entry(kind, value=0.0):
+    """One wall of eQ::data::parameters["boundaries"] as eQ::boundaryCondition writes it (src/eQ.h:397-418)."""
+    if kind == "Dirichlet":
+        return ["Dirichlet", [0.0, 1.0, float(value)]]
+    if kind == "Neumann":
+        return ["Neumann", [1.0, 0.0, float(value)]]
+    if kind == "Robin":
+        return ["Robin", [1.0 if value == 0.0 else float(value), 1.0, 0.0]]
+    raise ValueError(kind)
+
+
+def default_parameters(width, height, npm=2.0, **over):
+    """The eQ::data::parameters keys the path reads (SURVEY 8b), with the shipped defaults of src/main.cpp."""
+    P = {"nodesPerMicronSignaling": float(npm), "lengthScaling": 5.0, "boundaryType": "DIRICHLET_0",
+         "trapType": "NOWALLED", "simulationTrapWidthMicrons": width, "simulationTrapHeightMicrons": height,
+         "simulationFlowRate": 120.0, "simulationChannelLengthLeft": 100.0, "simulationChannelLengthRight": 100.0,
+         "channelSolverNumberIterations": 4}
+    P.update(over)
+    return P
+
+
+def problem_from_parameters(P, dt, D, width, height, npm) -> Problem:
+    """fenicsClassInit + createHSL's boundary decoding + setRobinBoundaryConditions restated
+    (src/fHSL.cpp:37-53,242-243,281-283,331-364,436-574)."""
+    import math
+    nH = int(math.ceil(height * npm)) + 1
+    nW = int(math.ceil(width * npm)) + 1
+    v = float(P["simulationFlowRate"])
+    left_rate, right_rate = robin_rates(v, D, float(P["simulationChannelLengthLeft"]), float(P["simulationChannelLengthRight"]))
+    h = 1.0 / float(P["nodesPerMicronSignaling"])
+    well = 10.0 * (25.0 / float(P["lengthScaling"])) * h
+    bt = [NEUMANN] * 4
+    bv = [0.0] * 4
+    channels = False
+    btype, ttype = P["boundaryType"], P["trapType"]
+    if btype == "MICROFLUIDIC_TRAP":
+        if ttype == "H_TRAP":
+            left_rate = right_rate = v
+        rates = (left_rate, right_rate)
+        for w, name in ((LEFT, "left"), (RIGHT, "right"), (TOP, "top"), (BOTTOM, "bottom")):
+            d = P["boundaries"][name][1]
+            if d[0] == 0.0:
+                if w in (TOP, BOTTOM) and d[2] == -1.0:
+                    bt[w] = DIRICHLET_CHANNEL
+                else:
+                    bt[w], bv[w] = DIRICHLET, d[2]
+            elif d[1] == 0.0:
+                bt[w] = NEUMANN
+            elif w in (LEFT, RIGHT):
+                bt[w], bv[w] = ROBIN, rates[w]
+        channels = ttype != "H_TRAP"
+    elif btype == "DIRICHLET_UPDATE":
+        bt = [DIRICHLET] * 4
+    elif btype == "DIRICHLET_0":
+        on = {"NOWALLED": (1, 1, 1, 1), "THREEWALLED": (0, 0, 0, 1), "TWOWALLED": (0, 0, 1, 1), "ONEWALLED": (1, 1, 0, 1)}.get(ttype, (0, 0, 0, 0))
+        bt = [DIRICHLET if o else NEUMANN for o in on]
+    elif btype == "NEUMANN_3WALLED_TEST":
+        bt = [DIRICHLET, DIRICHLET, NEUMANN, DIRICHLET]
+    else:
+        bt = [DIRICHLET] * 4
+    return Problem(nW=nW, nH=nH, h=width / (nW - 1), hy=height / (nH - 1), dt=dt, D=D, bc_type=tuple(bt), bc_value=tuple(bv),
+                   channels=channels, channel_v=v, channel_r=(left_rate, right_rate),
+                   channel_iters=int(P["channelSolverNumberIterations"]), well_scaling=well)
+
+
+class FenicsReference:
+    """fenicsInterface itself (one layer, one process)."""
+
+    def __init__(self, P, dt, D, width, height, npm, channel_velocity=0.0):
+        import json
+        R = fenics_ref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libeq_fenics_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+        self.R = R
+        h = R.ref_fenics_create(json.dumps(P).encode(), C.c_double(dt), C.c_double(D), C.c_double(width), C.c_double(height),
+                                C.c_double(npm), C.c_double(channel_velocity))
+        if not h:
+            raise RuntimeError("fenicsInterface: " + R.ref_fenics_last_error().decode())
+        self.h = C.c_void_p(h)
+        a, b, c = C.c_long(), C.c_long(), C.c_long()
+        R.ref_fenics_sizes(self.h, C.byref(a), C.byref(b), C.byref(c))
+        self.nW, self.nH, self.nC = a.value, b.value, c.value
+        self.N = self.nW * self.nH
+
+    def mesh(self):
+        xy = np.zeros(2 * self.N)
+        dof = np.zeros(self.N, dtype=np.int32)
+        self.R.ref_fenics_mesh(self.h, _dp(xy), dof.ctypes.data_as(C.POINTER(C.c_int)))
+        return xy.reshape(-1, 2), dof
+
+    def lookup(self):
+        t = np.zeros(self.N, dtype=np.int64)
+        self.R.ref_fenics_lookup(self.h, t.ctypes.data_as(c_lp))
+        return t.reshape(self.nH, self.nW)
+
+    def set_field(self, u):
+        self.R.ref_fenics_set_field(self.h, _dp(np.ascontiguousarray(u, dtype=np.float64)))
+
+    def field(self):
+        u = np.zeros(self.N)
+        self.R.ref_fenics_get_field(self.h, _dp(u))
+        return u
+
+    def set_tensor(self, d11, d22, d12):
+        self.R.ref_fenics_set_tensor(self.h, _dp(np.ascontiguousarray(d11)), _dp(np.ascontiguousarray(d22)), _dp(np.ascontiguousarray(d12)))
+
+    def set_channels(self, top, bottom):
+        self.R.ref_fenics_set_channels(self.h, _dp(np.ascontiguousarray(top)), _dp(np.ascontiguousarray(bottom)))
+
+    def channels(self):
+        t, b, ft, fb = (np.zeros(self.nC) for _ in range(4))
+        self.R.ref_fenics_get_channels(self.h, _dp(t), _dp(b), _dp(ft), _dp(fb))
+        return t, b, ft, fb
+
+    def set_boundary_value(self, v):
+        self.R.ref_fenics_set_boundary_value(self.h, C.c_double(v))
+
+    def step(self):
+        if self.R.ref_fenics_step(self.h) != 0:
+            raise RuntimeError("fenicsInterface::stepDiffusion: " + self.R.ref_fenics_last_error().decode())
+
+    def total_boundary_flux(self):
+        return float(self.R.ref_fenics_total_boundary_flux(self.h))
+
+    def robin(self):
+        v = [C.c_double() for _ in range(5)]
+        self.R.ref_fenics_robin(self.h, *[C.byref(x) for x in v])
+        return dict(trap_left=v[0].value, trap_right=v[1].value, chan_left=v[2].value, chan_right=v[3].value, well=v[4].value)
+
+    def close(self):
+        if self.h:
+            self.R.ref_fenics_destroy(self.h)
+            self.h = None

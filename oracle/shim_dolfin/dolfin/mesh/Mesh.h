@@ -1,0 +1,1 @@
+#include "dolfin_mini.h"

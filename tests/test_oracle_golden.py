@@ -208,3 +208,117 @@ def test_cells_live_against_the_compiled_reference_classes(oracle, capfd):
     for a, b in zip(tens, oracle.cells_tensor(rec, npm, ref.nH, ref.nW, 1.5, 0.6)):
         assert np.array_equal(a, b)
     ref.close()
+
+
+# --------------------------------------------------------------------------
+# The P1 step: golden vectors produced by the reference's OWN class fenicsInterface (src/fHSL.cpp) compiled in place on
+# the one-process DOLFIN interface shim (tests/golden/make_golden_fenics.py).
+# --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def fenics_golden():
+    with open(os.path.join(HERE, "golden", "fenics_ref.json")) as f:
+        return json.load(f)
+
+
+def _fenics_problem(oracle, c):
+    p = oracle.problem_from_parameters(c["parameters"], c["dt"], c["D"], float(c["width"]), float(c["height"]), c["npm"])
+    if "tensor" in c:
+        p.d11, p.d22, p.d12 = (np.array(t) for t in c["tensor"])
+    return p
+
+
+def _close(a, b, tol):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return np.linalg.norm(a - b) <= tol * max(np.linalg.norm(b), 1e-300)
+
+
+def test_fenics_golden_file_is_substantial(fenics_golden):
+    names = {c["name"] for c in fenics_golden["cases"]}
+    assert len(fenics_golden["cases"]) >= 28
+    assert {"default_trap_nowalled", "dirichlet_update_well", "h_trap_robin", "microfluidic_channels",
+            "microfluidic_channels_noflow", "microfluidic_mixed_walls", "anisotropic_tensor"} <= names
+    assert {(c["width"], c["height"], c["npm"]) for c in fenics_golden["cases"]} >= {(10, 4, 2.0), (7, 3, 4.0), (6, 5, 1.0)}
+
+
+def test_fenics_set_up_matches_the_reference_class(oracle, fenics_golden):
+    """fenicsClassInit / createHSL / setRobinBoundaryConditions (src/fHSL.cpp:195-364,436-574): node counts, evenly
+    spread vertices, identity vertex->dof map and row-major (iy,jx)->dof lookup (the 'bit-exact lookup' of SURVEY 8a
+    a12), Robin rates as bound into the trap forms (after the H_TRAP override) and into the channel forms (before
+    it), and the channel well volume."""
+    for c in fenics_golden["cases"]:
+        p = _fenics_problem(oracle, c)
+        assert (p.nW, p.nH) == (c["nW"], c["nH"]), c["name"]
+        assert c["dof_is_identity"] and c["lookup_is_row_major"]
+        assert np.allclose(c["mesh_first_row_x"], np.arange(p.nW) * p.h, rtol=0, atol=1e-15 * c["width"])
+        assert np.allclose(c["mesh_first_col_y"], np.arange(p.nH) * (p.hy or p.h), rtol=0, atol=1e-15 * c["height"])
+        r = c["robin"]
+        assert p.well_scaling == r["well"]
+        for w, key in ((0, "trap_left"), (1, "trap_right")):
+            if p.bc_type[w] == oracle.ROBIN:
+                assert p.bc_value[w] == r[key], c["name"]
+        if p.channels:
+            assert p.channel_r == (r["chan_left"], r["chan_right"]), c["name"]
+
+
+def test_fenics_step_matches_the_reference_class(oracle, fenics_golden):
+    """fenicsInterface::stepDiffusion (src/fHSL.cpp:98-161) itself -- trap solve on the reference's own element
+    kernels, wall flux, channel sub-steps, flux functional -- against oracle.step on the same inputs, every
+    boundary / trap type the reference decodes, three geometries.  The only arithmetic that differs is the order of
+    the sums in assembly and the elimination order of the direct solve: fields to 1e-11, channels to 1e-10."""
+    worst = {"u": 0.0, "chan": 0.0, "flux": 0.0}
+    for c in fenics_golden["cases"]:
+        p = _fenics_problem(oracle, c)
+        s = oracle.new_state(p)
+        for st in c["steps"]:
+            if "boundary_value" in st:
+                p.bc_value = (st["boundary_value"],) * 4             # setBoundaryValues, src/fHSL.cpp:601-604
+            s.u = np.array(st["u_in"])
+            s = oracle.step(p, s)
+            want = np.array(st["u_out"])
+            assert _close(s.u, want, 1e-11), (c["name"], c["npm"])
+            worst["u"] = max(worst["u"], np.linalg.norm(s.u - want) / np.linalg.norm(want))
+            # the functional is a sum with cancellation: measure it against the sum of the magnitudes it adds up
+            scale = p.D * p.dt * np.abs(want).sum() / min(p.h, p.hy or p.h)
+            assert abs(s.total_boundary_flux - st["total_boundary_flux"]) <= 1e-12 * scale, c["name"]
+            worst["flux"] = max(worst["flux"], abs(s.total_boundary_flux - st["total_boundary_flux"]) / scale)
+            if p.channels:
+                fb, ft = oracle.compute_boundary_flux(p, s.u)
+                fscale = np.abs(want).max() * p.D * p.dt / p.well_scaling
+                assert np.abs(ft - st["flux_top"]).max() <= 1e-11 * fscale and np.abs(fb - st["flux_bottom"]).max() <= 1e-11 * fscale
+                assert _close(s.top, st["top"], 1e-10) and _close(s.bottom, st["bottom"], 1e-10), c["name"]
+                worst["chan"] = max(worst["chan"], np.linalg.norm(s.top - st["top"]) / np.linalg.norm(st["top"]))
+            else:
+                assert not np.any(st["top"]) and not np.any(st["bottom"])
+    assert worst["u"] > 0.0     # not a copy: two different eliminations
+
+
+def test_fenics_live_against_the_compiled_reference_class(oracle):
+    """Where oracle/_ref/libeq_fenics_ref.so is present (build container; it travels to the GPU box): the default
+    trap as shipped (100 x 20 um at 2 nodes/um = 201 x 41 nodes, DIRICHLET_0 + NOWALLED, src/main.cpp:490,494,511-534)
+    and the microfluidic trap with channels at that size, fresh random data, several steps."""
+    if oracle.fenics_ref_lib() is None:
+        pytest.skip("oracle/_ref/libeq_fenics_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(5)
+    chan = {k: oracle.bc_entry("Dirichlet", -1.0) for k in ("top", "bottom")}
+    chan.update({k: oracle.bc_entry("Robin") for k in ("left", "right")})
+    for over, steps in ((dict(), 2), (dict(boundaryType="MICROFLUIDIC_TRAP", boundaries=chan,
+                                           simulationChannelLengthLeft=20.0, simulationChannelLengthRight=20.0,
+                                           channelSolverNumberIterations=6), 2)):
+        P = oracle.default_parameters(100, 20, 2.0, **over)
+        F = oracle.FenicsReference(P, 0.1, 1200.0, 100.0, 20.0, 2.0)
+        assert (F.nW, F.nH) == (201, 41)
+        p = oracle.problem_from_parameters(P, 0.1, 1200.0, 100.0, 20.0, 2.0)
+        s = oracle.new_state(p)
+        u = rng.uniform(0, 50, p.N)
+        for _ in range(steps):
+            F.set_field(u)
+            s.u = u.copy()
+            F.step()
+            s = oracle.step(p, s)
+            uf = F.field()
+            assert _close(s.u, uf, 1e-11)
+            if p.channels:
+                t, b, _, _ = F.channels()
+                assert _close(s.top, t, 1e-10) and _close(s.bottom, b, 1e-10)
+            u = uf + rng.uniform(0, 5, p.N)
+        F.close()
