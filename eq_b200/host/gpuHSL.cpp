@@ -35,10 +35,11 @@ void gpuHSL::setRobinBoundaryConditions()
     }
 }
 
-// src/fHSL.cpp:37-53 + fenicsClassInit (:195-328) + createHSL's boundary decode (:436-574)
-void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
+// src/fHSL.cpp:37-53 + fenicsClassInit (:195-328) + createHSL's boundary decode (:436-574), host arithmetic only:
+// fills the C-ABI parameter block from myParams and cfg (no device call, so the decoding is testable without a GPU
+// against what the reference class itself binds into its forms, tests/test_host_decode.py)
+void gpuHSL::decodeParameters(eqgpu_params &p)
 {
-    myParams = initParams;
     // cell counts, then +1 for node counts (src/fHSL.cpp:242-243,281-283)
     nodesH = unsigned(ceil(myParams.trapHeightMicrons * myParams.nodesPerMicron)) + 1;
     nodesW = unsigned(ceil(myParams.trapWidthMicrons * myParams.nodesPerMicron)) + 1;
@@ -46,7 +47,6 @@ void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
     wellScaling = 10.0 * (25.0 / cfg.lengthScaling) * h_sim;  // src/fHSL.cpp:47
     setRobinBoundaryConditions();
 
-    eqgpu_params p;
     eqgpu_default_params(&p);
     p.nW = int(nodesW);
     p.nH = int(nodesH);
@@ -94,6 +94,13 @@ void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
     } else {  // :572-573
         for (int w = 0; w < 4; ++w) p.bc_type[w] = EQGPU_BC_DIRICHLET;
     }
+}
+
+void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
+{
+    myParams = initParams;
+    eqgpu_params p;
+    decodeParameters(p);
     int rc = eqgpu_create(&p, &h);
     if (rc != EQGPU_OK) throw std::runtime_error(std::string("gpuHSL: eqgpu_create failed: ") + eqgpu_last_error(nullptr));
 

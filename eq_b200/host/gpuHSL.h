@@ -67,6 +67,9 @@ public:
     // fenicsInterface's extra surface
     void setBoundaryValues(const double);    // src/fHSL.cpp:601-604
     void setRobinBoundaryConditions();       // src/fHSL.cpp:331-364
+    // what initDiffusion hands eqgpu_create: node counts, spacings, per-wall types/values, channel wiring -- decoded
+    // from myParams and cfg exactly as fenicsClassInit / createHSL decode them (src/fHSL.cpp:242-283,436-574)
+    void decodeParameters(eqgpu_params &p);
     size_t nodesH = 0, nodesW = 0;
     std::vector<double> solution_vector;     // N doubles; Simulation Isend/Irecv's into it
     std::vector<double> topChannelData, bottomChannelData;

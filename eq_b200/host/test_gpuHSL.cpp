@@ -3,6 +3,12 @@
 // fields for comparison with the oracle.
 //   test_gpuHSL <case> <in.bin> <out.bin>
 // in.bin : doubles [W, H, npm, dt, D, nsteps, ncells, <ncells*16 records>, <N deposits added before each step>]
+// Cases "decode" and "golden" take the whole configuration from the file instead (tests/test_host_decode.py,
+// tests/test_zz_fenics_golden_gpu.py): after the 7 header doubles (ncells = 0) come
+//   [boundaryType code, trapType code, boundaries[4][3], lengthScaling, simulationFlowRate, channel length left, right,
+//    channelSolverNumberIterations, hasTensor], then 3N tensor doubles if hasTensor, then per step [wall value or NaN, N field].
+// "decode" makes no device call: it writes the parameter block gpuHSL::decodeParameters hands eqgpu_create.
+// "golden" writes [nW, nH] and per step [N field, nW top channel, nW bottom channel, totalBoundaryFlux].
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,6 +73,66 @@ int main(int argc, char **argv)
             std::vector<double> zero(2 * solver->gridNodesX, 0.0);
             fwrite(zero.data(), sizeof(double), zero.size(), f);
             fwrite(flux.data(), sizeof(double), flux.size(), f);
+            fclose(f);
+            solver->finalize();
+        } catch (const std::exception &e) {
+            fprintf(stderr, "%s\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
+
+    if (kase == "decode" || kase == "golden") {
+        static const char *btypes[] = {"DIRICHLET_0", "DIRICHLET_UPDATE", "MICROFLUIDIC_TRAP", "NEUMANN_3WALLED_TEST", "SOMETHING_ELSE"};
+        static const char *ttypes[] = {"NOWALLED", "THREEWALLED", "TWOWALLED", "ONEWALLED", "H_TRAP"};
+        const double *c = in.data() + 7;
+        gpuHSL::config cfg;
+        cfg.boundaryType = btypes[int(c[0])];
+        cfg.trapType = ttypes[int(c[1])];
+        for (int w = 0; w < 4; ++w) for (int k = 0; k < 3; ++k) cfg.boundaries[w][k] = c[2 + 3 * w + k];
+        cfg.lengthScaling = c[14]; cfg.simulationFlowRate = c[15];
+        cfg.simulationChannelLengthLeft = c[16]; cfg.simulationChannelLengthRight = c[17];
+        cfg.channelSolverNumberIterations = int(c[18]);
+        const bool hasTensor = c[19] != 0.0;
+        const double *rest = c + 20;
+        std::shared_ptr<gpuHSL> solver = std::make_shared<gpuHSL>(cfg);
+        FILE *f = nullptr;
+        try {
+            if (kase == "decode") {
+                solver->myParams = p;
+                eqgpu_params q;
+                solver->decodeParameters(q);
+                const double out[] = {double(q.nW), double(q.nH), q.hx, q.hy, q.dt, q.D,
+                                      double(q.bc_type[0]), double(q.bc_type[1]), double(q.bc_type[2]), double(q.bc_type[3]),
+                                      q.bc_value[0], q.bc_value[1], q.bc_value[2], q.bc_value[3],
+                                      double(q.channels), double(q.channel_iters), q.channel_v, q.channel_r[0], q.channel_r[1],
+                                      q.well_scaling, q.robin_s[0], q.robin_s[1]};
+                f = fopen(argv[3], "wb");
+                fwrite(out, sizeof(double), sizeof out / sizeof out[0], f);
+                fclose(f);
+                return 0;
+            }
+            solver->initDiffusion(p);
+            const size_t N = solver->solution_vector.size();
+            if (hasTensor) {   // what the controller's MPI transfer would have written (src/simulation.cpp:503-505)
+                std::copy(rest, rest + N, solver->D11->begin());
+                std::copy(rest + N, rest + 2 * N, solver->D22->begin());
+                std::copy(rest + 2 * N, rest + 3 * N, solver->D12->begin());
+                rest += 3 * N;
+            }
+            f = fopen(argv[3], "wb");
+            double hdr[2] = {double(solver->nodesW), double(solver->nodesH)};
+            fwrite(hdr, sizeof(double), 2, f);
+            for (int s = 0; s < nsteps; ++s) {
+                if (rest[0] == rest[0]) solver->setBoundaryValues(rest[0]);   // not NaN: src/simulation.cpp:602
+                std::copy(rest + 1, rest + 1 + N, solver->solution_vector.begin());
+                rest += 1 + N;
+                solver->stepDiffusion();
+                fwrite(solver->solution_vector.data(), sizeof(double), N, f);
+                fwrite(solver->topChannelData.data(), sizeof(double), solver->nodesW, f);
+                fwrite(solver->bottomChannelData.data(), sizeof(double), solver->nodesW, f);
+                fwrite(&solver->totalBoundaryFlux, sizeof(double), 1, f);
+            }
             fclose(f);
             solver->finalize();
         } catch (const std::exception &e) {

@@ -7,16 +7,30 @@
  *
  * PARITY PINNING: the reference (jwinkle/eQ) ships no tests, golden vectors or
  * fixtures for this path, and DOLFIN/PETSc/Chipmunk are
- * absent, so the full solve cannot be run here.  What IS pinned: the element
+ * absent, so the reference executable cannot be built here.  What IS pinned: the element
  * kernels below are checked bit-for-bit against the reference's own
  * FFC-generated tabulate_tensor bodies, compiled in place from
  * /root/reference/fenics/{hslD,AdvectionDiffusion,boundary}.h under a UFC/DOLFIN
  * shim (oracle/Makefile -> oracle/_ref/libeq_ufc_ref.so; tests/test_oracle_ref.py),
  * and golden vectors produced by those compiled kernels are committed under
- * tests/golden/.  Mesh generation, assembly, Dirichlet application and the
- * sparse direct solve are DOLFIN 2019.1.0 / PETSc [ext] and are restated from
- * their published algorithms; the rod predicate restates Chipmunk 7.0.1 [ext]
- * (cpBodyWorldToLocal, cpvcross).  Those parts are "parity unpinned".
+ * tests/golden/.
+ * The P1 step IS pinned against the reference's own class: fenicsInterface
+ * (src/fHSL.{h,cpp}, src/Expressions.h and every generated form header it
+ * includes) is compiled in place on a one-process DOLFIN interface shim
+ * (oracle/shim_dolfin/, oracle/fenics_ref.cpp -> oracle/_ref/libeq_fenics_ref.so)
+ * and initDiffusion / createHSL / setRobinBoundaryConditions / stepDiffusion /
+ * computeBoundaryFlux / setBoundaryValues themselves run on the reference's own
+ * element kernels; oracle.py's problem_from_parameters + step (eqo_assemble,
+ * eqo_dirichlet_mask, eqo_compute_boundary_flux, eqo_channel_substeps,
+ * eqo_boundary_functional below, SuperLU) agree with it to 1e-11 on every
+ * boundary / trap type the reference decodes, the anisotropic tensor and three
+ * geometries (28 golden cases, tests/golden/fenics_ref.json).  What stays
+ * restated there is DOLFIN 2019.1.0 [ext] -- RectangleMesh("right") /
+ * IntervalMesh numbering, the assembly loop, DirichletBC::apply (identity
+ * rows, list order) and the direct solve -- now inside the shim, written from
+ * DOLFIN's documented behaviour: the reference does not vendor DOLFIN, no
+ * DOLFIN build exists in this image, and the reference ships no golden vectors
+ * (SURVEY.md section 4), so that layer is "parity unpinned" in the strict sense.
  * The finite-difference solver IS pinned end to end: the reference's own class
  * diffusionPETSc (diffuclass.{h,cpp}) is compiled in place on a one-process
  * PETSc/MPI/boost interface shim (oracle/shim_petsc/, oracle/petsc_ref.cpp ->

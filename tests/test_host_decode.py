@@ -1,0 +1,76 @@
+"""The C++ drop-in class gpuHSL decodes eQ::data::parameters into the C-ABI parameter block exactly as the reference
+class decodes them into its forms: `gpuHSL::decodeParameters` (eq_b200/host/gpuHSL.cpp, host arithmetic only -- no
+device call, so this runs without a GPU) against the values the reference's OWN fenicsInterface bound
+(tests/golden/fenics_ref.json, written by src/fHSL.cpp compiled in place: createHSL :436-574,
+setRobinBoundaryConditions :331-364, fenicsClassInit :242-283, initDiffusion :45-47)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "eq_b200", "host", "test_gpuHSL")
+BTYPES = ["DIRICHLET_0", "DIRICHLET_UPDATE", "MICROFLUIDIC_TRAP", "NEUMANN_3WALLED_TEST"]
+TTYPES = ["NOWALLED", "THREEWALLED", "TWOWALLED", "ONEWALLED", "H_TRAP"]
+
+
+def config_block(c, nsteps=0):
+    """The doubles the driver's "decode" / "golden" cases read (eq_b200/host/test_gpuHSL.cpp header)."""
+    P = c["parameters"]
+    b = P.get("boundaries")
+    walls = [b[w][1] if b else [0.0, 1.0, 0.0] for w in ("left", "right", "top", "bottom")]
+    bt = BTYPES.index(P["boundaryType"]) if P["boundaryType"] in BTYPES else 4
+    head = [c["width"], c["height"], c["npm"], c["dt"], c["D"], nsteps, 0]
+    cfg = [bt, TTYPES.index(P["trapType"])] + [v for w in walls for v in w] + [
+        P["lengthScaling"], P["simulationFlowRate"], P["simulationChannelLengthLeft"], P["simulationChannelLengthRight"],
+        P["channelSolverNumberIterations"], 1.0 if "tensor" in c else 0.0]
+    return np.array(head + cfg, dtype=np.float64)
+
+
+@pytest.fixture(scope="module")
+def exe():
+    if not os.path.exists(EXE):
+        subprocess.run(["make", "-C", os.path.dirname(EXE), "all"], check=True, stdout=subprocess.DEVNULL)
+    return EXE
+
+
+@pytest.fixture(scope="module")
+def fenics_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "fenics_ref.json")) as f:
+        return json.load(f)
+
+
+def test_gpuHSL_decodes_parameters_like_the_reference_class(exe, fenics_golden, tmp_path, oracle):
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    seen = set()
+    for c in fenics_golden["cases"]:
+        config_block(c).tofile(fin)
+        subprocess.run([exe, "decode", str(fin), str(fout)], check=True)
+        q = np.fromfile(fout)
+        nW, nH, hx, hy, dt, D = q[:6]
+        bc_type, bc_value = q[6:10].astype(int), q[10:14]
+        channels, iters, chan_v, chan_rl, chan_rr, well, s1, s2 = q[14:22]
+        r = c["robin"]
+        name = (c["name"], c["npm"])
+        # node counts and the evenly spread vertices (fenicsClassInit, RectangleMesh)
+        assert (nW, nH) == (c["nW"], c["nH"]), name
+        assert np.allclose(np.arange(c["nW"]) * hx, c["mesh_first_row_x"], rtol=0, atol=1e-15 * c["width"])
+        assert np.allclose(np.arange(c["nH"]) * hy, c["mesh_first_col_y"], rtol=0, atol=1e-15 * c["height"])
+        assert (dt, D) == (c["dt"], c["D"]) and (s1, s2) == (0.0, 0.0)
+        # Robin rates: what the reference bound into the trap's forms (after the H_TRAP override) and the channels'
+        for w, key in ((0, "trap_left"), (1, "trap_right")):
+            if bc_type[w] == oracle.ROBIN:
+                assert bc_value[w] == r[key], name
+        # same wall types as the oracle's decoding, which the golden steps validate against the reference's solve
+        p = oracle.problem_from_parameters(c["parameters"], c["dt"], c["D"], float(c["width"]), float(c["height"]), c["npm"])
+        assert tuple(bc_type) == tuple(p.bc_type), name
+        assert tuple(bc_value) == tuple(float(v) for v in p.bc_value), name
+        assert bool(channels) == p.channels, name
+        if p.channels:
+            assert (chan_rl, chan_rr) == (r["chan_left"], r["chan_right"]), name
+            assert well == r["well"], name       # channel node volume, src/fHSL.cpp:47
+            assert int(iters) == c["parameters"]["channelSolverNumberIterations"] and chan_v == c["parameters"]["simulationFlowRate"]
+        seen.add(tuple(bc_type))
+    assert len(seen) >= 8      # the golden set walks through every branch of the decoding
