@@ -7,6 +7,7 @@
 #ifdef EQ_B200_IN_EQ_TREE
 #include "eQ.h"
 #else
+#include <cmath>
 #include <map>
 #include <memory>
 #include <string>
@@ -16,7 +17,31 @@ typedef int MPI_Comm;  // opaque here; Simulation passes the layer communicator 
 
 namespace eQ {
 struct data {
-    struct record {};
+    // src/eQ.h:136-180: what a data-recording grid exposes to the writer (nearest-node lookup at the
+    // data resolution); only the members gpuHSL::writeDataFiles reads
+    class tensor {
+    public:
+        enum rank { SCALAR = 0, VECTOR = 1, NUM_RANKS };
+        tensor(size_t n, size_t y, size_t x, size_t thisRank) : nh(y * n + 1), nw(x * n + 1), nodesPerMicron(double(n)), rank_(thisRank)
+        {
+            for (size_t i = 0; i <= rank_; ++i) grid.push_back(std::vector<double>(nh * nw, 0.0));
+        }
+        size_t getRank() { return rank_; }
+        size_t index(double x, double y) const { return size_t(round(y * nodesPerMicron)) * nw + size_t(round(x * nodesPerMicron)); }
+        double eval(double x, double y) { return grid[0][index(x, y)]; }
+        std::pair<double, double> evalVector(double x, double y) { return std::make_pair(grid[0][index(x, y)], grid[1][index(x, y)]); }
+        std::vector<std::vector<double>> grid;   // row-major nh x nw per component
+        size_t nh, nw;
+    private:
+        double nodesPerMicron;
+        size_t rank_;
+    };
+    struct record {   // src/eQ.h:95-101
+        int type;
+        size_t index;
+        std::string fileName;
+        std::shared_ptr<tensor> data;
+    };
     using files_t = std::vector<record>;
     // the reference returns nlohmann::json from getBoundaryFlux(); {"totalFlux": v} is all it carries
     using parametersType = std::map<std::string, double>;
@@ -41,7 +66,7 @@ public:
         double nodesPerMicron;
         double trapChannelVelocity;
     };
-    virtual ~diffusionSolver() = default;
+    // (no virtual destructor upstream either: Simulation holds the solver by its concrete type)
     virtual void initDiffusion(eQ::diffusionSolver::params &) = 0;
     virtual void stepDiffusion() {}
     virtual eQ::data::parametersType getBoundaryFlux(void) { return {}; }

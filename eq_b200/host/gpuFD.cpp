@@ -119,6 +119,7 @@ void gpuFD::writeDiffusionFiles(double timestamp)
     snprintf(name, sizeof name, "%s_%s_%012.4f.vtk", initData.directoryName.c_str(), initData.objectName.c_str(), timestamp);
     std::ofstream f(name);
     if (!f) return;
+    f.precision(17);   // round-trip doubles
     f << "# vtk DataFile Version 3.0\nHSL t=" << timestamp << "\nASCII\nDATASET STRUCTURED_POINTS\n";
     f << "DIMENSIONS " << gridNodesX << " " << gridNodesY << " 1\nORIGIN 0 0 0\nSPACING " << initData.h << " "
       << initData.h << " 1\n";

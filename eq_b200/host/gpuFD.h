@@ -30,7 +30,7 @@ public:
     };
 
     gpuFD() = default;
-    ~gpuFD() override;
+    ~gpuFD();   // eQ::diffusionSolver has no virtual destructor (src/eQ.h:302-330)
 
     std::string boundaryType = "DIRICHLET_0";   // eQ::data::parameters["boundaryType"] (diffuclass.cpp:68)
     int device = 0;

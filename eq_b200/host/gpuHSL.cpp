@@ -14,6 +14,47 @@ void gpuHSL::check(int rc, const char *what)
 
 gpuHSL::~gpuHSL() { finalize(); }
 
+// src/fHSL.cpp:27-34 + the data-recording branch of fenicsClassInit (:223-234,281-283): a vertex grid over the trap
+// at the data resolution -- note the reference rounds the trap size up BEFORE scaling here, unlike the solver branch
+gpuHSL::gpuHSL(const eQ::diffusionSolver::params &recorderParams) : myParams(recorderParams), isDataRecordingNode(true)
+{
+    nodesH = unsigned(ceil(myParams.trapHeightMicrons) * myParams.nodesPerMicron) + 1;
+    nodesW = unsigned(ceil(myParams.trapWidthMicrons) * myParams.nodesPerMicron) + 1;
+    shell->mesh->n = nodesH * nodesW;
+}
+
+// src/fHSL.cpp:637-654: every registered data grid is sampled at the mesh vertices (scalarDataExpression /
+// vectorDataExpression, src/Expressions.h:45-73 -> eQ::data::tensor::eval, nearest node) and written out with the
+// time stamp; one legacy-VTK file per grid and time instead of dolfin::File's PVD series.
+void gpuHSL::writeDataFiles(double timestamp)
+{
+    if (!myParams.dataFiles) return;
+    const double hx = myParams.trapWidthMicrons / double(nodesW - 1), hy = myParams.trapHeightMicrons / double(nodesH - 1);
+    for (auto &file : *myParams.dataFiles) {
+        if (!file.data) continue;
+        char name[768];
+        snprintf(name, sizeof name, "%s%s_%012.4f.vtk", myParams.filePath.c_str(), file.fileName.c_str(), timestamp);
+        std::ofstream f(name);
+        if (!f) continue;
+        f.precision(17);
+        const bool vec = (eQ::data::tensor::rank::VECTOR == file.data->getRank());
+        f << "# vtk DataFile Version 3.0\n" << file.fileName << " t=" << timestamp << "\nASCII\nDATASET STRUCTURED_POINTS\n";
+        f << "DIMENSIONS " << nodesW << " " << nodesH << " 1\nORIGIN 0 0 0\nSPACING " << hx << " " << hy << " 1\n";
+        f << "POINT_DATA " << nodesW * nodesH << "\n";
+        if (vec) f << "VECTORS data double\n";
+        else f << "SCALARS data double 1\nLOOKUP_TABLE default\n";
+        for (size_t i = 0; i < nodesH; ++i)
+            for (size_t j = 0; j < nodesW; ++j) {
+                const double x = double(j) * hx, y = double(i) * hy;
+                if (vec) {
+                    const auto v = file.data->evalVector(x, y);
+                    f << v.first << " " << v.second << " 0\n";
+                } else
+                    f << file.data->eval(x, y) << "\n";
+            }
+    }
+}
+
 void gpuHSL::finalize()
 {
     if (h) { eqgpu_destroy(h); h = nullptr; }
@@ -204,6 +245,7 @@ void gpuHSL::writeDiffusionFiles(double timestamp)
     snprintf(name, sizeof name, "%s_%012.4f.vtk", myParams.filePath.c_str(), timestamp);
     std::ofstream f(name);
     if (!f) return;
+    f.precision(17);   // round-trip doubles
     const double hx = myParams.trapWidthMicrons / double(nodesW - 1), hy = myParams.trapHeightMicrons / double(nodesH - 1);
     f << "# vtk DataFile Version 3.0\nHSL t=" << timestamp << "\nASCII\nDATASET STRUCTURED_POINTS\n";
     f << "DIMENSIONS " << nodesW << " " << nodesH << " 1\nORIGIN 0 0 0\nSPACING " << hx << " " << hy << " 1\n";

@@ -51,7 +51,10 @@ public:
 
     gpuHSL() = default;
     explicit gpuHSL(const config &c) : cfg(c) {}
-    ~gpuHSL() override;
+    // the data-recording constructor (src/fHSL.cpp:27-34): the controller uses the same class, with no solver behind
+    // it, to write the ABM's data grids over a mesh at nodesPerMicronData (src/simulation.cpp:556-580)
+    explicit gpuHSL(const eQ::diffusionSolver::params &recorderParams);
+    ~gpuHSL();   // eQ::diffusionSolver has no virtual destructor (src/eQ.h:302-330)
 
     config cfg;
     eQ::diffusionSolver::params myParams;
@@ -63,6 +66,7 @@ public:
     eQ::data::parametersType getBoundaryFlux(void) override;     // {"totalFlux": totalBoundaryFlux}
     void writeDiffusionFiles(double timestamp) override;         // src/fHSL.cpp:630-636 (VTK ImageData instead of PVD)
     void finalize(void) override;
+    void writeDataFiles(double timestamp);                       // src/fHSL.cpp:637-654 (legacy VTK instead of PVD)
 
     // fenicsInterface's extra surface
     void setBoundaryValues(const double);    // src/fHSL.cpp:601-604
@@ -93,6 +97,7 @@ public:
 
 private:
     eqgpu_solver *h = nullptr;
+    bool isDataRecordingNode = false;
     bool tensorFromCells = false;
     double leftRate = 0.0, rightRate = 0.0, channelFlowVelocity = 0.0;
     bool tensorDirty = false;

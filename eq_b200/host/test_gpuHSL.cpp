@@ -82,6 +82,27 @@ int main(int argc, char **argv)
         return 0;
     }
 
+    if (kase == "recorder") {
+        // the controller's data-recording use of the class (src/simulation.cpp:556-580): no solver, no device call.
+        // One scalar and one vector grid with recognisable values; argv[3] is the file-path prefix.
+        const size_t n = size_t(npm), y = size_t(H), x = size_t(W);
+        auto sc = std::make_shared<eQ::data::tensor>(n, y, x, eQ::data::tensor::rank::SCALAR);
+        auto ve = std::make_shared<eQ::data::tensor>(n, y, x, eQ::data::tensor::rank::VECTOR);
+        for (size_t i = 0; i < sc->nh; ++i)
+            for (size_t j = 0; j < sc->nw; ++j) {
+                sc->grid[0][i * sc->nw + j] = 1000.0 * double(i) + double(j) + 1.0 / 3.0;
+                ve->grid[0][i * ve->nw + j] = double(i);
+                ve->grid[1][i * ve->nw + j] = -double(j);
+            }
+        p.dataFiles = std::make_shared<eQ::data::files_t>();
+        p.dataFiles->push_back(eQ::data::record{0, 0, "scalarGrid", sc});
+        p.dataFiles->push_back(eQ::data::record{1, 1, "vectorGrid", ve});
+        p.filePath = argv[3];
+        gpuHSL recorder(p);
+        recorder.writeDataFiles(in[5]);
+        printf("%zu %zu\n", recorder.nodesW, recorder.nodesH);
+        return 0;
+    }
     if (kase == "decode" || kase == "golden") {
         static const char *btypes[] = {"DIRICHLET_0", "DIRICHLET_UPDATE", "MICROFLUIDIC_TRAP", "NEUMANN_3WALLED_TEST", "SOMETHING_ELSE"};
         static const char *ttypes[] = {"NOWALLED", "THREEWALLED", "TWOWALLED", "ONEWALLED", "H_TRAP"};

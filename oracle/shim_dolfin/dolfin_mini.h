@@ -84,6 +84,15 @@ public:
 };
 extern Parameters parameters;
 template <class... A> inline void info(A...) {}
+inline std::string dolfin_version() { return "2019.1.0 (interface shim)"; }
+inline std::string ufc_signature() { return "shim"; }
+inline std::string git_commit_hash() { return "shim"; }
+class SubSystemsManager
+{
+public:
+  static SubSystemsManager& singleton() { static SubSystemsManager s; return s; }
+  static void finalize() {}
+};
 
 // ---- meshes ---------------------------------------------------------------------------------------------------
 class MeshTopology

@@ -74,3 +74,40 @@ def test_gpuHSL_decodes_parameters_like_the_reference_class(exe, fenics_golden, 
             assert int(iters) == c["parameters"]["channelSolverNumberIterations"] and chan_v == c["parameters"]["simulationFlowRate"]
         seen.add(tuple(bc_type))
     assert len(seen) >= 8      # the golden set walks through every branch of the decoding
+
+
+def test_data_recorder_writes_the_grids(exe, tmp_path):
+    """gpuHSL's data-recording constructor + writeDataFiles (the controller's use of the class,
+    src/fHSL.cpp:27-34,223-234,637-654; src/simulation.cpp:556-580): node counts ceil(H)*npm + 1, every registered
+    grid sampled at the mesh vertices, scalar and vector ranks, values round-trip exactly.  No device call."""
+    W, H, npm, t = 12.0, 5.0, 1.0, 30.0
+    fin = tmp_path / "in.bin"
+    np.array([W, H, npm, 0.1, 1200.0, t, 0], dtype=np.float64).tofile(fin)
+    prefix = str(tmp_path) + "/"
+    r = subprocess.run([exe, "recorder", str(fin), prefix], check=True, capture_output=True, text=True)
+    nW, nH = (int(v) for v in r.stdout.split())
+    assert (nW, nH) == (13, 6)
+
+    def read(name):
+        lines = open(os.path.join(prefix, f"{name}_{t:012.4f}.vtk")).read().splitlines()
+        assert lines[4] == f"DIMENSIONS {nW} {nH} 1" and lines[7] == f"POINT_DATA {nW * nH}"
+        start = 9 if lines[8].startswith("VECTORS") else 10
+        return lines[8], np.array([[float(v) for v in l.split()] for l in lines[start:start + nW * nH]])
+
+    kind, sc = read("scalarGrid")
+    assert kind.startswith("SCALARS")
+    i, j = np.mgrid[0:nH, 0:nW]
+    assert np.array_equal(sc[:, 0], (1000.0 * i + j + 1.0 / 3.0).ravel())
+    kind, ve = read("vectorGrid")
+    assert kind.startswith("VECTORS")
+    assert np.array_equal(ve[:, 0], i.ravel().astype(float)) and np.array_equal(ve[:, 1], -j.ravel().astype(float))
+
+
+def test_reference_controller_compiles_against_the_drop_in():
+    """src/simulation.{h,cpp} of the reference with INTEGRATION.md's three edits, compiled (syntax and types) against
+    gpuHSL on the reference's real src/eQ.h: every member the controller reaches into exists with a compatible type.
+    Needs the reference tree (build container)."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("/root/reference absent")
+    r = subprocess.run(["python", os.path.join(ROOT, "scripts", "check_dropin_compiles.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
