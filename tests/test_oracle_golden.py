@@ -322,3 +322,47 @@ def test_fenics_live_against_the_compiled_reference_class(oracle):
                 assert _close(s.top, t, 1e-10) and _close(s.bottom, b, 1e-10)
             u = uf + rng.uniform(0, 5, p.N)
         F.close()
+
+
+# --------------------------------------------------------------------------
+# BASELINE configs[0], the default trap as shipped, run by the reference's own classes on both sides of the
+# controller <-> HSL-rank exchange (tests/golden/make_golden_coupled.py): eQabm::updateCells + fenicsInterface::
+# stepDiffusion, 20 steps, 32 rods.
+# --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def coupled_golden():
+    with open(os.path.join(HERE, "golden", "coupled_ref.json")) as f:
+        return json.load(f)
+
+
+def test_coupled_default_trap_matches_the_reference_classes(oracle, coupled_golden):
+    """The oracle's cell loop + P1 step against the reference's coupled run: per-cell samples and fields to 1e-10
+    over 20 steps (the sample feeds back into the deposit, so an error anywhere would grow), rods grown and bent
+    through the reference's ratchet at step 10.  Also the premise of the GPU's fused mode on this colony: sampling
+    all rods before depositing equals the reference's sequential loop bit for bit when rods do not overlap."""
+    c = coupled_golden
+    npm, a1 = c["npm"], c["a1"]
+    p = oracle.problem_from_parameters(c["parameters"], c["dt"], c["D"], float(c["width"]), float(c["height"]), npm)
+    assert (p.nW, p.nH) == (201, 41) and p.bc_type == (1, 1, 1, 1)
+    a0 = np.array(c["a0"])
+    rec = np.array(c["records0"])
+    centers, ang = rec[:, 11:13], np.arctan2(rec[:, 15], rec[:, 14])
+    assert np.array_equal(oracle.make_cells(centers, ang, rec[:, 13], float(c["width"]), float(c["height"])), rec)
+    s = oracle.new_state(p)
+    for k, st in enumerate(c["steps"], start=1):
+        if k == 10:
+            rec = np.array(c["records10"])
+            assert np.sum(rec[:, 5] > rec[:, 4]) >= 5           # ratcheted rods from here on
+        u_seq, g = oracle.update_cells_sequential(rec, npm, p.nH, p.nW, a0, a1, s.u)
+        g_all = oracle.gather(rec, npm, p.nH, p.nW, s.u)
+        u_all = oracle.scatter(rec, npm, p.nH, p.nW, a0 + a1 * g_all, s.u)
+        assert np.array_equal(g, g_all) and np.array_equal(u_seq, u_all)
+        assert np.allclose(g, st["gathered"], rtol=1e-10, atol=1e-300), k
+        s.u = u_seq
+        s = oracle.step(p, s)
+        assert abs(s.u.sum() - st["sum"]) <= 1e-10 * abs(st["sum"]) and abs(np.linalg.norm(s.u) - st["norm"]) <= 1e-10 * st["norm"]
+        assert abs(s.total_boundary_flux - st["total_boundary_flux"]) <= 1e-12 * p.D * p.dt * np.abs(s.u).sum() / p.h
+        if str(k) in c["fields"]:
+            want = np.array(c["fields"][str(k)])
+            assert np.linalg.norm(s.u - want) <= 1e-10 * np.linalg.norm(want), k
+    assert s.u.max() > 1.0     # the colony did build up a signal

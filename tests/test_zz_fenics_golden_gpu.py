@@ -83,3 +83,28 @@ def test_cpp_gpuHSL_matches_the_reference_class(oracle, tmp_path, c):
         flux = out[o + p.N + 2 * p.nW]
         o += p.N + 2 * p.nW + 1
         check_step(c, p, st, u, t, b, flux)
+
+
+def test_coupled_default_trap_matches_the_reference_classes(oracle):
+    """BASELINE configs[0]: the default trap as shipped (201 x 41 nodes, DIRICHLET_0, 32 rods), 20 coupled steps run by
+    the reference's own eQabm::updateCells + fenicsInterface::stepDiffusion (tests/golden/coupled_ref.json), against
+    the GPU's fused mode: cell records up, gather, deposit a0 + a1 * sample, resident step -- the field never leaves
+    HBM.  Per-cell samples and fields within 1e-8 (the samples feed back into the deposits)."""
+    with open(os.path.join(ROOT, "tests", "golden", "coupled_ref.json")) as f:
+        c = json.load(f)
+    npm, a1, a0 = c["npm"], c["a1"], np.array(c["a0"])
+    p = oracle.problem_from_parameters(c["parameters"], c["dt"], c["D"], float(c["width"]), float(c["height"]), npm)
+    g = E.GpuHSL(p.nW, p.nH, h=p.h, hy=p.hy, dt=p.dt, D=p.D, bc_type=p.bc_type, bc_value=p.bc_value)
+    g.upload_cells(np.array(c["records0"]), npm)
+    for k, st in enumerate(c["steps"], start=1):
+        if k == 10:
+            g.upload_cells(np.array(c["records10"]), npm)
+        sampled = g.gather()
+        assert rel(sampled, st["gathered"]) < TOL or not np.any(st["gathered"]), k
+        g.scatter(a0 + a1 * sampled)
+        g.step()
+        scale = p.D * p.dt * max(abs(st["sum"]), 1e-300) / p.h
+        assert abs(g.totalBoundaryFlux - st["total_boundary_flux"]) <= 1e-8 * scale, k
+        if str(k) in c["fields"]:
+            assert rel(g.get_field(), c["fields"][str(k)]) < TOL, k
+    g.close()
