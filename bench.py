@@ -55,43 +55,101 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py), polled every 5 ms: the
+    default timed region is about 0.1 s, shorter than nvidia-smi's start-up, which is why the first round's lines said
+    "unavailable"; `nvidia-smi -lms` stays as the fallback when NVML cannot be loaded."""
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.uuid = uuid
+        self.rows = []          # (sm_mhz, sm_max_mhz, set of reason names)
         self.proc = None
+        self.halt = threading.Event()
+        self.ready = threading.Event()
+        self.source = None
 
-    def run(self):
+    def _nvml_handle(self, nv):
+        if self.uuid:
+            for u in (f"GPU-{self.uuid}", str(self.uuid)):
+                try:
+                    return nv.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                except Exception:
+                    pass
+        idx = self.index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        parts = [v for v in vis.split(",") if v.strip()]
+        if parts and self.index < len(parts) and parts[self.index].strip().isdigit():
+            idx = int(parts[self.index])
+        return nv.nvmlDeviceGetHandleByIndex(idx)
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = self._nvml_handle(nv)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        self.source = "nvml"
+        while not self.halt.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            r = int(get_reasons(h))
+            self.rows.append((sm, mx, {n for n, b in bits.items() if r & b}))
+            self.ready.set()
+            time.sleep(0.005)
+        nv.nvmlShutdown()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        self.source = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits", "-lms", "20"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            c = [v.strip() for v in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                self.rows.append((float(c[0]), float(c[1]),
+                                  {n for n, v in zip(self.NAMES, c[2:6]) if v.lower().startswith("active")}))
+                self.ready.set()
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+            if self.halt.is_set():
+                break
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            try:
+                self._run_smi()
+            except Exception:
+                pass
+        self.ready.set()
+
+    def wait_ready(self, timeout=5.0):
+        """Block until the first sample has arrived, so that a short timed region is covered."""
+        self.ready.wait(timeout)
+        self.mark = len(self.rows)
+
+    def stop(self):
+        self.halt.set()
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2.0)
+        rows = self.rows[getattr(self, "mark", 0):] or self.rows
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        reasons = set()
+        for r in rows:
+            reasons |= r[2]
+        return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_max_mhz": float(max(r[1] for r in rows)),
+                "reasons": sorted(reasons), "samples": len(rows), "source": self.source}
 
 
 def cpu_baseline(sample_n=512, threads=1):
@@ -382,9 +440,13 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     sampler.start()
-    time.sleep(0.3)
+    sampler.wait_ready()
     l0 = g.stats().kernel_launches
     ms = timed(step_resident, args.steps)
     launches = g.stats().kernel_launches - l0
