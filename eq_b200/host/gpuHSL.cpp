@@ -171,8 +171,13 @@ void gpuHSL::pushTensorIfChanged()
     // The controller sends D11/D22/D12 every step (src/simulation.cpp:503-505) but as shipped they
     // stay 1,1,0 (SURVEY.md finding 5): only a non-trivial tensor switches the variable-tensor operator on.
     if (tensorFromCells) return;   // the tensor was rasterised on the device (setDiffusionTensorFromCells)
-    bool iso = true;
     const size_t N = solution_vector.size();
+    // Looking for a change means reading 3N doubles on the host: nothing at the shipped 201 x 41 nodes, ten times the
+    // GPU's whole step at 2048^2.  Large meshes therefore wait to be told (notifyTensorChanged) unless cfg says scan.
+    const bool scan = cfg.tensorScan > 0 || (cfg.tensorScan < 0 && N <= (size_t(1) << 18));
+    if (!scan && !tensorPending) return;
+    tensorPending = false;
+    bool iso = true;
     for (size_t k = 0; k < N && iso; ++k)
         iso = ((*D11)[k] == 1.0 && (*D22)[k] == 1.0 && (*D12)[k] == 0.0);
     if (!iso) {

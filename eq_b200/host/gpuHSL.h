@@ -35,6 +35,10 @@ public:
         double simulationChannelLengthRight = 20.0;
         int channelSolverNumberIterations = 48;     // src/main.cpp:426-429
         int device = 0;                             // CUDA device of this layer
+        // D11/D22/D12 are host vectors the controller may overwrite at any time (src/simulation.cpp:503-505); finding out
+        // costs a pass over 3N doubles.  -1: look every step up to 2^18 nodes, above that only after
+        // notifyTensorChanged(); 0: only after notifyTensorChanged(); 1: look every step whatever the size
+        int tensorScan = -1;
         double rtol = 1e-12;
     };
 
@@ -92,6 +96,7 @@ public:
     void stepDiffusionResident();                            // stepDiffusion without the host round trip
     void fetchSolution();                                    // device field -> solution_vector
 
+    void notifyTensorChanged() { tensorPending = true; }     // D11/D22/D12 were rewritten (see config::tensorScan)
     eqgpu_solver *handle() { return h; }
     int lastIterations() const;
 
@@ -100,7 +105,7 @@ private:
     bool isDataRecordingNode = false;
     bool tensorFromCells = false;
     double leftRate = 0.0, rightRate = 0.0, channelFlowVelocity = 0.0;
-    bool tensorDirty = false;
+    bool tensorDirty = false, tensorPending = false;
     void check(int rc, const char *what);
     void pushTensorIfChanged();
 };
