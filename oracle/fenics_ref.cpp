@@ -153,3 +153,90 @@ REF_API void ref_fenics_robin(void *h, double *trap_left, double *trap_right, do
     *chan_right = cr ? double(*cr) : 0.0;
     *well = f.wellScaling;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's three trap forms (fenics/hsl.ufl, hslRobin.ufl, hslD.ufl -- the north star names all three; the
+// shipped fenicsInterface instantiates hslD only, src/fHSL.cpp:23) assembled through their own generated wrappers and
+// kernels on RectangleMesh(nx, ny, "right"), with ARBITRARY constants: source f, Robin rates and external
+// concentrations s (both zero as shipped, so the stepDiffusion golden cases never exercise them), tensor fields.
+// which: 0 hsl (D, dt, f), 1 hslRobin (ds(0) = left wall, ds(1) = right wall), 2 hslD (ds(1) = left, ds(2) = right).
+// Out: the matrix as triplets (row-major by row, ascending column; returns nnz) and the load vector.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+class FieldExpression : public dolfin::Expression {   // nearest-vertex lookup, like AnisotropicDiffusionTensor
+public:
+    FieldExpression(const double *v, size_t nxp, double hx, double hy, double dflt) : v(v), nxp(nxp), hx(hx), hy(hy), dflt(dflt) {}
+    void eval(dolfin::Array<double> &values, const dolfin::Array<double> &x) const override
+    {
+        values[0] = v ? v[size_t(round(x[1] / hy)) * nxp + size_t(round(x[0] / hx))] : dflt;
+    }
+    const double *v; size_t nxp; double hx, hy, dflt;
+};
+template <class A, class L>
+long assemble_pair(A &a, L &l, size_t n, long *rows, long *cols, double *vals, double *b)
+{
+    dolfin::SparseSystem sa, sl;
+    sa.A.assign(n, {}); sa.b.assign(n, 0.0);
+    sl.b.assign(n, 0.0);
+    dolfin::assemble_form(a, &sa, true, nullptr);
+    dolfin::assemble_form(l, &sl, false, nullptr);
+    long k = 0;
+    for (size_t i = 0; i < n; ++i)
+        for (const auto &e : sa.A[i]) { rows[k] = (long)i; cols[k] = (long)e.first; vals[k] = e.second; ++k; }
+    for (size_t i = 0; i < n; ++i) b[i] = sl.b[i];
+    return k;
+}
+}
+
+REF_API long ref_form_assemble(int which, int nx, int ny, double W, double H, double D, double dt, double f,
+                               double rA, double sA, double rB, double sB, const double *d11, const double *d22,
+                               const double *d12, const double *u0, long *rows, long *cols, double *vals, double *b)
+{
+    try {
+        auto mesh = std::make_shared<dolfin::RectangleMesh>(0, dolfin::Point(0.0, 0.0), dolfin::Point(W, H), nx, ny, "right");
+        const size_t n = mesh->num_vertices();
+        auto cD = std::make_shared<dolfin::Constant>(D), cdt = std::make_shared<dolfin::Constant>(dt),
+             cf = std::make_shared<dolfin::Constant>(f), crA = std::make_shared<dolfin::Constant>(rA),
+             csA = std::make_shared<dolfin::Constant>(sA), crB = std::make_shared<dolfin::Constant>(rB),
+             csB = std::make_shared<dolfin::Constant>(sB);
+        auto left = std::make_shared<DirichletBoundary_TrapEdge>(H, W, DirichletBoundary_TrapEdge::LEFT);
+        auto right = std::make_shared<DirichletBoundary_TrapEdge>(H, W, DirichletBoundary_TrapEdge::RIGHT);
+        if (which == 0) {
+            auto V = std::make_shared<hsl::FunctionSpace>(mesh);
+            auto fu0 = std::make_shared<dolfin::Function>(V);
+            fu0->vector()->set_local(std::vector<double>(u0, u0 + n));
+            hsl::Form_a a(V, V); hsl::Form_L l(V);
+            a.D = cD; a.dt = cdt; l.u0 = fu0; l.dt = cdt; l.f = cf;
+            return assemble_pair(a, l, n, rows, cols, vals, b);
+        }
+        if (which == 1) {
+            auto V = std::make_shared<hslRobin::FunctionSpace>(mesh);
+            auto fu0 = std::make_shared<dolfin::Function>(V);
+            fu0->vector()->set_local(std::vector<double>(u0, u0 + n));
+            auto mf = std::make_shared<dolfin::MeshFunction<size_t>>(mesh, mesh->topology().dim() - 1, 99);
+            left->mark(*mf, 0); right->mark(*mf, 1);
+            hslRobin::Form_a a(V, V); hslRobin::Form_L l(V);
+            a.D = cD; a.dt = cdt; a.r0 = crA; a.r1 = crB;
+            l.u0 = fu0; l.dt = cdt; l.f = cf; l.r0 = crA; l.s0 = csA; l.r1 = crB; l.s1 = csB;
+            a.ds = mf; l.ds = mf;
+            return assemble_pair(a, l, n, rows, cols, vals, b);
+        }
+        auto V = std::make_shared<hslD::FunctionSpace>(mesh);
+        auto fu0 = std::make_shared<dolfin::Function>(V);
+        fu0->vector()->set_local(std::vector<double>(u0, u0 + n));
+        auto mf = std::make_shared<dolfin::MeshFunction<size_t>>(mesh, mesh->topology().dim() - 1, 0);
+        left->mark(*mf, 1); right->mark(*mf, 2);
+        const double hx = W / nx, hy = H / ny;
+        auto e11 = std::make_shared<FieldExpression>(d11, size_t(nx) + 1, hx, hy, 1.0);
+        auto e22 = std::make_shared<FieldExpression>(d22, size_t(nx) + 1, hx, hy, 1.0);
+        auto e12 = std::make_shared<FieldExpression>(d12, size_t(nx) + 1, hx, hy, 0.0);
+        hslD::Form_a a(V, V); hslD::Form_L l(V);
+        a.D = cD; a.D11 = e11; a.D22 = e22; a.D12 = e12; a.dt = cdt; a.r1 = crA; a.r2 = crB;
+        l.u0 = fu0; l.dt = cdt; l.f = cf; l.r1 = crA; l.s1 = csA; l.r2 = crB; l.s2 = csB;
+        a.ds = mf; l.ds = mf;
+        return assemble_pair(a, l, n, rows, cols, vals, b);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}

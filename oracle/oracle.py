@@ -860,3 +860,26 @@ class FenicsReference:
         if self.h:
             self.R.ref_fenics_destroy(self.h)
             self.h = None
+
+
+def fenics_form_assemble(which, nW, nH, W, H, D, dt, f=0.0, rA=0.0, sA=0.0, rB=0.0, sB=0.0, tensor=None, u0=None):
+    """a and L of one of the reference's three trap forms -- "hsl", "hslRobin", "hslD" (fenics/*.ufl) -- assembled by the
+    reference's own generated wrappers and kernels on the DOLFIN shim, with arbitrary constants (source f, Robin rates
+    rA/rB on the left/right wall and external concentrations sA/sB).  Returns (scipy CSR matrix, load vector)."""
+    import scipy.sparse as sp
+    R = fenics_ref_lib()
+    if R is None:
+        raise RuntimeError("oracle/_ref/libeq_fenics_ref.so missing")
+    R.ref_form_assemble.restype = C.c_long
+    N = nW * nH
+    rows, cols = np.zeros(7 * N, dtype=np.int64), np.zeros(7 * N, dtype=np.int64)
+    vals, b = np.zeros(7 * N), np.zeros(N)
+    u0 = np.zeros(N) if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+    t = [np.ascontiguousarray(x, dtype=np.float64) for x in tensor] if tensor is not None else [None] * 3
+    nnz = R.ref_form_assemble(C.c_int({"hsl": 0, "hslRobin": 1, "hslD": 2}[which]), C.c_int(nW - 1), C.c_int(nH - 1),
+                              C.c_double(W), C.c_double(H), C.c_double(D), C.c_double(dt), C.c_double(f),
+                              C.c_double(rA), C.c_double(sA), C.c_double(rB), C.c_double(sB), _dp(t[0]), _dp(t[1]), _dp(t[2]),
+                              _dp(u0), rows.ctypes.data_as(c_lp), cols.ctypes.data_as(c_lp), _dp(vals), _dp(b))
+    if nnz < 0:
+        raise RuntimeError(R.ref_fenics_last_error().decode())
+    return sp.csr_matrix((vals[:nnz], (rows[:nnz], cols[:nnz])), shape=(N, N)), b

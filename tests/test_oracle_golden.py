@@ -366,3 +366,38 @@ def test_coupled_default_trap_matches_the_reference_classes(oracle, coupled_gold
             want = np.array(c["fields"][str(k)])
             assert np.linalg.norm(s.u - want) <= 1e-10 * np.linalg.norm(want), k
     assert s.u.max() > 1.0     # the colony did build up a signal
+
+
+def test_three_trap_forms_live_against_the_generated_wrappers(oracle):
+    """fenics/hsl.ufl, hslRobin.ufl and hslD.ufl (the north star names all three; fenicsInterface instantiates hslD)
+    assembled by the reference's own generated wrappers + kernels on the DOLFIN shim, with the constants the shipped
+    run leaves at zero switched ON (Robin external concentrations s, both rates different, a rough tensor):
+    the oracle's assembly equals hslD's to rounding (1e-15 of the largest entry), and hsl / hslRobin are hslD with
+    the identity tensor without / with the Robin terms -- so the one operator the GPU implements covers all three."""
+    if oracle.fenics_ref_lib() is None:
+        pytest.skip("oracle/_ref/libeq_fenics_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(2)
+    for (nW, nH, W, H, D, dt) in ((13, 9, 6.0, 4.0, 640.0, 0.05), (21, 9, 10.0, 4.0, 1200.0, 0.1), (8, 15, 7.0, 7.0, 35.0, 0.1)):
+        N = nW * nH
+        u0 = rng.uniform(0, 5, N)
+        rA, sA, rB, sB = 3.5, 0.3, 0.7, 0.1
+        p = oracle.Problem(nW=nW, nH=nH, h=W / (nW - 1), hy=H / (nH - 1), dt=dt, D=D, bc_type=(2, 2, 0, 0),
+                           bc_value=(rA, rB, 0, 0), robin_s=(sA, sB))
+        A, b = oracle.fenics_form_assemble("hslD", nW, nH, W, H, D, dt, rA=rA, sA=sA, rB=rB, sB=sB, u0=u0)
+        bands, bo = oracle.assemble(p, u0)
+        assert abs(A - oracle.bands_to_csr(p, bands)).max() <= 1e-15 * abs(A).max()
+        assert np.abs(b - bo).max() <= 1e-15 * np.abs(b).max()
+        A1, b1 = oracle.fenics_form_assemble("hslRobin", nW, nH, W, H, D, dt, rA=rA, sA=sA, rB=rB, sB=sB, u0=u0)
+        assert abs(A1 - A).max() <= 1e-15 * abs(A).max() and np.abs(b1 - b).max() <= 1e-15 * np.abs(b).max()
+        A0, b0 = oracle.fenics_form_assemble("hsl", nW, nH, W, H, D, dt, u0=u0)
+        A2, b2 = oracle.fenics_form_assemble("hslD", nW, nH, W, H, D, dt, u0=u0)
+        assert abs(A0 - A2).max() <= 1e-15 * abs(A2).max() and np.abs(b0 - b2).max() <= 1e-15 * np.abs(b2).max()
+        assert abs(A - A2).max() > 0         # the Robin terms are really there
+        # rough tensor: hslD against the oracle's tensor assembly
+        a = rng.uniform(0, np.pi, N)
+        t = (1.0 * np.cos(a) ** 2 + 0.2 * np.sin(a) ** 2, 1.0 * np.sin(a) ** 2 + 0.2 * np.cos(a) ** 2, 0.8 * np.sin(a) * np.cos(a))
+        p.d11, p.d22, p.d12 = t
+        At, bt = oracle.fenics_form_assemble("hslD", nW, nH, W, H, D, dt, rA=rA, sA=sA, rB=rB, sB=sB, tensor=t, u0=u0)
+        bands, bo = oracle.assemble(p, u0)
+        assert abs(At - oracle.bands_to_csr(p, bands)).max() <= 1e-14 * abs(At).max()
+        assert np.abs(bt - bo).max() <= 1e-15 * np.abs(bt).max()
