@@ -175,6 +175,12 @@ def main():
                 if K == 7 and k == steps - 1:
                     print(f"#   step {k}: cond of the scaled Gram matrix, first differences {np.linalg.cond(N_):.1e}, "
                           f"backward differences {np.linalg.cond(Nw):.1e}", flush=True)
+                # the fit as a CORRECTION to a known good guess (k_ls_gram's "form 1" for K = 3): x = g + W c with the
+                # normal equations fitted to the residual of g, so that no coefficient near 1 multiplies ||A h0|| ~ ||b||;
+                # g = previous solution (corr) or the fixed extrapolation of the same depth (corrX)
+                for tag, g0, ag0 in (("corr", hist[0], imgs[0]), ("corrX", Wm.sum(axis=1), AWm.sum(axis=1))):
+                    rg0 = b - ag0
+                    cands[f"{tag} {K}"] = g0 + Wm @ (np.linalg.solve(Nw + 1e-13 * np.eye(K), (AWm * sw).T @ rg0) * sw)
                 # ... plus one step of iterative refinement: the true residual of the fitted guess is fitted again
                 c1 = np.linalg.solve(Nw + 1e-13 * np.eye(K), (AWm * sw).T @ b) * sw
                 r1 = b - AWm @ c1
