@@ -30,7 +30,7 @@ from make_golden_cells import quiet  # noqa: E402
 W, H, NPM, DT, D, NCELLS, NSTEPS = 100, 20, 2.0, 0.1, 1200.0, 32, 20
 
 
-def main():
+def main(path=None):
     if O.cell_ref_lib() is None or O.fenics_ref_lib() is None:
         raise SystemExit("oracle/_ref libraries missing: run `make -C oracle ref` where /root/reference exists")
     rng = np.random.default_rng(20261017)
@@ -71,11 +71,11 @@ def main():
             out["fields"][str(k)] = u.tolist()
     F.close()
     abm.close()
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "coupled_ref.json")
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "coupled_ref.json")
     with open(path, "w") as f:
         json.dump(out, f)
     print(f"wrote {path}: {NSTEPS} steps, {n} cells, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

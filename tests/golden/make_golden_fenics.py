@@ -54,7 +54,7 @@ CASES = [
 GEOMETRIES = [(10, 4, 2.0, 0.1, 1200.0), (7, 3, 4.0, 0.05, 640.0), (6, 5, 1.0, 0.1, 35.0)]
 
 
-def main():
+def main(path=None):
     if O.fenics_ref_lib() is None:
         raise SystemExit("oracle/_ref/libeq_fenics_ref.so missing: run `make -C oracle ref` where /root/reference exists")
     rng = np.random.default_rng(20261017)
@@ -98,11 +98,11 @@ def main():
                 u = uf + rng.uniform(0, 5, F.N)
             F.close()
             out["cases"].append(case)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fenics_ref.json")
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "fenics_ref.json")
     with open(path, "w") as f:
         json.dump(out, f)
     print(f"wrote {path}: {len(out['cases'])} cases, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -401,3 +401,18 @@ def test_three_trap_forms_live_against_the_generated_wrappers(oracle):
         bands, bo = oracle.assemble(p, u0)
         assert abs(At - oracle.bands_to_csr(p, bands)).max() <= 1e-14 * abs(At).max()
         assert np.abs(bt - bo).max() <= 1e-15 * np.abs(bt).max()
+
+
+@pytest.mark.parametrize("script,name", [("make_golden_fenics.py", "fenics_ref.json"), ("make_golden_coupled.py", "coupled_ref.json")])
+def test_committed_golden_vectors_are_what_the_generators_produce(oracle, tmp_path, script, name):
+    """The committed fixtures are reproducible from the reference tree: re-running the committed generator against
+    oracle/_ref (the reference's classes compiled in place) gives the committed file, number for number."""
+    import subprocess
+    import sys
+    if oracle.fenics_ref_lib() is None or oracle.cell_ref_lib() is None or not os.path.isdir("/root/reference/src"):
+        pytest.skip("needs /root/reference and oracle/_ref")
+    out = tmp_path / name
+    subprocess.run([sys.executable, os.path.join(HERE, "golden", script), str(out)], check=True, capture_output=True,
+                   cwd=os.path.join(HERE, "golden"))
+    with open(out) as f, open(os.path.join(HERE, "golden", name)) as g:
+        assert json.load(f) == json.load(g)
