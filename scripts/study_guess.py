@@ -98,6 +98,7 @@ class MG:
         r = b - A @ x
         stop = rtol * np.linalg.norm(b)
         it = 0
+        self.last_r = r              # the RECURRENCE residual at exit (what the GPU has in HBM when the step ends)
         if np.linalg.norm(r) <= stop:
             return x, 0
         z = self.vcycle(0, r)

@@ -59,7 +59,9 @@ def main():
         best = min(cands, key=lambda name: np.linalg.norm(cands[name][1]))
         u, it = mg.pcg(b, cands[best][0] * free)
         its.append(it); picks.append(best)
-        hist.insert(0, u.copy()); imgs.insert(0, A @ u)
+        # image of the new solution: one more operator walk, or -- free -- b minus the residual vector the PCG recurrence
+        # left behind (STUDY_RECURRENCE=1): they differ by the recurrence drift
+        hist.insert(0, u.copy()); imgs.insert(0, (b - mg.last_r) * free if os.environ.get("STUDY_RECURRENCE") else A @ u)
         hist, imgs = hist[:8], imgs[:8]
     print(f"{n}x{n} {policy} {K if policy == 'corrX' else ''}: mean iterations over steps 10..109 = {np.mean(its[10:]):.2f} "
           f"(first 10: {its[:10]}, every 10th after: {its[10::10]}, picks at 10/30/60/109: "
