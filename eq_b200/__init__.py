@@ -35,7 +35,7 @@ API_SYMBOLS = [
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
     "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
     "eqgpu_last_guess", "eqgpu_cells_tensor", "eqgpu_get_tensor",
-    "eqgpu_ls_solve3",
+    "eqgpu_ls_solve3", "eqgpu_ring_solve",
 ]
 
 
@@ -131,6 +131,18 @@ def ls_solve3(G, f, bb):
     if rc != 0:
         raise EqGpuError("eqgpu_ls_solve3 failed")
     return c, pred.value
+
+
+def ring_solve(G, f):
+    """Host-only hook: the device's K x K normal-equation solve of warm-start mode 7.  G = full symmetric K x K Gram
+    matrix (packed here), f = right-hand side -> correction coefficients c[K]."""
+    G, f = np.asarray(G, dtype=np.float64), _f64(f)
+    K = f.size
+    packed = _f64(np.concatenate([G[i, i:] for i in range(K)]))
+    c = np.zeros(K)
+    if lib().eqgpu_ring_solve(C.c_int(K), _dp(packed), _dp(f), _dp(c)) != 0:
+        raise EqGpuError("eqgpu_ring_solve failed")
+    return c
 
 
 def default_params() -> Params:

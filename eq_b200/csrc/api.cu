@@ -79,7 +79,7 @@ int eqgpu_solver_path(eqgpu_solver *s)
 int eqgpu_set_warm_start(eqgpu_solver *s, int mode)
 {
     if (!s) return EQGPU_EINVAL;
-    if (mode < 0 || mode > 6) { s->set_error("warm-start mode must be 0..6"); return EQGPU_EINVAL; }
+    if (mode < 0 || mode > 7) { s->set_error("warm-start mode must be 0..7"); return EQGPU_EINVAL; }
     s->warm = mode;
     return 0;
 }
@@ -88,6 +88,13 @@ int eqgpu_ls_solve3(const double *G, const double *f, double bb, double *c, doub
 {
     if (!G || !f || !c || !pred) return EQGPU_EINVAL;
     solver_ls_solve3(G, f, bb, c, pred);
+    return 0;
+}
+
+int eqgpu_ring_solve(int K, const double *G, const double *f, double *c)
+{
+    if (!G || !f || !c || K < 1 || K > 7) return EQGPU_EINVAL;
+    solver_ring_solve(K, G, f, c);
     return 0;
 }
 

@@ -68,6 +68,10 @@ struct CGScalars {
     double rr_init;   // squared residual of the starting guess (measured in k_impose with ls, else the candidate's)
     double rrF, part_rrF;   // cubic extrapolation of the last four solutions (warm mode 5)
     double rrG;             // quartic extrapolation of the last five (warm mode 6)
+    // image ring (warm mode 7): weights of the backward differences nabla^j h0 in the guess (1 + least-squares
+    // correction), the squared residual the fit predicts, the ring depth used
+    double ringw[8], rrR;
+    int ring_k, pad3;
 };
 
 struct Level {
@@ -121,6 +125,13 @@ struct eqgpu_solver {
                                    // extrapolation of the last four, 6 = 5 + quartic of the last five
                                    // (solver_setup: 4 up to 512^2 nodes, 6 above)
     int last_guess = 0;
+    // warm mode 7 (opt-in; profiles/r01_guess_study.md): ring of the last RING_MAX solutions and of their images
+    // A_ff h (free rows), slot (ring_head + i) % RING_MAX = i-th newest; ring_b keeps this step's reduced right-hand
+    // side until the step ends, when the new image is b - r_final (no operator walk)
+    double *ring_h[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *ring_a[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *ring_b = nullptr, *ring_partials = nullptr;
+    int ring_n = 0, ring_head = 0;
     int ls_form = 1;               // least-squares guess: 1 = correction to h0 fitted to r1 on {A h0, d1, d1-d2}; 0 = first form
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration
@@ -184,6 +195,8 @@ int solver_rhs(eqgpu_solver *s, const double *du0, double *db);
 int solver_refresh_levels(eqgpu_solver *s);
 int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes);
 void solver_ls_solve3(const double G[6], const double f[3], double bb, double c[3], double *pred);
+// host-side entry for the CPU tests of the K x K ring fit (eqgpu_ring_solve); G packed upper triangle, row-major
+void solver_ring_solve(int K, const double *G, const double *f, double *c);
 // ---- slab.cu ----
 int slab_init_comm(eqgpu_solver *s, const void *unique_id);
 void slab_destroy_comm(eqgpu_solver *s);

@@ -664,6 +664,205 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warm mode 7 (opt-in, written after round 1's GPU budget was spent -- first run is round 2's): image ring.
+// The solver keeps the last K <= 7 solutions h_i AND their images a_i = A_ff h_i on the free rows (the newest image is
+// b~ - r_final of its own step: no operator walk).  In the backward-difference basis nabla^j h0 (the Newton form, in
+// which the fixed extrapolation through K solutions is the all-ones combination) the guess is
+//     u = sum_j (1 + c_j) nabla^j h0 ,      c = argmin || rho - sum_j c_j nabla^j a0 || ,  rho = b~ - sum_j nabla^j a0
+// i.e. a least-squares CORRECTION to the fixed extrapolation, fitted to its residual through the K x K normal equations.
+// CPU study (profiles/r01_guess_study.md, a model of this solver that reproduces mode 6's 2.66 iterations per step):
+// 1.5 iterations per step with K = 7, 1.96 with K = 5; the same fit of b~ itself, or in the first-difference basis, is
+// lost to the conditioning of the Gram matrix (1e16 against 1e12 here, and the right-hand side is 1e-10 ||b|| here).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RING_MAX = 7;
+struct RingPtrs { const double *p[RING_MAX]; };
+
+// out[j] = nabla^j v_0 = sum_i (-1)^i C(j,i) v_i, j < K (t is consumed)
+template <int K>
+__device__ __forceinline__ void backward_differences(double (&t)[K], double (&out)[K])
+{
+    out[0] = t[0];
+#pragma unroll
+    for (int j = 1; j < K; ++j) {
+#pragma unroll
+        for (int i = 0; i < K - j; ++i) t[i] = t[i] - t[i + 1];
+        out[j] = t[0];
+    }
+}
+
+// K x K normal equations G c = f, G packed upper triangle row-major (K(K+1)/2 entries).  Columns scaled to unit norm,
+// vanishing columns dropped, ridge 1e-13, Gaussian elimination with partial pivoting (ls_solve3's recipe for any K).
+__host__ __device__ __noinline__ void ring_solve(int K, const double *G, const double *f, double *c)
+{
+    double M[RING_MAX][RING_MAX + 1], d[RING_MAX], y[RING_MAX];
+    bool on[RING_MAX];
+    auto at = [&](int i, int j) { if (i > j) { const int t = i; i = j; j = t; } return G[i * K - i * (i - 1) / 2 + (j - i)]; };
+    double gmax = 0.0;
+    for (int i = 0; i < K; ++i) gmax = fmax(gmax, at(i, i));
+    for (int i = 0; i < K; ++i) {
+        const double g = at(i, i);
+        on[i] = g > 0.0 && g > 1e-30 * gmax;
+        d[i] = on[i] ? sqrt(g) : 1.0;
+    }
+    for (int i = 0; i < K; ++i) {
+        for (int j = 0; j < K; ++j) M[i][j] = (on[i] && on[j]) ? at(i, j) / (d[i] * d[j]) : 0.0;
+        M[i][i] = on[i] ? M[i][i] + 1e-13 : 1.0;
+        M[i][K] = on[i] ? f[i] / d[i] : 0.0;
+    }
+    bool ok = true;
+    for (int k = 0; k < K && ok; ++k) {
+        int piv = k;
+        for (int i = k + 1; i < K; ++i) if (fabs(M[i][k]) > fabs(M[piv][k])) piv = i;
+        if (!(fabs(M[piv][k]) > 1e-300)) { ok = false; break; }
+        if (piv != k) for (int j = 0; j <= K; ++j) { const double t = M[k][j]; M[k][j] = M[piv][j]; M[piv][j] = t; }
+        for (int i = k + 1; i < K; ++i) {
+            const double m = M[i][k] / M[k][k];
+            for (int j = k; j <= K; ++j) M[i][j] -= m * M[k][j];
+        }
+    }
+    for (int i = 0; i < K; ++i) y[i] = 0.0;
+    if (ok)
+        for (int i = K - 1; i >= 0; --i) {
+            double t = M[i][K];
+            for (int j = i + 1; j < K; ++j) t -= M[i][j] * y[j];
+            y[i] = t / M[i][i];
+        }
+    bool finite = ok;
+    for (int i = 0; i < K; ++i) { c[i] = (ok && on[i]) ? y[i] / d[i] : 0.0; finite = finite && isfinite(c[i]); }
+    if (!finite) for (int i = 0; i < K; ++i) c[i] = 0.0;   // no correction: the fixed extrapolation stands
+}
+
+void solver_ring_solve(int K, const double *G, const double *f, double *c)
+{
+    if (K >= 1 && K <= RING_MAX) ring_solve(K, G, f, c);
+}
+
+// Pass 1: one flat pass over b~ and the K images.  Sums the Gram matrix of nabla^j a0, its products with rho and
+// ||rho||^2; the last block solves for the correction and leaves the weights 1 + c_j and the predicted squared
+// residual in sc.  Dirichlet rows hold zeros in b~ and in every image, so they drop out of the sums.
+template <int K>
+__global__ void __launch_bounds__(256)
+k_ring_gram(size_t n, const double *__restrict__ rB, RingPtrs a, double *partials, unsigned *counter, CGScalars *sc)
+{
+    constexpr int NG = K * (K + 1) / 2, NS = NG + K + 1;
+    double v[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) v[q] = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        double t[K], da[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) t[i] = __ldg(a.p[i] + g);
+        backward_differences<K>(t, da);
+        double rho = __ldg(rB + g);
+#pragma unroll
+        for (int j = 0; j < K; ++j) rho -= da[j];
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int j = i; j < K; ++j) v[q++] += da[i] * da[j];
+#pragma unroll
+        for (int i = 0; i < K; ++i) v[NG + i] += da[i] * rho;
+        v[NG + K] += rho * rho;
+    }
+    double tot[NS];
+    if (grid_reduce<NS>(v, partials, counter, tot)) {
+        double c[RING_MAX];
+        ring_solve(K, tot, tot + NG, c);
+        // predicted squared residual of the corrected guess; rounding noise below ~1e-16 of the sums, so the true one is
+        // summed again by k_ring_impose.  A coefficient multiplies the rounding error of its difference (2^j ulp of
+        // |A h0|) into the gap between the residual vector formed and the true residual: refuse wild fits.
+        double q = tot[NG + K], amp = 0.0;
+        for (int i = 0; i < K; ++i) {
+            q -= 2.0 * c[i] * tot[NG + i];
+            amp += fabs(c[i]) * (double)(1 << i);
+            for (int j = 0; j < K; ++j) {
+                const int lo = i < j ? i : j, hi = i < j ? j : i;
+                q += c[i] * tot[lo * K - lo * (lo - 1) / 2 + (hi - lo)] * c[j];
+            }
+        }
+        if (!(amp <= 1.0e4) || !isfinite(q)) { for (int i = 0; i < K; ++i) c[i] = 0.0; q = tot[NG + K]; }
+        for (int i = 0; i < RING_MAX + 1; ++i) sc->ringw[i] = i < K ? 1.0 + c[i] : 0.0;
+        sc->rrR = fmax(q, 0.0);
+        sc->ring_k = K;
+    }
+}
+
+// Pass 2: pick between the field as given (0), zero (1) and the ring guess (8) by squared residual, form u and r,
+// impose u_d = g_d, sum the TRUE squared residual of what was formed and set up the PCG scalars (k_impose's job).
+// On entry r = b~ - A u0 (k_init_tile without history) and rB = b~.
+template <int K>
+__global__ void __launch_bounds__(BX *BY)
+k_ring_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r, const double *__restrict__ rB,
+              RingPtrs h, RingPtrs a, CGScalars *sc, double rtol, int max_iters, double *partials, unsigned *counter)
+{
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    int pick = 0;
+    double best = sc->rr0;
+    if (sc->bnorm2 < best) { best = sc->bnorm2; pick = 1; }
+    if (sc->rrR <= best) { best = sc->rrR; pick = 8; }
+    double v[1] = {0.0};
+    if (i >= L.own0 && i < L.own1 && j < L.nx) {
+        const size_t g = (size_t)i * L.nx + j;
+        const bool dir = is_dirichlet(L, i, j);
+        if (dir) u[g] = dir_value(L, dd, i, j);
+        else if (pick == 1) { u[g] = 0.0; r[g] = rB[g]; }
+        else if (pick == 8) {
+            double t[K], dv[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) t[k] = __ldg(h.p[k] + g);
+            backward_differences<K>(t, dv);
+            double un = 0.0;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) un += sc->ringw[k] * dv[k];      // smallest terms first
+#pragma unroll
+            for (int k = 0; k < K; ++k) t[k] = __ldg(a.p[k] + g);
+            backward_differences<K>(t, dv);
+            double corr = 0.0;
+#pragma unroll
+            for (int k = K - 1; k >= 0; --k) corr += sc->ringw[k] * dv[k];
+            u[g] = un;
+            r[g] = rB[g] - corr;
+        }
+        if (!dir) v[0] = r[g] * r[g];
+    }
+    double tot[1];
+    if (grid_reduce<1>(v, partials, counter, tot)) {
+        const double stop2 = rtol * rtol * sc->bnorm2;
+        sc->rr = tot[0];
+        sc->rr_init = tot[0];
+        sc->stop2 = stop2;
+        sc->iters = 0;
+        sc->max_iters = max_iters;
+        sc->done = (tot[0] <= stop2) ? 1 : 0;
+        sc->rz_old = 1.0;
+        sc->rz_new = 0.0;
+        sc->x_stamp = 0;
+        sc->x_applied = 0;
+        sc->guess = pick;
+    }
+}
+
+// End of a converged step: the image of the solution just found, a = A_ff u_f = b~ - r_final (free rows; both vectors
+// are zero on Dirichlet rows).
+__global__ void __launch_bounds__(256)
+k_ring_image(size_t n, const double *__restrict__ rB, const double *__restrict__ r, double *__restrict__ a)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) a[g] = __ldg(rB + g) - __ldg(r + g);
+}
+
+template <int K>
+static void launch_ring(eqgpu_solver *s, const LevelDev &L, const DirData &dd, const RingPtrs &h, const RingPtrs &a, int nb1,
+                        dim3 g0, dim3 blk, double rtol, int max_iters)
+{
+    k_ring_gram<K><<<nb1, 256, 0, s->stream>>>(s->N, s->z, a, s->ring_partials, s->counters + 6, s->sc);
+    k_ring_impose<K><<<g0, blk, 0, s->stream>>>(L, dd, s->u, s->r, s->z, h, a, s->sc, rtol, max_iters, s->partials,
+                                                 s->counters + 7);
+}
+
 // rz_new = r . z
 __global__ void __launch_bounds__(256)
 k_dot(size_t n, const double *__restrict__ a, const double *__restrict__ b, CGScalars *sc,
@@ -1272,7 +1471,7 @@ int solver_setup(eqgpu_solver *s)
         // start: on by default up to 512^2 nodes
         // ... and the cubic extrapolation of the last four solutions above
         s->warm = (size_t)p.nW * p.nH <= (size_t)512 * 512 ? 4 : 6;
-        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 6));
+        if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 7));
         if (const char *e = getenv("EQGPU_LS_FORM")) s->ls_form = atoi(e) != 0 ? 1 : 0;   // tuning knob
         if ((s->defer_x || s->slab) && s->init_tile && s->warm > 0) {
             for (int k = 0; k < 5; ++k) {
@@ -1320,6 +1519,10 @@ void solver_teardown(eqgpu_solver *s)
     if (s->graph_exec2) { cudaGraphExecDestroy(s->graph_exec2); s->graph_exec2 = nullptr; }
     for (int k = 0; k < 5; ++k) { cudaFree(s->uh[k]); s->uh[k] = nullptr; }
     for (int k = 0; k < 2; ++k) { cudaFree(s->dk[k]); s->dk[k] = nullptr; }
+    for (int k = 0; k < 7; ++k) { cudaFree(s->ring_h[k]); s->ring_h[k] = nullptr; cudaFree(s->ring_a[k]); s->ring_a[k] = nullptr; }
+    cudaFree(s->ring_b); s->ring_b = nullptr;
+    cudaFree(s->ring_partials); s->ring_partials = nullptr;
+    s->ring_n = 0;
     s->hist = 0;
     if (s->ev_fork) { cudaEventDestroy(s->ev_fork); s->ev_fork = nullptr; }
     if (s->ev_join) { cudaEventDestroy(s->ev_join); s->ev_join = nullptr; }
@@ -1829,7 +2032,20 @@ static int pcg(eqgpu_solver *s)
     // (single GPU: the deferred-x step tail stores the history; slabs: a device copy + halo exchange)
     // (variable tensor, one GPU: k_init_hist evaluates the candidates per node, a device copy stores the history)
     const bool hist_tensor = T && !sl && s->warm > 0 && s->uh[0] != nullptr && getenv("EQGPU_TENSOR_COLD") == nullptr;
-    const bool keep_hist = hist_tensor || (!T && s->init_tile && s->fused && (sl || s->defer_x) && s->warm > 0 && s->uh[0]);
+    // warm mode 7: image ring (single GPU, isotropic fused path with the deferred-x step tail); it replaces the
+    // uh[]/dk[] history below.  Elsewhere mode 7 behaves as mode 3.
+    const bool ring = !T && !sl && s->warm == 7 && s->init_tile && fused && s->defer_x;
+    if (ring && !s->ring_b) {
+        for (int k = 0; k < RING_MAX; ++k) {
+            EQ_CUDA(cudaMalloc(&s->ring_h[k], sizeof(double) * s->N));
+            EQ_CUDA(cudaMalloc(&s->ring_a[k], sizeof(double) * s->N));
+        }
+        EQ_CUDA(cudaMalloc(&s->ring_b, sizeof(double) * s->N));
+        EQ_CUDA(cudaMalloc(&s->ring_partials, sizeof(double) * 40 * s->max_blocks));
+        s->ring_n = 0;
+        s->ring_head = 0;
+    }
+    const bool keep_hist = !ring && (hist_tensor || (!T && s->init_tile && s->fused && (sl || s->defer_x) && s->warm > 0 && s->uh[0]));
     // history depth: modes 1-3 use that many solutions, 4 three (+ least squares), 5 four (+ cubic; one GPU,
     // isotropic path)
     const int nh_max = (s->warm >= 5 && !sl && !T) ? (s->warm >= 6 ? 5 : 4) : std::min(s->warm, 3);
@@ -1867,9 +2083,30 @@ static int pcg(eqgpu_solver *s)
                                        s->counters + 4, sc);
         s->launches++;
     }
-    k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->pv2, s->uh[0], s->uh[1], s->uh[2], nh, s->sc,
-                                 rtol, max_iters, ls ? 1 + s->ls_form : 0, s->partials, s->counters + 5, s->uh[3], l0.t,
-                                 s->uh[4], d4ok ? s->dk[s->dk_cur] : nullptr);
+    const int ring_k = ring ? std::min(s->ring_n, RING_MAX) : 0;
+    if (ring) {
+        // this step's reduced right-hand side, kept for the image of its solution (z is the V-cycle's vector later)
+        EQ_CUDA(cudaMemcpyAsync(s->ring_b, s->z, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
+    }
+    if (ring_k >= 2) {
+        RingPtrs rh, ra;
+        for (int k = 0; k < RING_MAX; ++k) {
+            rh.p[k] = s->ring_h[(s->ring_head + k) % RING_MAX];
+            ra.p[k] = s->ring_a[(s->ring_head + k) % RING_MAX];
+        }
+        switch (ring_k) {
+        case 2: launch_ring<2>(s, L, dd, rh, ra, nb1, g0, blk, rtol, max_iters); break;
+        case 3: launch_ring<3>(s, L, dd, rh, ra, nb1, g0, blk, rtol, max_iters); break;
+        case 4: launch_ring<4>(s, L, dd, rh, ra, nb1, g0, blk, rtol, max_iters); break;
+        case 5: launch_ring<5>(s, L, dd, rh, ra, nb1, g0, blk, rtol, max_iters); break;
+        case 6: launch_ring<6>(s, L, dd, rh, ra, nb1, g0, blk, rtol, max_iters); break;
+        default: launch_ring<7>(s, L, dd, rh, ra, nb1, g0, blk, rtol, max_iters); break;
+        }
+        s->launches++;
+    } else
+        k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->pv2, s->uh[0], s->uh[1], s->uh[2], nh, s->sc,
+                                     rtol, max_iters, ls ? 1 + s->ls_form : 0, s->partials, s->counters + 5, s->uh[3], l0.t,
+                                     s->uh[4], d4ok ? s->dk[s->dk_cur] : nullptr);
     s->launches += 2;
 
     int issued = 0;
@@ -1929,7 +2166,9 @@ static int pcg(eqgpu_solver *s)
         const bool spec = fused && s->defer_x && !s->p.channels;
         if (fused && s->defer_x) {
             // ... and, for the next step's warm start, leave a copy of the solution in the older history slot
-            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[4] : nullptr);
+            // (ring mode: into the ring's oldest slot, which becomes the newest once the step has converged)
+            double *const ring_slot = ring ? s->ring_h[(s->ring_head + RING_MAX - 1) % RING_MAX] : nullptr;
+            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[4] : ring_slot);
             k_mark_x<<<1, 1, 0, st>>>(sc);
             s->launches += 2;
         }
@@ -1953,6 +2192,13 @@ static int pcg(eqgpu_solver *s)
                 sqrt(fabs(h.rrD) / b2),
                 sqrt(fabs(h.rrE) / b2), sqrt(fabs(h.rrF) / b2), sqrt(fabs(h.rrL) / b2), h.guess,
                 sqrt(fabs(h.rr_init) / b2), h.lsc[0], h.lsc[1], h.lsc[2], h.iters, sqrt(h.rr / b2));
+    }
+    if (ring && s->sc_host->rr <= s->sc_host->stop2) {   // solution copied by k_finish_x; its image is b~ - r_final
+        const int slot = (s->ring_head + RING_MAX - 1) % RING_MAX;
+        k_ring_image<<<nb1, 256, 0, st>>>(s->N, s->ring_b, s->r, s->ring_a[slot]);
+        s->launches++;
+        s->ring_head = slot;
+        s->ring_n = std::min(s->ring_n + 1, RING_MAX);
     }
     if (keep_hist && s->sc_host->rr <= s->sc_host->stop2) {   // the copy just written is now the newest solution
         if (sl) {   // slabs: copy now (owned rows are final), then bring the halo rows of the copy up to date

@@ -212,6 +212,9 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
  * residual-minimising combination of the last three solutions (a 3x3 least-squares problem solved on the
  * device; its span contains the previous solution and both extrapolations).  5: mode 3 plus the cubic
  * extrapolation of the last four solutions; 6: mode 5 plus the quartic extrapolation of the last five.
+ * 7 (opt-in, NOT yet run on a GPU: written after round 1's GPU budget was spent): image ring -- the last seven
+ * solutions and their images, guess = fixed extrapolation plus a least-squares correction in the
+ * backward-difference basis (profiles/r01_guess_study.md).
  * Default: 4 for meshes up to 512^2 nodes, 6 above (measured: the
  * least-squares combination saves up to four iterations per step on small or quasi-steady problems and costs
  * half an iteration at 2048^2).  The stopping test is relative to the right-hand side in every mode, so
@@ -220,12 +223,18 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
  * mode 0 is what runs). */
 EQGPU_API int eqgpu_set_warm_start(eqgpu_solver *s, int mode);
 /* Which guess the last step started from: 0 field as given, 1 zero, 2 previous solution, 3 linear,
- * 4 quadratic extrapolation, 5 least-squares combination, 6 cubic, 7 quartic extrapolation. */
+ * 4 quadratic extrapolation, 5 least-squares combination, 6 cubic, 7 quartic extrapolation, 8 image-ring guess
+ * (mode 7). */
 EQGPU_API int eqgpu_last_guess(eqgpu_solver *s);
 /* Host-only (no device): the 3x3 least-squares solve warm-start mode 4 runs on the device, for the CPU tests.
  * G = {a0.a0, a0.a1, a0.a2, a1.a1, a1.a2, a2.a2}, f = {a0.b, a1.b, a2.b}, bb = b.b; c minimises
  * ||b - c0 a0 - c1 a1 - c2 a2||, *pred is the predicted squared residual (1e300 if the solve failed). */
 EQGPU_API int eqgpu_ls_solve3(const double *G, const double *f, double bb, double *c, double *pred);
+/* Host-only (no device): the K x K (K <= 7) normal-equation solve of warm-start mode 7 (image ring: least-squares
+ * correction to the fixed extrapolation in the backward-difference basis; opt-in).
+ * G = packed upper triangle of the Gram matrix, row-major (K(K+1)/2 entries), f = its right-hand side; c = the
+ * correction coefficients (all zero if the solve failed: the fixed extrapolation stands). */
+EQGPU_API int eqgpu_ring_solve(int K, const double *G, const double *f, double *c);
 /* Times `reps` back-to-back launches of one named kernel on the solver's
  * stream with CUDA events (for bench.py's roofline line).  Returns the average
  * milliseconds per launch and the algorithmic bytes one launch must move
