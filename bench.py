@@ -503,7 +503,10 @@ def main():
                        "relres": relres, "rtol": 1e-12, "mg_levels": int(g.stats().levels),
                        "parallelism": f"layer-per-gpu x{world}",
                        "l2": "working set (6 fine fp64 vectors = 201 MB + MG hierarchy) exceeds the 126 MB L2; no explicit flush",
-                       "initial_guess": "best of {zero, previous solution, linear / quadratic / cubic / quartic extrapolation "
+                       "initial_guess": ("image ring (warm mode 7, opt-in): fixed extrapolation through the last <= 7 solutions plus a "
+                                         "least-squares correction in the backward-difference basis; stop test relative to the "
+                                         "right-hand side (rtol 1e-12) whatever the guess") if os.environ.get("EQGPU_WARM") == "7" else
+                                        "best of {zero, previous solution, linear / quadratic / cubic / quartic extrapolation "
                                         "of the previous solutions} (warm mode 6; mode 4, the default up to 512^2 nodes, has "
                                         "the least-squares combination of the last three instead of cubic and quartic), "
                                         "picked on the device by residual norm; stop test relative to the right-hand side "

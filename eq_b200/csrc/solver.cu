@@ -2199,6 +2199,11 @@ static int pcg(eqgpu_solver *s)
         s->launches++;
         s->ring_head = slot;
         s->ring_n = std::min(s->ring_n + 1, RING_MAX);
+    } else if (ring) {
+        // not converged: the step tail has overwritten the oldest solution slot with this iterate while its image
+        // slot still belongs to the old one -- a pair that no longer matches would make the next guess's residual
+        // vector wrong, so the ring starts over
+        s->ring_n = 0;
     }
     if (keep_hist && s->sc_host->rr <= s->sc_host->stop2) {   // the copy just written is now the newest solution
         if (sl) {   // slabs: copy now (owned rows are final), then bring the halo rows of the copy up to date
