@@ -535,10 +535,13 @@ def main():
                          # level 0 (presmooth 18, postsmooth 26, apply_p 32, update_r 24, update_x 24) + 44/3 on the
                          # coarser levels; per step 224 B/DOF for the warm start (k_init_tile 96, k_impose 96,
                          # k_finish_x 32; isotropic one-GPU path with the five-solution history)
-                         "step_algorithmic": (lambda bts: {"bytes": bts, "gbs": bts / (ms_step * 1e-3) / 1e9,
-                                                           "frac": bts / (ms_step * 1e-3) / 1e9 / peak,
-                                                           "formula": "N*(224 + (124 + 44/3)*mean_iterations)"})(
-                             N * (224.0 + (124.0 + 44.0 / 3.0) * iters_mean))},
+                         # (warm mode 7, image ring at depth 7: k_init_tile without history 24, copy of the right-hand
+                         # side 16, k_ring_gram 64, k_ring_impose 136, k_finish_x 32, k_ring_image 24 = 296)
+                         "step_algorithmic": (lambda fixed: (lambda bts: {
+                             "bytes": bts, "gbs": bts / (ms_step * 1e-3) / 1e9, "frac": bts / (ms_step * 1e-3) / 1e9 / peak,
+                             "formula": f"N*({fixed:.0f} + (124 + 44/3)*mean_iterations)"})(
+                             N * (fixed + (124.0 + 44.0 / 3.0) * iters_mean)))(
+                             296.0 if os.environ.get("EQGPU_WARM") == "7" else 224.0)},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_fd() if args.config == 6 else cpu_baseline()
