@@ -34,7 +34,7 @@ def main():
     n, policy = int(sys.argv[1]), sys.argv[2]
     K = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     p = O.Problem(nW=n, nH=n)
-    mg = S.MG(p)
+    mg = S.MG(p, nu=int(os.environ.get("STUDY_NU", "3")))   # sweeps per smoothing pass on every level (GPU: 3 on level 0, 4 below)
     A, free = mg.levels[0]["A"], mg.levels[0]["free"]
     cells = O.synthetic_colony(int(20000 * (n / 2048.0) ** 2), p.W, p.H)
     u = np.zeros(p.N)
@@ -63,7 +63,7 @@ def main():
         # left behind (STUDY_RECURRENCE=1): they differ by the recurrence drift
         hist.insert(0, u.copy()); imgs.insert(0, (b - mg.last_r) * free if os.environ.get("STUDY_RECURRENCE") else A @ u)
         hist, imgs = hist[:8], imgs[:8]
-    print(f"{n}x{n} {policy} {K if policy == 'corrX' else ''}: mean iterations over steps 10..109 = {np.mean(its[10:]):.2f} "
+    print(f"{n}x{n} nu={os.environ.get('STUDY_NU', '3')} {policy} {K if policy == 'corrX' else ''}: mean iterations over steps 10..109 = {np.mean(its[10:]):.2f} "
           f"(first 10: {its[:10]}, every 10th after: {its[10::10]}, picks at 10/30/60/109: "
           f"{picks[10]}, {picks[30]}, {picks[60]}, {picks[109]}; {time.time() - t0:.0f} s)", flush=True)
 
