@@ -326,13 +326,14 @@ class GpuHSL:
         """Starting guess of the PCG solve: 0 = field as given or zero, 1 = also the previous solution,
         2 = also the linear, 3 = also the quadratic extrapolation of the previous solutions, 4 = also the residual-minimising
         (least-squares) combination of the last three solutions, 5 = mode 3 plus the cubic extrapolation of the
-        last four, 6 = mode 5 plus the quartic extrapolation of the last five.  Default: 4 up to 512^2 nodes,
-        6 above."""
+        last four, 6 = mode 5 plus the quartic extrapolation of the last five, 7 = image ring (opt-in: the last seven
+        solutions and their images, fixed extrapolation plus a least-squares correction in the backward-difference
+        basis).  Default: 4 up to 512^2 nodes, 6 above."""
         self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
 
     def last_guess(self) -> int:
         """0 field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic extrapolation, 5 least-squares
-        combination, 6 cubic, 7 quartic extrapolation (last step's start)."""
+        combination, 6 cubic, 7 quartic extrapolation, 8 image-ring guess (last step's start)."""
         return int(lib().eqgpu_last_guess(self._h))
 
     def set_scatter_mode(self, mode: int):
