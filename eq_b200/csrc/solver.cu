@@ -2083,7 +2083,9 @@ static int pcg(eqgpu_solver *s)
                                        s->counters + 4, sc);
         s->launches++;
     }
-    const int ring_k = ring ? std::min(s->ring_n, RING_MAX) : 0;
+    int ring_depth = RING_MAX;
+    if (const char *e = getenv("EQGPU_RING_DEPTH")) ring_depth = std::max(2, std::min(atoi(e), RING_MAX));   // tuning knob
+    const int ring_k = ring ? std::min(s->ring_n, ring_depth) : 0;
     if (ring) {
         // this step's reduced right-hand side, kept for the image of its solution (z is the V-cycle's vector later)
         EQ_CUDA(cudaMemcpyAsync(s->ring_b, s->z, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, st));
