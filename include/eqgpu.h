@@ -212,7 +212,8 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
  * residual-minimising combination of the last three solutions (a 3x3 least-squares problem solved on the
  * device; its span contains the previous solution and both extrapolations).  5: mode 3 plus the cubic
  * extrapolation of the last four solutions; 6: mode 5 plus the quartic extrapolation of the last five.
- * 7 (opt-in, NOT yet run on a GPU: written after round 1's GPU budget was spent): image ring -- the last seven
+ * 7 (opt-in; first run on a B200 in the last seconds of round 1, profiles/r01_ring_first_run.json: 1.46 iterations
+ * per step against mode 6's 2.66 on the 2048^2 bench, same field): image ring -- the last seven
  * solutions and their images, guess = fixed extrapolation plus a least-squares correction in the
  * backward-difference basis (profiles/r01_guess_study.md).
  * Default: 4 for meshes up to 512^2 nodes, 6 above (measured: the
