@@ -131,7 +131,7 @@ struct eqgpu_solver {
     double *ring_h[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *ring_a[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *ring_b = nullptr, *ring_partials = nullptr;
-    int ring_n = 0, ring_head = 0;
+    int ring_n = 0, ring_head = 0, ring_prev_iters = 0;
     int ls_form = 1;               // least-squares guess: 1 = correction to h0 fitted to r1 on {A h0, d1, d1-d2}; 0 = first form
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration

@@ -2114,6 +2114,10 @@ static int pcg(eqgpu_solver *s)
 
     int issued = 0;
     int chunk = s->st.iterations > 0 ? std::max(1, s->st.iterations) : 4;
+    // ring mode: the count flips between 1 and 2 (or reaches 0) late in a run; an iteration issued in vain costs a dozen
+    // early-exit launches, one issued too late a host round trip and a second step tail, so predict the larger of the
+    // last two counts
+    if (ring && s->st.steps > 0) chunk = std::max(1, std::max(s->st.iterations, s->ring_prev_iters));
     s->graph_phase = 0;   // odd iterations leave their search direction in pv2, even ones in pv (k_update_x flush)
     double *const p_odd = s->pv2, *const p_even = s->pv;
     if (fused && !s->slab && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
@@ -2184,6 +2188,7 @@ static int pcg(eqgpu_solver *s)
         if (s->sc_host->done || issued >= max_iters) break;
         chunk = 1;
     }
+    s->ring_prev_iters = s->st.iterations;
     s->st.iterations = s->sc_host->iters;
     s->last_guess = s->sc_host->guess;
     if (getenv("EQGPU_LS_DEBUG")) {   // debugging aid: the candidates' residuals relative to the zero guess's
