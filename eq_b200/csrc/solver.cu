@@ -2035,14 +2035,25 @@ static int pcg(eqgpu_solver *s)
     const bool hist_tensor = T && !sl && s->warm > 0 && s->uh[0] != nullptr && getenv("EQGPU_TENSOR_COLD") == nullptr;
     // warm mode 7: image ring (single GPU, isotropic fused path with the deferred-x step tail); it replaces the
     // uh[]/dk[] history below.  Elsewhere mode 7 behaves as mode 3.
-    const bool ring = !T && !sl && s->warm == 7 && s->init_tile && fused && s->defer_x;
-    if (ring && !s->ring_b) {
-        for (int k = 0; k < RING_MAX; ++k) {
-            EQ_CUDA(cudaMalloc(&s->ring_h[k], sizeof(double) * s->N));
-            EQ_CUDA(cudaMalloc(&s->ring_a[k], sizeof(double) * s->N));
+    bool ring = !T && !sl && s->warm == 7 && s->init_tile && fused && s->defer_x;
+    if (ring && !s->ring_b) {   // 15 more fine-level vectors: if they do not fit, mode 6 is what runs
+        bool ok = true;
+        for (int k = 0; k < RING_MAX && ok; ++k)
+            ok = cudaMalloc(&s->ring_h[k], sizeof(double) * s->N) == cudaSuccess &&
+                 cudaMalloc(&s->ring_a[k], sizeof(double) * s->N) == cudaSuccess;
+        ok = ok && cudaMalloc(&s->ring_partials, sizeof(double) * 40 * s->max_blocks) == cudaSuccess;
+        ok = ok && cudaMalloc(&s->ring_b, sizeof(double) * s->N) == cudaSuccess;
+        if (!ok) {
+            (void)cudaGetLastError();
+            for (int k = 0; k < RING_MAX; ++k) {
+                cudaFree(s->ring_h[k]); s->ring_h[k] = nullptr;
+                cudaFree(s->ring_a[k]); s->ring_a[k] = nullptr;
+            }
+            cudaFree(s->ring_partials); s->ring_partials = nullptr;
+            cudaFree(s->ring_b); s->ring_b = nullptr;
+            s->warm = 6;
+            ring = false;
         }
-        EQ_CUDA(cudaMalloc(&s->ring_b, sizeof(double) * s->N));
-        EQ_CUDA(cudaMalloc(&s->ring_partials, sizeof(double) * 40 * s->max_blocks));
         s->ring_n = 0;
         s->ring_head = 0;
     }
