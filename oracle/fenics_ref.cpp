@@ -37,9 +37,9 @@ REF_API const char *ref_fenics_last_error() { return g_err.c_str(); }
 REF_API void *ref_fenics_create(const char *params_json, double dt, double D, double widthMicrons, double heightMicrons,
                                 double npm, double channelVelocity)
 {
+    std::streambuf *keep = std::cout.rdbuf();
+    std::ostringstream sink;
     try {
-        std::streambuf *keep = std::cout.rdbuf();
-        std::ostringstream sink;
         std::cout.rdbuf(sink.rdbuf());          // the reference narrates its set-up on stdout
         auto j = eQ::data::parametersType::parse(params_json);
         eQ::data::parameters = j;
@@ -56,6 +56,7 @@ REF_API void *ref_fenics_create(const char *params_json, double dt, double D, do
         std::cout.rdbuf(keep);
         return r;
     } catch (const std::exception &e) {
+        std::cout.rdbuf(keep);
         g_err = e.what();
         return nullptr;
     }

@@ -564,7 +564,12 @@ class DirichletBC
 {
 public:
   DirichletBC(std::shared_ptr<const FunctionSpace> V, std::shared_ptr<const GenericFunction> g, std::shared_ptr<const SubDomain> sub)
-    : _V(V), _g(g), _sub(sub) {}
+    : _V(V), _g(g), _sub(sub)
+  {
+    // the reference reaches this with a null sub-domain for DIRICHLET_0 + a trap type its four `if`s do not name
+    // (src/fHSL.cpp:559-566, e.g. H_TRAP): undefined behaviour upstream, a clean error here
+    if (!sub) dolfin_error("DirichletBC", "create boundary condition", "null sub-domain");
+  }
   // "topological" search: dofs of the boundary facets that lie inside the sub-domain, values g(x_dof)
   void get_boundary_values(std::map<std::size_t, double>& bv) const
   {

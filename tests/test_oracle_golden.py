@@ -416,3 +416,73 @@ def test_committed_golden_vectors_are_what_the_generators_produce(oracle, tmp_pa
                    cwd=os.path.join(HERE, "golden"))
     with open(out) as f, open(os.path.join(HERE, "golden", name)) as g:
         assert json.load(f) == json.load(g)
+
+
+def test_fenics_fuzz_live_against_the_compiled_reference_class(oracle):
+    """60 random configurations through the reference's own fenicsInterface and through the oracle: random integer trap
+    sizes, 1 / 2 / 4 nodes per micron, dt, D, flow rate (both branches of the Robin-rate formula), channel lengths,
+    sub-step counts, every boundary type with random wall kinds and values, a random tensor on a third of them,
+    two steps each.  Needs oracle/_ref (build container)."""
+    if oracle.fenics_ref_lib() is None:
+        pytest.skip("oracle/_ref/libeq_fenics_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(20261018)
+    kinds = [("Dirichlet", None), ("Neumann", None), ("Robin", None)]
+    seen = set()
+    for trial in range(60):
+        W, H = int(rng.integers(3, 12)), int(rng.integers(2, 8))
+        npm = float(rng.choice([1.0, 2.0, 4.0]))
+        dt, D = float(rng.choice([0.02, 0.1, 0.5])), float(rng.choice([35.0, 640.0, 1200.0, 3.0e4]))
+        btype = str(rng.choice(["DIRICHLET_0", "DIRICHLET_UPDATE", "MICROFLUIDIC_TRAP", "NEUMANN_3WALLED_TEST", "OTHER"]))
+        ttype = str(rng.choice(["NOWALLED", "THREEWALLED", "TWOWALLED", "ONEWALLED", "H_TRAP"]))
+        over = dict(boundaryType=btype, trapType=ttype, simulationFlowRate=float(rng.choice([0.0, 12.0, 120.0])),
+                    simulationChannelLengthLeft=float(rng.uniform(5, 200)), simulationChannelLengthRight=float(rng.uniform(5, 200)),
+                    channelSolverNumberIterations=int(rng.integers(1, 7)), lengthScaling=float(rng.choice([1.0, 5.0])))
+        if btype == "MICROFLUIDIC_TRAP":
+            walls = {}
+            for name in ("left", "right", "top", "bottom"):
+                k = kinds[int(rng.integers(0, 3))][0]
+                v = float(rng.uniform(0, 3)) if k == "Dirichlet" else 0.0
+                if k == "Dirichlet" and name in ("top", "bottom") and rng.uniform() < 0.4:
+                    v = -1.0                                           # "the channel Function"
+                walls[name] = oracle.bc_entry(k, v)
+            over["boundaries"] = walls
+        P = oracle.default_parameters(W, H, npm, **over)
+        if btype == "DIRICHLET_0" and ttype == "H_TRAP":
+            # a combination the reference does not define: its four `if`s leave the sub-domain null and DirichletBC is
+            # built on it (src/fHSL.cpp:559-568) -- the shim reports it, DOLFIN would dereference it
+            with pytest.raises(RuntimeError, match="null sub-domain"):
+                oracle.FenicsReference(P, dt, D, float(W), float(H), npm)
+            continue
+        F = oracle.FenicsReference(P, dt, D, float(W), float(H), npm)
+        p = oracle.problem_from_parameters(P, dt, D, float(W), float(H), npm)
+        assert (p.nW, p.nH) == (F.nW, F.nH)
+        if trial % 3 == 0:
+            a = rng.uniform(0, np.pi, p.N)
+            p.d11, p.d22, p.d12 = 1.3 * np.cos(a) ** 2 + 0.4 * np.sin(a) ** 2, 1.3 * np.sin(a) ** 2 + 0.4 * np.cos(a) ** 2, 0.9 * np.sin(a) * np.cos(a)
+            F.set_tensor(p.d11, p.d22, p.d12)
+        s = oracle.new_state(p)
+        u = rng.uniform(0, 50, p.N)
+        for step in range(2):
+            if btype == "DIRICHLET_UPDATE":
+                v = float(rng.uniform(0, 5))
+                F.set_boundary_value(v)
+                p.bc_value = (v,) * 4
+            F.set_field(u)
+            s.u = u.copy()
+            F.step()
+            s = oracle.step(p, s)
+            uf = F.field()
+            assert _close(s.u, uf, 1e-10), (trial, P, step)
+            if p.channels:
+                t, b, _, _ = F.channels()
+                # the wall flux is a difference of neighbouring rows (tiny under a Neumann wall), so the channels inherit
+                # the solve's rounding relative to the FIELD's scale: dt D / well * 1e-13 max|u| per step
+                tol = 1e-10 * p.dt * p.D / p.well_scaling * np.abs(uf).max()
+                assert np.abs(s.top - t).max() <= tol + 1e-9 * np.abs(t).max(), (trial, P, step)
+                assert np.abs(s.bottom - b).max() <= tol + 1e-9 * np.abs(b).max(), (trial, P, step)
+            scale = p.D * p.dt * np.abs(uf).sum() / min(p.h, p.hy or p.h)
+            assert abs(s.total_boundary_flux - F.total_boundary_flux()) <= 1e-11 * scale, (trial, P)
+            u = uf + rng.uniform(0, 5, p.N)
+        seen.add((btype, p.bc_type, p.channels))
+        F.close()
+    assert len(seen) >= 15
