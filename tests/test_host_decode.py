@@ -111,3 +111,41 @@ def test_reference_controller_compiles_against_the_drop_in():
         pytest.skip("/root/reference absent")
     r = subprocess.run(["python", os.path.join(ROOT, "scripts", "check_dropin_compiles.py")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_gpuHSL_decoding_fuzz_against_the_oracle(exe, tmp_path, oracle):
+    """Random parameter sets through gpuHSL::decodeParameters and through the oracle's decoding (which the live fuzz of
+    tests/test_oracle_golden.py holds against the reference class itself): same node counts, wall types, wall values,
+    Robin rates and channel wiring, exactly."""
+    rng = np.random.default_rng(7)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    for trial in range(80):
+        W, H = int(rng.integers(3, 200)), int(rng.integers(2, 60))
+        npm = float(rng.choice([1.0, 2.0, 4.0]))
+        btype = str(rng.choice(BTYPES + ["SOMETHING_ELSE"]))
+        ttype = str(rng.choice(TTYPES))
+        P = oracle.default_parameters(W, H, npm, boundaryType=btype, trapType=ttype,
+                                      simulationFlowRate=float(rng.choice([0.0, 1e-7, 12.0, 120.0])),
+                                      simulationChannelLengthLeft=float(rng.uniform(5, 200)),
+                                      simulationChannelLengthRight=float(rng.uniform(5, 200)),
+                                      channelSolverNumberIterations=int(rng.integers(1, 60)), lengthScaling=float(rng.choice([1.0, 5.0])))
+        if btype == "MICROFLUIDIC_TRAP":
+            walls = {}
+            for name in ("left", "right", "top", "bottom"):
+                k = str(rng.choice(["Dirichlet", "Neumann", "Robin"]))
+                v = float(rng.uniform(0, 3)) if k == "Dirichlet" else 0.0
+                if k == "Dirichlet" and name in ("top", "bottom") and rng.uniform() < 0.4:
+                    v = -1.0
+                walls[name] = oracle.bc_entry(k, v)
+            P["boundaries"] = walls
+        c = {"parameters": P, "width": W, "height": H, "npm": npm, "dt": float(rng.choice([0.02, 0.1])), "D": float(rng.choice([35.0, 1200.0]))}
+        config_block(c).tofile(fin)
+        subprocess.run([exe, "decode", str(fin), str(fout)], check=True)
+        q = np.fromfile(fout)
+        p = oracle.problem_from_parameters(P, c["dt"], c["D"], float(W), float(H), npm)
+        assert (int(q[0]), int(q[1])) == (p.nW, p.nH) and (q[2], q[3]) == (p.h, p.hy), (trial, P)
+        assert tuple(q[6:10].astype(int)) == tuple(p.bc_type), (trial, P)
+        assert tuple(q[10:14]) == tuple(float(v) for v in p.bc_value), (trial, P)
+        assert bool(q[14]) == p.channels, (trial, P)
+        if p.channels:
+            assert (int(q[15]), q[16], q[17], q[18], q[19]) == (p.channel_iters, p.channel_v, p.channel_r[0], p.channel_r[1], p.well_scaling), (trial, P)
