@@ -144,6 +144,7 @@ void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
     decodeParameters(p);
     int rc = eqgpu_create(&p, &h);
     if (rc != EQGPU_OK) throw std::runtime_error(std::string("gpuHSL: eqgpu_create failed: ") + eqgpu_last_error(nullptr));
+    if (cfg.warmStart >= 0) check(eqgpu_set_warm_start(h, cfg.warmStart), "eqgpu_set_warm_start");
 
     const size_t N = nodesH * nodesW;
     solution_vector.assign(N, 0.0);  // src/fHSL.cpp:583-584

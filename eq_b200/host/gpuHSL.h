@@ -40,6 +40,9 @@ public:
         // notifyTensorChanged(); 0: only after notifyTensorChanged(); 1: look every step whatever the size
         int tensorScan = -1;
         double rtol = 1e-12;
+        // starting guess of the iterative solve (eqgpu_set_warm_start): -1 = the library's default for the mesh size,
+        // 0..7 as in include/eqgpu.h (7 = image ring, opt-in)
+        int warmStart = -1;
     };
 
     // what simulation.cpp reads through `diffusionSolver->shell->...` (src/simulation.cpp:298-308)
