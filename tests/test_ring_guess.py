@@ -1,4 +1,4 @@
-"""Warm-start mode 7 (image ring; opt-in, its kernels have not run on a GPU yet): what can be pinned without one.
+"""Warm-start mode 7 (image ring; opt-in, first GPU run: profiles/r01_ring_first_run.json): what can be pinned without a GPU.
 The K x K normal-equation solve the device runs (eqgpu_ring_solve, host-callable) and the algebra of the guess
 -- backward differences, fixed extrapolation = all-ones combination, least-squares correction fitted to the
 extrapolation's residual, image of a solution = b~ - r -- on histories from a real oracle run, against numpy's
