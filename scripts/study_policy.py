@@ -41,7 +41,15 @@ def main():
     hist, imgs, its, picks = [], [], [], []
     t0 = time.time()
     for k in range(110):
-        u0 = O.scatter(cells, 2.0, p.nH, p.nW, np.full(len(cells), 100.0), u)
+        # STUDY_SOURCE=osc: every rod's secretion oscillates (period 40 steps = 4 min, random phase per rod) the way a
+        # synthetic gene oscillator would drive it, instead of the bench's constant 100 nM per step
+        if os.environ.get("STUDY_SOURCE") == "osc":
+            if k == 0:
+                phase = np.random.default_rng(5).uniform(0, 2 * np.pi, len(cells))
+            amount = 100.0 * (1.0 + 0.8 * np.sin(2 * np.pi * k / 40.0 + phase))
+        else:
+            amount = np.full(len(cells), 100.0)
+        u0 = O.scatter(cells, 2.0, p.nH, p.nW, amount, u)
         _, b = O.assemble(p, u0, want_matrix=False)
         b = b * free
         depth = {"mode6": 5, "ext7": 7}.get(policy, 5 if policy == "corrX" and K < 5 else max(5, K))
@@ -63,7 +71,7 @@ def main():
         # left behind (STUDY_RECURRENCE=1): they differ by the recurrence drift
         hist.insert(0, u.copy()); imgs.insert(0, (b - mg.last_r) * free if os.environ.get("STUDY_RECURRENCE") else A @ u)
         hist, imgs = hist[:8], imgs[:8]
-    print(f"{n}x{n} nu={os.environ.get('STUDY_NU', '3')} {policy} {K if policy == 'corrX' else ''}: mean iterations over steps 10..109 = {np.mean(its[10:]):.2f} "
+    print(f"{n}x{n} source={os.environ.get('STUDY_SOURCE', 'const')} nu={os.environ.get('STUDY_NU', '3')} {policy} {K if policy == 'corrX' else ''}: mean iterations over steps 10..109 = {np.mean(its[10:]):.2f} "
           f"(first 10: {its[:10]}, every 10th after: {its[10::10]}, picks at 10/30/60/109: "
           f"{picks[10]}, {picks[30]}, {picks[60]}, {picks[109]}; {time.time() - t0:.0f} s)", flush=True)
 
