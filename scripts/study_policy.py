@@ -43,7 +43,17 @@ def main():
     for k in range(110):
         # STUDY_SOURCE=osc: every rod's secretion oscillates (period 40 steps = 4 min, random phase per rod) the way a
         # synthetic gene oscillator would drive it, instead of the bench's constant 100 nM per step
-        if os.environ.get("STUDY_SOURCE") == "osc":
+        if os.environ.get("STUDY_SOURCE") == "move":
+            # the colony expands: every rod drifts away from the trap centre by 0.02 um per step (a tenth of eQ's growth
+            # speed scale; node spacing 0.5 um), so the set of nodes a rod deposits into changes every few steps
+            if k == 0:
+                ctr0 = cells[:, 11:13].copy()
+                ang0, len0 = np.arctan2(cells[:, 15], cells[:, 14]), cells[:, 13].copy()
+                mid = np.array([p.W / 2, p.H / 2])
+                dirn = (ctr0 - mid) / np.maximum(np.linalg.norm(ctr0 - mid, axis=1, keepdims=True), 1e-9)
+            cells = O.make_cells(ctr0 + 0.02 * k * dirn, ang0, len0, p.W, p.H)
+            amount = np.full(len(cells), 100.0)
+        elif os.environ.get("STUDY_SOURCE") == "osc":
             if k == 0:
                 phase = np.random.default_rng(5).uniform(0, 2 * np.pi, len(cells))
             amount = 100.0 * (1.0 + 0.8 * np.sin(2 * np.pi * k / 40.0 + phase))
