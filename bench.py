@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- HSL diffusion steps/sec at the 2048^2 mesh (BASELINE.json metric).
 
-A "step" = one pass of the hot path over one layer: gather (readHSL) ->
-scatter-add (writeHSL) -> backward-Euler solve to rel. residual 1e-12 ->
-boundary-flux functional, i.e. eQabm::updateCells' lambdas + fenicsInterface::
-stepDiffusion (src/abm/eQabm.cpp:268-359, src/fHSL.cpp:98-161) for BASELINE
-configs[2]: synthetic 2048^2-node trap, 20k rods, single GPU.
+A "step" = one pass of the hot path over one layer: cell records for this step (the rods have moved) ->
+gather (readHSL) -> scatter-add (writeHSL) -> backward-Euler solve to rel. residual 1e-12 -> boundary-flux
+functional, i.e. eQabm::updateCells' lambdas + fenicsInterface::stepDiffusion (src/abm/eQabm.cpp:254-425,
+src/fHSL.cpp:98-161) for BASELINE configs[2]: synthetic 2048^2-node trap, 20k rods, single GPU.
 
-N > 1 (torchrun, one rank per GPU): one independent HSL layer per GPU, the
-reference's own MPI model (src/simulation.cpp:628-645) -> weak scaling, no
-data-path collective.
+The colony CHANGES every step by default (--colony moving: rods advance 0.05-0.2 node per step and turn; `growing`
+adds exponential growth with the ratchet and division) because eQ recomputes every rod's node set each step; the
+static colony of round 1 (whose history-based starting guesses are unrepresentatively good) and a cold start are
+timed beside it and reported as value_static / value_cold.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N > 1 (torchrun, one rank per GPU): one independent HSL layer per GPU, the reference's own MPI model
+(src/simulation.cpp:628-645) -> weak scaling, no data-path collective; plus a second leg, `slab`: ONE mesh of
+16384 x (2048 N) nodes cut into N row slabs with NCCL halo exchange and CG all-reduce (BASELINE configs[4]),
+preceded by an in-run parity check of the slab solver.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--colony static|moving|growing]
 """
 import argparse
 import json
@@ -37,8 +42,9 @@ WORKLOAD = ("configs[2]: synthetic 2048x2048-node trap mesh (h=0.5, dt=0.1, D=12
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a level-0 kernel from the committed
-    `ncu --set full` capture (profiles/ncu_traffic.json, written by profiles/ncu_summary.py); None if absent."""
+    """STATIC cross-reference, not measured in this run: DRAM bytes per launch (dram__bytes_read.sum +
+    dram__bytes_write.sum) of a level-0 kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by profiles/ncu_summary.py); None if absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             return float(json.load(f)["kernels"][kernel]["dram_bytes"])
@@ -55,9 +61,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py), polled every 5 ms: the
-    default timed region is about 0.1 s, shorter than nvidia-smi's start-up, which is why the first round's lines said
-    "unavailable"; `nvidia-smi -lms` stays as the fallback when NVML cannot be loaded."""
+    """SM clock + throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py), polled every 5 ms;
+    `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index, uuid=None):
@@ -152,167 +157,238 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(rows), "source": self.source}
 
 
-def cpu_baseline(sample_n=512, threads=1):
-    """Restated reference CPU path ("Fenics-equivalent": re-assemble, DirichletBC, sparse direct LU
-    every step, src/fHSL.cpp:104-108) on a bounded sample, scaled to the 2048^2 metric by DOF count."""
-    from oracle import oracle as O
-    p = O.Problem(nW=sample_n, nH=sample_n, h=H, dt=DT, D=D)
-    cells = O.synthetic_colony(int(NCELLS * (sample_n / NW) ** 2), p.W, p.H)
-    u = np.zeros(p.N)
-    t0 = time.perf_counter()
-    amount = 100.0 + 0.0 * O.gather(cells, NPM, p.nH, p.nW, u)
-    u = O.scatter(cells, NPM, p.nH, p.nW, amount, u)
-    s = O.new_state(p)
-    s.u = u
-    O.step(p, s, solver="lu")
-    dt = time.perf_counter() - t0
-    value = (1.0 / dt) * (p.N / float(NW * NH))
-    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": (f"one full step (gather+scatter+assemble+DirichletBC+SuperLU factor/solve+flux) on a "
-                       f"{sample_n}x{sample_n} mesh with {len(cells)} rods in {dt:.2f} s, scaled by DOF ratio "
-                       f"{p.N}/{NW * NH} to the 2048^2 metric (LU cost is superlinear, so this flatters the CPU)"),
-            "seconds": dt}
+# ---------------------------------------------------------------------------------------------------------------
+# workload: the record sets of a colony that changes (eq_b200/colony.py; host side, numpy)
+# ---------------------------------------------------------------------------------------------------------------
+def colony_record_sets(mode, n, W, Hh, nsets, seed):
+    """[nsets, ncells, 16] cell records of successive steps (one set for a static colony)."""
+    from eq_b200.colony import Colony
+    col = Colony(n, W, Hh, npm=NPM, mode=mode, seed=seed, dt=DT)
+    sets = [col.records()]
+    for _ in range(1 if mode == "static" else nsets - 1):
+        col.advance()
+        sets.append(col.records())
+    if mode == "static":
+        sets = sets[:1]
+    return np.ascontiguousarray(np.stack(sets))
 
 
-def cpu_baseline_fd():
-    """diffusionPETSc's own CPU path restated (oracle/eq_oracle.c: ApplyBoundaryConditions + matrix-free
-    MyMatMult + unpreconditioned BiCGStab to PETSc's default rtol 1e-5, diffuclass.cpp:386-413) on the FULL
-    2048^2 workload, OpenMP over all host cores (upstream: one DMDA decomposition over MPI ranks)."""
-    from oracle import oracle as O
-    p = O.Problem(nW=NW, nH=NH, h=H, dt=DT, D=D)
-    cells = O.synthetic_colony(NCELLS, p.W, p.H)
-    u = np.zeros(p.N)
-    steps, iters = 3, []
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        amount = 100.0 + 0.0 * O.gather(cells, NPM, p.nH, p.nW, u)
-        u = O.scatter(cells, NPM, p.nH, p.nW, amount, u)
-        u, it, _ = O.fd_step_krylov(p, u)
-        iters.append(int(it))
-    dt = (time.perf_counter() - t0) / steps
-    cores = int(O.lib().eqo_num_threads())
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"{steps} full steps at 2048x2048 with {len(cells)} rods (gather + scatter + ApplyBoundaryConditions "
-                       f"+ matrix-free BiCGStab to rtol 1e-5, {iters} iterations; the GPU solves to 1e-12), "
-                       f"{dt:.2f} s per step on {cores} OpenMP threads"),
-            "seconds": dt * steps}
+# Algorithmic bytes per DOF of the once-per-step passes, by starting-guess mode (DESIGN.md section 5): k_init_tile
+# (reads u0 and the history tiles it walks, writes r1, b~ and the difference images), k_impose / the ring pair (reads
+# what the picked guess combines, writes u and r), k_finish_x (32), the ring's image walk (16).
+FIXED_BYTES = {0: 88, 1: 112, 2: 144, 3: 176, 4: 208, 5: 200, 6: 224, 7: 272}
 
 
+def pingpong(k, R):
+    """0 1 .. R-1 R-2 .. 1 0 1 ..: every step of the replay is one small move of the rods, never a jump back."""
+    if R == 1:
+        return 0
+    k %= 2 * (R - 1)
+    return k if k < R else 2 * (R - 1) - k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path on the box's host cores, at the FULL configuration, nothing extrapolated
+# ---------------------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; the Fenics/PETSc original cannot be
-    built here) timed on the host cores."""
+    """--impl reference.  The Fenics/PETSc executable cannot be built here, so this times the
+    restated reference CPU path (oracle/, `kind: port`) on configs[2] exactly: 2048^2 nodes, 20k rods that move,
+    every step = gather + scatter + one backward-Euler solve.
+      value            diffusionPETSc's own algorithm (diffuclass.cpp:191-275,386-413,786-862: ApplyBoundaryConditions +
+                       matrix-free MyMatMult + unpreconditioned BiCGStab to PETSc's default rtol 1e-5), OpenMP on all
+                       host cores, for exactly --warmup + --steps steps.  It is the FASTER of the reference's two
+                       solvers and runs at the reference's own (looser) tolerance, so value/this is conservative.
+      matched_tolerance  the P1 operator of fenics/hslD.ufl (what fenicsInterface assembles) solved to the GPU arm's
+                       rtol 1e-12 by Jacobi-CG on all cores, timed on a bounded number of full-size steps.
+      lu               fenicsInterface's own solver is a sparse LU every step (src/fHSL.cpp:104-108): SuperLU of this
+                       matrix is NOT run inside the driver's run (one factorisation takes minutes); the measured
+                       figure from profiles/r02_cpu_lu.json is quoted, labelled as such.
+    Under torchrun rank 0 alone runs; the N layers of the GPU arm would share the same host cores, so the CPU
+    aggregate does not grow with N."""
     if rank != 0:
         return
     from oracle import oracle as O
-    n = 320
-    p = O.Problem(nW=n, nH=n, h=H, dt=DT, D=D)
-    cells = O.synthetic_colony(int(NCELLS * (n / NW) ** 2), p.W, p.H)
-    s = O.new_state(p)
+    p = O.Problem(nW=NW, nH=NH, h=H, dt=DT, D=D)
+    total = args.warmup + args.steps
+    nsets = min(total + 1, 64)
+    recs = colony_record_sets(args.colony, NCELLS, p.W, p.H, nsets, 12345)
+    ncells = recs.shape[1]
+    amount = np.full(ncells, 100.0)
+    cores = int(O.lib().eqo_num_threads())
+    u = np.zeros(p.N)
+    iters = []
 
-    def one():
-        amount = 100.0 + 0.0 * O.gather(cells, NPM, p.nH, p.nW, s.u)
-        s.u = O.scatter(cells, NPM, p.nH, p.nW, amount, s.u)
-        O.step(p, s, solver="lu")
+    def fd_step(k):
+        nonlocal u
+        c = recs[pingpong(k, len(recs))]
+        O.gather(c, NPM, p.nH, p.nW, u)
+        u0 = O.scatter(c, NPM, p.nH, p.nW, amount, u)
+        u, it, _ = O.fd_step_krylov(p, u0)
+        iters.append(int(it))
 
-    for _ in range(args.warmup):
-        one()
+    t_start = time.perf_counter()
+    for k in range(args.warmup):
+        fd_step(k)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one()
+    for k in range(args.steps):
+        fd_step(args.warmup + k)
     dt = (time.perf_counter() - t0) / args.steps
-    value = (1.0 / dt) * (p.N / float(NW * NH))
-    sample = (f"each step = one full step on a {n}x{n} mesh with {len(cells)} rods (SuperLU, 1 thread: one MPI "
-              f"rank per layer upstream), scaled by DOF ratio to 2048^2")
-    # Where the reference's own class was compiled (oracle/_ref/libeq_fenics_ref.so: src/fHSL.cpp on the one-process
-    # DOLFIN interface shim), run it beside the port on a smaller sample: same answer, and the port is the FASTER of
-    # the two (SuperLU against the shim's banded LU), so the headline ratio is taken against the stronger CPU number.
-    ref_class = None
-    if O.fenics_ref_lib() is not None:
-        m, npm_ = 160, NPM
-        Wm = (m - 1) / npm_
-        P = O.default_parameters(int(round(Wm)), int(round(Wm)), npm_)
-        try:
-            F = O.FenicsReference(P, DT, D, float(int(round(Wm))), float(int(round(Wm))), npm_)
-            q = O.problem_from_parameters(P, DT, D, float(int(round(Wm))), float(int(round(Wm))), npm_)
-            rng = np.random.default_rng(3)
-            u = rng.uniform(0, 50, q.N)
-            F.set_field(u)
-            t1 = time.perf_counter()
-            F.step()
-            t_ref = time.perf_counter() - t1
-            sq = O.new_state(q)
-            sq.u = u.copy()
-            t1 = time.perf_counter()
-            O.step(q, sq, solver="lu")
-            t_port = time.perf_counter() - t1
-            uf = F.field()
-            ref_class = {"mesh": f"{q.nW}x{q.nH}", "seconds_reference_class_on_shim": t_ref, "seconds_port": t_port,
-                         "rel_l2_port_vs_reference_class": float(np.linalg.norm(sq.u - uf) / np.linalg.norm(uf))}
-            F.close()
-        except Exception as e:  # the checker's checker must not take the arm down
-            ref_class = {"error": str(e)}
+    value = 1.0 / dt
+    # matched tolerance, bounded: 1-2 further full-size steps with the P1 operator to 1e-12
+    matched = None
+    if not args.no_matched:
+        k_m = 1 if args.bounded else 2
+        um = u.copy()
+        t1 = time.perf_counter()
+        its = []
+        for k in range(k_m):
+            c = recs[pingpong(total + k, len(recs))]
+            O.gather(c, NPM, p.nH, p.nW, um)
+            u0 = O.scatter(c, NPM, p.nH, p.nW, amount, um)
+            um, it, rel = O.solve_cg(p, u0, rtol=1e-12, x0=um)
+            its.append(int(it))
+        dm = (time.perf_counter() - t1) / k_m
+        matched = {"value": 1.0 / dt if dm <= 0 else 1.0 / dm, "unit": UNIT, "seconds_per_step": dm, "steps_timed": k_m,
+                   "solver": "P1 operator (fenics/hslD.ufl) assembled to 7 bands + Jacobi-preconditioned CG, rtol 1e-12, "
+                             "started from the previous solution", "iterations": its, "cores": cores}
+    lu = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_cpu_lu.json")) as f:
+            lu = json.load(f)
+            lu["note"] = "quoted from profiles/r02_cpu_lu.json (measured once, outside this run)"
+    except Exception:
+        pass
+    sample = (f"{args.warmup}+{args.steps} FULL steps at {NW}x{NH} with {ncells} rods ({args.colony} colony): gather + "
+              f"scatter + ApplyBoundaryConditions + matrix-free BiCGStab to rtol 1e-5 (diffusionPETSc restated; "
+              f"{int(np.mean(iters[-args.steps:]))} iterations per step), {dt:.2f} s per step on {cores} OpenMP threads; "
+              f"nothing scaled or extrapolated")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (NW * NH) / p.N,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if ref_class is not None:
-        line["reference_class_check"] = ref_class
+            "data": "synthetic", "config": {"workload": WORKLOAD, "colony": args.colony, "rods": ncells,
+                                            "solver": "diffusionPETSc path: 5-point FD, unpreconditioned BiCGStab, rtol 1e-5",
+                                            "same_config": True, "extrapolated": False},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "matched_tolerance": matched, "lu": lu,
+            "scales_with_n": False,
+            "scales_with_n_note": "the N layers of an N-GPU run share this box's host cores: the CPU's aggregate "
+                                  "layer-steps/s is this figure at every N",
+            "wall_seconds": time.perf_counter() - t_start}
     print(json.dumps(line), flush=True)
 
 
-def run_slab(args, rank, local_rank, world):
-    """--mode slab: BASELINE configs[4] style -- one mesh split into row slabs over the GPUs of the box,
-    one-row halo exchange + CG all-reduce over NCCL.  16384 columns, 2048 rows and 25k rods per GPU
-    (= the 16384^2 / 200k-rod configuration at 8 GPUs)."""
+def cpu_baseline_subprocess(colony):
+    """cpu_baseline of the GPU arm: the reference arm on a bounded sample (3 + 1 full-size steps, about 20-40 s of CPU
+    work), run in a SUBPROCESS so that the GPU arm's own process never maps anything under oracle/."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3",
+           "--bounded", "--colony", colony]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        cb = line["cpu_baseline"]
+        cb["matched_tolerance"] = line.get("matched_tolerance")
+        cb["lu"] = line.get("lu")
+        return cb
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+
+
+def oracle_lu_subprocess(nW, nH, seed, path):
+    """Checker for the slab leg: the oracle's direct solve of one seeded step, in a subprocess (see above)."""
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle import oracle as O;"
+            "p = O.Problem(nW=%d, nH=%d, h=%r, dt=%r, D=%r);"
+            "u0 = np.random.default_rng(%d).uniform(0.0, 50.0, p.N); np.save(%r, O.solve_lu(p, u0))"
+            % (ROOT, nW, nH, H, DT, D, seed, path))
+    subprocess.run([sys.executable, "-c", code], check=True, timeout=600)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slab leg (N > 1): BASELINE configs[4] -- one mesh in N row slabs, halo exchange + CG all-reduce over NCCL
+# ---------------------------------------------------------------------------------------------------------------
+def run_slab_leg(args, rank, local_rank, world, stream, ids_fn):
     import torch
     import torch.distributed as dist
     import eq_b200 as E
-    from oracle import oracle as O
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = {}
+    # (1) parity first: a 384 x 256 problem on the same N ranks against the oracle's LU, <= 1e-8 or no slab number
+    pW, pH, seed = 384, max(256, 32 * world), 4242
+    path = f"/tmp/eq_b200_slab_check_{os.getpid()}.npy"
+    ok = True
+    if rank == 0:
+        try:
+            oracle_lu_subprocess(pW, pH, seed, path)
+        except Exception as e:
+            ok = False
+            out["parity"] = {"error": f"checker failed: {e}"}
+    g = E.GpuHSL(pW, pH, h=H, dt=DT, D=D, device=local_rank, stream=stream.cuda_stream, slab=(rank, world, ids_fn()))
+    u0 = np.random.default_rng(seed).uniform(0.0, 50.0, pW * pH)
+    g.set_field(u0)
+    g.step()
+    mine = np.zeros(pW * pH)
+    g.get_field(out=mine)
+    r0, r1 = g.slab_rows()
+    part = torch.zeros(pW * pH, dtype=torch.float64, device="cuda")
+    part[r0 * pW:r1 * pW] = torch.from_numpy(mine[r0 * pW:r1 * pW]).cuda()
+    dist.all_reduce(part)
+    it_small = int(g.stats().iterations)
+    g.close()
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda", dtype=torch.float64)
+    if rank == 0 and ok:
+        ref = np.load(path)
+        os.remove(path)
+        err = float(np.linalg.norm(part.cpu().numpy() - ref) / np.linalg.norm(ref))
+        out["parity"] = {"mesh": f"{pW}x{pH}", "ranks": world, "rel_l2_vs_oracle_lu": err, "tolerance": 1e-8,
+                         "pcg_iterations": it_small, "ok": bool(err <= 1e-8)}
+        flag[0] = 1.0 if err <= 1e-8 else 0.0
+    dist.broadcast(flag, src=0)
+    if flag.item() == 0.0:
+        out["skipped"] = "slab parity self-check failed: no slab number is reported"
+        return out
+    # (2) the timed leg: 16384 columns, 2048 rows and 25k rods per GPU (= 16384^2 / 200k rods at 8 GPUs)
     nW, nH, ncells = args.slab_cols, 2048 * world, 25000 * world
-    ids = [E.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    stream = torch.cuda.current_stream()
-    g = E.GpuHSL(nW, nH, h=H, dt=DT, D=D, device=local_rank, stream=stream.cuda_stream, slab=(rank, world, ids[0]))
-    cells = O.synthetic_colony(ncells, (nW - 1) * H, (nH - 1) * H, seed=777)
-    g.upload_cells(cells, NPM)
-    g.set_amounts(np.full(len(cells), 100.0))
+    g = E.GpuHSL(nW, nH, h=H, dt=DT, D=D, device=local_rank, stream=stream.cuda_stream, slab=(rank, world, ids_fn()))
+    k_steps, k_warm = max(3, min(args.steps, 20)), 3
+    recs = colony_record_sets(args.colony, ncells, (nW - 1) * H, (nH - 1) * H, k_steps + k_warm + 1, 777)
+    rec_dev = torch.from_numpy(recs).cuda()
+    nrec = recs.shape[1]
+    stride = nrec * 16 * 8
+    g.upload_cells(recs[0], NPM)
+    g.set_amounts(np.full(nrec, 100.0))
+    its = []
 
-    def step():
+    def step(k):
+        g.upload_cells_device(rec_dev.data_ptr() + pingpong(k, len(recs)) * stride, nrec, NPM)
         g.gather_resident()
         g.scatter_resident()
         g.step()
+        its.append(int(g.stats().iterations))
 
-    for _ in range(args.warmup):
-        step()
+    for k in range(k_warm):
+        step(k)
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = g.stats().kernel_launches
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
+    for k in range(k_steps):
+        step(k_warm + k)
     e1.record(stream)
     dist.barrier(); torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    if rank == 0:
-        N = nW * nH
-        print(json.dumps({
-            "metric": f"hsl_diffusion_steps_per_sec_{nW}x{nH}_row_slab", "value": args.steps / (ms / 1e3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[4] style: {nW}x{nH} mesh in {world} row slabs of 2048 rows, {len(cells)} rods, "
-                                   "fused tile kernels with 6-row NCCL halo exchange + CG all-reduce",
-                       "pcg_iterations": int(g.stats().iterations), "relres": g.stats().relres,
-                       "mg_levels": int(g.stats().levels), "dof_updates_per_sec": N * args.steps / (ms / 1e3)},
-            "gpu_launches": int(g.stats().kernel_launches - l0)}), flush=True)
+    ms = float(t.item()) / k_steps
+    st = g.stats()
+    comm = g.comm_stats() if hasattr(g, "comm_stats") else {}
+    out.update({"metric": f"hsl_diffusion_steps_per_sec_{nW}x{nH}_row_slab", "value": 1e3 / ms, "unit": UNIT,
+                "ms_per_step": ms, "steps": k_steps, "warmup": k_warm, "scaling": "weak",
+                "workload": f"configs[4] style: {nW}x{nH} nodes in {world} row slabs of 2048 rows, {nrec} rods "
+                            f"({args.colony} colony)",
+                "pcg_iterations_mean": float(np.mean(its[-k_steps:])), "relres": st.relres,
+                "mg_levels": int(st.levels), "dof_updates_per_sec": nW * nH * 1e3 / ms,
+                "gpu_launches": int(st.kernel_launches - l0), "comm": comm})
     g.close()
-    dist.barrier()
-    dist.destroy_process_group()
+    return out
 
 
 def main():
@@ -321,7 +397,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)    # 100 steps after 10 warm-up
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="eq_b200")
+    ap.add_argument("--colony", default="moving", choices=["static", "moving", "growing"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the row-slab leg")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip value_static / value_cold / e2e_compat")
+    ap.add_argument("--bounded", action="store_true", help="reference arm: the bounded cpu_baseline sample")
+    ap.add_argument("--no-matched", action="store_true", help="reference arm: skip the matched-tolerance steps")
     ap.add_argument("--mode", default="layers", choices=["layers", "slab"])
     ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 6, 7],
                     help="BASELINE.json configs index+1: 3 = the headline 2048^2 workload (default); 2 = dual layers "
@@ -338,21 +419,32 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.mode == "slab":
-        if world < 2:
-            raise SystemExit("--mode slab needs torchrun with >= 2 ranks")
-        run_slab(args, rank, local_rank, world)
-        return
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import eq_b200 as E
-    from oracle import oracle as O  # synthetic colony generator + cpu_baseline only
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream()
+
+    def nccl_ids():
+        ids = [E.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        return ids[0]
+
+    if args.mode == "slab":   # the slab leg alone (development aid; the default N > 1 run carries it as `slab`)
+        if world < 2:
+            raise SystemExit("--mode slab needs torchrun with >= 2 ranks")
+        slab = run_slab_leg(args, rank, local_rank, world, stream, nccl_ids)
+        if rank == 0:
+            print(json.dumps({"n_gpus": world, "higher_is_better": True, "dtype": "f64", "data": "synthetic", **slab}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     global NW, NH, WORKLOAD, METRIC
     kw = {}
     Dl = D
@@ -363,7 +455,9 @@ def main():
         METRIC = "hsl_diffusion_steps_per_sec_2048x2048_robin"
     elif args.config == 4:  # MICROFLUIDIC_TRAP: Robin left/right, channel Dirichlet top/bottom, 48 CN sub-steps
         NW = NH = 4096
-        rl, rr = O.robin_rates(120.0, D, 20.0, 20.0)
+        # Robin rates of src/fHSL.cpp:331-364 for v = 120, D = 1200, channel lengths 20 / 20
+        pe = 120.0 * 20.0 / D
+        rl, rr = 120.0 / (1.0 - np.exp(-pe)), 120.0 / (np.exp(pe) - 1.0)
         kw = dict(bc_type=(2, 2, 3, 3), bc_value=(rl, rr, 0.0, 0.0), channels=True, channel_v=120.0,
                   channel_r=(rl, rr), channel_iters=48, well_scaling=10.0 * (25.0 / 5.0) * 0.5)
         WORKLOAD = "configs[3]: channel-flow trap (1-D advection-diffusion channels, 48 CN sub-steps) at 4096x4096, 20k rods"
@@ -377,90 +471,38 @@ def main():
         METRIC = "hsl_diffusion_steps_per_sec_2048x2048_tensor"
     tensor_feed = args.config == 7
     W = (NW - 1) * H
-    cells = O.synthetic_colony(NCELLS, W, W, seed=12345 + rank)
-    ncells = len(cells)
+    N = NW * NH
+
+    # record sets: enough distinct steps for the longest leg, replayed forwards then backwards
+    nsets = min(args.warmup + args.steps + 1, 128)
+    recs = colony_record_sets(args.colony, NCELLS, W, W, nsets, 12345 + rank)
+    ncells = recs.shape[1]
+    rec_dev = torch.from_numpy(recs).cuda()
+    rec_pin = torch.from_numpy(recs).pin_memory()
+    stride = ncells * 16 * 8
     amount = np.full(ncells, 100.0)  # nM per step
+    warm_env = "EQGPU_WARM" in os.environ
 
     def make_solver(warm=None):
         s = E.GpuHSL(NW, NH, h=H, dt=DT, D=Dl, device=local_rank, stream=stream.cuda_stream,
                      smooth_sweeps=int(os.environ.get("EQ_NU", "0")), **kw)
-        if warm is not None:
+        if warm is not None and not warm_env:
             s.set_warm_start(warm)
-        s.upload_cells(cells, NPM)
+        s.upload_cells(recs[0], NPM)
         s.set_amounts(amount)
         return s
-
-    # Starting-guess policy.  The library default above 512^2 nodes is mode 6 (fixed extrapolations).  Mode 7, the image
-    # ring (profiles/r01_guess_study.md), first ran on a B200 in the last seconds of round 1 (gpurun_out/ring_quick.json:
-    # 1.46 iterations per step against 2.66, same field to 1e-13) and is opt-in in the library until the whole GPU suite
-    # has seen it; the bench opts in, but only after checking it against mode 6 on this very workload first: 30 steps
-    # with both, fields must agree to 1e-9, else the run falls back to the default and says so.
-    warm_mode = int(os.environ["EQGPU_WARM"]) if "EQGPU_WARM" in os.environ else (4 if NW * NH <= 512 * 512 else 6)
-    ring_check = None
-    if "EQGPU_WARM" not in os.environ and NW * NH > 512 * 512 and args.config == 3:   # the headline workload, the one it has run on
-        try:
-            fields = {}
-            for mode in (6, 7):
-                c = make_solver(mode)
-                for _ in range(30):
-                    c.gather_resident()
-                    c.scatter_resident()
-                    c.step()
-                fields[mode] = (c.get_field(), int(c.last_guess()))
-                c.close()
-            diff = float(np.linalg.norm(fields[7][0] - fields[6][0]) / np.linalg.norm(fields[6][0]))
-            ring_check = {"steps": 30, "rel_l2_mode7_vs_mode6": diff, "mode7_last_guess": fields[7][1],
-                          "ok": bool(diff < 1e-9 and fields[7][1] == 8)}
-        except Exception as e:
-            ring_check = {"error": str(e), "ok": False}
-        if ring_check["ok"]:
-            warm_mode = 7
-    g = make_solver(None if "EQGPU_WARM" in os.environ else warm_mode)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    it_hist = []
-
-    def step_resident():
-        g.gather_resident()
-        g.scatter_resident()
-        if tensor_feed:
-            g.cells_tensor(1.5, 0.6)
-        g.step()
-        it_hist.append(g.stats().iterations)   # host-side read of the last step's count (the step has synchronised)
-
-    # pinned host buffers for the end-to-end legs
-    rec_pin = torch.from_numpy(cells.copy()).pin_memory()
-    amt_pin = torch.from_numpy(amount.copy()).pin_memory()
-    out_pin = torch.zeros(ncells, dtype=torch.float64).pin_memory()
-    fld_pin = torch.zeros(NW * NH, dtype=torch.float64).pin_memory()
-    import ctypes as C
-    dpp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
-    L = E.lib()
-
-    def step_e2e():
-        # fused drop-in: only per-cell data crosses PCIe (cell records in, sampled HSL out, deposits in)
-        g._ck(L.eqgpu_cells_upload(g._h, dpp(rec_pin), C.c_int64(ncells), C.c_double(NPM)))
-        g._ck(L.eqgpu_cells_gather(g._h, dpp(out_pin)))
-        g._ck(L.eqgpu_cells_scatter(g._h, dpp(amt_pin)))
-        if tensor_feed:
-            g.cells_tensor(1.5, 0.6)
-        g.step()
-        return g.stats().total_boundary_flux
-
-    def step_compat():
-        # strict drop-in: fenicsInterface's host solution_vector in and out every step
-        g.step_host_ptr(fld_pin.data_ptr())
-
-    def timed(fn, k):
+    def timed(fn, k0, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(k):
-            fn()
+        for i in range(k):
+            fn(k0 + i)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -470,113 +512,213 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(args.warmup):
-        step_resident()
-    try:
-        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
-    except Exception:
-        uuid = None
-    sampler = ClockSampler(local_rank, uuid)
-    sampler.start()
-    sampler.wait_ready()
-    l0 = g.stats().kernel_launches
-    ms = timed(step_resident, args.steps)
-    launches = g.stats().kernel_launches - l0
-    iters = g.stats().iterations
-    iters_mean = float(np.mean(it_hist[-args.steps:]))
-    relres = g.stats().relres
-    clocks = sampler.stop()
-    ms_step = ms / args.steps
-    value = world * args.steps / (ms / 1e3)
+    def resident_leg(s, sets, warmup, steps, sample=False):
+        """W untimed + K timed device-resident steps on solver s; the records of step k are record set pingpong(k)."""
+        R = len(sets)
+        its = []
 
-    for _ in range(3):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
-    # compat leg: the run goes on, but the field now lives on the host as in the reference: each step the host
-    # adds the deposits to solution_vector (writeHSL on the CPU, outside the timed region) and hands it in;
-    # the solution comes back in the same buffer.  (Restarting every step from one fixed field would let the
-    # warm start return the previous, identical answer in zero iterations.)
-    fld_pin.copy_(torch.from_numpy(g.get_field()))
-    dep_t = torch.from_numpy(O.scatter(cells, NPM, NH, NW, amount, np.zeros(NW * NH)))
-    kc = max(3, args.steps // 5)
-    ms_compat = 0.0
-    for it in range(3 + kc):
-        fld_pin.add_(dep_t)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step_compat()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        if it >= 3:
-            ms_compat += e0.elapsed_time(e1) / kc
-    if world > 1:
-        t = torch.tensor([ms_compat], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_compat = float(t.item())
+        def step(k):
+            if R > 1:
+                s.upload_cells_device(rec_dev.data_ptr() + pingpong(k, R) * stride, ncells, NPM)
+            s.gather_resident()
+            s.scatter_resident()
+            if tensor_feed:
+                s.cells_tensor(1.5, 0.6)
+            s.step()
+            its.append(int(s.stats().iterations))   # host-side read of the last step's count (the step has synchronised)
+
+        for k in range(warmup):
+            step(k)
+        sampler = None
+        if sample:
+            try:
+                uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            except Exception:
+                uuid = None
+            sampler = ClockSampler(local_rank, uuid)
+            sampler.start()
+            sampler.wait_ready()
+        l0 = s.stats().kernel_launches
+        ms = timed(step, warmup, steps)
+        res = {"ms_per_step": ms / steps, "value": world * steps / (ms / 1e3), "launches": int(s.stats().kernel_launches - l0),
+               "iterations_mean": float(np.mean(its[-steps:])), "iterations_last": int(its[-1]),
+               "relres": float(s.stats().relres), "next_k": warmup + steps}
+        if sampler:
+            res["clocks"] = sampler.stop()
+        return res
+
+    # ---- the headline leg: the colony named by --colony (moving by default), library-default starting guess -------------
+    g = make_solver()
+    main_leg = resident_leg(g, recs, args.warmup, args.steps, sample=True)
+    ms_step, value = main_leg["ms_per_step"], main_leg["value"]
+    kpos = main_leg["next_k"]
+    warm_mode = int(g.warm_mode())
+
+    # ---- true residual of one more step, through the verification hooks (outside every timed region) ---------------------
+    true_relres = None
+    if hasattr(g, "build_rhs") and not tensor_feed and NW * NH <= 2048 * 2048:
+        try:
+            if len(recs) > 1:
+                g.upload_cells_device(rec_dev.data_ptr() + pingpong(kpos, len(recs)) * stride, ncells, NPM)
+            g.gather_resident()
+            g.scatter_resident()
+            u0 = g.get_field()
+            g.step()
+            kpos += 1
+            u1 = g.get_field()
+            b = g.build_rhs(u0)
+            Au = g.apply_operator(u1, constrained=False)
+            free = np.ones((NH, NW), dtype=bool)
+            bt = kw.get("bc_type", (1, 1, 1, 1))
+            if bt[0] in (1, 3): free[:, 0] = False
+            if bt[1] in (1, 3): free[:, -1] = False
+            if bt[2] in (1, 3): free[-1, :] = False
+            if bt[3] in (1, 3): free[0, :] = False
+            f = free.ravel()
+            true_relres = float(np.linalg.norm((b - Au)[f]) / np.linalg.norm(b[f])) if not kw.get("channels") else None
+        except Exception as e:   # the check must not take the measurement down
+            true_relres = f"unavailable: {e}"
+
+    # ---- end to end: per-step H2D of this step's records and deposits from pinned host memory, D2H of the samples --------
+    amt_pin = torch.from_numpy(amount.copy()).pin_memory()
+    out_pin = torch.zeros(ncells, dtype=torch.float64).pin_memory()
+    dpp = lambda t, off=0: C.cast(t.data_ptr() + off, C.POINTER(C.c_double))
+    L = E.lib()
+    R = len(recs)
+
+    def step_e2e(k):
+        # fused drop-in: only per-cell data crosses PCIe (cell records in, sampled HSL out, deposits in, flux out)
+        g._ck(L.eqgpu_cells_upload(g._h, dpp(rec_pin, pingpong(k, R) * stride), C.c_int64(ncells), C.c_double(NPM)))
+        g._ck(L.eqgpu_cells_gather(g._h, dpp(out_pin)))
+        g._ck(L.eqgpu_cells_scatter(g._h, dpp(amt_pin)))
+        if tensor_feed:
+            g.cells_tensor(1.5, 0.6)
+        g.step()
+        return g.stats().total_boundary_flux
+
+    for i in range(3):
+        step_e2e(kpos + i)
+    kpos += 3
+    ms_e2e = timed(step_e2e, kpos, args.steps) / args.steps
+    kpos += args.steps
+
+    side = {}
+    ms_compat = None
+    if not args.no_side_legs:
+        # compat leg: the strict fenicsInterface contract -- the field lives on the host, each step the host adds this
+        # step's deposits to solution_vector (writeHSL on the CPU, outside the timed region) and hands the whole vector
+        # in; the solution comes back in the same buffer.  The deposits of four successive record sets are rasterised
+        # once, by the device's own scatter kernel, before the leg.
+        fld_pin = torch.zeros(N, dtype=torch.float64).pin_memory()
+        cur = g.get_field()
+        deps = []
+        for q in range(4 if R > 1 else 1):
+            if R > 1:
+                g.upload_cells(recs[pingpong(kpos + q, R)], NPM)
+            g.set_field(np.zeros(N))
+            g.scatter(amount)
+            deps.append(torch.from_numpy(g.get_field()))
+        g.set_field(cur)
+        fld_pin.copy_(torch.from_numpy(cur))
+        kc = max(3, args.steps // 5)
+        ms_compat = 0.0
+        for it in range(3 + kc):
+            fld_pin.add_(deps[pingpong(it, len(deps))])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            g.step_host_ptr(fld_pin.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if it >= 3:
+                ms_compat += e0.elapsed_time(e1) / kc
+        if world > 1:
+            t = torch.tensor([ms_compat], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_compat = float(t.item())
+        # the same workload with a colony that never changes (round 1's headline) and from a cold start
+        if args.colony != "static":
+            s2 = make_solver()
+            side["static"] = resident_leg(s2, recs[:1], args.warmup, args.steps)
+            s2.close()
+        s3 = make_solver(0)
+        side["cold"] = resident_leg(s3, recs, args.warmup, min(args.steps, 30))
+        s3.close()
+
+    slab = None
+    if world > 1 and not args.no_slab and args.config == 3:
+        try:
+            slab = run_slab_leg(args, rank, local_rank, world, stream, nccl_ids)
+        except Exception as e:
+            slab = {"error": str(e)}
 
     if rank == 0:
         peak, peak_src = peaks()
-        # dominant kernel, timed alone with CUDA events on the launching stream
+        # level-0 kernels timed alone with CUDA events on the launching stream, L2 flushed before every launch
         roof = {}
         for name in ("presmooth", "postsmooth", "apply_p", "update_r", "update_xr"):
             try:
-                kms, kbytes = g.bench_kernel(name, 50)
+                kms, kbytes = g.bench_kernel(name, 30)
             except E.EqGpuError:
                 continue
             roof[name] = {"ms": kms, "bytes": kbytes, "gbs": kbytes / (kms * 1e-3) / 1e9}
         dom = max(roof, key=lambda k: roof[k]["ms"])
-        N = NW * NH
+        iters_mean = main_leg["iterations_mean"]
+        fixed = float(FIXED_BYTES.get(warm_mode, 224))
+        per_it = 124.0 + 44.0 / 3.0
+        bts = N * (fixed + per_it * iters_mean)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rods": ncells, "pcg_iterations": int(iters),
-                       "pcg_iterations_mean": iters_mean,
-                       "relres": relres, "rtol": 1e-12, "mg_levels": int(g.stats().levels),
-                       "parallelism": f"layer-per-gpu x{world}",
-                       "l2": "working set (6 fine fp64 vectors = 201 MB + MG hierarchy) exceeds the 126 MB L2; no explicit flush",
-                       "initial_guess": ("image ring (warm mode 7, opt-in): fixed extrapolation through the last <= 7 solutions plus a "
-                                         "least-squares correction in the backward-difference basis; stop test relative to the "
-                                         "right-hand side (rtol 1e-12) whatever the guess") if warm_mode == 7 else
-                                        "best of {zero, previous solution, linear / quadratic / cubic / quartic extrapolation "
-                                        "of the previous solutions} (warm mode 6; mode 4, the default up to 512^2 nodes, has "
-                                        "the least-squares combination of the last three instead of cubic and quartic), "
-                                        "picked on the device by residual norm; stop test relative to the right-hand side "
-                                        "(rtol 1e-12) whatever the guess",
-                       "warm_mode": warm_mode, "ring_check": ring_check,
-                       "last_guess": int(g.last_guess()),
+            "config": {"workload": WORKLOAD, "colony": args.colony, "rods": ncells,
+                       "colony_note": "rods advance 0.05-0.2 node per step along their axis and turn (+ exponential growth, "
+                                      "ratchet and division with `growing`); every step uses that step's records"
+                                      if args.colony != "static" else "records never change",
+                       "pcg_iterations": main_leg["iterations_last"], "pcg_iterations_mean": iters_mean,
+                       "relres": main_leg["relres"], "true_relres_next_step": true_relres, "rtol": 1e-12,
+                       "mg_levels": int(g.stats().levels), "parallelism": f"layer-per-gpu x{world}",
+                       "l2": "working set (6 fine fp64 vectors = 201 MB + MG hierarchy) exceeds the 126 MB L2; no explicit flush "
+                             "in the step legs; the isolated-kernel roofline timings flush L2 before every launch",
+                       "warm_mode": warm_mode, "last_guess": int(g.last_guess()),
                        "dof_updates_per_sec": value * N},
-            "clocks": clocks,
+            "clocks": main_leg.get("clocks"),
             "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": int(rec_pin.numel() * 8 + amt_pin.numel() * 8),
+                    "h2d_bytes_per_step": int(ncells * 16 * 8 + amt_pin.numel() * 8),
                     "d2h_bytes_per_step": int(out_pin.numel() * 8 + 8),
-                    "path": "eqgpu_cells_upload+gather+scatter+step with pinned host buffers (field stays in HBM)"},
-            "e2e_compat": {"value": world * 1e3 / ms_compat, "unit": UNIT,
-                           "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
-                           "path": "eqgpu_step_host: fenicsInterface::stepDiffusion contract, full solution_vector in/out"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": f"k_{dom} (level 0, 2048^2)", "achieved": roof[dom]["gbs"],
+                    "path": "eqgpu_cells_upload (this step's records) + gather + scatter + step with pinned host buffers "
+                            "(field stays in HBM)"},
+            "gpu_launches": main_leg["launches"],
+            "roofline": {"bound": "hbm", "kernel": f"k_{dom} (level 0, {NW}x{NH})", "achieved": roof[dom]["gbs"],
                          "peak": peak, "unit": "GB/s", "frac": roof[dom]["gbs"] / peak,
                          "traffic": ncu_traffic(dom) if (NW, NH) == (2048, 2048) else None,
-                         "traffic_note": "bytes/launch, dram__bytes_read.sum + dram__bytes_write.sum from the ncu "
-                                         "--set full capture in profiles/ (below the algorithmic bytes where "
-                                         "freshly written vectors are still in the 126 MB L2)",
+                         "traffic_note": "STATIC: bytes/launch, dram__bytes_read.sum + dram__bytes_write.sum from the committed "
+                                         "ncu --set full capture in profiles/, not measured in this run",
+                         "timing": "each launch bracketed by CUDA events on the launching stream, L2 flushed "
+                                   "(256 MB memset) before every launch",
                          "peak_source": peak_src, "kernels": roof,
                          "step_ideal_frac": (16.0 * N / (ms_step * 1e-3) / 1e9) / peak,
-                         # whole step, algorithmic bytes of DESIGN.md section 5: per PCG iteration 124 B/DOF on
-                         # level 0 (presmooth 18, postsmooth 26, apply_p 32, update_r 24, update_x 24) + 44/3 on the
-                         # coarser levels; per step 224 B/DOF for the warm start (k_init_tile 96, k_impose 96,
-                         # k_finish_x 32; isotropic one-GPU path with the five-solution history)
-                         # (warm mode 7, image ring at depth 7: k_init_tile without history 24, copy of the right-hand
-                         # side 16, k_ring_gram 64, k_ring_impose 136, k_finish_x 32, k_ring_image 24 = 296)
-                         "step_algorithmic": (lambda fixed: (lambda bts: {
-                             "bytes": bts, "gbs": bts / (ms_step * 1e-3) / 1e9, "frac": bts / (ms_step * 1e-3) / 1e9 / peak,
-                             "formula": f"N*({fixed:.0f} + (124 + 44/3)*mean_iterations)"})(
-                             N * (fixed + (124.0 + 44.0 / 3.0) * iters_mean)))(
-                             296.0 if warm_mode == 7 else 224.0)},
+                         # whole step, algorithmic bytes of DESIGN.md section 5: per PCG iteration 124 B/DOF on level 0
+                         # (presmooth 18, postsmooth 26, apply_p 32, update_r 24, update_x 24) + 44/3 on the coarser
+                         # levels; per step the starting-guess and step-tail passes (`fixed`, by warm mode)
+                         "step_algorithmic": {"bytes": bts, "gbs": bts / (ms_step * 1e-3) / 1e9,
+                                              "frac": bts / (ms_step * 1e-3) / 1e9 / peak,
+                                              "formula": f"N*({fixed:.0f} + (124 + 44/3)*mean_iterations)"}},
         }
+        if ms_compat is not None:
+            line["e2e_compat"] = {"value": world * 1e3 / ms_compat, "unit": UNIT,
+                                  "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
+                                  "path": "eqgpu_step_host: fenicsInterface::stepDiffusion contract, full solution_vector in/out"}
+        if "static" in side:
+            line["value_static"] = side["static"]["value"]
+            line["config"]["static"] = {k: side["static"][k] for k in ("ms_per_step", "iterations_mean", "launches")}
+        if "cold" in side:
+            line["value_cold"] = side["cold"]["value"]
+            line["config"]["cold"] = {k: side["cold"][k] for k in ("ms_per_step", "iterations_mean", "launches")}
+        line["value_" + args.colony] = value
+        if slab is not None:
+            line["slab"] = slab
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_fd() if args.config == 6 else cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline_subprocess(args.colony)
         print(json.dumps(line), flush=True)
     g.close()
     if world > 1:

@@ -35,7 +35,7 @@ API_SYMBOLS = [
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
     "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
     "eqgpu_last_guess", "eqgpu_cells_tensor", "eqgpu_get_tensor",
-    "eqgpu_ls_solve3", "eqgpu_ring_solve",
+    "eqgpu_ls_solve3", "eqgpu_ring_solve", "eqgpu_cells_upload_device", "eqgpu_get_warm_start",
 ]
 
 
@@ -242,9 +242,12 @@ class GpuHSL:
     def get_field(self, out=None):
         """Whole-field host array; in slab mode only this rank's owned rows are (over)written."""
         if out is not None:
-            u = _f64(out)
-            self._ck(lib().eqgpu_get_field(self._h, _dp(u)))
-            return u
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous
+                    and out.size == self.N):
+                raise ValueError("get_field(out=...) needs a C-contiguous float64 array of nW*nH elements "
+                                 "(anything else would be copied and the caller's buffer never written)")
+            self._ck(lib().eqgpu_get_field(self._h, _dp(out)))
+            return out
         u = np.zeros(self.N)
         self._ck(lib().eqgpu_get_field(self._h, _dp(u)))
         return u
@@ -310,6 +313,12 @@ class GpuHSL:
         self._ck(lib().eqgpu_cells_upload(self._h, _dp(rec), C.c_int64(self.ncells),
                                           C.c_double(nodes_per_micron)))
 
+    def upload_cells_device(self, dev_ptr: int, ncells: int, nodes_per_micron):
+        """eqgpu_cells_upload_device: records already in HBM (stream-ordered copy, no host sync)."""
+        self.ncells = int(ncells)
+        self._ck(lib().eqgpu_cells_upload_device(self._h, C.cast(dev_ptr, C.POINTER(C.c_double)), C.c_int64(self.ncells),
+                                                 C.c_double(nodes_per_micron)))
+
     def raster(self, cap=512):
         counts = np.zeros(self.ncells, dtype=np.int32)
         nodes = np.full((self.ncells, cap), -1, dtype=np.int64)
@@ -330,6 +339,9 @@ class GpuHSL:
         solutions and their images, fixed extrapolation plus a least-squares correction in the backward-difference
         basis).  Default: 4 up to 512^2 nodes, 6 above."""
         self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
+
+    def warm_mode(self) -> int:
+        return int(lib().eqgpu_get_warm_start(self._h))
 
     def last_guess(self) -> int:
         """0 field as given, 1 zero, 2 previous solution, 3 linear, 4 quadratic extrapolation, 5 least-squares

@@ -84,6 +84,8 @@ int eqgpu_set_warm_start(eqgpu_solver *s, int mode)
     return 0;
 }
 
+int eqgpu_get_warm_start(eqgpu_solver *s) { return s ? s->warm : EQGPU_EINVAL; }
+
 int eqgpu_ls_solve3(const double *G, const double *f, double bb, double *c, double *pred)
 {
     if (!G || !f || !c || !pred) return EQGPU_EINVAL;
@@ -348,26 +350,46 @@ int eqgpu_get_channel_flux(eqgpu_solver *s, double *ft, double *fb)
     return 0;
 }
 
+static int cells_reserve(eqgpu_solver *s, int64_t n)
+{
+    if (n <= s->cells_cap) return 0;
+    cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt);
+    s->cells = nullptr; s->cell_vals = nullptr; s->cell_counts = nullptr; s->cell_amt = nullptr;
+    s->cells_cap = 0;
+    const int64_t cap = n + n / 4 + 64;
+    EQ_CUDA(cudaMalloc(&s->cells, sizeof(double) * EQGPU_CELL_STRIDE * cap));
+    EQ_CUDA(cudaMalloc(&s->cell_vals, sizeof(double) * cap));
+    EQ_CUDA(cudaMalloc(&s->cell_amt, sizeof(double) * cap));
+    EQ_CUDA(cudaMemset(s->cell_amt, 0, sizeof(double) * cap));
+    EQ_CUDA(cudaMalloc(&s->cell_counts, sizeof(int32_t) * cap));
+    s->cells_cap = cap;
+    return 0;
+}
+
 int eqgpu_cells_upload(eqgpu_solver *s, const double *rec, int64_t n, double npm)
 {
     CHECK_S(s);
     if (n < 0 || (n > 0 && !rec) || !(npm > 0)) { s->set_error("bad cell upload arguments"); return EQGPU_EINVAL; }
-    if (n > s->cells_cap) {
-        cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt);
-        s->cells = nullptr; s->cell_vals = nullptr; s->cell_counts = nullptr; s->cell_amt = nullptr;
-        const int64_t cap = n + n / 4 + 64;
-        EQ_CUDA(cudaMalloc(&s->cells, sizeof(double) * EQGPU_CELL_STRIDE * cap));
-        EQ_CUDA(cudaMalloc(&s->cell_vals, sizeof(double) * cap));
-        EQ_CUDA(cudaMalloc(&s->cell_amt, sizeof(double) * cap));
-        EQ_CUDA(cudaMemset(s->cell_amt, 0, sizeof(double) * cap));
-        EQ_CUDA(cudaMalloc(&s->cell_counts, sizeof(int32_t) * cap));
-        s->cells_cap = cap;
-    }
+    int rc = cells_reserve(s, n);
+    if (rc) return rc;
     s->ncells = n;
     s->counts_valid = false;
     s->npm = npm;
     if (n) EQ_CUDA(cudaMemcpyAsync(s->cells, rec, sizeof(double) * EQGPU_CELL_STRIDE * n, cudaMemcpyHostToDevice, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int eqgpu_cells_upload_device(eqgpu_solver *s, const double *d_rec, int64_t n, double npm)
+{
+    CHECK_S(s);
+    if (n < 0 || (n > 0 && !d_rec) || !(npm > 0)) { s->set_error("bad cell upload arguments"); return EQGPU_EINVAL; }
+    int rc = cells_reserve(s, n);
+    if (rc) return rc;
+    s->ncells = n;
+    s->counts_valid = false;
+    s->npm = npm;
+    if (n) EQ_CUDA(cudaMemcpyAsync(s->cells, d_rec, sizeof(double) * EQGPU_CELL_STRIDE * n, cudaMemcpyDeviceToDevice, s->stream));
     return 0;
 }
 
@@ -379,7 +401,11 @@ int eqgpu_cells_raster(eqgpu_solver *s, int32_t *counts, int64_t *nodes, int32_t
     long long *d_nodes = nullptr;
     if (cap > 0) {
         EQ_CUDA(cudaMalloc(&d_nodes, sizeof(long long) * (size_t)cap * s->ncells));
-        EQ_CUDA(cudaMemsetAsync(d_nodes, 0xff, sizeof(long long) * (size_t)cap * s->ncells, s->stream));
+        if (cudaMemsetAsync(d_nodes, 0xff, sizeof(long long) * (size_t)cap * s->ncells, s->stream) != cudaSuccess) {
+            cudaFree(d_nodes);
+            s->set_error("raster scratch memset failed");
+            return EQGPU_ECUDA;
+        }
     }
     int rc = cells_raster(s, s->cell_counts, d_nodes, cap);
     if (!rc) {

@@ -439,11 +439,8 @@ static int cells_scatter_binned(eqgpu_solver *s, const double *d_amount)
     const int blocks = (int)((n + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK), tb = (int)((n + 255) / 256);
     const Level &l0 = s->levels[0];
     const size_t smem = sizeof(double) * BIN_W * BIN_W;
-    static bool attr_set = false;
-    if (!attr_set) {
-        EQ_CUDA(cudaFuncSetAttribute(k_cells_scatter_binned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // per device, not per process: set on every call (a host-side table write)
+    EQ_CUDA(cudaFuncSetAttribute(k_cells_scatter_binned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EQ_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(int) * (ntiles + 1), s->stream));
     k_cells_raster<<<blocks, 32 * CELLS_PER_BLOCK, 0, s->stream>>>(s->cells, n, s->npm, nH, nW, nte, s->cell_counts,
                                                                    nullptr, 0);

@@ -102,15 +102,22 @@ int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth)
     if (!below && !above) return 0;
     const size_t nx = (size_t)L.nx, cnt = nx * depth;
     EQ_NCCL(g_nccl.GroupStart());
+    // an error inside the group still closes it (an open group would swallow every later NCCL call of the process)
+    ncclResult_t bad = (ncclResult_t)0;
+    auto note = [&](ncclResult_t r) { if (r != 0 && bad == 0) bad = r; };
     if (below) {
-        EQ_NCCL(g_nccl.Send(v + (size_t)L.own0 * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
-        EQ_NCCL(g_nccl.Recv(v + (size_t)(L.own0 - depth) * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+        note(g_nccl.Send(v + (size_t)L.own0 * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+        note(g_nccl.Recv(v + (size_t)(L.own0 - depth) * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
     }
     if (above) {
-        EQ_NCCL(g_nccl.Send(v + (size_t)(L.own1 - depth) * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
-        EQ_NCCL(g_nccl.Recv(v + (size_t)L.own1 * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+        note(g_nccl.Send(v + (size_t)(L.own1 - depth) * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+        note(g_nccl.Recv(v + (size_t)L.own1 * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
     }
-    EQ_NCCL(g_nccl.GroupEnd());
+    note(g_nccl.GroupEnd());
+    if (bad != 0) {
+        s->set_error(std::string("halo exchange: ") + g_nccl.GetErrorString(bad));
+        return EQGPU_ECUDA;
+    }
     return 0;
 }
 

@@ -33,7 +33,7 @@ void gpuFD::create()
     for (int w = 0; w < 4; ++w) {
         if (Nc[w] == 0.0) {
             p.bc_type[w] = EQGPU_BC_DIRICHLET;
-            p.bc_value[w] = Dc[w] != 0.0 ? BV[w] / Dc[w] : BV[w];
+            p.bc_value[w] = BV[w];   // ApplyBoundaryConditions writes RHS = BV and ignores Dc ("if N==0, then D must be 1", diffuclass.cpp:232)
         } else if (Dc[w] == 0.0) {
             if (BV[w] != 0.0) throw std::runtime_error("gpuFD: a non-zero pure-Neumann flux is not supported");
             p.bc_type[w] = EQGPU_BC_NEUMANN;

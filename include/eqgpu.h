@@ -162,6 +162,9 @@ EQGPU_API int eqgpu_get_channel_flux(eqgpu_solver *s, double *flux_top, double *
  *  src/abm/Ecoli.cpp:36-63). */
 #define EQGPU_CELL_STRIDE 16
 EQGPU_API int eqgpu_cells_upload(eqgpu_solver *s, const double *records, int64_t ncells, double nodes_per_micron);
+/* Same, from records that already sit in DEVICE memory (a controller that stages several steps of records in HBM,
+ * or builds them on the device): a stream-ordered device-to-device copy, no host synchronisation. */
+EQGPU_API int eqgpu_cells_upload_device(eqgpu_solver *s, const double *d_records, int64_t ncells, double nodes_per_micron);
 /* findInteriorPoints: counts[k] points of cell k, node ids (iy*nW+jx) in the
  * reference's push_back order into nodes[k*cap .. ] (at most cap written). */
 EQGPU_API int eqgpu_cells_raster(eqgpu_solver *s, int32_t *counts, int64_t *nodes, int32_t cap);
@@ -223,6 +226,8 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
  * eqgpu_set_field, and is kept on the single-GPU isotropic path only (elsewhere the call is accepted and
  * mode 0 is what runs). */
 EQGPU_API int eqgpu_set_warm_start(eqgpu_solver *s, int mode);
+/* The mode in effect (the size-dependent default, EQGPU_WARM, or the last eqgpu_set_warm_start). */
+EQGPU_API int eqgpu_get_warm_start(eqgpu_solver *s);
 /* Which guess the last step started from: 0 field as given, 1 zero, 2 previous solution, 3 linear,
  * 4 quadratic extrapolation, 5 least-squares combination, 6 cubic, 7 quartic extrapolation, 8 image-ring guess
  * (mode 7). */

@@ -10,6 +10,7 @@
 #include "abm/eQabm.h"   // /root/reference/src/abm/eQabm.h (-I$(REF)/src)
 
 #include <cstring>
+#include "../eq_b200/host/cellRecords.h"
 
 // src/main.cpp:44 defines this static in the executable; the parity pin is not linked against main.cpp
 eQ::data::parametersType eQ::data::parameters;
@@ -119,16 +120,9 @@ REF_API void ref_abm_move_cell(void *h, long k, double ax, double ay, double aan
 // The 16-double record of include/eqgpu.h, read from the reference's own objects, for cell k in list order.
 REF_API void ref_abm_record(void *h, long k, double *rec)
 {
+    // the PRODUCT's record builder (eq_b200/host/cellRecords.h), instantiated on the reference's own Ecoli
     auto c = nth_cell((CellRef *)h, k);
-    const cpmEcoli &m = *c->cpmCell;
-    const cpVect p = cpBodyGetPosition(m.bodyA);
-    rec[0] = p.x; rec[1] = p.y;
-    rec[2] = m.bodyA->transform.a; rec[3] = m.bodyA->transform.b;      // rot = (cos, sin) of bodyA
-    rec[4] = m.offset; rec[5] = m.vertsA[1].x; rec[6] = m.radius;
-    rec[7] = c->polePositionA.first; rec[8] = c->polePositionA.second;
-    rec[9] = c->polePositionB.first; rec[10] = c->polePositionB.second;
-    rec[11] = c->getCenter_x(); rec[12] = c->getCenter_y(); rec[13] = c->getLengthMicrons();
-    rec[14] = cos(c->getAngle()); rec[15] = sin(c->getAngle());
+    eqgpu::cellRecord(*c, rec);
 }
 
 REF_API int ref_abm_point_in_cell(void *h, long k, double x, double y)

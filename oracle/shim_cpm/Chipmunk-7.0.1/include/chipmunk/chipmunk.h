@@ -91,6 +91,8 @@ static inline void cpBodySetPosition(cpBody *b, cpVect p) { b->p = p; cp_shim_se
 static inline void cpBodySetAngle(cpBody *b, cpFloat a) { b->a = a; cp_shim_set_transform(b); }
 static inline void cpBodySetVelocity(cpBody *b, cpVect v) { b->v = v; }
 static inline cpVect cpBodyGetPosition(const cpBody *b) { return cpTransformPoint(b->transform, cpvzero); }
+// cpBody.c (7.0.1): the unit rotation vector stored by cpBodySetAngle, (cos a, sin a)
+static inline cpVect cpBodyGetRotation(const cpBody *b) { return cpv(b->transform.a, b->transform.b); }
 static inline cpFloat cpBodyGetAngle(const cpBody *b) { return b->a; }
 static inline cpVect cpBodyGetVelocity(const cpBody *b) { return b->v; }
 static inline cpFloat cpBodyGetAngularVelocity(const cpBody *b) { return b->w; }
