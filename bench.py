@@ -370,6 +370,7 @@ def run_slab_leg(args, rank, local_rank, world, stream, ids_fn):
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = g.stats().kernel_launches
+    c0 = g.comm_stats()
     e0.record(stream)
     for k in range(k_steps):
         step(k_warm + k)
@@ -379,7 +380,14 @@ def run_slab_leg(args, rank, local_rank, world, stream, ids_fn):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / k_steps
     st = g.stats()
-    comm = g.comm_stats() if hasattr(g, "comm_stats") else {}
+    c1 = g.comm_stats()
+    it_sum = max(1, sum(its[-k_steps:]))
+    comm = {"allreduce_calls_per_step": (c1["allreduce_calls"] - c0["allreduce_calls"]) / k_steps,
+            "allreduce_calls_per_iteration": (c1["allreduce_calls"] - c0["allreduce_calls"] - 2 * k_steps) / it_sum,
+            "allreduce_doubles_per_step": (c1["allreduce_doubles"] - c0["allreduce_doubles"]) / k_steps,
+            "halo_exchanges_per_step": (c1["halo_exchanges"] - c0["halo_exchanges"]) / k_steps,
+            "halo_bytes_sent_per_step_this_rank": (c1["halo_bytes_sent"] - c0["halo_bytes_sent"]) / k_steps,
+            "transport": "NCCL send/recv + all-reduce over NVLink/NVSwitch, stream-ordered"}
     out.update({"metric": f"hsl_diffusion_steps_per_sec_{nW}x{nH}_row_slab", "value": 1e3 / ms, "unit": UNIT,
                 "ms_per_step": ms, "steps": k_steps, "warmup": k_warm, "scaling": "weak",
                 "workload": f"configs[4] style: {nW}x{nH} nodes in {world} row slabs of 2048 rows, {nrec} rods "

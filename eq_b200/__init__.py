@@ -35,7 +35,7 @@ API_SYMBOLS = [
     "eqgpu_bench_kernel", "eqgpu_create_slab", "eqgpu_nccl_unique_id", "eqgpu_slab_rows",
     "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
     "eqgpu_last_guess", "eqgpu_cells_tensor", "eqgpu_get_tensor",
-    "eqgpu_ls_solve3", "eqgpu_ring_solve", "eqgpu_cells_upload_device", "eqgpu_get_warm_start",
+    "eqgpu_ls_solve3", "eqgpu_ring_solve", "eqgpu_cells_upload_device", "eqgpu_get_warm_start", "eqgpu_apply_preconditioner", "eqgpu_comm_stats",
 ]
 
 
@@ -292,6 +292,13 @@ class GpuHSL:
         self._ck(lib().eqgpu_apply_operator(self._h, _dp(x), _dp(y), C.c_int(1 if constrained else 0)))
         return y
 
+    def apply_preconditioner(self, r):
+        """z = B r: one V-cycle of the PCG preconditioner (verification hook; r zero on Dirichlet rows)."""
+        r = _f64(r)
+        z = np.empty(self.N)
+        self._ck(lib().eqgpu_apply_preconditioner(self._h, _dp(r), _dp(z)))
+        return z
+
     def build_rhs(self, u0):
         u0 = _f64(u0)
         b = np.empty(self.N)
@@ -339,6 +346,13 @@ class GpuHSL:
         solutions and their images, fixed extrapolation plus a least-squares correction in the backward-difference
         basis).  Default: 4 up to 512^2 nodes, 6 above."""
         self._ck(lib().eqgpu_set_warm_start(self._h, C.c_int(mode)))
+
+    def comm_stats(self) -> dict:
+        """Row-slab mode: cumulative communication counters of this rank (eqgpu_comm_stats)."""
+        out = (C.c_int64 * 4)()
+        self._ck(lib().eqgpu_comm_stats(self._h, out))
+        return {"allreduce_calls": int(out[0]), "allreduce_doubles": int(out[1]), "halo_exchanges": int(out[2]),
+                "halo_bytes_sent": int(out[3])}
 
     def warm_mode(self) -> int:
         return int(lib().eqgpu_get_warm_start(self._h))

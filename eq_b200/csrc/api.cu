@@ -81,6 +81,15 @@ int eqgpu_set_warm_start(eqgpu_solver *s, int mode)
     if (!s) return EQGPU_EINVAL;
     if (mode < 0 || mode > 7) { s->set_error("warm-start mode must be 0..7"); return EQGPU_EINVAL; }
     s->warm = mode;
+    s->nh_cap = 5; s->low_gain_steps = 0; s->probe_countdown = 0;
+    return 0;
+}
+
+int eqgpu_comm_stats(eqgpu_solver *s, int64_t out[4])
+{
+    if (!s || !out) return EQGPU_EINVAL;
+    out[0] = s->comm_allreduce_calls; out[1] = s->comm_allreduce_doubles; out[2] = s->comm_exchange_groups;
+    out[3] = s->comm_halo_bytes;
     return 0;
 }
 
@@ -500,6 +509,19 @@ int eqgpu_apply_operator(eqgpu_solver *s, const double *hx, double *hy, int cons
     if (rc) return rc;
     EQ_CUDA(cudaMemcpyAsync(hy, s->Ap, bytes, cudaMemcpyDeviceToHost, s->stream));
     EQ_CUDA(cudaMemsetAsync(s->pv, 0, bytes, s->stream));
+    EQ_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int eqgpu_apply_preconditioner(eqgpu_solver *s, const double *hr, double *hz)
+{
+    CHECK_S(s);
+    if (!hr || !hz) return EQGPU_EINVAL;
+    const size_t bytes = sizeof(double) * s->N;
+    EQ_CUDA(cudaMemcpyAsync(s->r, hr, bytes, cudaMemcpyHostToDevice, s->stream));
+    int rc = solver_precond(s);
+    if (rc) return rc;
+    EQ_CUDA(cudaMemcpyAsync(hz, s->z, bytes, cudaMemcpyDeviceToHost, s->stream));
     EQ_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }

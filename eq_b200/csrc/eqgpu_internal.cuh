@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libeqgpu.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -48,6 +49,9 @@ struct LevelDev {
     // pre-offset so that row gi lives at ptr[gi*nx]), rows [wlo, whi) may be written by this rank, and
     // tile rows start at the even row tbase.  Single GPU: 0, ny, 0, ny, 0.
     int slo, shi, wlo, whi, tbase;
+    // closed form of the padded cell sizes (uniform cells, only the last one may be narrower): regular and last cell
+    // widths / heights of the GLOBAL grid, so that set-up code needs no global loads (mg_stream.cuh)
+    double hxr, hxl, hyr, hyl;
 };
 
 struct CGScalars {
@@ -72,6 +76,8 @@ struct CGScalars {
     // correction), the squared residual the fit predicts, the ring depth used
     double ringw[8], rrR;
     int ring_k, pad3;
+    // slab mode, start of a step: the five rank-local sums of k_init_tile travel in ONE all-reduce
+    double red_src[6], red_dst[6];
 };
 
 struct Level {
@@ -83,6 +89,9 @@ struct Level {
     double *d_hx = nullptr, *d_ihx = nullptr, *d_hy = nullptr, *d_ihy = nullptr;
     double *x = nullptr, *b = nullptr, *t = nullptr;  // solution, rhs, scratch
     double *t11 = nullptr, *t22 = nullptr, *t12 = nullptr;
+    // streaming smoothers (mg_stream.cuh): TMA descriptors of the level's b and t vectors (row pitch 16-byte aligned)
+    CUtensorMap map_b{}, map_t{};
+    bool tma = false;
     size_t n() const { return (size_t)dev.nx * dev.ny; }
 };
 
@@ -125,6 +134,10 @@ struct eqgpu_solver {
                                    // extrapolation of the last four, 6 = 5 + quartic of the last five
                                    // (solver_setup: 4 up to 512^2 nodes, 6 above)
     int last_guess = 0;
+    // adaptive history depth: when the extrapolations stop paying (a colony whose rods move: the change of the sources is
+    // not predictable from the history) only the previous solution is walked; the full depth is probed again periodically
+    int nh_cap = 5, low_gain_steps = 0, probe_countdown = 0;
+    bool warm_adaptive = true;
     // warm mode 7 (opt-in; profiles/r01_guess_study.md): ring of the last RING_MAX solutions and of their images
     // A_ff h (free rows), slot (ring_head + i) % RING_MAX = i-th newest; ring_b keeps this step's reduced right-hand
     // side until the step ends, when the new image is b - r_final (no operator walk)
@@ -140,12 +153,20 @@ struct eqgpu_solver {
     bool slab = false;
     int slab_rank = 0, slab_world = 1;
     void *nccl_comm = nullptr;
+    long long comm_allreduce_calls = 0, comm_allreduce_doubles = 0, comm_exchange_groups = 0, comm_halo_bytes = 0;   // cumulative, this rank
     int halo = 1;                  // halo rows kept per neighbour (1 unfused, 6 for the tile kernels)
     bool slab_fused = false;
     int scatter_mode = 0;          // 0 direct global atomics, 1 shared-memory-binned
     int *bin_ints = nullptr;       // binned scatter scratch
     long long bin_cap_cells = 0;
     int bin_cap_tiles = 0;
+    CUtensorMap map_z{}, map_pv{}, map_pv2{};   // level-0 z and the two search-direction buffers (ks_apply_p)
+    bool tma_p = false;
+    const double *map_pv_ptr = nullptr;   // the buffer map_pv describes
+    bool stream_uni = true;        // constant-bank coefficient instances where every column is regular or Dirichlet
+    bool stream_apply = false;     // ks_apply_p instead of the tile k_apply_p
+    bool stream_smooth = false;    // warp-streaming smoothers (mg_stream.cuh) instead of the shared-memory tile kernels
+    int stream_min_nodes = 0;      // ... on levels with at least this many nodes
     bool use_cluster = false;      // deepest levels on a 16-CTA cluster (k_ctail) instead of one CTA (k_tail)
     int ctail_first = 0, ctail_ncta = 0;
     size_t ctail_smem = 0;
@@ -192,6 +213,7 @@ void solver_teardown(eqgpu_solver *s);
 int solver_step(eqgpu_solver *s);
 int solver_apply(eqgpu_solver *s, const double *dx, double *dy, bool constrained);
 int solver_rhs(eqgpu_solver *s, const double *du0, double *db);
+int solver_precond(eqgpu_solver *s);   // z = B r on the solver's own vectors (verification hook)
 int solver_refresh_levels(eqgpu_solver *s);
 int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes);
 void solver_ls_solve3(const double G[6], const double f[3], double bb, double c[3], double *pred);
@@ -202,6 +224,7 @@ int slab_init_comm(eqgpu_solver *s, const void *unique_id);
 void slab_destroy_comm(eqgpu_solver *s);
 int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth = 1);  // halo rows of a level vector (local view)
 int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count);  // sum over ranks, stream-ordered
+int slab_exchange2(eqgpu_solver *s, const LevelDev &L, double *v1, double *v2, int depth);   // two vectors, one NCCL group
 int slab_unique_id(void *out128);
 // ---- cells.cu ----
 int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap);

@@ -95,7 +95,7 @@ void slab_destroy_comm(eqgpu_solver *s)
 
 // Refresh `depth` halo rows of a level vector (local view L): my first/last `depth` owned rows go to the
 // neighbours below/above, theirs arrive in my halo rows.  Stream-ordered; every rank issues the same sequence.
-int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth)
+int slab_exchange2(eqgpu_solver *s, const LevelDev &L, double *v1, double *v2, int depth)
 {
     ncclComm_t comm = (ncclComm_t)s->nccl_comm;
     const bool below = L.own0 > 0, above = L.own1 < L.ny;
@@ -105,15 +105,23 @@ int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth)
     // an error inside the group still closes it (an open group would swallow every later NCCL call of the process)
     ncclResult_t bad = (ncclResult_t)0;
     auto note = [&](ncclResult_t r) { if (r != 0 && bad == 0) bad = r; };
-    if (below) {
-        note(g_nccl.Send(v + (size_t)L.own0 * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
-        note(g_nccl.Recv(v + (size_t)(L.own0 - depth) * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
-    }
-    if (above) {
-        note(g_nccl.Send(v + (size_t)(L.own1 - depth) * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
-        note(g_nccl.Recv(v + (size_t)L.own1 * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+    double *vs[2] = {v1, v2};
+    for (int q = 0; q < 2; ++q) {
+        double *v = vs[q];
+        if (!v) continue;
+        if (below) {
+            note(g_nccl.Send(v + (size_t)L.own0 * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+            note(g_nccl.Recv(v + (size_t)(L.own0 - depth) * nx, cnt, ncclFloat64, s->slab_rank - 1, comm, s->stream));
+            s->comm_halo_bytes += (long long)cnt * 8;
+        }
+        if (above) {
+            note(g_nccl.Send(v + (size_t)(L.own1 - depth) * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+            note(g_nccl.Recv(v + (size_t)L.own1 * nx, cnt, ncclFloat64, s->slab_rank + 1, comm, s->stream));
+            s->comm_halo_bytes += (long long)cnt * 8;
+        }
     }
     note(g_nccl.GroupEnd());
+    s->comm_exchange_groups++;
     if (bad != 0) {
         s->set_error(std::string("halo exchange: ") + g_nccl.GetErrorString(bad));
         return EQGPU_ECUDA;
@@ -121,8 +129,12 @@ int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth)
     return 0;
 }
 
+int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth) { return slab_exchange2(s, L, v, nullptr, depth); }
+
 int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count)
 {
     EQ_NCCL(g_nccl.AllReduce(src, dst, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)s->nccl_comm, s->stream));
+    s->comm_allreduce_calls++;
+    s->comm_allreduce_doubles += count;
     return 0;
 }

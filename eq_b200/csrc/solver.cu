@@ -8,6 +8,7 @@
 #include "eqgpu_internal.cuh"
 #include "mg_fused.cuh"
 #include "mg_cluster.cuh"
+#include "mg_stream.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -401,9 +402,9 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
     }
     double tot[6];
     if (grid_reduce<6>(v, partials, counter, tot)) {
-        if (slab) {
-            sc->part_rr0 = tot[0]; sc->part_b2 = tot[1]; sc->part_rrD = tot[2]; sc->part_rrE = tot[3];
-            sc->part_rrF = tot[4];
+        if (slab) {   // rank-local sums: one all-reduce of five doubles follows, k_slab_unpack hands them out
+            sc->red_src[0] = tot[0]; sc->red_src[1] = tot[1]; sc->red_src[2] = tot[2]; sc->red_src[3] = tot[3];
+            sc->red_src[4] = tot[4];
         } else {
             sc->rr0 = tot[0]; sc->bnorm2 = tot[1]; sc->rrD = tot[2]; sc->rrE = tot[3]; sc->rrF = tot[4];
             sc->rrG = d4ok ? tot[5] : 1.0e300;
@@ -1082,6 +1083,13 @@ k_finish_x(size_t n, double *__restrict__ x, const double *__restrict__ p_odd, c
 
 __global__ void k_mark_x(CGScalars *sc) { sc->x_applied = sc->x_stamp; }
 
+// slab mode: the rank-summed start-of-step norms (one fused all-reduce) to where k_impose reads them
+__global__ void k_slab_unpack(CGScalars *sc)
+{
+    sc->rr0 = sc->red_dst[0]; sc->bnorm2 = sc->red_dst[1]; sc->rrD = sc->red_dst[2]; sc->rrE = sc->red_dst[3];
+    sc->rrF = sc->red_dst[4];
+}
+
 // iteration bookkeeping when ||r||^2 had to be summed over ranks first (slab mode)
 __global__ void k_book(CGScalars *sc)
 {
@@ -1270,6 +1278,7 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
         L.cD = a * b / 12.0;
     }
     L.icC = 1.0 / L.cC;
+    L.hxr = lv.hx_host.front(); L.hxl = lv.hx_host.back(); L.hyr = lv.hy_host.front(); L.hyl = lv.hy_host.back();
     L.hx = lv.d_hx; L.ihx = lv.d_ihx; L.hy = lv.d_hy; L.ihy = lv.d_ihy;
     L.d11 = lv.t11; L.d22 = lv.t22; L.d12 = lv.t12;
     // global view for the tile kernels: whole-grid index logic, windows saying which rows are stored / owned
@@ -1290,6 +1299,7 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
 
 static CTailDesc make_ctail_desc(eqgpu_solver *s, int first, int ncta);
 static CoarseW coarse_weights(eqgpu_solver *s);
+static bool make_field_map(CUtensorMap *map, double *base, int nx, int ny);
 
 int solver_setup(eqgpu_solver *s)
 {
@@ -1386,6 +1396,24 @@ int solver_setup(eqgpu_solver *s)
     }
     s->levels[0].x = s->z;
     s->levels[0].b = s->r;
+    // streaming smoothers: single GPU, isotropic operator; TMA descriptors where the pitch allows them
+    s->stream_smooth = !s->slab;
+    if (const char *e = getenv("EQGPU_STREAM")) s->stream_smooth = atoi(e) != 0 && !s->slab;
+    s->stream_min_nodes = 0;
+    if (const char *e = getenv("EQGPU_STREAM_MIN")) s->stream_min_nodes = atoi(e);
+    s->stream_uni = getenv("EQGPU_STREAM_UNI") == nullptr || atoi(getenv("EQGPU_STREAM_UNI")) != 0;
+    s->stream_apply = s->stream_smooth;
+    if (const char *e = getenv("EQGPU_STREAM_APPLY")) s->stream_apply = atoi(e) != 0 && s->stream_smooth;
+    s->map_pv_ptr = s->pv;
+    s->tma_p = s->stream_apply && getenv("EQGPU_NO_TMA") == nullptr &&
+               make_field_map(&s->map_z, s->z, s->levels[0].dev.nx, s->levels[0].dev.ny) &&
+               make_field_map(&s->map_pv, s->pv, s->levels[0].dev.nx, s->levels[0].dev.ny) &&
+               make_field_map(&s->map_pv2, s->pv2, s->levels[0].dev.nx, s->levels[0].dev.ny);
+    for (size_t l = 0; l + 1 < s->levels.size(); ++l) {
+        Level &lv = s->levels[l];
+        lv.tma = s->stream_smooth && getenv("EQGPU_NO_TMA") == nullptr &&
+                 make_field_map(&lv.map_b, lv.b, lv.dev.nx, lv.dev.ny) && make_field_map(&lv.map_t, lv.t, lv.dev.nx, lv.dev.ny);
+    }
     // ---- reductions ------------------------------------------------------
     dim3 g0 = grid2d(s->levels[0].dev);
     s->max_blocks = std::max<int>(g0.x * g0.y, 8 * s->num_sms);
@@ -1497,6 +1525,7 @@ int solver_setup(eqgpu_solver *s)
         s->warm = (size_t)p.nW * p.nH <= (size_t)512 * 512 ? 4 : 6;
         if (const char *e = getenv("EQGPU_WARM")) s->warm = std::max(0, std::min(atoi(e), 7));
         if (const char *e = getenv("EQGPU_LS_FORM")) s->ls_form = atoi(e) != 0 ? 1 : 0;   // tuning knob
+        if (const char *e = getenv("EQGPU_WARM_ADAPTIVE")) s->warm_adaptive = atoi(e) != 0;
         if ((s->defer_x || s->slab) && s->init_tile && s->warm > 0) {
             for (int k = 0; k < 5; ++k) {
                 EQ_CUDA(cudaMalloc(&s->uh[k], sizeof(double) * s->N));
@@ -1790,6 +1819,170 @@ static inline bool use_t32(const eqgpu_solver *s, const LevelDev &L, int to64)
     return (int)(g.x * g.y) < s->t32_below;
 }
 
+// ---- streaming smoothers (mg_stream.cuh): host side -------------------------------------------------------------------
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA descriptor of an nx x ny fp64 field (row-major, pitch nx) with a box of RB rows x 64 columns; false when the
+// driver entry point is missing or the pitch is not a multiple of 16 bytes (odd nx): the caller stages with cp.async.
+static bool make_field_map(CUtensorMap *map, double *base, int nx, int ny)
+{
+    static PFN_tensorMapEncodeTiled enc = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            enc = (PFN_tensorMapEncodeTiled)fn;
+        (void)cudaGetLastError();
+    }
+    if (!enc || (nx & 1) || (((size_t)base) & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
+    const cuuint64_t gstride[1] = {(cuuint64_t)nx * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)STRM::SWID, (cuuint32_t)STRM::RB};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool use_stream(const eqgpu_solver *s, const Level &lv)
+{
+    // (the only irregular rows the kernels tabulate are 0, ny-2 and ny-1: true for the uniform meshes and their
+    // coarsenings this library builds)
+    return s->stream_smooth && !s->slab && (long long)lv.dev.nx * lv.dev.ny >= s->stream_min_nodes && lv.dev.nx >= 8 &&
+           lv.dev.ny >= 8 && lv.dev.ireg_hi >= lv.dev.ny - 3;
+}
+
+// Every in-grid column of the level is regular or Dirichlet: the UNI kernel instances apply (coefficients as constant-bank
+// operands).  Natural-boundary wall columns and the narrower last cell of a coarse grid need per-lane sets.
+static bool uniform_columns(const LevelDev &F)
+{
+    return (F.dirmask & 1u) && (F.dirmask & 2u) && F.jreg_hi >= F.nx - 2 && F.ireg_hi >= 1;
+}
+
+template <int NU>
+static STRM::UniCoef<NU> uni_coef(const LevelDev &F, const SmoothW &sw)
+{
+    STRM::UniCoef<NU> U;
+    U.nC = -F.cC; U.nE = -F.cEW; U.nW = -F.cEW; U.nN = -F.cNS; U.nS = -F.cNS; U.nNE = -F.cD; U.nSW = -F.cD;
+    for (int k = 0; k < NU; ++k) U.wic[k] = sw.w[k] * F.icC;
+    return U;
+}
+
+// Resident CTAs of a streaming kernel on the whole device (registers decide: 64-thread CTAs of 100-250 registers).
+template <class K>
+static int stream_slots(const eqgpu_solver *s, K kernel, size_t smem)
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * STRM::WPC, smem) != cudaSuccess || nb < 1) nb = 4;
+    (void)cudaGetLastError();
+    return nb * s->num_sms;
+}
+
+// Task shape: strips of 64 columns, chunks of hs owned rows.  `lag` = rows the last sweep trails the entering row plus
+// what the output stage needs (pre: 2NU + 1, post: 2NU, apply: 2).  hs is chosen so that the grid is a whole number of
+// waves of resident CTAs (a 1.03-wave grid takes two task durations) at the smallest walked-rows x waves product.
+static STRM::StreamGeom stream_geom(const eqgpu_solver *s, const LevelDev &F, int halo, int lag, int slots)
+{
+    STRM::StreamGeom G;
+    G.halo = halo;
+    const int so = STRM::SWID - 2 * G.halo;
+    G.nstrips = (F.nx + so - 1) / so;
+    const int cx = (G.nstrips + STRM::WPC - 1) / STRM::WPC;
+    long long best = -1;
+    G.hs = 16;
+    for (int hs = 12; hs <= 192; hs += 2) {
+        const int nch = (F.ny + hs - 1) / hs;
+        const long long waves = ((long long)cx * nch + slots - 1) / slots;
+        const int steps = ((hs + halo + lag + STRM::RB - 1) / STRM::RB) * STRM::RB;
+        const long long cost = waves * (steps + 14);   // + set-up and drain of a task, in walk steps
+        if (best < 0 || cost <= best) { best = cost; G.hs = hs; }
+    }
+    if (const char *e = getenv("EQGPU_STREAM_HS")) G.hs = std::max(2, atoi(e) & ~1);   // tuning knob
+    G.nchunks = (F.ny + G.hs - 1) / G.hs;
+    G.nblk = (G.hs + G.halo + lag + STRM::RB - 1) / STRM::RB;
+    return G;
+}
+
+template <int NU>
+static void launch_pre_stream(eqgpu_solver *s, cudaStream_t st, int l, bool pdl_ok)
+{
+    Level &lv = s->levels[l], &cv = s->levels[l + 1];
+    const SmoothW sw = smooth_weights_n(NU);
+    const size_t smem = STRM::WPC * STRM::NSLOT * STRM::BLK_BYTES + STRM::WPC * STRM::NSLOT * sizeof(unsigned long long);
+    const CGScalars *scc = s->sc;
+    const STRM::UniCoef<NU> U = uni_coef<NU>(lv.dev, sw);
+    const int halo = (NU + 2) & ~1;   // even, >= NU + 1: the restriction reads one residual further
+#define SPRE(TMA, UNI)                                                                                               \
+    do {                                                                                                             \
+        const STRM::StreamGeom G = stream_geom(s, lv.dev, halo, 2 * NU + 1,                                          \
+                                               stream_slots(s, STRM::ks_presmooth<NU, TMA, UNI>, smem));             \
+        const dim3 grid((G.nstrips + STRM::WPC - 1) / STRM::WPC, G.nchunks);                                         \
+        LAUNCH_K(pdl_ok, (STRM::ks_presmooth<NU, TMA, UNI>), grid, dim3(32 * STRM::WPC), smem, st, lv.dev, cv.dev,   \
+                 lv.map_b, (const double *)lv.b, lv.t, cv.b, sw, U, G, scc);                                         \
+    } while (0)
+    const bool uni = s->stream_uni && uniform_columns(lv.dev);
+    if (lv.tma) { if (uni) SPRE(true, true); else SPRE(true, false); }
+    else { if (uni) SPRE(false, true); else SPRE(false, false); }
+#undef SPRE
+}
+
+template <int NU>
+static void launch_post_stream(eqgpu_solver *s, cudaStream_t st, int l)
+{
+    Level &lv = s->levels[l], &cv = s->levels[l + 1];
+    const SmoothW sw = smooth_weights_n(NU);
+    const size_t smem = 2 * STRM::WPC * STRM::NSLOT * STRM::BLK_BYTES + STRM::WPC * STRM::NSLOT * STRM::CBLK_BYTES +
+                        STRM::WPC * STRM::NSLOT * sizeof(unsigned long long);
+    double *out_dot = &s->sc->rz_new;
+    const STRM::UniCoef<NU> U = uni_coef<NU>(lv.dev, sw);
+    const int halo = (NU + 1) & ~1;   // even, >= NU
+#define SPOST(DOT, TMA, UNI)                                                                                          \
+    do {                                                                                                              \
+        const STRM::StreamGeom G = stream_geom(s, lv.dev, halo, 2 * NU,                                               \
+                                               stream_slots(s, STRM::ks_postsmooth<NU, DOT, TMA, UNI>, smem));        \
+        const dim3 grid((G.nstrips + STRM::WPC - 1) / STRM::WPC, G.nchunks);                                          \
+        LAUNCH_K(true, (STRM::ks_postsmooth<NU, DOT, TMA, UNI>), grid, dim3(32 * STRM::WPC), smem, st, lv.dev, cv.dev, \
+                 lv.map_b, lv.map_t, (const double *)lv.b, (const double *)lv.t, lv.x, (const double *)cv.x, sw, U, G, \
+                 s->sc, s->partials, s->counters + 1, out_dot);                                                       \
+    } while (0)
+    const bool uni = s->stream_uni && uniform_columns(lv.dev);
+    if (l == 0) {
+        if (lv.tma) { if (uni) SPOST(true, true, true); else SPOST(true, true, false); }
+        else { if (uni) SPOST(true, false, true); else SPOST(true, false, false); }
+    } else {
+        if (lv.tma) { if (uni) SPOST(false, true, true); else SPOST(false, true, false); }
+        else { if (uni) SPOST(false, false, true); else SPOST(false, false, false); }
+    }
+#undef SPOST
+}
+
+// p' = z + beta p, Ap', p'.Ap' on level 0 (pin -> pout)
+static void launch_apply_stream(eqgpu_solver *s, cudaStream_t st, bool pdl_ok, double *pin, double *pout)
+{
+    Level &l0 = s->levels[0];
+    const LevelDev &F = l0.dev;
+    const size_t smem = 2 * STRM::WPC * STRM::NSLOT * STRM::BLK_BYTES + STRM::WPC * STRM::NSLOT * sizeof(unsigned long long);
+    const CUtensorMap &mp = pin == s->map_pv_ptr ? s->map_pv : s->map_pv2;   // the descriptors belong to buffers, and pv / pv2 swap
+    SmoothW sw1{};
+    const STRM::UniCoef<1> U = uni_coef<1>(F, sw1);
+#define SAPPLY(TMA, UNI)                                                                                              \
+    do {                                                                                                              \
+        const STRM::StreamGeom G = stream_geom(s, F, 2, 2, stream_slots(s, STRM::ks_apply_p<TMA, UNI>, smem));        \
+        const dim3 grid((G.nstrips + STRM::WPC - 1) / STRM::WPC, G.nchunks);                                          \
+        LAUNCH_K(pdl_ok, (STRM::ks_apply_p<TMA, UNI>), grid, dim3(32 * STRM::WPC), smem, st, F, s->map_z, mp,         \
+                 (const double *)s->z, (const double *)pin, pout, s->Ap, U, G, s->sc, s->partials, s->counters + 2,   \
+                 &s->sc->pAp);                                                                                        \
+    } while (0)
+    const bool uni = s->stream_uni && uniform_columns(F);
+    if (s->tma_p) { if (uni) SAPPLY(true, true); else SAPPLY(true, false); }
+    else { if (uni) SAPPLY(false, true); else SAPPLY(false, false); }
+#undef SAPPLY
+}
+
 template <int NU>
 static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
 {
@@ -1799,6 +1992,12 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
     const LevelDev &F = TV(s, lv), &Cc = TV(s, cv);
     const CGScalars *scc = s->sc;
     const bool pdl_ok = l > 0;   // level 0 opens the iteration
+    if (use_stream(s, lv)) {
+        launch_pre_stream<NU>(s, st, l, pdl_ok);
+        s->launches++;
+        trace_mark(st);
+        return;
+    }
     xch(s, lv, lv.b, NU + 1);
     if (use_t32(s, F, 64 - H2)) {
         const size_t tsm = 3 * TN32 * sizeof(double);
@@ -1824,6 +2023,12 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
     Level &lv = s->levels[l], &cv = s->levels[l + 1];
     const SmoothW sw = smooth_weights_n(NU);
     const LevelDev &F = TV(s, lv), &Cc = TV(s, cv);
+    if (use_stream(s, lv)) {
+        launch_post_stream<NU>(s, st, l);
+        s->launches++;
+        trace_mark(st);
+        return;
+    }
     xch(s, cv, cv.x, NU + 1);   // coarse correction rows reached by the prolongation of my halo
     xch(s, lv, lv.t, NU);       // pre-smoothed iterate; lv.b halos are still valid from the pre-smoothing exchange
     double *out_dot = s->slab ? &s->sc->part_rz : &s->sc->rz_new;
@@ -1969,8 +2174,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     }
     if (sl) {
         slab_allreduce(s, &sc->part_rz, &sc->rz_new, 1);
-        slab_exchange(s, Ll, s->z, 1);
-        slab_exchange(s, Ll, s->pv, 1);
+        slab_exchange2(s, Ll, s->z, s->pv, 1);   // one NCCL group for both one-row halos
     }
     const dim3 tg = tile_grid(L, 64 - 2);
     if (s->defer_x) {
@@ -1980,9 +2184,12 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
             s->launches++;
         }
     }
-    LAUNCH_K(!sl && (!s->defer_x || s->join_pdl), T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
-             (const double *)VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc, s->partials, s->counters + 2,
-             sl ? &sc->part_pAp : &sc->pAp);
+    if (use_stream(s, l0) && s->stream_apply)
+        launch_apply_stream(s, st, !s->defer_x || s->join_pdl, s->pv, s->pv2);
+    else
+        LAUNCH_K(!sl && (!s->defer_x || s->join_pdl), T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
+                 (const double *)VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc, s->partials, s->counters + 2,
+                 sl ? &sc->part_pAp : &sc->pAp);
     trace_mark(st);
     std::swap(s->pv, s->pv2);
     if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
@@ -2083,7 +2290,7 @@ static int pcg(eqgpu_solver *s)
     // history depth: modes 1-3 use that many solutions, 4 three (+ least squares), 5 four (+ cubic; one GPU,
     // isotropic path)
     const int nh_max = (s->warm >= 5 && !sl && !T) ? (s->warm >= 6 ? 5 : 4) : std::min(s->warm, 3);
-    const int nh = keep_hist ? std::min(s->hist, nh_max) : 0;
+    const int nh = keep_hist ? std::min(s->hist, std::min(nh_max, s->warm_adaptive ? s->nh_cap : 5)) : 0;
     // least-squares combination of the history beside the fixed extrapolations (single GPU: its nine sums
     // are not rank-reduced)
     const bool ls = keep_hist && s->warm == 4 && !sl && nh >= 2;
@@ -2099,8 +2306,9 @@ static int pcg(eqgpu_solver *s)
                                                         sl ? 1 : 0, s->dk[s->dk_cur], wrote_dk ? s->dk[s->dk_cur ^ 1] : nullptr,
                                                         d4ok ? 1 : 0);
         if (sl) {
-            slab_allreduce(s, &sc->part_rrD, &sc->rrD, 1);
-            slab_allreduce(s, &sc->part_rrE, &sc->rrE, 1);
+            slab_allreduce(s, sc->red_src, sc->red_dst, 5);
+            k_slab_unpack<<<1, 1, 0, st>>>(sc);
+            s->launches++;
         }
     } else if (hist_tensor)
         k_init_hist<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2, rs_l,
@@ -2108,7 +2316,7 @@ static int pcg(eqgpu_solver *s)
     else
         k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
                                       sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
-    if (sl) {  // rank-sum the two start residuals
+    if (sl && !(!T && s->init_tile)) {  // per-node k_init: rank-sum the two start residuals
         slab_allreduce(s, &sc->part_rr0, &sc->rr0, 1);
         slab_allreduce(s, &sc->part_b2, &sc->bnorm2, 1);
     }
@@ -2230,6 +2438,26 @@ static int pcg(eqgpu_solver *s)
                 sqrt(fabs(h.rrE) / b2), sqrt(fabs(h.rrF) / b2), sqrt(fabs(h.rrL) / b2), h.guess,
                 sqrt(fabs(h.rr_init) / b2), h.lsc[0], h.lsc[1], h.lsc[2], h.iters, sqrt(h.rr / b2));
     }
+    if (s->warm_adaptive && keep_hist && !T && !sl) {
+        // Did the extrapolations pay?  gain = squared residual of the previous solution over the best higher candidate's.
+        // Below 4 (a factor 2 in norm, a fifth of a PCG iteration) for three steps running, the operator walks over the
+        // older solutions cost more than they save: walk the newest one only.  The history keeps rotating at full depth,
+        // and every 64 steps the full depth is probed again for one step.
+        const CGScalars &h = *s->sc_host;
+        if (nh >= 2) {
+            double hi = h.rrD;
+            if (nh >= 3) hi = std::min(hi, h.rrE);
+            if (nh >= 4) hi = std::min(hi, h.rrF);
+            if (d4ok) hi = std::min(hi, h.rrG);
+            if (ls) hi = std::min(hi, h.rrL);
+            const bool low = !(hi * 4.0 < h.rr0);
+            s->low_gain_steps = low ? s->low_gain_steps + 1 : 0;
+            if (s->low_gain_steps >= 3 && s->hist >= std::min(nh_max, 3)) { s->nh_cap = 1; s->probe_countdown = 64; }
+        } else if (s->nh_cap == 1 && s->hist >= 2 && --s->probe_countdown <= 0) {
+            s->nh_cap = 5;
+            s->low_gain_steps = 2;   // one probing step: back to the short history at once if it still does not pay
+        }
+    }
     if (ring && s->sc_host->rr <= s->sc_host->stop2) {   // solution copied by k_finish_x; its image by one operator walk
         const int slot = (s->ring_head + RING_MAX - 1) % RING_MAX;
         k_ring_image<<<g0, blk, 0, st>>>(L, s->u, s->ring_a[slot]);
@@ -2302,6 +2530,26 @@ int solver_apply(eqgpu_solver *s, const double *dx, double *dy, bool constrained
     return 0;
 }
 
+// Verification hook: one V-cycle on the solver's own r -> z, outside any PCG state.
+int solver_precond(eqgpu_solver *s)
+{
+    if (s->tensor || s->slab || !s->fused || s->levels.size() < 2) {
+        s->set_error("the preconditioner hook serves the fused isotropic single-GPU path");
+        return EQGPU_ESTATE;
+    }
+    cudaStream_t st = s->stream;
+    EQ_CUDA(cudaMemsetAsync(s->sc, 0, sizeof(CGScalars), st));
+    const bool pdl = s->pdl;
+    s->pdl = false;
+    s->x_forked = false;
+    vcycle_fused(s, st);
+    if (s->x_forked) cudaStreamWaitEvent(st, s->ev_join, 0);
+    s->pdl = pdl;
+    EQ_CUDA(cudaStreamSynchronize(st));
+    EQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int solver_rhs(eqgpu_solver *s, const double *du0, double *db)
 {
     const LevelDev &L = s->levels[0].dev;
@@ -2344,23 +2592,17 @@ int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, do
             *alg_bytes = 24.0 * s->N;
         } else if (nm == "apply_p") {  // read z,p write p',Ap: 32 B/DOF
             const dim3 tg((L.nx + 61) / 62, (L.ny + 61) / 62);
-            T64::k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2, &s->sc->pAp);
+            if (use_stream(s, l0) && s->stream_apply) launch_apply_stream(s, st, false, s->pv, s->pv2);
+            else T64::k_apply_p<<<tg, 256, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, s->sc, s->partials, s->counters + 2, &s->sc->pAp);
             *alg_bytes = 32.0 * s->N;
         } else if (nm == "presmooth" || nm == "postsmooth") {
-            if (!s->fused || (s->use_cluster ? s->ctail_first : s->tail_first) == 0 || s->nu != 3) return false;
-            Level &cv = s->levels[1];
-            const size_t tsm = 2 * TN64 * sizeof(double);
-            const SmoothW sw = smooth_weights(s);
-            if (nm == "presmooth") {  // read b, write x and b_coarse: 16 + 2 B/DOF
-                const int to = 64 - 8;
-                const dim3 tg((L.nx + to - 1) / to, (L.ny + to - 1) / to);
-                T64::k_presmooth<3, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, cv.b, sw, s->sc);
+            // the level-0 smoother launches of the V-cycle as the solver issues them (streaming kernels by default)
+            if (!s->fused || s->levels.size() < 2 || s->nu != 3 || s->slab) return false;
+            if (nm == "presmooth") {   // read b, write x and b_coarse: 16 + 2 B/DOF
+                launch_pre<3>(s, st, 0);
                 *alg_bytes = 18.0 * s->N;
-            } else {  // read x, b, x_coarse, write x: 24 + 2 B/DOF
-                const int to = 64 - 6;
-                const dim3 tg((L.nx + to - 1) / to, (L.ny + to - 1) / to);
-                T64::k_postsmooth<3, true, 8><<<tg, 512, tsm, st>>>(L, cv.dev, s->r, l0.t, s->z, cv.x, sw, s->sc,
-                                                                    s->partials, s->counters + 1, &s->sc->rz_new);
+            } else {   // read x, b, x_coarse, write x: 24 + 2 B/DOF
+                launch_post<3>(s, st, 0);
                 *alg_bytes = 26.0 * s->N;
             }
         } else return false;

@@ -181,6 +181,10 @@ int main(int argc, char **argv)
     } else { fprintf(stderr, "unknown case\n"); return 2; }
 
     std::shared_ptr<gpuHSL> solver = std::make_shared<gpuHSL>(cfg);  // simulation.cpp:207
+    // EQ_TEST_SNAPSHOT=<prefix>: the controller's field snapshot (src/main.cpp:148-162 -> writeDiffusionFiles,
+    // src/fHSL.cpp:630-636) after the last step, for the read-back test
+    const char *snap = getenv("EQ_TEST_SNAPSHOT");
+    if (snap) p.filePath = snap;
     try {
         solver->initDiffusion(p);                                    // simulation.cpp:244
         const size_t N = solver->solution_vector.size();
@@ -197,6 +201,7 @@ int main(int argc, char **argv)
             } else
                 flux.push_back(solver->getBoundaryFlux()["totalFlux"]);
         }
+        if (snap) solver->writeDiffusionFiles(double(nsteps) * dt);
         FILE *f = fopen(argv[3], "wb");
         double hdr[3] = {double(solver->nodesW), double(solver->nodesH), double(solver->lastIterations())};
         fwrite(hdr, sizeof(double), 3, f);

@@ -226,6 +226,13 @@ EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
  * eqgpu_set_field, and is kept on the single-GPU isotropic path only (elsewhere the call is accepted and
  * mode 0 is what runs). */
 EQGPU_API int eqgpu_set_warm_start(eqgpu_solver *s, int mode);
+/* Row-slab mode: cumulative communication counters of this rank since creation -- out[0] all-reduce calls,
+ * out[1] doubles all-reduced, out[2] halo exchanges (one NCCL group each), out[3] halo bytes sent.  Zeros on one GPU. */
+EQGPU_API int eqgpu_comm_stats(eqgpu_solver *s, int64_t out[4]);
+/* Verification hook (single GPU, isotropic operator): z = B r, one application of the multigrid preconditioner
+ * (the V-cycle of the PCG iteration) to a host vector r (zero on Dirichlet rows); host arrays of nW*nH doubles.
+ * Lets the tests compare the streaming smoothers with the shared-memory tile kernels and check the symmetry of B. */
+EQGPU_API int eqgpu_apply_preconditioner(eqgpu_solver *s, const double *r, double *z);
 /* The mode in effect (the size-dependent default, EQGPU_WARM, or the last eqgpu_set_warm_start). */
 EQGPU_API int eqgpu_get_warm_start(eqgpu_solver *s);
 /* Which guess the last step started from: 0 field as given, 1 zero, 2 previous solution, 3 linear,

@@ -135,3 +135,33 @@ def test_boundary_well_loop(oracle, tmp_path):
     assert rel(got["u"], u) < 1e-8
     assert np.allclose(got["flux"], trace, rtol=1e-6, atol=1e-12)
     assert trace[-1] > 0.0
+
+
+def test_field_snapshot_reads_back_to_the_last_digit(oracle, tmp_path, monkeypatch):
+    """gpuHSL::writeDiffusionFiles (the drop-in for fenicsInterface::writeDiffusionFiles, src/fHSL.cpp:630-636, called by
+    the controller every recording interval, src/main.cpp:148-162): the legacy-VTK snapshot it writes after the last
+    step holds the solution vector in natural node order, 17 significant digits, so reading it back gives the field
+    bit for bit; the header carries the mesh."""
+    W, H, npm, dt, D, nsteps = 100.0, 20.0, 2.0, 0.1, 1200.0, 3
+    p = oracle.Problem(nW=201, nH=41, h=0.5, dt=dt, D=D)
+    rng = np.random.default_rng(3)
+    deposit = rng.uniform(0.0, 7.0, p.N) * (rng.uniform(size=p.N) < 0.02)
+    prefix = str(tmp_path / "hsl_snapshot")
+    monkeypatch.setenv("EQ_TEST_SNAPSHOT", prefix)
+    got = run_case(oracle, tmp_path, "default", W, H, npm, dt, D, nsteps, np.zeros((0, 16)), deposit)
+    path = "%s_%012.4f.vtk" % (prefix, nsteps * dt)
+    assert os.path.exists(path), os.listdir(tmp_path)
+    lines = open(path).read().split("\n")
+    assert lines[0].startswith("# vtk DataFile") and lines[2] == "ASCII" and lines[3] == "DATASET STRUCTURED_POINTS"
+    head = {l.split()[0]: l.split()[1:] for l in lines[4:10] if l}
+    assert [int(v) for v in head["DIMENSIONS"]] == [201, 41, 1]
+    assert [float(v) for v in head["SPACING"]][:2] == [0.5, 0.5]
+    assert int(head["POINT_DATA"][0]) == p.N and head["SCALARS"][:2] == ["u", "double"]
+    k = lines.index("LOOKUP_TABLE default")
+    vals = np.array([float(v) for v in lines[k + 1:k + 1 + p.N]])
+    assert np.array_equal(vals, got["u"])                     # bit for bit
+    s = oracle.new_state(p)
+    for _ in range(nsteps):
+        s.u = s.u + deposit
+        s = oracle.step(p, s)
+    assert rel(vals, s.u) < 1e-8
