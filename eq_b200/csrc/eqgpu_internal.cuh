@@ -163,6 +163,7 @@ struct eqgpu_solver {
     CUtensorMap map_z{}, map_pv{}, map_pv2{};   // level-0 z and the two search-direction buffers (ks_apply_p)
     bool tma_p = false;
     const double *map_pv_ptr = nullptr;   // the buffer map_pv describes
+    bool stream_pipe = true;       // warp-specialised sweep pipelines (PIPE::kp_*) on TMA-capable levels
     bool stream_uni = true;        // constant-bank coefficient instances where every column is regular or Dirichlet
     bool stream_apply = false;     // ks_apply_p instead of the tile k_apply_p
     bool stream_smooth = false;    // warp-streaming smoothers (mg_stream.cuh) instead of the shared-memory tile kernels

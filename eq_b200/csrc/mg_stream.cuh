@@ -22,6 +22,7 @@
 // that are irregular (row 0, the rows above ireg_hi) take a slow path that evaluates the general row (stencil_iso).
 #pragma once
 #include <cuda.h>
+#include <cuda/std/type_traits>
 #include "eqgpu_internal.cuh"
 #include "mg_fused.cuh"
 
@@ -708,3 +709,466 @@ ks_apply_p(LevelDev F, const __grid_constant__ CUtensorMap map_z, const __grid_c
 }
 
 }  // namespace STRM
+
+// ============================================================================================================================
+// Warp-specialised sweep pipeline (the form the streaming smoothers ship in on TMA-capable levels).
+//
+// Measured on the B200 (scripts/micro/dfma_bench.cu): a dependent DFMA issues after 9 cycles, one warp alone sustains
+// 0.42 DFMA per cycle and four warps x four independent chains already saturate the SM's FP64 pipe (1.82 warp-DFMA per
+// cycle).  The one-warp-does-all-sweeps kernels above nevertheless issue one instruction per ~5 cycles per warp: with
+// every sweep's window in the same thread they need 230-255 registers, which leaves ptxas no room to interleave the
+// chains and the SM room for only eight warps.  Here the sweeps of a task (one 64-column strip x one row chunk) are
+// spread over the WARPS of a CTA instead:
+//     warp 0            rows of b (TMA ring)           -> sweeps 1+2 -> ring H0
+//     warp k            rows of x_{k+1} (ring H_{k-1}) -> sweep k+2  -> ring H_k
+//     last warp         rows of x_NU                   -> residual, restriction, stores        (pre-smoothing)
+// Each warp keeps ONE three-row window (12 doubles) and its own coefficient sets, takes its input rows from shared
+// memory, publishes its output rows to shared memory, and has no loop-carried dependency through its arithmetic at all,
+// so consecutive walk steps overlap freely.  West/east neighbours still come from warp shuffles.  Hand-off between the
+// warps is by blocks of RB rows through mbarrier full/empty pairs (no __syncthreads in the walk); every warp reads the
+// rows of b it needs from the shared TMA ring, which the last warp releases.
+//
+// Row bookkeeping: element s of warp k's INPUT sequence is fine row y0 + s - 2k; at step s the warp emits the update of
+// the middle row of its window BEFORE the entering row is pushed, i.e. row y0 + s - 2(k+1), whose right-hand side is
+// element s - LG of the b sequence, LG = 2(k+1).  Block m of any sequence is elements 6m .. 6m+5.
+// ============================================================================================================================
+namespace PIPE {
+using namespace STRM;
+
+constexpr int NHS = 2;          // hand-off ring slots (blocks of RB rows) between two consecutive sweeps
+constexpr int PFB = 2;          // blocks of b (and xin) staged ahead of the first warp
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// shared-memory layout of one task (CTA)
+template <int NU, bool POST>
+struct Layout {
+    static constexpr int NSB = NU + 1 + PFB;                       // b ring: blocks m-NU .. m live, PFB ahead
+    static constexpr int NSX = 1 + PFB;                            // xin ring (first warp only)
+    static constexpr int CSLOT = (CBLK_BYTES + 127) / 128 * 128;
+    static constexpr int B_OFF = 0;
+    static constexpr int X_OFF = B_OFF + NSB * BLK_BYTES;
+    static constexpr int C_OFF = X_OFF + (POST ? NSX * BLK_BYTES : 0);
+    static constexpr int H_OFF = C_OFF + (POST ? NSX * CSLOT : 0);
+    static constexpr int NH = NU - 1;                              // hand-off rings
+    static constexpr int BAR_OFF = H_OFF + NH * NHS * BLK_BYTES;
+    // barriers: full_b[NSB], empty_b[NSB], full_x[NSX], then per hand-off ring full[NHS], empty[NHS]
+    static constexpr int NBAR = 2 * NSB + NSX + NH * 2 * NHS;
+    static constexpr int BYTES = BAR_OFF + NBAR * 8;
+};
+
+struct Ctx {
+    unsigned char *smem;
+    unsigned long long *bars;
+    int lane, nblk;
+    bool has_reg;
+};
+
+// the lane's two values of row `row` of a block
+__device__ __forceinline__ double2 blk_ld(const unsigned char *blk, int row, int lane)
+{
+    return *reinterpret_cast<const double2 *>(blk + row * (SWID * 8) + lane * 16);
+}
+__device__ __forceinline__ void blk_st(unsigned char *blk, int row, int lane, double a, double b)
+{
+    *reinterpret_cast<double2 *>(blk + row * (SWID * 8) + lane * 16) = make_double2(a, b);
+}
+
+// right-hand side of the row a warp with lag LG emits at step u of block m: element 6m + u - LG of the b sequence
+// (zero before the first staged row).  bcur / bprev / bprev2: the b blocks m, m-1, m-2.
+template <int LG>
+__device__ __forceinline__ double2 b_of(int u, int m, const unsigned char *bcur, const unsigned char *bprev,
+                                        const unsigned char *bprev2, int lane)
+{
+    const int e = u - LG;                       // relative to the first element of block m
+    if (e >= 0) return blk_ld(bcur, e, lane);
+    if (e >= -RB) return m >= 1 ? blk_ld(bprev, e + RB, lane) : make_double2(0.0, 0.0);
+    return m >= 2 ? blk_ld(bprev2, e + 2 * RB, lane) : make_double2(0.0, 0.0);
+}
+
+template <int NU, bool POST>
+__device__ __forceinline__ const unsigned char *b_block(const Ctx &c, int m)
+{
+    using L = Layout<NU, POST>;
+    return c.smem + L::B_OFF + (size_t)((m + L::NSB) % L::NSB) * BLK_BYTES;
+}
+
+// ---- middle warp k (1 <= k <= NU-2): x_{k+1} -> x_{k+2} (pre) / sweep k+1 (post); also the post-smoother's last warp ----
+template <int NU, int K, bool POST, bool LAST, bool DOT>
+__device__ __forceinline__ void role_mid(const Ctx &c, const LevelDev &F, const Task &T, const Coef<NU> &ca, const Coef<NU> &cb,
+                                         const IrrTab<NU> &irr, double *__restrict__ x, double &dot)
+{
+    using L = Layout<NU, POST>;
+    constexpr int LG = 2 * (K + 1), WI = POST ? K : K + 1;   // weight index of this warp's sweep
+    unsigned long long *full_b = c.bars, *empty_b = c.bars + L::NSB;
+    unsigned long long *full_in = c.bars + 2 * L::NSB + L::NSX + (K - 1) * 2 * NHS, *empty_in = full_in + NHS;
+    unsigned long long *full_out = c.bars + 2 * L::NSB + L::NSX + K * 2 * NHS, *empty_out = full_out + NHS;
+    unsigned char *hin = c.smem + L::H_OFF + (size_t)(K - 1) * NHS * BLK_BYTES;
+    unsigned char *hout = c.smem + L::H_OFF + (size_t)K * NHS * BLK_BYTES;
+    const int lane = c.lane;
+    double win[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) win[r][q] = 0.0;
+    for (int m = 0; m < c.nblk; ++m) {
+        const int hs = m % NHS, i0 = T.y0 + m * RB - 2 * K;   // fine row of the first entering element
+        mbar_wait(full_in + hs, (m / NHS) & 1);
+        if (!LAST) mbar_wait(empty_out + hs, ((m / NHS) & 1) ^ 1);
+        mbar_wait(full_b + (m % L::NSB), (m / L::NSB) & 1);   // rows of b up to block m are in place
+        const unsigned char *bi = hin + (size_t)hs * BLK_BYTES;
+        unsigned char *bo_ = hout + (size_t)hs * BLK_BYTES;
+        const unsigned char *b0 = b_block<NU, POST>(c, m), *b1 = b_block<NU, POST>(c, m - 1), *b2 = b_block<NU, POST>(c, m - 2);
+        // every input row of the block is loaded before the first output row is stored: the hand-off rings and the b ring
+        // are the same shared array to the compiler, so a load after a store could not be moved above it and the six
+        // steps of a block would run one after the other (950 cycles per step in the first version of this kernel)
+        double2 xin[RB], bin[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) { xin[u] = blk_ld(bi, u, lane); bin[u] = b_of<LG>(u, m, b0, b1, b2, lane); }
+        auto body = [&](auto fc) {
+            constexpr bool fast = decltype(fc)::value;
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const int r = i0 + u - 2;
+                Coef<NU> la, lb;
+                if (fast) { la = ca; lb = cb; } else row_coef<NU>(F, r, ca, cb, irr, la, lb);
+                const double2 bv = bin[u];
+                double ra, rbv;
+                node_pair<NU>(win, la, lb, bv.x, bv.y, ra, rbv);
+                const double va = fma(la.wic[WI], ra, win[1][1]), vb = fma(lb.wic[WI], rbv, win[1][2]);
+                if (!LAST) blk_st(bo_, u, lane, va, vb);
+                else if (T.own_cols && r >= T.lo_y && r < T.hi_y) {
+                    store_pair(x, F, r, T.j0, va, vb);
+                    if (DOT) dot += va * bv.x + (T.j0 + 1 < F.nx ? vb * bv.y : 0.0);
+                }
+                push_row(win, xin[u].x, xin[u].y);
+            }
+        };
+        if (c.has_reg && i0 - 3 >= 1 && i0 + RB - 1 <= F.ireg_hi) body(cuda::std::true_type{});
+        else body(cuda::std::false_type{});
+        __syncwarp();
+        if (lane == 0) {
+            if (!LAST) mbar_arrive(full_out + hs);
+            mbar_arrive(empty_in + hs);
+            // the last warp has read every row of b before block m + 1 - ceil(2NU/6): release one block per iteration
+            if (LAST && m >= (2 * NU + RB - 1) / RB) mbar_arrive(empty_b + ((m - (2 * NU + RB - 1) / RB) % L::NSB));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// pre-smoothing pipeline: NU warps
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int NU>
+__global__ void __launch_bounds__(32 * NU)
+kp_presmooth(LevelDev F, LevelDev Cc, const __grid_constant__ CUtensorMap map_b, double *__restrict__ x,
+             double *__restrict__ bc, SmoothW sw, StreamGeom G, const CGScalars *sc)
+{
+    pdl_trigger();
+    using L = Layout<NU, false>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int stage = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Ctx c;
+    c.smem = smem_raw;
+    c.bars = reinterpret_cast<unsigned long long *>(smem_raw + L::BAR_OFF);
+    c.lane = lane;
+    c.nblk = G.nblk;
+    c.has_reg = F.ireg_hi >= 1;
+    unsigned long long *full_b = c.bars, *empty_b = c.bars + L::NSB;
+    const Task T = make_task(F, G, blockIdx.x, blockIdx.y);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < L::NBAR; ++q) mbar_init(c.bars + q, 1);
+        fence_barrier_init();
+    }
+    // the lane's coefficient sets (regular row) and the irregular-row table: set-up constants only
+    Coef<NU> ca, cb;
+    regular_coefs<NU>(F, T.j0, sw, ca, cb);
+    IrrTab<NU> irr;
+    fill_irr<NU>(F, T.j0, sw, T.y0 - 2 * NU - 4, T.y0 + G.nblk * RB, irr);
+    __syncthreads();   // barriers initialised (the only block-wide barrier of the kernel)
+    pdl_wait();
+    if (sc->done) return;
+    double dummy = 0.0;
+
+    if (stage == 0) {
+        // ---- warp 0: b -> x1 (pointwise) -> x2 ------------------------------------------------------------------------------
+        unsigned long long *full_out = c.bars + 2 * L::NSB + L::NSX, *empty_out = full_out + NHS;
+        unsigned char *hout = smem_raw + L::H_OFF;
+        if (lane == 0)
+            for (int q = 0; q <= PFB && q < c.nblk; ++q) {
+                mbar_expect_tx(full_b + q, BLK_BYTES);
+                tma_load_2d(smem_raw + L::B_OFF + (size_t)q * BLK_BYTES, &map_b, full_b + q, T.ox, T.y0 + q * RB);
+            }
+        double win[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) win[r][q] = 0.0;
+        for (int m = 0; m < c.nblk; ++m) {
+            const int slot = m % L::NSB, hs = m % NHS, i0 = T.y0 + m * RB;
+            mbar_wait(full_b + slot, (m / L::NSB) & 1);
+            mbar_wait(empty_out + hs, ((m / NHS) & 1) ^ 1);
+            const unsigned char *b0 = b_block<NU, false>(c, m), *b1 = b_block<NU, false>(c, m - 1);
+            unsigned char *bo_ = hout + (size_t)hs * BLK_BYTES;
+            double2 bin[RB], bin2[RB];   // all loads of the block before its first store (see role_mid)
+#pragma unroll
+            for (int u = 0; u < RB; ++u) { bin[u] = blk_ld(b0, u, lane); bin2[u] = b_of<2>(u, m, b0, b1, b1, lane); }
+            auto body = [&](auto fc) {
+                constexpr bool fast = decltype(fc)::value;
+#pragma unroll
+                for (int u = 0; u < RB; ++u) {
+                    const int i = i0 + u;
+                    Coef<NU> la, lb;
+                    // x2 on row i-2 from the x1 window (rows i-3 .. i-1)
+                    if (fast) { la = ca; lb = cb; } else row_coef<NU>(F, i - 2, ca, cb, irr, la, lb);
+                    const double2 bv2 = bin2[u];
+                    double ra, rbv;
+                    node_pair<NU>(win, la, lb, bv2.x, bv2.y, ra, rbv);
+                    blk_st(bo_, u, lane, fma(la.wic[1], ra, win[1][1]), fma(lb.wic[1], rbv, win[1][2]));
+                    // x1 on the entering row i
+                    if (!fast) row_coef<NU>(F, i, ca, cb, irr, la, lb);
+                    push_row(win, la.wic[0] * bin[u].x, lb.wic[0] * bin[u].y);
+                }
+            };
+            if (c.has_reg && i0 - 3 >= 1 && i0 + RB - 1 <= F.ireg_hi) body(cuda::std::true_type{});
+            else body(cuda::std::false_type{});
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(full_out + hs);
+                const int mp = m + PFB + 1;   // next block to stage: its slot was last used by block mp - NSB
+                if (mp < c.nblk) {
+                    const int sp = mp % L::NSB;
+                    mbar_wait(empty_b + sp, ((mp / L::NSB) & 1) ^ 1);
+                    fence_proxy_async();
+                    mbar_expect_tx(full_b + sp, BLK_BYTES);
+                    tma_load_2d(smem_raw + L::B_OFF + (size_t)sp * BLK_BYTES, &map_b, full_b + sp, T.ox, T.y0 + mp * RB);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (stage < NU - 1) {
+        if (NU == 3 || stage == 1) role_mid<NU, 1, false, false, false>(c, F, T, ca, cb, irr, nullptr, dummy);
+        else role_mid<NU, (NU > 3 ? 2 : 1), false, false, false>(c, F, T, ca, cb, irr, nullptr, dummy);
+    } else {
+        // ---- last warp: x_NU -> residual, restriction, stores ------------------------------------------------------------------
+        constexpr int K = NU - 1, LG = 2 * NU;
+        unsigned long long *full_in = c.bars + 2 * L::NSB + L::NSX + (K - 1) * 2 * NHS, *empty_in = full_in + NHS;
+        unsigned char *hin = smem_raw + L::H_OFF + (size_t)(K - 1) * NHS * BLK_BYTES;
+        const bool cj0 = T.j0 >= 0 && T.j0 < F.nx;
+        const double wE = (T.j0 + 1 < F.nx && is_mid(T.j0 + 1, F.nx)) ? 0.5 : 0.0;
+        const double wW = (T.j0 - 1 >= 0 && is_mid(T.j0 - 1, F.nx)) ? 0.5 : 0.0;
+        const bool cj1 = (T.j0 + 1 == F.nx - 1) && !is_mid(T.j0 + 1, F.nx) && T.j0 + 1 >= T.lo_x && T.j0 + 1 < T.hi_x;
+        const int J0 = T.j0 >> 1;
+        double win[3][4], rw[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            rw[r][0] = rw[r][1] = rw[r][2] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) win[r][q] = 0.0;
+        }
+        for (int m = 0; m < c.nblk; ++m) {
+            const int hs = m % NHS, i0 = T.y0 + m * RB - 2 * K;
+            mbar_wait(full_in + hs, (m / NHS) & 1);
+            mbar_wait(full_b + (m % L::NSB), (m / L::NSB) & 1);
+            const unsigned char *bi = hin + (size_t)hs * BLK_BYTES;
+            const unsigned char *b0 = b_block<NU, false>(c, m), *b1 = b_block<NU, false>(c, m - 1), *b2 = b_block<NU, false>(c, m - 2);
+            double2 xin[RB], bin[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) { xin[u] = blk_ld(bi, u, lane); bin[u] = b_of<LG>(u, m, b0, b1, b2, lane); }
+            auto body = [&](auto fc) {
+                constexpr bool fast = decltype(fc)::value;
+#pragma unroll
+                for (int u = 0; u < RB; ++u) {
+                    const int r = i0 + u - 2;   // the row whose residual is formed
+                    Coef<NU> la, lb;
+                    if (fast) { la = ca; lb = cb; } else row_coef<NU>(F, r, ca, cb, irr, la, lb);
+                    const double2 bv = bin[u];
+                    double ra, rbv;
+                    node_pair<NU>(win, la, lb, bv.x, bv.y, ra, rbv);
+                    if (T.own_cols && r >= T.lo_y && r < T.hi_y) store_pair(x, F, r, T.j0, win[1][1], win[1][2]);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { rw[0][q] = rw[1][q]; rw[1][q] = rw[2][q]; }
+                    rw[2][1] = ra; rw[2][2] = rbv;
+                    rw[2][0] = __shfl_up_sync(0xffffffffu, rbv, 1);
+                    // restriction at rc = r - 1 (middle residual row) when it is a coarse row; y0 is even, so rc is even
+                    // exactly when u is odd
+                    const int rc = r - 1;
+                    const bool even = fast ? ((u & 1) == 1) : ((rc & 1) == 0);
+                    if ((even || (!fast && rc == F.ny - 1)) && rc >= T.lo_y && rc < T.hi_y) {
+                        const int I = coarse_lo(rc, F.ny, Cc.ny);
+                        const double wN = fast ? 0.5 : ((rc + 1 < F.ny && is_mid(rc + 1, F.ny)) ? 0.5 : 0.0);
+                        const double wS = fast ? 0.5 : ((rc - 1 >= 0 && is_mid(rc - 1, F.ny)) ? 0.5 : 0.0);
+                        if (T.own_cols && cj0) {
+                            double v = rw[1][1] + wE * rw[1][2] + wW * rw[1][0] + wN * rw[2][1] + wS * rw[0][1] +
+                                       (2.0 * wN * wE) * rw[2][2] + (2.0 * wS * wW) * rw[0][0];
+                            if (is_dirichlet(Cc, I, J0)) v = 0.0;
+                            bc[(size_t)I * Cc.nx + J0] = v;
+                        }
+                        if (cj1) {
+                            double v = rw[1][2] + wN * rw[2][2] + wS * rw[0][2];
+                            if (is_dirichlet(Cc, I, Cc.nx - 1)) v = 0.0;
+                            bc[(size_t)I * Cc.nx + Cc.nx - 1] = v;
+                        }
+                    }
+                    push_row(win, xin[u].x, xin[u].y);
+                }
+            };
+            if (c.has_reg && i0 - 4 >= 1 && i0 + RB - 1 <= F.ireg_hi) body(cuda::std::true_type{});
+            else body(cuda::std::false_type{});
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(empty_in + hs);
+                if (m >= (LG + RB - 1) / RB) mbar_arrive(empty_b + ((m - (LG + RB - 1) / RB) % L::NSB));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// post-smoothing pipeline: NU warps.  Warp 0 prolongates (x0 = xin + P xc) and does sweep 1, warp k sweep k+1, the last
+// warp stores the result and sums x.b
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int NU, bool DOT>
+__global__ void __launch_bounds__(32 * NU)
+kp_postsmooth(LevelDev F, LevelDev Cc, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
+              double *__restrict__ x, const double *__restrict__ xc, SmoothW sw, StreamGeom G, CGScalars *sc,
+              double *partials, unsigned *counter, double *out_dot)
+{
+    pdl_trigger();
+    using L = Layout<NU, true>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int stage = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Ctx c;
+    c.smem = smem_raw;
+    c.bars = reinterpret_cast<unsigned long long *>(smem_raw + L::BAR_OFF);
+    c.lane = lane;
+    c.nblk = G.nblk;
+    c.has_reg = F.ireg_hi >= 1;
+    unsigned long long *full_b = c.bars, *empty_b = c.bars + L::NSB, *full_x = c.bars + 2 * L::NSB;
+    const Task T = make_task(F, G, blockIdx.x, blockIdx.y);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < L::NBAR; ++q) mbar_init(c.bars + q, 1);
+        fence_barrier_init();
+    }
+    Coef<NU> ca, cb;
+    regular_coefs<NU>(F, T.j0, sw, ca, cb);
+    IrrTab<NU> irr;
+    fill_irr<NU>(F, T.j0, sw, T.y0 - 2 * NU - 4, T.y0 + G.nblk * RB, irr);
+    __syncthreads();
+    pdl_wait();
+    double dot = 0.0;
+    if (!sc->done) {
+        if (stage == 0) {
+            unsigned long long *full_out = c.bars + 2 * L::NSB + L::NSX, *empty_out = full_out + NHS;
+            unsigned char *hout = smem_raw + L::H_OFF, *rx = smem_raw + L::X_OFF, *rcs = smem_raw + L::C_OFF;
+            const int J0 = T.j0 >> 1, CJ0 = T.ox >> 1;
+            const bool in0 = T.j0 >= 0 && T.j0 < F.nx, in1 = T.j0 + 1 >= 0 && T.j0 + 1 < F.nx;
+            const bool mid1 = in1 && is_mid(T.j0 + 1, F.nx);
+            const double m0 = (in0 && !(((F.dirmask & 1u) && T.j0 == 0) || ((F.dirmask & 2u) && T.j0 == F.nx - 1))) ? 1.0 : 0.0;
+            const double m1 = (in1 && !(((F.dirmask & 1u) && T.j0 + 1 == 0) || ((F.dirmask & 2u) && T.j0 + 1 == F.nx - 1))) ? 1.0 : 0.0;
+            auto stage_in = [&](int q) {   // block q of b, xin (TMA) and of the coarse patch (cp.async)
+                const int sb = q % L::NSB, sx = q % L::NSX;
+                if (lane == 0) {
+                    mbar_expect_tx(full_b + sb, BLK_BYTES);
+                    tma_load_2d(smem_raw + L::B_OFF + (size_t)sb * BLK_BYTES, &map_b, full_b + sb, T.ox, T.y0 + q * RB);
+                    mbar_expect_tx(full_x + sx, BLK_BYTES);
+                    tma_load_2d(rx + (size_t)sx * BLK_BYTES, &map_x, full_x + sx, T.ox, T.y0 + q * RB);
+                }
+                double *dst = reinterpret_cast<double *>(rcs + (size_t)sx * L::CSLOT);
+                const int I0 = (T.y0 + q * RB) >> 1;
+                for (int e = lane; e < CROWS * CCOLS; e += 32) {
+                    const int row = e / CCOLS, col = e - row * CCOLS;
+                    const int I = I0 + row, J = CJ0 + col;
+                    if (I >= 0 && I < Cc.ny && J >= 0 && J < Cc.nx) cp_async8(dst + e, xc + (size_t)I * Cc.nx + J);
+                    else dst[e] = 0.0;
+                }
+            };
+            for (int q = 0; q <= PFB; ++q) {
+                if (q < c.nblk) stage_in(q);
+                cp_async_commit();
+            }
+            double win[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) win[r][q] = 0.0;
+            for (int m = 0; m < c.nblk; ++m) {
+                const int sx = m % L::NSX, hs = m % NHS, i0 = T.y0 + m * RB;
+                cp_async_wait<PFB>();
+                mbar_wait(full_b + (m % L::NSB), (m / L::NSB) & 1);
+                mbar_wait(full_x + sx, (m / L::NSX) & 1);
+                mbar_wait(empty_out + hs, ((m / NHS) & 1) ^ 1);
+                __syncwarp();
+                const double *cp = reinterpret_cast<const double *>(rcs + (size_t)sx * L::CSLOT) + (J0 - CJ0);
+                const unsigned char *b0 = b_block<NU, true>(c, m), *b1 = b_block<NU, true>(c, m - 1);
+                const unsigned char *xi = rx + (size_t)sx * BLK_BYTES;
+                unsigned char *bo_ = hout + (size_t)hs * BLK_BYTES;
+                double2 xin[RB], bin[RB];   // all loads of the block before its first store (see role_mid)
+                double cl[CROWS][2];        // the lane's coarse column and its east neighbour, the rows under the block
+#pragma unroll
+                for (int u = 0; u < RB; ++u) { xin[u] = blk_ld(xi, u, lane); bin[u] = b_of<2>(u, m, b0, b1, b1, lane); }
+#pragma unroll
+                for (int q = 0; q < CROWS; ++q) { cl[q][0] = cp[q * CCOLS]; cl[q][1] = cp[q * CCOLS + 1]; }
+                auto body = [&](auto fc) {
+                    constexpr bool fast = decltype(fc)::value;
+#pragma unroll
+                    for (int u = 0; u < RB; ++u) {
+                        const int i = i0 + u;
+                        Coef<NU> la, lb;
+                        // sweep 1 on row i-2 from the window of the prolongated iterate
+                        if (fast) { la = ca; lb = cb; } else row_coef<NU>(F, i - 2, ca, cb, irr, la, lb);
+                        const double2 bv = bin[u];
+                        double ra, rbv;
+                        node_pair<NU>(win, la, lb, bv.x, bv.y, ra, rbv);
+                        blk_st(bo_, u, lane, fma(la.wic[0], ra, win[1][1]), fma(lb.wic[0], rbv, win[1][2]));
+                        // prolongation on the entering row i
+                        const bool rowin = fast || (i >= 0 && i < F.ny);
+                        const bool odd = fast ? ((u & 1) != 0) : ((i & 1) != 0);
+                        const bool mi = odd && (fast || i != F.ny - 1);
+                        // coarse row under row i: patch row u/2; an odd last row sits on the patch row above
+                        const int q0 = (u >> 1) + ((odd && !mi) ? 1 : 0);
+                        double pa, pb;
+                        if (!mi) {
+                            pa = cl[q0][0];
+                            pb = mid1 ? 0.5 * (cl[q0][0] + cl[q0][1]) : cl[q0][1];
+                        } else {
+                            pa = 0.5 * (cl[q0][0] + cl[q0 + 1][0]);
+                            pb = mid1 ? 0.5 * (cl[q0][0] + cl[q0 + 1][1]) : 0.5 * (cl[q0][1] + cl[q0 + 1][1]);
+                        }
+                        double rm = rowin ? 1.0 : 0.0;
+                        if (!fast && rowin && (((F.dirmask & 8u) && i == 0) || ((F.dirmask & 4u) && i == F.ny - 1))) rm = 0.0;
+                        push_row(win, rm * m0 * (xin[u].x + pa), rm * m1 * (xin[u].y + pb));
+                    }
+                };
+                if (c.has_reg && i0 - 3 >= 1 && i0 + RB - 1 <= F.ireg_hi) body(cuda::std::true_type{});
+                else body(cuda::std::false_type{});
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_out + hs);
+                const int mp = m + PFB + 1;
+                if (mp < c.nblk) {
+                    if (lane == 0) {
+                        mbar_wait(empty_b + (mp % L::NSB), ((mp / L::NSB) & 1) ^ 1);
+                        fence_proxy_async();
+                    }
+                    __syncwarp();
+                    stage_in(mp);
+                }
+                cp_async_commit();
+            }
+        } else if (stage == NU - 1) {
+            role_mid<NU, NU - 1, true, true, DOT>(c, F, T, ca, cb, irr, x, dot);
+        } else {
+            if (NU == 3 || stage == 1) role_mid<NU, 1, true, false, false>(c, F, T, ca, cb, irr, nullptr, dot);
+            else role_mid<NU, (NU > 3 ? 2 : 1), true, false, false>(c, F, T, ca, cb, irr, nullptr, dot);
+        }
+    }
+    if (DOT) {
+        double v[1] = {dot}, tot[1];
+        if (grid_reduce<1>(v, partials, counter, tot) && !sc->done) *out_dot = tot[0];
+    }
+}
+
+}  // namespace PIPE

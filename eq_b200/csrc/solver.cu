@@ -1397,10 +1397,13 @@ int solver_setup(eqgpu_solver *s)
     s->levels[0].x = s->z;
     s->levels[0].b = s->r;
     // streaming smoothers: single GPU, isotropic operator; TMA descriptors where the pitch allows them
-    s->stream_smooth = !s->slab;
+    // (opt-in, EQGPU_STREAM=1: measured slower than the tile kernels on the B200 -- 49-93 us against 40 us for the level-0
+    // pre-smoother, profiles/r02_stream_smoothers.md -- and kept for the record of that experiment)
+    s->stream_smooth = false;
     if (const char *e = getenv("EQGPU_STREAM")) s->stream_smooth = atoi(e) != 0 && !s->slab;
     s->stream_min_nodes = 0;
     if (const char *e = getenv("EQGPU_STREAM_MIN")) s->stream_min_nodes = atoi(e);
+    s->stream_pipe = getenv("EQGPU_STREAM_PIPE") == nullptr || atoi(getenv("EQGPU_STREAM_PIPE")) != 0;
     s->stream_uni = getenv("EQGPU_STREAM_UNI") == nullptr || atoi(getenv("EQGPU_STREAM_UNI")) != 0;
     s->stream_apply = s->stream_smooth;
     if (const char *e = getenv("EQGPU_STREAM_APPLY")) s->stream_apply = atoi(e) != 0 && s->stream_smooth;
@@ -1874,10 +1877,10 @@ static STRM::UniCoef<NU> uni_coef(const LevelDev &F, const SmoothW &sw)
 
 // Resident CTAs of a streaming kernel on the whole device (registers decide: 64-thread CTAs of 100-250 registers).
 template <class K>
-static int stream_slots(const eqgpu_solver *s, K kernel, size_t smem)
+static int stream_slots(const eqgpu_solver *s, K kernel, size_t smem, int threads = 32 * STRM::WPC)
 {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * STRM::WPC, smem) != cudaSuccess || nb < 1) nb = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 4;
     (void)cudaGetLastError();
     return nb * s->num_sms;
 }
@@ -1885,20 +1888,21 @@ static int stream_slots(const eqgpu_solver *s, K kernel, size_t smem)
 // Task shape: strips of 64 columns, chunks of hs owned rows.  `lag` = rows the last sweep trails the entering row plus
 // what the output stage needs (pre: 2NU + 1, post: 2NU, apply: 2).  hs is chosen so that the grid is a whole number of
 // waves of resident CTAs (a 1.03-wave grid takes two task durations) at the smallest walked-rows x waves product.
-static STRM::StreamGeom stream_geom(const eqgpu_solver *s, const LevelDev &F, int halo, int lag, int slots)
+static STRM::StreamGeom stream_geom(const eqgpu_solver *s, const LevelDev &F, int halo, int lag, int slots,
+                                    int wpc = STRM::WPC, int fill = 14)
 {
     STRM::StreamGeom G;
     G.halo = halo;
     const int so = STRM::SWID - 2 * G.halo;
     G.nstrips = (F.nx + so - 1) / so;
-    const int cx = (G.nstrips + STRM::WPC - 1) / STRM::WPC;
+    const int cx = (G.nstrips + wpc - 1) / wpc;
     long long best = -1;
     G.hs = 16;
     for (int hs = 12; hs <= 192; hs += 2) {
         const int nch = (F.ny + hs - 1) / hs;
         const long long waves = ((long long)cx * nch + slots - 1) / slots;
         const int steps = ((hs + halo + lag + STRM::RB - 1) / STRM::RB) * STRM::RB;
-        const long long cost = waves * (steps + 14);   // + set-up and drain of a task, in walk steps
+        const long long cost = waves * (steps + fill);   // + set-up, pipeline fill and drain of a task, in walk steps
         if (best < 0 || cost <= best) { best = cost; G.hs = hs; }
     }
     if (const char *e = getenv("EQGPU_STREAM_HS")) G.hs = std::max(2, atoi(e) & ~1);   // tuning knob
@@ -1983,6 +1987,44 @@ static void launch_apply_stream(eqgpu_solver *s, cudaStream_t st, bool pdl_ok, d
 #undef SAPPLY
 }
 
+// warp-specialised sweep pipelines (PIPE::kp_*): one CTA of NU warps per task, TMA-staged levels only
+template <int NU>
+static void launch_pre_pipe(eqgpu_solver *s, cudaStream_t st, int l, bool pdl_ok)
+{
+    Level &lv = s->levels[l], &cv = s->levels[l + 1];
+    const SmoothW sw = smooth_weights_n(NU);
+    const size_t smem = PIPE::Layout<NU, false>::BYTES;
+    static bool attr = false;   // per process and device-independent here: raising the limit is idempotent
+    if (!attr || true) cudaFuncSetAttribute(PIPE::kp_presmooth<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+    const CGScalars *scc = s->sc;
+    const STRM::StreamGeom G = stream_geom(s, lv.dev, (NU + 2) & ~1, 2 * NU + 1,
+                                           stream_slots(s, PIPE::kp_presmooth<NU>, smem, 32 * NU), 1, 12 + 6 * NU);
+    LAUNCH_K(pdl_ok, (PIPE::kp_presmooth<NU>), dim3(G.nstrips, G.nchunks), dim3(32 * NU), smem, st, lv.dev, cv.dev, lv.map_b,
+             lv.t, cv.b, sw, G, scc);
+}
+
+template <int NU>
+static void launch_post_pipe(eqgpu_solver *s, cudaStream_t st, int l)
+{
+    Level &lv = s->levels[l], &cv = s->levels[l + 1];
+    const SmoothW sw = smooth_weights_n(NU);
+    const size_t smem = PIPE::Layout<NU, true>::BYTES;
+    double *out_dot = &s->sc->rz_new;
+#define PPOST(DOT)                                                                                                  \
+    do {                                                                                                            \
+        cudaFuncSetAttribute(PIPE::kp_postsmooth<NU, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        const STRM::StreamGeom G = stream_geom(s, lv.dev, (NU + 1) & ~1, 2 * NU,                                    \
+                                               stream_slots(s, PIPE::kp_postsmooth<NU, DOT>, smem, 32 * NU), 1,     \
+                                               12 + 6 * NU);                                                        \
+        LAUNCH_K(true, (PIPE::kp_postsmooth<NU, DOT>), dim3(G.nstrips, G.nchunks), dim3(32 * NU), smem, st, lv.dev, \
+                 cv.dev, lv.map_b, lv.map_t, lv.x, (const double *)cv.x, sw, G, s->sc, s->partials,                 \
+                 s->counters + 1, out_dot);                                                                         \
+    } while (0)
+    if (l == 0) PPOST(true); else PPOST(false);
+#undef PPOST
+}
+
 template <int NU>
 static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
 {
@@ -1993,7 +2035,8 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
     const CGScalars *scc = s->sc;
     const bool pdl_ok = l > 0;   // level 0 opens the iteration
     if (use_stream(s, lv)) {
-        launch_pre_stream<NU>(s, st, l, pdl_ok);
+        if (s->stream_pipe && lv.tma && NU >= 3) launch_pre_pipe<(NU >= 3 ? NU : 3)>(s, st, l, pdl_ok);
+        else launch_pre_stream<NU>(s, st, l, pdl_ok);
         s->launches++;
         trace_mark(st);
         return;
@@ -2024,7 +2067,8 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
     const SmoothW sw = smooth_weights_n(NU);
     const LevelDev &F = TV(s, lv), &Cc = TV(s, cv);
     if (use_stream(s, lv)) {
-        launch_post_stream<NU>(s, st, l);
+        if (s->stream_pipe && lv.tma && NU >= 3) launch_post_pipe<(NU >= 3 ? NU : 3)>(s, st, l);
+        else launch_post_stream<NU>(s, st, l);
         s->launches++;
         trace_mark(st);
         return;
