@@ -232,7 +232,7 @@ class GpuHSL:
     def path(self) -> dict:
         b = lib().eqgpu_solver_path(self._h)
         return {"fused": bool(b & 1), "slab": bool(b & 2), "slab_fused": bool(b & 4), "cluster_tail": bool(b & 8),
-                "tiled_coarsest": bool(b & 16), "tensor": bool(b & 32)}
+                "tiled_coarsest": bool(b & 16), "tensor": bool(b & 32), "register_tile_levels": (b >> 8) & 15}
 
     def slab_rows(self):
         a, b = C.c_int32(), C.c_int32()

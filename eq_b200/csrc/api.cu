@@ -1,4 +1,5 @@
 // extern "C" entry points of libeqgpu.so (include/eqgpu.h).
+#include <algorithm>
 #include "eqgpu_internal.cuh"
 #include <cstring>
 #include <new>
@@ -72,8 +73,11 @@ int eqgpu_slab_plan(int32_t nH, int32_t world, int32_t rank, int32_t max_levels,
 int eqgpu_solver_path(eqgpu_solver *s)
 {
     if (!s) return EQGPU_EINVAL;
+    int rt_levels = 0;
+    if (s->rt_smooth && !s->tensor)
+        for (const auto &lv : s->levels) rt_levels += (lv.rt_pre.on && lv.rt_post.on) ? 1 : 0;
     return (s->fused ? 1 : 0) | (s->slab ? 2 : 0) | (s->slab_fused ? 4 : 0) | (s->use_cluster ? 8 : 0) |
-           (s->tile_coarsest ? 16 : 0) | (s->tensor ? 32 : 0);
+           (s->tile_coarsest ? 16 : 0) | (s->tensor ? 32 : 0) | (std::min(rt_levels, 15) << 8);
 }
 
 int eqgpu_set_warm_start(eqgpu_solver *s, int mode)

@@ -52,7 +52,14 @@ struct LevelDev {
     // closed form of the padded cell sizes (uniform cells, only the last one may be narrower): regular and last cell
     // widths / heights of the GLOBAL grid, so that set-up code needs no global loads (mg_stream.cuh)
     double hxr, hxl, hyr, hyl;
+    // tile-list launches (mg_rt.cuh): when set, a tile kernel's CTA q works on tile (tlist[2q], tlist[2q+1]) of the level's
+    // tl_gx x tl_gy tile grid instead of (blockIdx.x, blockIdx.y), and a reduction it takes part in is shared with another
+    // kernel: one partial per tile of the whole grid, tl_gx * tl_gy arrivals in all
+    const int *tlist;
+    int tl_gx, tl_gy;
 };
+
+struct SmoothW { double w[4]; };          // per-sweep Jacobi weights (Chebyshev roots)
 
 struct CGScalars {
     double rz_old, rz_new, pAp, rr, bnorm2, stop2, rr0;
@@ -81,8 +88,8 @@ struct CGScalars {
 };
 
 struct Level {
-    LevelDev dev;    // local view (row 0 = first stored row): unfused kernels
-    LevelDev gdev;   // global view for the tile kernels (== dev on a single GPU)
+    LevelDev dev{};    // local view (row 0 = first stored row): unfused kernels
+    LevelDev gdev{};   // global view for the tile kernels (== dev on a single GPU)
     double *d_hy_g = nullptr, *d_ihy_g = nullptr;  // slab mode: padded row sizes of the whole grid
     std::vector<double> hx_host, hy_host;  // unpadded cell sizes (global grid)
     int g0 = 0, g1 = 0;                    // owned global rows [g0, g1)
@@ -92,6 +99,14 @@ struct Level {
     // streaming smoothers (mg_stream.cuh): TMA descriptors of the level's b and t vectors (row pitch 16-byte aligned)
     CUtensorMap map_b{}, map_t{};
     bool tma = false;
+    // register-tile smoothers (mg_rt.cuh): 64 x 64 TMA boxes of b and t, the rectangle of regular tiles they take, the list
+    // of the remaining (perimeter) tiles for the shared-memory tile kernels; one set per kernel shape (pre, post)
+    CUtensorMap map_b64{}, map_t64{};
+    struct RtPlan {
+        bool on = false;
+        int gx = 0, gy = 0, bx0 = 0, by0 = 0, nbx = 0, nby = 0, nperim = 0;
+        int *d_tlist = nullptr;
+    } rt_pre, rt_post;
     size_t n() const { return (size_t)dev.nx * dev.ny; }
 };
 
@@ -163,6 +178,13 @@ struct eqgpu_solver {
     CUtensorMap map_z{}, map_pv{}, map_pv2{};   // level-0 z and the two search-direction buffers (ks_apply_p)
     bool tma_p = false;
     const double *map_pv_ptr = nullptr;   // the buffer map_pv describes
+    bool rt_smooth = true;         // register-tile smoothers (mg_rt.cuh) on the interior tiles of the large levels
+    int rt_min_tiles = 148;        // ... of levels with at least this many regular tiles
+    int rt_ctas = 0;               // persistent CTAs of a register-tile kernel (2 per SM)
+    cudaStream_t rt_stream = nullptr;   // perimeter tiles run beside the interior ones
+    cudaEvent_t ev_rt_fork = nullptr, ev_rt_join = nullptr;
+    unsigned *rt_sched = nullptr;  // tile counters of the persistent kernels
+    bool pdl_block = false;        // the next launch follows a stream join: no programmatic edge
     bool stream_pipe = true;       // warp-specialised sweep pipelines (PIPE::kp_*) on TMA-capable levels
     bool stream_uni = true;        // constant-bank coefficient instances where every column is regular or Dirichlet
     bool stream_apply = false;     // ks_apply_p instead of the tile k_apply_p
@@ -217,6 +239,12 @@ int solver_rhs(eqgpu_solver *s, const double *du0, double *db);
 int solver_precond(eqgpu_solver *s);   // z = B r on the solver's own vectors (verification hook)
 int solver_refresh_levels(eqgpu_solver *s);
 int solver_bench(eqgpu_solver *s, const char *name, int reps, double *avg_ms, double *alg_bytes);
+// ---- smooth_rt.cu ----
+int rt_setup(eqgpu_solver *s);       // after the hierarchy exists: plans, descriptors, counters
+void rt_teardown(eqgpu_solver *s);
+// interior tiles of level l on `st` (the caller has forked the perimeter tiles); false: this level does not use them
+void rt_launch_pre(eqgpu_solver *s, cudaStream_t st, int l, int nu, const SmoothW &sw, bool pdl_ok);
+void rt_launch_post(eqgpu_solver *s, cudaStream_t st, int l, int nu, const SmoothW &sw, bool dot, double *out_dot);
 void solver_ls_solve3(const double G[6], const double f[3], double bb, double c[3], double *pred);
 // host-side entry for the CPU tests of the K x K ring fit (eqgpu_ring_solve); G packed upper triangle, row-major
 void solver_ring_solve(int K, const double *G, const double *f, double *c);
@@ -516,5 +544,43 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, u
     }
     if (tid == 0) *counter = 0u;
     return tid == 0;
+}
+
+// Reduction shared by the CTAs of SEVERAL kernels (tile-list launches): every tile of a level leaves one partial sum in
+// partials[tile], whichever kernel worked on it; a CTA then reports how many tiles it has finished, and the CTA whose report
+// completes the `total` tiles sums the partials in a fixed order (warp 0, lane-strided, then the shuffle tree), so the
+// result does not depend on which kernel or CTA came last.  Block-level part: the sum of v over the CTA in a fixed order,
+// valid in thread 0 (sm: >= 32 doubles of shared memory; contains a __syncthreads).
+__device__ __forceinline__ double cta_sum(double v, double *sm)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+    const double w = warp_sum(v);
+    if (lane == 0) sm[warp] = w;
+    __syncthreads();
+    double tot = 0.0;
+    if (tid == 0)
+        for (int k = 0; k < nwarps; ++k) tot += sm[k];
+    return tot;
+}
+// Called by all threads of a CTA after thread 0 has stored its partial(s); mine = tiles this CTA reports.
+// Returns true in thread 0 of the completing CTA with the total in *out.
+__device__ __forceinline__ bool tiles_arrive(double *partials, unsigned *counter, unsigned mine, unsigned total, double *out)
+{
+    __shared__ bool last_;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(counter, mine);
+        last_ = (t + mine == total);
+    }
+    __syncthreads();
+    if (!last_) return false;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        double w = 0.0;
+        for (unsigned b = threadIdx.x; b < total; b += 32) w += __ldcg(partials + b);
+        w = warp_sum(w);
+        if (threadIdx.x == 0) { *out = w; *counter = 0u; }
+    }
+    return threadIdx.x == 0;
 }
 #endif

@@ -25,7 +25,6 @@
 #define MAX_LEVELS 16
 #define MAX_CHEB 24
 
-struct SmoothW { double w[4]; };          // per-sweep Jacobi weights (Chebyshev roots)
 struct CoarseW { int n; double w[MAX_CHEB]; };
 
 // coarse node J <-> fine node min(2J, nf-1)

@@ -1512,6 +1512,10 @@ int solver_setup(eqgpu_solver *s)
         EQ_CUDA(cudaFuncSetAttribute((T64::k_postsmooth<NU, false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3)); \
         break;
         for (int q = 1; q <= 4; ++q) switch (q) { SET_SMEM(1) SET_SMEM(2) SET_SMEM(3) SET_SMEM(4) }
+        // tile-list instances beside the register-tile kernels (even halo: one extra node where the sweep count asks for an odd one)
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_presmooth<4, 8, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_postsmooth<3, true, 8, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+        EQ_CUDA(cudaFuncSetAttribute((T64::k_postsmooth<3, false, 8, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
         EQ_CUDA(cudaFuncSetAttribute((T64::k_coarsest<4>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm3));
         if (const char *e = getenv("EQGPU_TILE_COARSEST")) s->tile_coarsest = atoi(e) != 0 || !s->tail_fits || s->slab;
         // Levels whose 64-node tiling gives fewer than t32_below CTAs are latency-bound (one big tile per
@@ -1555,6 +1559,10 @@ int solver_setup(eqgpu_solver *s)
         }
         s->pdl = !s->slab;   // slab mode has NCCL calls between the kernels
         if (const char *e = getenv("EQGPU_PDL")) s->pdl = atoi(e) != 0 && !s->slab;
+        {
+            int rc = rt_setup(s);
+            if (rc) return rc;
+        }
 
 #undef SET_SMEM
     }
@@ -1563,6 +1571,7 @@ int solver_setup(eqgpu_solver *s)
 
 void solver_teardown(eqgpu_solver *s)
 {
+    rt_teardown(s);
     for (auto &lv : s->levels) {
         cudaFree(lv.d_hx); cudaFree(lv.d_ihx); cudaFree(lv.d_hy); cudaFree(lv.d_ihy);
         cudaFree(lv.d_hy_g); cudaFree(lv.d_ihy_g);
@@ -1806,11 +1815,12 @@ static inline void xch(eqgpu_solver *s, Level &lv, double *v, int depth)
         cudaLaunchConfig_t cfg_{};                                                                        \
         cfg_.gridDim = (G); cfg_.blockDim = (B); cfg_.dynamicSmemBytes = (SM); cfg_.stream = (ST);        \
         cudaLaunchAttribute at_[1];                                                                       \
-        if (s->pdl && (PDL_OK)) {                                                                         \
+        if (s->pdl && (PDL_OK) && !s->pdl_block) {                                                        \
             at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                               \
             at_[0].val.programmaticStreamSerializationAllowed = 1;                                        \
             cfg_.attrs = at_; cfg_.numAttrs = 1;                                                          \
         }                                                                                                 \
+        s->pdl_block = false;   /* (set by a launch that ends in a stream join) */                        \
         cudaLaunchKernelEx(&cfg_, KERN, __VA_ARGS__);                                                     \
     } while (0)
 
@@ -2041,6 +2051,29 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
         trace_mark(st);
         return;
     }
+    if constexpr (NU == 3 || NU == 4) {
+        if (s->rt_smooth && lv.rt_pre.on) {
+            // interior tiles: register-tile kernel (smooth_rt.cu) on `st`; perimeter tiles: the general tile kernel on a
+            // tile list, beside it on a second stream (a parallel branch of the iteration graph)
+            constexpr int HX = (NU + 1) & 1;   // the register tiles need an even halo
+            cudaEventRecord(s->ev_rt_fork, st);
+            cudaStreamWaitEvent(s->rt_stream, s->ev_rt_fork, 0);
+            if (lv.rt_pre.nperim > 0) {
+                LevelDev Fp = F;
+                Fp.tlist = lv.rt_pre.d_tlist; Fp.tl_gx = lv.rt_pre.gx; Fp.tl_gy = lv.rt_pre.gy;
+                LAUNCH_K(false, (T64::k_presmooth<NU, 8, HX>), dim3(lv.rt_pre.nperim), dim3(512), 2 * TN64 * sizeof(double),
+                         s->rt_stream, Fp, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
+                s->launches++;
+            }
+            cudaEventRecord(s->ev_rt_join, s->rt_stream);
+            rt_launch_pre(s, st, l, NU, sw, pdl_ok);
+            cudaStreamWaitEvent(st, s->ev_rt_join, 0);
+            s->pdl_block = true;
+            s->launches++;
+            trace_mark(st);
+            return;
+        }
+    }
     xch(s, lv, lv.b, NU + 1);
     if (use_t32(s, F, 64 - H2)) {
         const size_t tsm = 3 * TN32 * sizeof(double);
@@ -2073,9 +2106,34 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
         trace_mark(st);
         return;
     }
+    double *out_dot = s->slab ? &s->sc->part_rz : &s->sc->rz_new;
+    if constexpr (NU == 3 || NU == 4) {
+        if (s->rt_smooth && lv.rt_post.on) {   // as in launch_pre; the r.z sum of level 0 is shared by the two kernels
+            constexpr int HX = NU & 1;
+            cudaEventRecord(s->ev_rt_fork, st);
+            cudaStreamWaitEvent(s->rt_stream, s->ev_rt_fork, 0);
+            if (lv.rt_post.nperim > 0) {
+                LevelDev Fp = F;
+                Fp.tlist = lv.rt_post.d_tlist; Fp.tl_gx = lv.rt_post.gx; Fp.tl_gy = lv.rt_post.gy;
+#define PERIM(DOT)                                                                                                       \
+    LAUNCH_K(false, (T64::k_postsmooth<NU, DOT, 8, HX>), dim3(lv.rt_post.nperim), dim3(512), 2 * TN64 * sizeof(double),    \
+             s->rt_stream, Fp, Cc, (const double *)VP(s, lv, lv.b), (const double *)VP(s, lv, lv.t), VP(s, lv, lv.x),     \
+             (const double *)VP(s, cv, cv.x), sw, s->sc, s->partials, s->counters + 1, out_dot)
+                if (l == 0) PERIM(true); else PERIM(false);
+#undef PERIM
+                s->launches++;
+            }
+            cudaEventRecord(s->ev_rt_join, s->rt_stream);
+            rt_launch_post(s, st, l, NU, sw, l == 0, out_dot);
+            cudaStreamWaitEvent(st, s->ev_rt_join, 0);
+            s->pdl_block = true;
+            s->launches++;
+            trace_mark(st);
+            return;
+        }
+    }
     xch(s, cv, cv.x, NU + 1);   // coarse correction rows reached by the prolongation of my halo
     xch(s, lv, lv.t, NU);       // pre-smoothed iterate; lv.b halos are still valid from the pre-smoothing exchange
-    double *out_dot = s->slab ? &s->sc->part_rz : &s->sc->rz_new;
 #define POST(NS, DOT, R, NT, G, SM)                                                                               \
     LAUNCH_K(true, (NS::k_postsmooth<NU, DOT, R>), G, dim3(NT), SM, st, F, Cc, (const double *)VP(s, lv, lv.b),   \
              (const double *)VP(s, lv, lv.t), VP(s, lv, lv.x), (const double *)VP(s, cv, cv.x), sw, s->sc,        \

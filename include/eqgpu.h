@@ -206,7 +206,8 @@ EQGPU_API int eqgpu_build_rhs(eqgpu_solver *s, const double *host_u0, double *ho
 EQGPU_API int eqgpu_field_device_ptr(eqgpu_solver *s, void **dev_ptr);
 EQGPU_API int eqgpu_sync(eqgpu_solver *s);
 /* Which code path the solver selected (diagnostics / tests): bit 0 fused tile kernels, 1 row-slab mode,
- * 2 fused kernels in slab mode, 3 cluster tail, 4 tiled coarsest solve, 5 variable tensor active. */
+ * 2 fused kernels in slab mode, 3 cluster tail, 4 tiled coarsest solve, 5 variable tensor active; bits 8-11: number of
+ * multigrid levels whose interior tiles run on the register-tile smoothers (TMA-staged, smooth_rt.cu). */
 EQGPU_API int eqgpu_solver_path(eqgpu_solver *s);
 /* Starting guess of the iterative solve that stands in for LinearVariationalSolver::solve()
  * (src/fHSL.cpp:106; the reference's LU has no such notion).  mode 0: the field as given or zero, whichever
