@@ -104,9 +104,10 @@ struct Level {
     CUtensorMap map_b64{}, map_t64{};
     struct RtPlan {
         bool on = false;
-        int gx = 0, gy = 0, bx0 = 0, by0 = 0, nbx = 0, nby = 0, nperim = 0;
-        int *d_tlist = nullptr;
+        int gx = 0, gy = 0, n = 0, nperim = 0;      // tiling, tiles of the register-tile kernel, tiles of the general kernel
+        int *d_tiles = nullptr, *d_tlist = nullptr;  // their (bx, by) lists
     } rt_pre, rt_post;
+    bool rt_tma = false;   // 16-byte row pitch: TMA staging (else the register-tile kernels load their rows directly)
     size_t n() const { return (size_t)dev.nx * dev.ny; }
 };
 

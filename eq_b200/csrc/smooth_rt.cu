@@ -13,9 +13,12 @@
 //     per vector onto an mbarrier, issued for the NEXT tile as soon as the warps have copied the current one into registers,
 //     so HBM latency hides behind the sweeps of the current tile; CTAs are persistent (two per SM) and draw tiles from a
 //     counter; results leave by 128-bit stores straight from registers;
-//   * only tiles of regular nodes are handled (constant coefficients as immediate operands); the perimeter tiles of a level
-//     (walls, Dirichlet rows, the narrower last cell of a coarse grid: ~10 % of the tiles at 2048^2) stay with the general
-//     shared-memory kernels, launched on a tile list beside this kernel (solver.cu: launch_pre / launch_post).
+//   * a tile qualifies when every node of its 64 x 64 window is regular (constant coefficients), outside the grid (TMA fills
+//     zeros) or on a Dirichlet wall: the latter two are held at zero by a per-lane column mask folded into the sweep weight
+//     and a per-row bit.  Tiles that hold natural-boundary wall nodes or the narrower last cell of a coarse grid stay with
+//     the general shared-memory kernels, launched on a tile list beside this kernel (solver.cu: launch_pre / launch_post);
+//     with Dirichlet walls all round (the shipped trap) level 0 has none.
+//   * levels with an odd row pitch (1025, 513, ...: no TMA) load their rows straight into the registers (TMA = false).
 // Halo: H nodes per side, H even (128-bit alignment of the owned columns) and >= the stencil passes of the kernel.
 //
 // Same mathematics as mg_tile.inc (Chebyshev-weighted Jacobi sweeps, full-weighting restriction = P^T, P1 prolongation), so
@@ -33,8 +36,9 @@ constexpr int PS = 36;            // row stride of the coarse patch (34 x 34 use
 constexpr int PATCH = 34;
 
 struct Geom {
-    int gx, gy;                  // tile grid of the whole level (shared with the tile-list kernel)
-    int bx0, by0, nbx, nby;      // rectangle of tiles handled here
+    int gx, gy;          // tile grid of the whole level (shared with the tile-list kernel)
+    int n;               // tiles handled here ...
+    const int *tiles;    // ... as (bx, by) pairs
 };
 
 // ---- mbarrier / TMA --------------------------------------------------------------------------------------------------
@@ -76,6 +80,42 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // xa / xb: columns 2l / 2l+1, rows 0 .. RW+1 of the window (0 and RW+1: the neighbouring warps' boundary rows)
 struct Coef { double cC, cEW, cNS, cD; };
 
+// What a lane knows about its two columns and eight rows of the current tile
+struct Lane {
+    int ox, oy, bx, by;
+    double cma, cmb;     // 1.0: free node column, 0.0: outside the grid or a Dirichlet wall column
+    bool ina, inb;       // column inside the grid
+    unsigned rowm;       // bit k: row k of the band is inside the grid and not a Dirichlet wall row
+    unsigned rowin;      // bit k: row k of the band is inside the grid
+};
+
+template <int H>
+__device__ __forceinline__ Lane lane_of(const LevelDev &F, const Geom &G, int t, int w, int lane)
+{
+    constexpr int TO = TS - 2 * H;
+    Lane L;
+    L.bx = __ldg(G.tiles + 2 * t);
+    L.by = __ldg(G.tiles + 2 * t + 1);
+    L.ox = L.bx * TO - H;
+    L.oy = F.tbase + L.by * TO - H;
+    const int ja = L.ox + 2 * lane, jb = ja + 1;
+    const bool dl = F.dirmask & 1u, dr = F.dirmask & 2u, dt = F.dirmask & 4u, db = F.dirmask & 8u;
+    L.ina = ja >= 0 && ja < F.nx;
+    L.inb = jb >= 0 && jb < F.nx;
+    L.cma = (L.ina && !(dl && ja == 0) && !(dr && ja == F.nx - 1)) ? 1.0 : 0.0;
+    L.cmb = (L.inb && !(dl && jb == 0) && !(dr && jb == F.nx - 1)) ? 1.0 : 0.0;
+    unsigned m = 0, in = 0;
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+        const int gi = L.oy + w * RW + k;
+        const bool inside = gi >= 0 && gi < F.ny;
+        in |= inside ? (1u << k) : 0u;
+        m |= (inside && !(db && gi == 0) && !(dt && gi == F.ny - 1)) ? (1u << k) : 0u;
+    }
+    L.rowm = m; L.rowin = in;
+    return L;
+}
+
 // exch[buf][warp][0 = bottom row, 1 = top row][64]
 __device__ __forceinline__ void band_publish(double *exch, int buf, int w, int lane, const double (&xa)[RW + 2],
                                              const double (&xb)[RW + 2])
@@ -93,13 +133,16 @@ __device__ __forceinline__ void band_halo(const double *exch, int buf, int w, in
     xa[0] = lo.x; xb[0] = lo.y; xa[RW + 1] = hi.x; xb[RW + 1] = hi.y;
 }
 
-// One pass over the band.  RESID false: x <- x + wd (b - A x) in place;  true: the residual b - A x of the band's rows goes
-// to rows (row0 .. row0+RW-1) of the 64-column shared array `rt`, x is left alone.
+// One pass over the band.  RESID false: x <- x + wd (b - A x) in place, wda / wdb = wd times the column masks;  true: the
+// residual b - A x of the band's rows (times the column masks wda / wdb) goes to rows row0 .. row0+RW-1 of the 64-column
+// shared array `rt`, x is left alone.  Rows whose bit in rowm is clear stay (are stored as) zero.
 // Lane 0's west partial and lane 31's east partial are their own values (the shuffle has no source): the outermost columns
 // of the tile belong to the ring that goes stale, one node per pass, like the outermost rows.
-template <bool RESID>
-__device__ __forceinline__ void band_pass(const Coef &c, double wd, const double (&ba)[RW], const double (&bb)[RW],
-                                          double (&xa)[RW + 2], double (&xb)[RW + 2], double *rt, int row0, int lane)
+// MASKED false (tiles strictly inside the walls): no masks, wda is the weight of both columns.
+template <bool RESID, bool MASKED>
+__device__ __forceinline__ void band_pass(const Coef &c, double wda, double wdb, unsigned rowm, const double (&ba)[RW],
+                                          const double (&bb)[RW], double (&xa)[RW + 2], double (&xb)[RW + 2], double *rt,
+                                          int row0, int lane)
 {
     double oa = xa[0], ob = xb[0];
 #pragma unroll
@@ -115,34 +158,109 @@ __device__ __forceinline__ void band_pass(const Coef &c, double wd, const double
         const double axa = fma(c.cC, ca, fma(c.cNS, na + oa, ea)) + pl;
         const double axb = fma(c.cC, cb, fma(c.cNS, nb + ob, wb)) + qr;
         const double ra = ba[k - 1] - axa, rb = bb[k - 1] - axb;
-        if (RESID) {
-            *reinterpret_cast<double2 *>(rt + (row0 + k - 1) * TS + 2 * lane) = make_double2(ra, rb);
+        if (!MASKED) {
+            if (RESID) {
+                *reinterpret_cast<double2 *>(rt + (row0 + k - 1) * TS + 2 * lane) = make_double2(ra, rb);
+            } else {
+                xa[k] = fma(wda, ra, ca);
+                xb[k] = fma(wda, rb, cb);
+            }
         } else {
-            xa[k] = fma(wd, ra, ca);
-            xb[k] = fma(wd, rb, cb);
+            const bool ok = (rowm >> (k - 1)) & 1u;
+            if (RESID) {
+                *reinterpret_cast<double2 *>(rt + (row0 + k - 1) * TS + 2 * lane) =
+                    make_double2(ok ? wda * ra : 0.0, ok ? wdb * rb : 0.0);
+            } else {
+                xa[k] = ok ? fma(wda, ra, ca) : 0.0;
+                xb[k] = ok ? fma(wdb, rb, cb) : 0.0;
+            }
         }
         oa = ca; ob = cb;
     }
 }
 
-// tile index -> origin
-template <int H>
-__device__ __forceinline__ void tile_origin(const LevelDev &F, const Geom &G, int t, int &bx, int &by, int &ox, int &oy)
+// the band's rows of a field, straight from global memory (levels without a TMA descriptor); zeros outside the grid
+__device__ __forceinline__ void band_load(const LevelDev &F, const Lane &L, const double *__restrict__ g, int w, int lane,
+                                          double (&va)[RW], double (&vb)[RW])
 {
-    constexpr int TO = TS - 2 * H;
-    by = G.by0 + t / G.nbx;
-    bx = G.bx0 + t - (t / G.nbx) * G.nbx;
-    ox = bx * TO - H;
-    oy = F.tbase + by * TO - H;
+    const int ja = L.ox + 2 * lane;
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+        const bool in = (L.rowin >> k) & 1u;
+        const double *q = g + (size_t)(L.oy + w * RW + k) * F.nx + ja;
+        va[k] = (in && L.ina) ? __ldg(q) : 0.0;
+        vb[k] = (in && L.inb) ? __ldg(q + 1) : 0.0;
+    }
+}
+
+// owned nodes of the band to global memory (xa / xb rows 1 .. RW)
+template <int H, bool TMA>
+__device__ __forceinline__ void band_store(const LevelDev &F, const Lane &L, double *__restrict__ x, int w, int lane,
+                                           const double (&xa)[RW + 2], const double (&xb)[RW + 2])
+{
+    if (lane < H / 2 || lane >= 32 - H / 2) return;
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+        const int ly = w * RW + k;
+        if (ly < H || ly >= TS - H || !((L.rowin >> k) & 1u)) continue;
+        double *q = x + (size_t)(L.oy + ly) * F.nx + L.ox + 2 * lane;
+        if (TMA) {   // even pitch, even origin: the pair is inside the grid or outside it together, and 16-byte aligned
+            if (L.ina) *reinterpret_cast<double2 *>(q) = make_double2(xa[k + 1], xb[k + 1]);
+        } else {
+            if (L.ina) q[0] = xa[k + 1];
+            if (L.inb) q[1] = xb[k + 1];
+        }
+    }
+}
+
+// persistent-CTA tile scheduler: ids are drawn from sched[0]; the last CTA to leave (sched[1]) resets both
+__device__ __forceinline__ void sched_leave(unsigned *sched)
+{
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(sched + 1, 1u);
+        if (prev == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; }
+    }
+}
+
+// the sweeps of one pre-smoothing tile: x = w0 D^-1 b, NU - 1 passes, the residual into rt
+template <int NU, bool MASKED>
+__device__ __forceinline__ void pre_sweeps(const Coef &c, const SmoothW &sw, double icC, const Lane &L, double *exch, int &buf,
+                                           int w, int lane, const double (&ba)[RW], const double (&bb)[RW],
+                                           double (&xa)[RW + 2], double (&xb)[RW + 2], double *rt)
+{
+    const double ma = MASKED ? L.cma : 1.0, mb = MASKED ? L.cmb : 1.0;
+    {
+        const double wda = sw.w[0] * icC * ma, wdb = sw.w[0] * icC * mb;
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+            const bool ok = !MASKED || ((L.rowm >> k) & 1u);
+            xa[k + 1] = ok ? wda * ba[k] : 0.0;
+            xb[k + 1] = ok ? wdb * bb[k] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int s = 1; s < NU; ++s) {
+        band_publish(exch, buf, w, lane, xa, xb);
+        __syncthreads();
+        band_halo(exch, buf, w, lane, xa, xb);
+        buf ^= 1;
+        band_pass<false, MASKED>(c, sw.w[s] * icC * ma, sw.w[s] * icC * mb, L.rowm, ba, bb, xa, xb, nullptr, 0, lane);
+    }
+    band_publish(exch, buf, w, lane, xa, xb);
+    __syncthreads();
+    band_halo(exch, buf, w, lane, xa, xb);
+    buf ^= 1;
+    band_pass<true, MASKED>(c, ma, mb, L.rowm, ba, bb, xa, xb, rt, w * RW, lane);
 }
 
 // =====================================================================================================================
 // pre-smoothing: NU sweeps from a zero guess, residual, restriction.        reads b        writes x, b_coarse
 // =====================================================================================================================
-template <int NU, int H>
+template <int NU, int H, bool TMA>
 __global__ void __launch_bounds__(NT, 2)
-k_pre_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMap map_b, double *__restrict__ x,
-         double *__restrict__ bc, const SmoothW sw, const Geom G, unsigned *sched, const CGScalars *sc)
+k_pre_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMap map_b, const double *__restrict__ b,
+         double *__restrict__ x, double *__restrict__ bc, const SmoothW sw, const Geom G, unsigned *sched,
+         const CGScalars *sc)
 {
     static_assert(H % 2 == 0 && H >= NU + 1, "even halo of at least NU + 1 nodes");
     constexpr int TO = TS - 2 * H, CT = TO / 2;
@@ -153,18 +271,17 @@ k_pre_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMa
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(exch + 2 * NWARP * 2 * TS);
     int *ids = reinterpret_cast<int *>(bar + 1);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int ntiles = G.nbx * G.nby;
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    const int ntiles = G.n;
+    if (TMA && tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     pdl_wait();
     if (sc->done) return;
     if (tid == 0) {
         const int t0 = (int)atomicAdd(sched, 2u);
         ids[0] = t0; ids[1] = t0 + 1;
-        if (t0 < ntiles) {
-            int bx, by, ox, oy;
-            tile_origin<H>(F, G, t0, bx, by, ox, oy);
+        if (TMA && t0 < ntiles) {
+            constexpr int TO_ = TS - 2 * H;
             mbar_expect_tx(bar, TS * TS * 8);
-            tma_load_2d(bbuf, &map_b, bar, ox, oy);
+            tma_load_2d(bbuf, &map_b, bar, __ldg(G.tiles + 2 * t0) * TO_ - H, F.tbase + __ldg(G.tiles + 2 * t0 + 1) * TO_ - H);
         }
     }
     __syncthreads();
@@ -174,129 +291,165 @@ k_pre_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMa
     const Coef c{F.cC, F.cEW, F.cNS, F.cD};
     const double icC = F.icC;
     while (cur < ntiles) {
-        int bx, by, ox, oy;
-        tile_origin<H>(F, G, cur, bx, by, ox, oy);
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        const Lane L = lane_of<H>(F, G, cur, w, lane);
         double ba[RW], bb[RW], xa[RW + 2], xb[RW + 2];
+        if (TMA) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
 #pragma unroll
-        for (int k = 0; k < RW; ++k) {
-            const double2 v = *reinterpret_cast<const double2 *>(bbuf + (w * RW + k) * TS + 2 * lane);
-            ba[k] = v.x; bb[k] = v.y;
+            for (int k = 0; k < RW; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(bbuf + (w * RW + k) * TS + 2 * lane);
+                ba[k] = v.x; bb[k] = v.y;
+            }
+        } else {
+            band_load(F, L, b, w, lane, ba, bb);
         }
-        __syncthreads();   // everyone holds its rows: the box may be refilled
+        __syncthreads();   // everyone holds its rows: the box may be refilled (and the previous tile's restriction is over)
         unsigned t_nn = 0;
         if (tid == 0) {
             t_nn = atomicAdd(sched, 1u);   // the tile after the next one; consumed at the end of this tile
-            if (nxt < ntiles) {
-                int bx2, by2, ox2, oy2;
-                tile_origin<H>(F, G, nxt, bx2, by2, ox2, oy2);
+            if (TMA && nxt < ntiles) {
                 fence_proxy_async();
                 mbar_expect_tx(bar, TS * TS * 8);
-                tma_load_2d(bbuf, &map_b, bar, ox2, oy2);
+                tma_load_2d(bbuf, &map_b, bar, __ldg(G.tiles + 2 * nxt) * TO - H, F.tbase + __ldg(G.tiles + 2 * nxt + 1) * TO - H);
             }
         }
-        // sweep 1 from zero: x = w0 D^-1 b
-        {
-            const double wd = sw.w[0] * icC;
-#pragma unroll
-            for (int k = 0; k < RW; ++k) { xa[k + 1] = wd * ba[k]; xb[k + 1] = wd * bb[k]; }
-        }
-#pragma unroll
-        for (int s = 1; s < NU; ++s) {
-            band_publish(exch, buf, w, lane, xa, xb);
-            __syncthreads();
-            band_halo(exch, buf, w, lane, xa, xb);
-            buf ^= 1;
-            band_pass<false>(c, sw.w[s] * icC, ba, bb, xa, xb, nullptr, 0, lane);
-        }
-        band_publish(exch, buf, w, lane, xa, xb);
-        __syncthreads();
-        band_halo(exch, buf, w, lane, xa, xb);
-        buf ^= 1;
-        band_pass<true>(c, 0.0, ba, bb, xa, xb, rt, w * RW, lane);
+        // (tiles strictly inside the walls take the unmasked instance: a CTA-uniform branch)
+        if (L.ox >= 1 && L.ox + TS <= F.nx - 1 && L.oy >= 1 && L.oy + TS <= F.ny - 1)
+            pre_sweeps<NU, false>(c, sw, icC, L, exch, buf, w, lane, ba, bb, xa, xb, rt);
+        else
+            pre_sweeps<NU, true>(c, sw, icC, L, exch, buf, w, lane, ba, bb, xa, xb, rt);
         if (tid == 0) ids[it & 1] = (int)t_nn;
-        // pre-smoothed iterate of the owned region
-        if (lane >= H / 2 && lane < 32 - H / 2) {
-#pragma unroll
-            for (int k = 0; k < RW; ++k) {
-                const int ly = w * RW + k;
-                if (ly >= H && ly < TS - H)
-                    *reinterpret_cast<double2 *>(x + (size_t)(oy + ly) * F.nx + ox + 2 * lane) = make_double2(xa[k + 1], xb[k + 1]);
-            }
-        }
+        band_store<H, TMA>(F, L, x, w, lane, xa, xb);   // pre-smoothed iterate of the owned region
         __syncthreads();   // residual tile complete (and ids[] visible)
         // restriction (P^T, full weighting on the six mesh neighbours): coarse nodes = even fine nodes of the owned region
+        // (masked residuals are zero, so walls need no special weights; a Dirichlet coarse node gets zero)
         {
-            const int I0 = (oy + H) >> 1, J0 = (ox + H) >> 1;
+            const int I0 = (L.oy + H) >> 1, J0 = (L.ox + H) >> 1;
             for (int q = tid; q < CT * CT; q += NT) {
                 const int cy = q / CT, cx = q - cy * CT;
+                const int gi = L.oy + H + 2 * cy, gj = L.ox + H + 2 * cx;
+                if (gi >= F.ny || gj >= F.nx) continue;
                 const int cc = (H + 2 * cy) * TS + H + 2 * cx;
                 const double h = rt[cc + 1] + rt[cc - 1] + rt[cc + TS] + rt[cc - TS] + rt[cc + TS + 1] + rt[cc - TS - 1];
-                bc[(size_t)(I0 + cy) * Cc.nx + J0 + cx] = rt[cc] + 0.5 * h;
+                bc[(size_t)(I0 + cy) * Cc.nx + J0 + cx] = is_dirichlet(Cc, I0 + cy, J0 + cx) ? 0.0 : rt[cc] + 0.5 * h;
             }
+            // even node counts: the last fine node is odd and has a coarse node of its own, a Dirichlet one here
+            const bool lastx = !(F.nx & 1) && L.ox + TS - H >= F.nx, lasty = !(F.ny & 1) && L.oy + TS - H >= F.ny;
+            if (lastx)
+                for (int cy = tid; cy < CT; cy += NT)
+                    if (L.oy + H + 2 * cy < F.ny) bc[(size_t)(I0 + cy) * Cc.nx + Cc.nx - 1] = 0.0;
+            if (lasty)
+                for (int cx = tid; cx < CT; cx += NT)
+                    if (L.ox + H + 2 * cx < F.nx) bc[(size_t)(Cc.ny - 1) * Cc.nx + J0 + cx] = 0.0;
+            if (lastx && lasty && tid == 0) bc[(size_t)Cc.ny * Cc.nx - 1] = 0.0;
         }
         const int nn = ids[it & 1];
         cur = nxt; nxt = nn;
         ++it;
         // (the next tile's first write to rt comes after two more __syncthreads: no barrier needed here)
     }
-    if (tid == 0) {
-        const unsigned prev = atomicAdd(sched + 1, 1u);
-        if (prev == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; }
-    }
+    sched_leave(sched);
 }
 
 // =====================================================================================================================
 // post-smoothing: x = xin + P x_coarse, NU sweeps (+ x.b).        reads b, xin, x_coarse        writes x
 // =====================================================================================================================
-__device__ __forceinline__ void patch_fetch(const LevelDev &Cc, const double *__restrict__ xc, int ox, int oy, int tid,
-                                            double (&pv)[5])
+// Coarse patch under a tile: PATCH x PATCH coarse nodes from (oy >> 1, ox >> 1), clamped to the coarse grid (values that
+// belong to nodes outside the fine grid are masked later), copied global -> shared asynchronously (8-byte LDGSTS: the
+// coarse pitch is odd), so the next tile's patch costs no registers while the current tile is swept.
+__device__ __forceinline__ void patch_copy_async(const LevelDev &Cc, const double *__restrict__ xc, int ox, int oy, int tid,
+                                                 double *patch)
 {
     const int J0 = ox >> 1, I0 = oy >> 1;
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
         const int e = tid + q * NT;
         const int ci = e / PATCH, cj = e - ci * PATCH;
-        pv[q] = e < PATCH * PATCH ? __ldg(xc + (size_t)min(I0 + ci, Cc.ny - 1) * Cc.nx + min(J0 + cj, Cc.nx - 1)) : 0.0;
+        if (e < PATCH * PATCH)
+            cp_async8(patch + ci * PS + cj,
+                      xc + (size_t)min(max(I0 + ci, 0), Cc.ny - 1) * Cc.nx + min(max(J0 + cj, 0), Cc.nx - 1));
     }
+    cp_async_commit();
 }
-__device__ __forceinline__ void patch_store(double *patch, int tid, const double (&pv)[5])
+
+// prolongation: tile rows / columns are even <=> coincident with a coarse node (the tile origin is even; the odd last node
+// of an even-sized grid is a Dirichlet node here and masked)
+template <bool MASKED>
+__device__ __forceinline__ void post_prolong(const Lane &L, const double *patch, int w, int lane, double (&xa)[RW + 2],
+                                             double (&xb)[RW + 2])
 {
+    double p0[5], p1[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int e = tid + q * NT;
-        const int ci = e / PATCH, cj = e - ci * PATCH;
-        if (e < PATCH * PATCH) patch[ci * PS + cj] = pv[q];
+    for (int j = 0; j < 5; ++j) {
+        p0[j] = patch[(w * (RW / 2) + j) * PS + lane];
+        p1[j] = patch[(w * (RW / 2) + j) * PS + lane + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+        const int j = k >> 1;
+        double pa, pb;
+        if (k & 1) {   // midpoint row
+            pa = 0.5 * (p0[j] + p0[j + 1]);
+            pb = 0.5 * (p0[j] + p1[j + 1]);
+        } else {
+            pa = 0.5 * (p0[j] + p0[j]);
+            pb = 0.5 * (p0[j] + p1[j]);
+        }
+        if (MASKED) {
+            const bool ok = (L.rowm >> k) & 1u;
+            xa[k + 1] = ok ? L.cma * (xa[k + 1] + pa) : 0.0;
+            xb[k + 1] = ok ? L.cmb * (xb[k + 1] + pb) : 0.0;
+        } else {
+            xa[k + 1] += pa;
+            xb[k + 1] += pb;
+        }
     }
 }
 
-template <int NU, int H, bool DOT>
+template <int NU, bool MASKED>
+__device__ __forceinline__ void post_sweeps(const Coef &c, const SmoothW &sw, double icC, const Lane &L, double *exch, int &buf,
+                                            int w, int lane, const double (&ba)[RW], const double (&bb)[RW],
+                                            double (&xa)[RW + 2], double (&xb)[RW + 2])
+{
+    const double ma = MASKED ? L.cma : 1.0, mb = MASKED ? L.cmb : 1.0;
+#pragma unroll
+    for (int s = 0; s < NU; ++s) {
+        band_publish(exch, buf, w, lane, xa, xb);
+        __syncthreads();
+        band_halo(exch, buf, w, lane, xa, xb);
+        buf ^= 1;
+        band_pass<false, MASKED>(c, sw.w[s] * icC * ma, sw.w[s] * icC * mb, L.rowm, ba, bb, xa, xb, nullptr, 0, lane);
+    }
+}
+
+template <int NU, int H, bool DOT, bool TMA>
 __global__ void __launch_bounds__(NT, 2)
 k_post_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMap map_b,
-          const __grid_constant__ CUtensorMap map_x, double *__restrict__ x, const double *__restrict__ xc, const SmoothW sw,
-          const Geom G, unsigned *sched, CGScalars *sc, double *partials, unsigned *counter, double *out_dot)
+          const __grid_constant__ CUtensorMap map_x, const double *__restrict__ b, const double *__restrict__ xin,
+          double *__restrict__ x, const double *__restrict__ xc, const SmoothW sw, const Geom G, unsigned *sched,
+          CGScalars *sc, double *partials, unsigned *counter, double *out_dot)
 {
     static_assert(H % 2 == 0 && H >= NU, "even halo of at least NU nodes");
+    constexpr int TO = TS - 2 * H;
     extern __shared__ __align__(128) unsigned char smraw[];
     double *bbuf = reinterpret_cast<double *>(smraw);   // TMA boxes: 64 x 64 each
     double *xbuf = bbuf + TS * TS;
     double *exch = xbuf + TS * TS;                      // 2 x NWARP x 2 x 64
-    double *patch = exch + 2 * NWARP * 2 * TS;          // PATCH rows of stride PS
-    double *red = patch + PATCH * PS;                   // 32 doubles
+    double *patch2 = exch + 2 * NWARP * 2 * TS;         // two buffers of PATCH rows of stride PS
+    double *red = patch2 + 2 * PATCH * PS;              // 32 doubles
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(red + 32);
     int *ids = reinterpret_cast<int *>(bar + 1);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int ntiles = G.nbx * G.nby;
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    const int ntiles = G.n;
+    if (TMA && tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     pdl_wait();
     if (sc->done) return;
     if (tid == 0) {
         const int t0 = (int)atomicAdd(sched, 2u);
         ids[0] = t0; ids[1] = t0 + 1;
-        if (t0 < ntiles) {
-            int bx, by, ox, oy;
-            tile_origin<H>(F, G, t0, bx, by, ox, oy);
+        if (TMA && t0 < ntiles) {
+            const int ox = __ldg(G.tiles + 2 * t0) * TO - H, oy = F.tbase + __ldg(G.tiles + 2 * t0 + 1) * TO - H;
             mbar_expect_tx(bar, 2 * TS * TS * 8);
             tma_load_2d(bbuf, &map_b, bar, ox, oy);
             tma_load_2d(xbuf, &map_x, bar, ox, oy);
@@ -305,93 +458,68 @@ k_post_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorM
     __syncthreads();
     int cur = ids[0], nxt = ids[1];
     if (cur < ntiles) {   // the first tile's coarse patch
-        int bx, by, ox, oy;
-        tile_origin<H>(F, G, cur, bx, by, ox, oy);
-        double pv[5];
-        patch_fetch(Cc, xc, ox, oy, tid, pv);
-        patch_store(patch, tid, pv);
+        patch_copy_async(Cc, xc, __ldg(G.tiles + 2 * cur) * TO - H, F.tbase + __ldg(G.tiles + 2 * cur + 1) * TO - H, tid, patch2);
+        cp_async_wait<0>();
     }
     unsigned phase = 0, mine = 0;
     int it = 0, buf = 0;
     const Coef c{F.cC, F.cEW, F.cNS, F.cD};
     const double icC = F.icC;
     while (cur < ntiles) {
-        int bx, by, ox, oy;
-        tile_origin<H>(F, G, cur, bx, by, ox, oy);
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        const Lane L = lane_of<H>(F, G, cur, w, lane);
         double ba[RW], bb[RW], xa[RW + 2], xb[RW + 2];
+        if (TMA) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
 #pragma unroll
-        for (int k = 0; k < RW; ++k) {
-            const double2 v = *reinterpret_cast<const double2 *>(bbuf + (w * RW + k) * TS + 2 * lane);
-            const double2 u = *reinterpret_cast<const double2 *>(xbuf + (w * RW + k) * TS + 2 * lane);
-            ba[k] = v.x; bb[k] = v.y; xa[k + 1] = u.x; xb[k + 1] = u.y;
+            for (int k = 0; k < RW; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(bbuf + (w * RW + k) * TS + 2 * lane);
+                const double2 u = *reinterpret_cast<const double2 *>(xbuf + (w * RW + k) * TS + 2 * lane);
+                ba[k] = v.x; bb[k] = v.y; xa[k + 1] = u.x; xb[k + 1] = u.y;
+            }
+        } else {
+            double ta[RW], tb[RW];
+            band_load(F, L, b, w, lane, ba, bb);
+            band_load(F, L, xin, w, lane, ta, tb);
+#pragma unroll
+            for (int k = 0; k < RW; ++k) { xa[k + 1] = ta[k]; xb[k + 1] = tb[k]; }
         }
         __syncthreads();   // boxes consumed, and the patch written at the end of the previous tile (or above) is visible
         unsigned t_nn = 0;
         if (tid == 0) {
             t_nn = atomicAdd(sched, 1u);
-            if (nxt < ntiles) {
-                int bx2, by2, ox2, oy2;
-                tile_origin<H>(F, G, nxt, bx2, by2, ox2, oy2);
+            if (TMA && nxt < ntiles) {
+                const int ox2 = __ldg(G.tiles + 2 * nxt) * TO - H, oy2 = F.tbase + __ldg(G.tiles + 2 * nxt + 1) * TO - H;
                 fence_proxy_async();
                 mbar_expect_tx(bar, 2 * TS * TS * 8);
                 tma_load_2d(bbuf, &map_b, bar, ox2, oy2);
                 tma_load_2d(xbuf, &map_x, bar, ox2, oy2);
             }
         }
-        // prolongation: tile rows / columns are even <=> coincident with a coarse node (the tile origin is even)
-        {
-            double p0[5], p1[5];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                p0[j] = patch[(w * (RW / 2) + j) * PS + lane];
-                p1[j] = patch[(w * (RW / 2) + j) * PS + lane + 1];
-            }
-#pragma unroll
-            for (int k = 0; k < RW; ++k) {
-                const int j = k >> 1;
-                if (k & 1) {   // midpoint row
-                    xa[k + 1] += 0.5 * (p0[j] + p0[j + 1]);
-                    xb[k + 1] += 0.5 * (p0[j] + p1[j + 1]);
-                } else {
-                    xa[k + 1] += 0.5 * (p0[j] + p0[j]);
-                    xb[k + 1] += 0.5 * (p0[j] + p1[j]);
-                }
-            }
-        }
-        // the next tile's patch: loads in flight during the sweeps, stored once every warp is past its prolongation
-        double pv[5];
-        const bool more = nxt < ntiles;
-        if (more) {
-            int bx2, by2, ox2, oy2;
-            tile_origin<H>(F, G, nxt, bx2, by2, ox2, oy2);
-            patch_fetch(Cc, xc, ox2, oy2, tid, pv);
-        }
-#pragma unroll
-        for (int s = 0; s < NU; ++s) {
-            band_publish(exch, buf, w, lane, xa, xb);
-            __syncthreads();
-            band_halo(exch, buf, w, lane, xa, xb);
-            buf ^= 1;
-            band_pass<false>(c, sw.w[s] * icC, ba, bb, xa, xb, nullptr, 0, lane);
-        }
-        if (more) patch_store(patch, tid, pv);   // (after >= 1 __syncthreads since the prolongation read the old patch)
+        const double *patch = patch2 + (it & 1) * PATCH * PS;
+        const bool inner = L.ox >= 1 && L.ox + TS <= F.nx - 1 && L.oy >= 1 && L.oy + TS <= F.ny - 1;   // CTA-uniform
+        if (inner) post_prolong<false>(L, patch, w, lane, xa, xb);
+        else post_prolong<true>(L, patch, w, lane, xa, xb);
+        // the next tile's patch into the other buffer (last read during the previous tile): in flight during the sweeps
+        if (nxt < ntiles)
+            patch_copy_async(Cc, xc, __ldg(G.tiles + 2 * nxt) * TO - H, F.tbase + __ldg(G.tiles + 2 * nxt + 1) * TO - H, tid,
+                             patch2 + ((it + 1) & 1) * PATCH * PS);
+        if (inner) post_sweeps<NU, false>(c, sw, icC, L, exch, buf, w, lane, ba, bb, xa, xb);
+        else post_sweeps<NU, true>(c, sw, icC, L, exch, buf, w, lane, ba, bb, xa, xb);
+        cp_async_wait<0>();   // my share of the next patch has landed; the barrier below publishes it
         if (tid == 0) ids[it & 1] = (int)t_nn;
-        double acc = 0.0;
-        if (lane >= H / 2 && lane < 32 - H / 2) {
+        band_store<H, TMA>(F, L, x, w, lane, xa, xb);
+        if (DOT) {
+            double acc = 0.0;
+            if (lane >= H / 2 && lane < 32 - H / 2) {
 #pragma unroll
-            for (int k = 0; k < RW; ++k) {
-                const int ly = w * RW + k;
-                if (ly >= H && ly < TS - H) {
-                    *reinterpret_cast<double2 *>(x + (size_t)(oy + ly) * F.nx + ox + 2 * lane) = make_double2(xa[k + 1], xb[k + 1]);
-                    if (DOT) acc += xa[k + 1] * ba[k] + xb[k + 1] * bb[k];
+                for (int k = 0; k < RW; ++k) {
+                    const int ly = w * RW + k;
+                    if (ly >= H && ly < TS - H) acc += xa[k + 1] * ba[k] + xb[k + 1] * bb[k];   // zero outside the grid
                 }
             }
-        }
-        if (DOT) {
             const double t = cta_sum(acc, red);   // contains the __syncthreads that publishes ids[] and the patch
-            if (tid == 0) partials[by * G.gx + bx] = t;
+            if (tid == 0) partials[L.by * G.gx + L.bx] = t;
             ++mine;
         } else {
             __syncthreads();
@@ -401,10 +529,7 @@ k_post_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorM
         ++it;
     }
     if (DOT && mine) tiles_arrive(partials, counter, mine, (unsigned)(G.gx * G.gy), out_dot);
-    if (tid == 0) {
-        const unsigned prev = atomicAdd(sched + 1, 1u);
-        if (prev == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; }
-    }
+    sched_leave(sched);
 }
 
 }  // namespace RT
@@ -416,7 +541,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// TMA descriptor of an nx x ny fp64 field (row-major, pitch nx) with a 64 x 64 box
+// TMA descriptor of an nx x ny fp64 field (row-major, pitch nx) with a 64 x 64 box; elements outside the field arrive as
+// zeros.  False when the driver entry point is missing or the pitch is not a multiple of 16 bytes (odd nx).
 static bool make_tile_map(CUtensorMap *map, double *base, int nx, int ny)
 {
     static PFN_encodeTiled enc = nullptr;
@@ -443,35 +569,40 @@ static int rt_halo_pre(int nu) { return (nu + 2) & ~1; }    // even, >= nu + 1
 static int rt_halo_post(int nu) { return (nu + 1) & ~1; }   // even, >= nu
 
 static const size_t RT_SMEM_PRE = (size_t)(2 * RT::TS * RT::TS + 2 * RT::NWARP * 2 * RT::TS) * 8 + 64;
-static const size_t RT_SMEM_POST = (size_t)(2 * RT::TS * RT::TS + 2 * RT::NWARP * 2 * RT::TS + RT::PATCH * RT::PS + 32) * 8 + 64;
+static const size_t RT_SMEM_POST = (size_t)(2 * RT::TS * RT::TS + 2 * RT::NWARP * 2 * RT::TS + 2 * RT::PATCH * RT::PS + 32) * 8 + 64;
 
-// The largest rectangle of tiles whose 64 x 64 window holds regular nodes only (the regular nodes form a rectangle, so the
-// regular tiles do), and the list of all other tiles of the level's gx x gy tiling with halo h.
+// Splits the gx x gy tiling (halo h) of a level into the tiles the register-tile kernel takes -- every node of the 64 x 64
+// window regular, outside the grid, or on a Dirichlet wall -- and the rest (tile list of the general kernel).
 static int plan_level(eqgpu_solver *s, const LevelDev &F, int h, Level::RtPlan &P)
 {
     const int to = RT::TS - 2 * h;
     P.on = false;
     P.gx = (F.nx + to - 1) / to;
     P.gy = (F.ny + to - 1) / to;
-    auto regx = [&](int b) { const int o = b * to - h; return o >= 1 && o + RT::TS - 1 <= F.jreg_hi; };
-    auto regy = [&](int b) { const int o = b * to - h; return o >= 1 && o + RT::TS - 1 <= F.ireg_hi; };
-    int bx0 = 0, bx1 = P.gx, by0 = 0, by1 = P.gy;
-    while (bx0 < bx1 && !regx(bx0)) ++bx0;
-    while (bx1 > bx0 && !regx(bx1 - 1)) --bx1;
-    while (by0 < by1 && !regy(by0)) ++by0;
-    while (by1 > by0 && !regy(by1 - 1)) --by1;
-    for (int b = bx0; b < bx1; ++b) if (!regx(b)) return 0;
-    for (int b = by0; b < by1; ++b) if (!regy(b)) return 0;
-    P.bx0 = bx0; P.by0 = by0; P.nbx = bx1 - bx0; P.nby = by1 - by0;
-    if (P.nbx * P.nby < s->rt_min_tiles) return 0;
-    std::vector<int> tl;
+    const bool dl = F.dirmask & 1u, dr = F.dirmask & 2u, dt = F.dirmask & 4u, db = F.dirmask & 8u;
+    auto line_ok = [&](int o, int n, int reg_hi, bool dlo, bool dhi) {
+        for (int q = std::max(o, 0); q <= std::min(o + RT::TS - 1, n - 1); ++q) {
+            const bool regular = q >= 1 && q <= reg_hi;
+            const bool dirichlet = (q == 0 && dlo) || (q == n - 1 && dhi);
+            if (!regular && !dirichlet) return false;
+        }
+        return true;
+    };
+    std::vector<int> mine, rest;
     for (int by = 0; by < P.gy; ++by)
-        for (int bx = 0; bx < P.gx; ++bx)
-            if (!(bx >= bx0 && bx < bx1 && by >= by0 && by < by1)) { tl.push_back(bx); tl.push_back(by); }
-    P.nperim = (int)tl.size() / 2;
+        for (int bx = 0; bx < P.gx; ++bx) {
+            const bool ok = line_ok(bx * to - h, F.nx, F.jreg_hi, dl, dr) && line_ok(by * to - h, F.ny, F.ireg_hi, db, dt);
+            std::vector<int> &v = ok ? mine : rest;
+            v.push_back(bx); v.push_back(by);
+        }
+    P.n = (int)mine.size() / 2;
+    P.nperim = (int)rest.size() / 2;
+    if (P.n < s->rt_min_tiles) return 0;
+    EQ_CUDA(cudaMalloc(&P.d_tiles, sizeof(int) * mine.size()));
+    EQ_CUDA(cudaMemcpy(P.d_tiles, mine.data(), sizeof(int) * mine.size(), cudaMemcpyHostToDevice));
     if (P.nperim > 0) {
-        EQ_CUDA(cudaMalloc(&P.d_tlist, sizeof(int) * tl.size()));
-        EQ_CUDA(cudaMemcpy(P.d_tlist, tl.data(), sizeof(int) * tl.size(), cudaMemcpyHostToDevice));
+        EQ_CUDA(cudaMalloc(&P.d_tlist, sizeof(int) * rest.size()));
+        EQ_CUDA(cudaMemcpy(P.d_tlist, rest.data(), sizeof(int) * rest.size(), cudaMemcpyHostToDevice));
     }
     P.on = true;
     return 0;
@@ -487,29 +618,41 @@ static bool set_smem(K kernel, size_t bytes)
 
 int rt_setup(eqgpu_solver *s)
 {
-    s->rt_smooth = !s->slab && s->fused && !s->tensor;
+    s->rt_smooth = !s->slab && s->fused;
     if (const char *e = getenv("EQGPU_RT")) s->rt_smooth = s->rt_smooth && atoi(e) != 0;
     if (const char *e = getenv("EQGPU_RT_MIN_TILES")) s->rt_min_tiles = std::max(1, atoi(e));
     if (!s->rt_smooth) return 0;
-    bool ok = set_smem(RT::k_pre_rt<3, 4>, RT_SMEM_PRE) && set_smem(RT::k_pre_rt<4, 6>, RT_SMEM_PRE) &&
-              set_smem(RT::k_post_rt<3, 4, true>, RT_SMEM_POST) && set_smem(RT::k_post_rt<3, 4, false>, RT_SMEM_POST) &&
-              set_smem(RT::k_post_rt<4, 4, true>, RT_SMEM_POST) && set_smem(RT::k_post_rt<4, 4, false>, RT_SMEM_POST);
+    bool ok = true;
+#define RT_SET(TMA)                                                                                                        \
+    ok = ok && set_smem(RT::k_pre_rt<3, 4, TMA>, RT_SMEM_PRE) && set_smem(RT::k_pre_rt<4, 6, TMA>, RT_SMEM_PRE) &&         \
+         set_smem(RT::k_post_rt<3, 4, true, TMA>, RT_SMEM_POST) && set_smem(RT::k_post_rt<3, 4, false, TMA>, RT_SMEM_POST) && \
+         set_smem(RT::k_post_rt<4, 4, true, TMA>, RT_SMEM_POST) && set_smem(RT::k_post_rt<4, 4, false, TMA>, RT_SMEM_POST)
+    RT_SET(true);
+    RT_SET(false);
+#undef RT_SET
     if (!ok) { s->rt_smooth = false; return 0; }
     s->rt_ctas = 2 * s->num_sms;
     if (const char *e = getenv("EQGPU_RT_CTAS")) s->rt_ctas = std::max(1, atoi(e));
     EQ_CUDA(cudaMalloc(&s->rt_sched, sizeof(unsigned) * 4));
     EQ_CUDA(cudaMemset(s->rt_sched, 0, sizeof(unsigned) * 4));
-    EQ_CUDA(cudaStreamCreateWithFlags(&s->rt_stream, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;   // highest priority: the few general tiles should start first, beside the others
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        EQ_CUDA(cudaStreamCreateWithPriority(&s->rt_stream, cudaStreamNonBlocking, prio_hi));
+    }
     EQ_CUDA(cudaEventCreateWithFlags(&s->ev_rt_fork, cudaEventDisableTiming));
     EQ_CUDA(cudaEventCreateWithFlags(&s->ev_rt_join, cudaEventDisableTiming));
-    int max_level = 1;   // levels 0 .. max_level may use the register-tile kernels
+    // levels 0 .. max_level may use the register-tile kernels.  Level 1 of the 2048^2 hierarchy (1025^2: odd pitch, no TMA,
+    // a narrower last cell, ~1 tile per CTA) measured no faster than the tile kernels: level 0 only unless asked
+    int max_level = 0;
     if (const char *e = getenv("EQGPU_RT_LEVELS")) max_level = atoi(e) - 1;
+    const bool no_tma = getenv("EQGPU_NO_TMA") != nullptr;
     for (size_t l = 0; l + 1 < s->levels.size() && (int)l <= max_level; ++l) {
         Level &lv = s->levels[l];
         const int nu = l == 0 ? s->nu : s->nuc;
         if (nu != 3 && nu != 4) continue;
-        if (!make_tile_map(&lv.map_b64, lv.b, lv.dev.nx, lv.dev.ny) || !make_tile_map(&lv.map_t64, lv.t, lv.dev.nx, lv.dev.ny))
-            continue;
+        lv.rt_tma = !no_tma && make_tile_map(&lv.map_b64, lv.b, lv.dev.nx, lv.dev.ny) &&
+                    make_tile_map(&lv.map_t64, lv.t, lv.dev.nx, lv.dev.ny);
         int rc = plan_level(s, lv.dev, rt_halo_pre(nu), lv.rt_pre);
         if (rc) return rc;
         rc = plan_level(s, lv.dev, rt_halo_post(nu), lv.rt_post);
@@ -521,8 +664,11 @@ int rt_setup(eqgpu_solver *s)
 void rt_teardown(eqgpu_solver *s)
 {
     for (auto &lv : s->levels) {
-        cudaFree(lv.rt_pre.d_tlist); lv.rt_pre.d_tlist = nullptr; lv.rt_pre.on = false;
-        cudaFree(lv.rt_post.d_tlist); lv.rt_post.d_tlist = nullptr; lv.rt_post.on = false;
+        for (Level::RtPlan *P : {&lv.rt_pre, &lv.rt_post}) {
+            cudaFree(P->d_tlist); P->d_tlist = nullptr;
+            cudaFree(P->d_tiles); P->d_tiles = nullptr;
+            P->on = false;
+        }
     }
     cudaFree(s->rt_sched); s->rt_sched = nullptr;
     if (s->ev_rt_fork) { cudaEventDestroy(s->ev_rt_fork); s->ev_rt_fork = nullptr; }
@@ -533,14 +679,14 @@ void rt_teardown(eqgpu_solver *s)
 static RT::Geom geom_of(const Level::RtPlan &P)
 {
     RT::Geom G;
-    G.gx = P.gx; G.gy = P.gy; G.bx0 = P.bx0; G.by0 = P.by0; G.nbx = P.nbx; G.nby = P.nby;
+    G.gx = P.gx; G.gy = P.gy; G.n = P.n; G.tiles = P.d_tiles;
     return G;
 }
 
 #define RT_LAUNCH(PDL_OK, KERN, SM, ST, ...)                                                              \
     do {                                                                                                  \
         cudaLaunchConfig_t cfg_{};                                                                        \
-        cfg_.gridDim = dim3(std::min(s->rt_ctas, G.nbx * G.nby)); cfg_.blockDim = dim3(RT::NT);           \
+        cfg_.gridDim = dim3(std::min(s->rt_ctas, G.n)); cfg_.blockDim = dim3(RT::NT);                     \
         cfg_.dynamicSmemBytes = (SM); cfg_.stream = (ST);                                                 \
         cudaLaunchAttribute at_[1];                                                                       \
         if (s->pdl && (PDL_OK) && !s->pdl_block) {                                                        \
@@ -557,21 +703,25 @@ void rt_launch_pre(eqgpu_solver *s, cudaStream_t st, int l, int nu, const Smooth
     Level &lv = s->levels[l], &cv = s->levels[l + 1];
     const RT::Geom G = geom_of(lv.rt_pre);
     const CGScalars *scc = s->sc;
-    if (nu == 3)
-        RT_LAUNCH(pdl_ok, (RT::k_pre_rt<3, 4>), RT_SMEM_PRE, st, lv.dev, cv.dev, lv.map_b64, lv.t, cv.b, sw, G, s->rt_sched, scc);
-    else
-        RT_LAUNCH(pdl_ok, (RT::k_pre_rt<4, 6>), RT_SMEM_PRE, st, lv.dev, cv.dev, lv.map_b64, lv.t, cv.b, sw, G, s->rt_sched, scc);
+    const double *b = lv.b;
+#define RT_PRE(NU, H, TMA) \
+    RT_LAUNCH(pdl_ok, (RT::k_pre_rt<NU, H, TMA>), RT_SMEM_PRE, st, lv.dev, cv.dev, lv.map_b64, b, lv.t, cv.b, sw, G, s->rt_sched, scc)
+    if (nu == 3) { if (lv.rt_tma) RT_PRE(3, 4, true); else RT_PRE(3, 4, false); }
+    else { if (lv.rt_tma) RT_PRE(4, 6, true); else RT_PRE(4, 6, false); }
+#undef RT_PRE
 }
 
 void rt_launch_post(eqgpu_solver *s, cudaStream_t st, int l, int nu, const SmoothW &sw, bool dot, double *out_dot)
 {
     Level &lv = s->levels[l], &cv = s->levels[l + 1];
     const RT::Geom G = geom_of(lv.rt_post);
-    const double *xc = cv.x;
-#define RT_POST(NU, DOT)                                                                                                  \
-    RT_LAUNCH(true, (RT::k_post_rt<NU, 4, DOT>), RT_SMEM_POST, st, lv.dev, cv.dev, lv.map_b64, lv.map_t64, lv.x, xc, sw, G, \
-              s->rt_sched + 2, s->sc, s->partials, s->counters + 1, out_dot)
-    if (nu == 3) { if (dot) RT_POST(3, true); else RT_POST(3, false); }
-    else { if (dot) RT_POST(4, true); else RT_POST(4, false); }
+    const double *xc = cv.x, *b = lv.b, *xin = lv.t;
+#define RT_POST(NU, DOT, TMA)                                                                                              \
+    RT_LAUNCH(true, (RT::k_post_rt<NU, 4, DOT, TMA>), RT_SMEM_POST, st, lv.dev, cv.dev, lv.map_b64, lv.map_t64, b, xin, lv.x, \
+              xc, sw, G, s->rt_sched + 2, s->sc, s->partials, s->counters + 1, out_dot)
+#define RT_POST2(NU, DOT) do { if (lv.rt_tma) RT_POST(NU, DOT, true); else RT_POST(NU, DOT, false); } while (0)
+    if (nu == 3) { if (dot) RT_POST2(3, true); else RT_POST2(3, false); }
+    else { if (dot) RT_POST2(4, true); else RT_POST2(4, false); }
+#undef RT_POST2
 #undef RT_POST
 }

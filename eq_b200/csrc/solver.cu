@@ -2056,19 +2056,22 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
             // interior tiles: register-tile kernel (smooth_rt.cu) on `st`; perimeter tiles: the general tile kernel on a
             // tile list, beside it on a second stream (a parallel branch of the iteration graph)
             constexpr int HX = (NU + 1) & 1;   // the register tiles need an even halo
-            cudaEventRecord(s->ev_rt_fork, st);
-            cudaStreamWaitEvent(s->rt_stream, s->ev_rt_fork, 0);
-            if (lv.rt_pre.nperim > 0) {
+            const bool fork = lv.rt_pre.nperim > 0;
+            if (fork) {
+                cudaEventRecord(s->ev_rt_fork, st);
+                cudaStreamWaitEvent(s->rt_stream, s->ev_rt_fork, 0);
                 LevelDev Fp = F;
                 Fp.tlist = lv.rt_pre.d_tlist; Fp.tl_gx = lv.rt_pre.gx; Fp.tl_gy = lv.rt_pre.gy;
                 LAUNCH_K(false, (T64::k_presmooth<NU, 8, HX>), dim3(lv.rt_pre.nperim), dim3(512), 2 * TN64 * sizeof(double),
                          s->rt_stream, Fp, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
                 s->launches++;
+                cudaEventRecord(s->ev_rt_join, s->rt_stream);
             }
-            cudaEventRecord(s->ev_rt_join, s->rt_stream);
             rt_launch_pre(s, st, l, NU, sw, pdl_ok);
-            cudaStreamWaitEvent(st, s->ev_rt_join, 0);
-            s->pdl_block = true;
+            if (fork) {
+                cudaStreamWaitEvent(st, s->ev_rt_join, 0);
+                s->pdl_block = true;
+            }
             s->launches++;
             trace_mark(st);
             return;
@@ -2110,9 +2113,10 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
     if constexpr (NU == 3 || NU == 4) {
         if (s->rt_smooth && lv.rt_post.on) {   // as in launch_pre; the r.z sum of level 0 is shared by the two kernels
             constexpr int HX = NU & 1;
-            cudaEventRecord(s->ev_rt_fork, st);
-            cudaStreamWaitEvent(s->rt_stream, s->ev_rt_fork, 0);
-            if (lv.rt_post.nperim > 0) {
+            const bool fork = lv.rt_post.nperim > 0;
+            if (fork) {
+                cudaEventRecord(s->ev_rt_fork, st);
+                cudaStreamWaitEvent(s->rt_stream, s->ev_rt_fork, 0);
                 LevelDev Fp = F;
                 Fp.tlist = lv.rt_post.d_tlist; Fp.tl_gx = lv.rt_post.gx; Fp.tl_gy = lv.rt_post.gy;
 #define PERIM(DOT)                                                                                                       \
@@ -2122,11 +2126,13 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
                 if (l == 0) PERIM(true); else PERIM(false);
 #undef PERIM
                 s->launches++;
+                cudaEventRecord(s->ev_rt_join, s->rt_stream);
             }
-            cudaEventRecord(s->ev_rt_join, s->rt_stream);
             rt_launch_post(s, st, l, NU, sw, l == 0, out_dot);
-            cudaStreamWaitEvent(st, s->ev_rt_join, 0);
-            s->pdl_block = true;
+            if (fork) {
+                cudaStreamWaitEvent(st, s->ev_rt_join, 0);
+                s->pdl_block = true;
+            }
             s->launches++;
             trace_mark(st);
             return;
