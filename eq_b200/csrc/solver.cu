@@ -216,7 +216,10 @@ __device__ __forceinline__ void frame_apply(const LevelDev &L, const DirData &dd
 // (D) and (E) are r1 - d1 and r1 - 2 d1 + d2), and the four squared norms.
 // Tiles that touch the irregular frame (wall rows/columns, their Dirichlet-adjacent neighbours, the
 // narrower last cell) take the general per-node path.
-__global__ void __launch_bounds__(INIT_THREADS)
+// NTH threads (1024: 4 rows per thread, one CTA per SM; 512: 8 rows, two CTAs per SM when the history is short: MAXH <= 1
+// keeps the register count at 64) and MAXH, the compile-time bound of nh.
+template <int NTH, int MAXH>
+__global__ void __launch_bounds__(NTH, NTH == 512 ? 2 : 1)
 k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *__restrict__ h0,
             const double *__restrict__ h1, const double *__restrict__ h2, const double *__restrict__ h3, int nh,
             double *__restrict__ r1, double *__restrict__ rB, double *__restrict__ d1o, double *__restrict__ d2o,
@@ -225,7 +228,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
 {
     // Row slabs: L is the rank's local view (halo rows included); only owned rows [own0, own1) are written
     // and summed, and the sums are rank-local partials (slab != 0) for the host to all-reduce.
-    constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = TSI * TSI / INIT_THREADS;
+    constexpr int TSI = 64, TPI = TSI + 2, TOI = TSI - 2, TROWS = TSI * TSI / NTH;
     extern __shared__ double sm_init[];   // five tiles: u0, h0, h1, h2, h3
     const int ox = blockIdx.x * TOI - 1, oy = blockIdx.y * TOI - 1;
     const int lx = threadIdx.x & (TSI - 1), ly0 = (threadIdx.x >> 6) * TROWS;
@@ -250,9 +253,9 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
         };
         stage(u, 0, true);
         stage(h0, 1, nh >= 1);
-        stage(h1, 2, nh >= 2);
-        stage(h2, 3, nh >= 3);
-        stage(h3, 4, nh >= 4);
+        stage(h1, 2, MAXH >= 2 && nh >= 2);
+        stage(h2, 3, MAXH >= 3 && nh >= 3);
+        stage(h3, 4, MAXH >= 4 && nh >= 4);
         // 7-point walk up the thread's column over tile q: mass row or operator row
         auto walk = [&](int q, bool mass, double (&out)[TROWS]) {
             const double *sp = sm_init + q * (TPI * TPI);
@@ -291,7 +294,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 }
             }
         }
-        if (nh >= 2) {
+        if (MAXH >= 2 && nh >= 2) {
             cp_async_wait<2>();
             __syncthreads();
             if (col) {
@@ -300,7 +303,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 for (int k = 0; k < TROWS; ++k) { d1[k] -= a[k]; d2[k] = a[k]; }
             }
         }
-        if (nh >= 3) {
+        if (MAXH >= 3 && nh >= 3) {
             cp_async_wait<1>();
             __syncthreads();
             if (col) {
@@ -309,7 +312,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 for (int k = 0; k < TROWS; ++k) { d2[k] -= a[k]; d3[k] = a[k]; }
             }
         }
-        if (nh >= 4) {
+        if (MAXH >= 4 && nh >= 4) {
             cp_async_wait<0>();
             __syncthreads();
             if (col) {
@@ -326,17 +329,17 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 const size_t g = (size_t)(oy + ly) * L.nx + gj;
                 r1[g] = c1[k];
                 v[0] += c1[k] * c1[k];
-                if (nh >= 2) {
+                if (MAXH >= 2 && nh >= 2) {
                     const double rd = c1[k] - d1[k];
                     d1o[g] = d1[k];
                     v[2] += rd * rd;
                 }
-                if (nh >= 3) {
+                if (MAXH >= 3 && nh >= 3) {
                     const double re = c1[k] - 2.0 * d1[k] + d2[k];
                     d2o[g] = d2[k];
                     v[3] += re * re;
                 }
-                if (nh >= 4) {   // cubic: b - A (4 h0 - 6 h1 + 4 h2 - h3) = r1 - 3 d1 + 3 d2 - d3
+                if (MAXH >= 4 && nh >= 4) {   // cubic: b - A (4 h0 - 6 h1 + 4 h2 - h3) = r1 - 3 d1 + 3 d2 - d3
                     const double rf = c1[k] - 3.0 * (d1[k] - d2[k]) - d3[k];
                     d3o[g] = d3[k];
                     v[4] += rf * rf;
@@ -365,7 +368,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
                 resB = b - ag;
                 v[0] += res1 * res1;
                 v[1] += resB * resB;
-                if (nh >= 2) {
+                if (MAXH >= 2 && nh >= 2) {
                     double ax1, ag1;
                     frame_apply(L, dd, c, h1, i, j, ax1, ag1);
                     e1 = ax - ax1;
@@ -392,9 +395,9 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
             }
             r1[g] = res1;
             rB[g] = resB;
-            if (nh >= 2) d1o[g] = e1;
-            if (nh >= 3) d2o[g] = e2;
-            if (nh >= 4) {
+            if (MAXH >= 2 && nh >= 2) d1o[g] = e1;
+            if (MAXH >= 3 && nh >= 3) d2o[g] = e2;
+            if (MAXH >= 4 && nh >= 4) {
                 d3o[g] = e3;
                 if (dk_next) dk_next[g] = e3;   // zero on Dirichlet rows, like every d
             }
@@ -651,6 +654,47 @@ k_impose(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r,
         const double stop2 = rtol * rtol * sc->bnorm2;
         // every block has read bnorm2/rr0/rrD/rrE before this block can be the last to
         // finish only if we do not overwrite them: keep them, write the rest.
+        sc->rr = best;
+        sc->rr_init = best;
+        sc->stop2 = stop2;
+        sc->iters = 0;
+        sc->max_iters = max_iters;
+        sc->done = (best <= stop2) ? 1 : 0;
+        sc->rz_old = 1.0;
+        sc->rz_new = 0.0;
+        sc->x_stamp = 0;
+        sc->x_applied = 0;
+        sc->guess = pick;
+    }
+}
+
+// k_impose for the short history (nh <= 1, no least-squares fit; one GPU, even row pitch): the candidates are the field as
+// given (nh == 0) or the previous solution, and zero; 128-bit accesses over the flat field, Dirichlet nodes by index.
+__global__ void __launch_bounds__(256)
+k_impose_prev(LevelDev L, DirData dd, double *__restrict__ u, double *__restrict__ r, const double *__restrict__ rB,
+              const double *__restrict__ h0, int nh, CGScalars *sc, double rtol, int max_iters)
+{
+    const double rr1 = sc->rr0, rrB = sc->bnorm2;
+    int pick = nh >= 1 ? 2 : 0;
+    double best = rr1;
+    if (rrB < best) { best = rrB; pick = 1; }
+    const size_t npairs = (size_t)L.nx * L.ny / 2;
+    const unsigned m = L.dirmask;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < npairs; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t g = 2 * q;
+        const int i = (int)(g / L.nx), j = (int)(g - (size_t)i * L.nx);
+        double2 uv;
+        if (pick == 2) uv = *reinterpret_cast<const double2 *>(h0 + g);
+        else if (pick == 1) { uv = make_double2(0.0, 0.0); *reinterpret_cast<double2 *>(r + g) = *reinterpret_cast<const double2 *>(rB + g); }
+        else uv = *reinterpret_cast<const double2 *>(u + g);
+        const bool rowd = ((m & 8u) && i == 0) || ((m & 4u) && i == L.ny - 1);
+        if (rowd || ((m & 1u) && j == 0)) uv.x = dir_value(L, dd, i, j);
+        if (rowd || ((m & 2u) && j + 1 == L.nx - 1)) uv.y = dir_value(L, dd, i, j + 1);
+        *reinterpret_cast<double2 *>(u + g) = uv;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // (the other blocks only read rr0 / bnorm2, which stay as they are)
+        const double stop2 = rtol * rtol * sc->bnorm2;
         sc->rr = best;
         sc->rr_init = best;
         sc->stop2 = stop2;
@@ -1306,7 +1350,8 @@ int solver_setup(eqgpu_solver *s)
     const eqgpu_params &p = s->p;
     s->N = (size_t)p.nW * p.nH;  // replaced by the local size once the slab window is known
     const double hx0 = p.hx, hy0 = p.hy > 0 ? p.hy : p.hx;
-    EQ_CUDA(cudaFuncSetAttribute(k_init_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, INIT_SMEM));
+    EQ_CUDA(cudaFuncSetAttribute((k_init_tile<INIT_THREADS, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, INIT_SMEM));
+    EQ_CUDA(cudaFuncSetAttribute((k_init_tile<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * INIT_SMEM / 5));
     s->nu = p.smooth_sweeps > 0 ? p.smooth_sweeps : 3;
     // one more sweep on the coarser levels: they are latency-bound, so it is nearly free, and it widens the
     // margin at the 8th iteration (relres 1.6e-13 vs 7.2e-13 at 2048^2; measured 488 vs 479 steps/s)
@@ -2409,10 +2454,15 @@ static int pcg(eqgpu_solver *s)
     if (!T && s->init_tile) {
         const dim3 gi((L.nx + 61) / 62, (L.ny + 61) / 62);
         // d3 scratch: the level-0 work vector t is free until the first pre-smoothing writes it
-        k_init_tile<<<gi, INIT_THREADS, INIT_SMEM, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], s->uh[3], nh, s->r, s->z,
-                                                        s->Ap, s->pv2, l0.t, rs_l, rs_r, s->partials, s->counters + 0, sc,
-                                                        sl ? 1 : 0, s->dk[s->dk_cur], wrote_dk ? s->dk[s->dk_cur ^ 1] : nullptr,
-                                                        d4ok ? 1 : 0);
+        // short history (a colony whose rods move; the first steps): two tiles, 512 threads, two CTAs per SM
+        if (nh <= 1 && !wrote_dk)
+            k_init_tile<512, 1><<<gi, 512, 2 * INIT_SMEM / 5, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], s->uh[3], nh, s->r,
+                                                                   s->z, s->Ap, s->pv2, l0.t, rs_l, rs_r, s->partials,
+                                                                   s->counters + 0, sc, sl ? 1 : 0, s->dk[s->dk_cur], nullptr, 0);
+        else
+            k_init_tile<INIT_THREADS, 4><<<gi, INIT_THREADS, INIT_SMEM, st>>>(
+                L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], s->uh[3], nh, s->r, s->z, s->Ap, s->pv2, l0.t, rs_l, rs_r, s->partials,
+                s->counters + 0, sc, sl ? 1 : 0, s->dk[s->dk_cur], wrote_dk ? s->dk[s->dk_cur ^ 1] : nullptr, d4ok ? 1 : 0);
         if (sl) {
             slab_allreduce(s, sc->red_src, sc->red_dst, 5);
             k_slab_unpack<<<1, 1, 0, st>>>(sc);
@@ -2451,7 +2501,9 @@ static int pcg(eqgpu_solver *s)
         default: launch_ring<7>(s, L, dd, rh, ra, nb1, g0, blk, rtol, max_iters); break;
         }
         s->launches++;
-    } else
+    } else if (!T && s->init_tile && !sl && nh <= 1 && !ls && !(L.nx & 1))
+        k_impose_prev<<<nb1, 256, 0, st>>>(L, dd, s->u, s->r, s->z, s->uh[0], nh, s->sc, rtol, max_iters);
+    else
         k_impose<<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, s->Ap, s->pv2, s->uh[0], s->uh[1], s->uh[2], nh, s->sc,
                                      rtol, max_iters, ls ? 1 + s->ls_form : 0, s->partials, s->counters + 5, s->uh[3], l0.t,
                                      s->uh[4], d4ok ? s->dk[s->dk_cur] : nullptr);
