@@ -164,6 +164,7 @@ struct eqgpu_solver {
     int ls_form = 1;               // least-squares guess: 1 = correction to h0 fitted to r1 on {A h0, d1, d1-d2}; 0 = first form
     bool init_tile = true;         // shared-tile k_init_tile instead of the per-node k_init (isotropic, one GPU)
     bool pdl = false;              // programmatic dependent launch between the kernels of a PCG iteration
+    bool t32_wide = false;         // 32-node tiles of a level with at most one tile per SM: one node per thread (1024 threads; measured no faster: the small levels are bound by kernel hand-off and load latency, not by the sweeps)
     int t32_below = 148;           // levels with fewer 64-node tiles than this run on 32-node tiles
     // row-slab mode (eqgpu_create_slab): this rank owns rows [levels[l].g0, levels[l].g1) of every level
     bool slab = false;

@@ -51,6 +51,15 @@ __device__ __forceinline__ double prolong_at(const LevelDev &F, const LevelDev &
     return 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx + 1));
 }
 
+// Debug build only (-DEQ_KTRACE): clock64() marks of CTA 0 of the pre-smoothing kernels, slot base by level width
+#ifdef EQ_KTRACE
+__device__ unsigned long long g_ktrace[256];
+#define KT_BASE(F) ((F).nx <= 130 ? 0 : (F).nx <= 258 ? 32 : (F).nx <= 514 ? 64 : (F).nx <= 1026 ? 96 : 128)
+#define KT(F, i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_ktrace[KT_BASE(F) + (i)] = clock64(); } while (0)
+#else
+#define KT(F, i) do { } while (0)
+#endif
+
 #define TS 64
 #define TSL 6
 namespace T64 {

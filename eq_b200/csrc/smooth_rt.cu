@@ -272,20 +272,20 @@ k_pre_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMa
     int *ids = reinterpret_cast<int *>(bar + 1);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int ntiles = G.n;
+    // The converged flag is read before the dependency wait (its writers have completed before any prologue that can
+    // overlap runs: see k_presmooth in mg_tile.inc).  The first two tiles of a CTA are static (blockIdx.x and blockIdx.x +
+    // gridDim.x), so the first TMA copy goes out the moment the predecessor's data is visible; the shared counter hands
+    // out the tiles from 2 * gridDim.x on.
+    const int done = sc->done;
     if (TMA && tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    int cur = blockIdx.x, nxt = blockIdx.x + gridDim.x;
     pdl_wait();
-    if (sc->done) return;
-    if (tid == 0) {
-        const int t0 = (int)atomicAdd(sched, 2u);
-        ids[0] = t0; ids[1] = t0 + 1;
-        if (TMA && t0 < ntiles) {
-            constexpr int TO_ = TS - 2 * H;
-            mbar_expect_tx(bar, TS * TS * 8);
-            tma_load_2d(bbuf, &map_b, bar, __ldg(G.tiles + 2 * t0) * TO_ - H, F.tbase + __ldg(G.tiles + 2 * t0 + 1) * TO_ - H);
-        }
+    if (TMA && tid == 0 && cur < ntiles && !done) {
+        mbar_expect_tx(bar, TS * TS * 8);
+        tma_load_2d(bbuf, &map_b, bar, __ldg(G.tiles + 2 * cur) * TO - H, F.tbase + __ldg(G.tiles + 2 * cur + 1) * TO - H);
     }
-    __syncthreads();
-    int cur = ids[0], nxt = ids[1];
+    if (done) return;
+    __syncthreads();   // the barrier's initialisation is visible to every thread
     unsigned phase = 0;
     int it = 0, buf = 0;
     const Coef c{F.cC, F.cEW, F.cNS, F.cD};
@@ -307,7 +307,7 @@ k_pre_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMa
         __syncthreads();   // everyone holds its rows: the box may be refilled (and the previous tile's restriction is over)
         unsigned t_nn = 0;
         if (tid == 0) {
-            t_nn = atomicAdd(sched, 1u);   // the tile after the next one; consumed at the end of this tile
+            t_nn = 2u * gridDim.x + atomicAdd(sched, 1u);   // the tile after the next one; consumed at the end of this tile
             if (TMA && nxt < ntiles) {
                 fence_proxy_async();
                 mbar_expect_tx(bar, TS * TS * 8);
@@ -442,25 +442,23 @@ k_post_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorM
     int *ids = reinterpret_cast<int *>(bar + 1);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int ntiles = G.n;
+    // (prologue as in k_pre_rt: flag before the dependency wait, static first tiles, first copies at once)
+    const int done = sc->done;
     if (TMA && tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    int cur = blockIdx.x, nxt = blockIdx.x + gridDim.x;
     pdl_wait();
-    if (sc->done) return;
-    if (tid == 0) {
-        const int t0 = (int)atomicAdd(sched, 2u);
-        ids[0] = t0; ids[1] = t0 + 1;
-        if (TMA && t0 < ntiles) {
-            const int ox = __ldg(G.tiles + 2 * t0) * TO - H, oy = F.tbase + __ldg(G.tiles + 2 * t0 + 1) * TO - H;
+    if (done) return;
+    if (cur < ntiles) {
+        const int ox = __ldg(G.tiles + 2 * cur) * TO - H, oy = F.tbase + __ldg(G.tiles + 2 * cur + 1) * TO - H;
+        if (TMA && tid == 0) {
             mbar_expect_tx(bar, 2 * TS * TS * 8);
             tma_load_2d(bbuf, &map_b, bar, ox, oy);
             tma_load_2d(xbuf, &map_x, bar, ox, oy);
         }
-    }
-    __syncthreads();
-    int cur = ids[0], nxt = ids[1];
-    if (cur < ntiles) {   // the first tile's coarse patch
-        patch_copy_async(Cc, xc, __ldg(G.tiles + 2 * cur) * TO - H, F.tbase + __ldg(G.tiles + 2 * cur + 1) * TO - H, tid, patch2);
+        patch_copy_async(Cc, xc, ox, oy, tid, patch2);   // the first tile's coarse patch
         cp_async_wait<0>();
     }
+    __syncthreads();   // the barrier's initialisation is visible to every thread
     unsigned phase = 0, mine = 0;
     int it = 0, buf = 0;
     const Coef c{F.cC, F.cEW, F.cNS, F.cD};
@@ -487,7 +485,7 @@ k_post_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorM
         __syncthreads();   // boxes consumed, and the patch written at the end of the previous tile (or above) is visible
         unsigned t_nn = 0;
         if (tid == 0) {
-            t_nn = atomicAdd(sched, 1u);
+            t_nn = 2u * gridDim.x + atomicAdd(sched, 1u);
             if (TMA && nxt < ntiles) {
                 const int ox2 = __ldg(G.tiles + 2 * nxt) * TO - H, oy2 = F.tbase + __ldg(G.tiles + 2 * nxt + 1) * TO - H;
                 fence_proxy_async();

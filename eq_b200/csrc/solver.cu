@@ -17,6 +17,9 @@
 #define BX 32
 #define BY 8
 constexpr int TN64 = 66 * 66, TN32 = 34 * 34;  // doubles per shared tile array (mg_tile.inc TN)
+// dynamic shared memory of the tile kernels: two or three tile arrays + the irregular-node table (mg_tile.inc TAB_DOUBLES)
+constexpr size_t SM64_2 = (2 * TN64 + 6 * 64 * 8) * sizeof(double), SM64_3 = (3 * TN64 + 6 * 64 * 8) * sizeof(double);
+constexpr size_t SM32_3 = (3 * TN32 + 6 * 32 * 8) * sizeof(double);
 // Can the deep-halo tile kernel do an n-sweep coarsest solve?  (64-node tile, halo n-1, owned region >= 8;
 // row slabs carry 6 halo rows.)
 static inline bool coarsest_tileable(const eqgpu_solver *s, int n)
@@ -1546,7 +1549,7 @@ int solver_setup(eqgpu_solver *s)
         const int nu = s->nu;
         if (nu > 4) { s->set_error("smooth_sweeps must be <= 4"); return EQGPU_EINVAL; }
         // 64-node tiles need more than the default 48 KB of dynamic shared memory (32-node tiles: 27.7 KB)
-        const int tsm = 2 * TN64 * (int)sizeof(double), tsm3 = 3 * TN64 * (int)sizeof(double);
+        const int tsm = (int)SM64_2, tsm3 = (int)SM64_3;
 #define SET_SMEM(NU)                                                                                         \
     case NU:                                                                                                 \
         EQ_CUDA(cudaFuncSetAttribute((T64::k_presmooth<NU, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));       \
@@ -1566,6 +1569,7 @@ int solver_setup(eqgpu_solver *s)
         // Levels whose 64-node tiling gives fewer than t32_below CTAs are latency-bound (one big tile per
         // SM, most SMs idle): they run on 32-node tiles, 256 threads, several CTAs per SM.
         if (const char *e = getenv("EQGPU_T32_BELOW")) s->t32_below = atoi(e);
+        if (const char *e = getenv("EQGPU_T32_WIDE")) s->t32_wide = atoi(e) != 0;
         if (const char *e = getenv("EQGPU_INIT_TILE")) s->init_tile = atoi(e) != 0;
         s->defer_x = !s->slab;
         if (const char *e = getenv("EQGPU_DEFER_X")) s->defer_x = atoi(e) != 0 && !s->slab;
@@ -2107,7 +2111,7 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
                 cudaStreamWaitEvent(s->rt_stream, s->ev_rt_fork, 0);
                 LevelDev Fp = F;
                 Fp.tlist = lv.rt_pre.d_tlist; Fp.tl_gx = lv.rt_pre.gx; Fp.tl_gy = lv.rt_pre.gy;
-                LAUNCH_K(false, (T64::k_presmooth<NU, 8, HX>), dim3(lv.rt_pre.nperim), dim3(512), 2 * TN64 * sizeof(double),
+                LAUNCH_K(false, (T64::k_presmooth<NU, 8, HX>), dim3(lv.rt_pre.nperim), dim3(512), SM64_2,
                          s->rt_stream, Fp, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
                 s->launches++;
                 cudaEventRecord(s->ev_rt_join, s->rt_stream);
@@ -2124,17 +2128,23 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
     }
     xch(s, lv, lv.b, NU + 1);
     if (use_t32(s, F, 64 - H2)) {
-        const size_t tsm = 3 * TN32 * sizeof(double);
-        LAUNCH_K(pdl_ok, (T32::k_presmooth<NU, 4>), tile_grid(F, 32 - H2), dim3(256), tsm, st, F, Cc, VP(s, lv, lv.b),
-                 VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
+        const size_t tsm = SM32_3;
+        const dim3 g32 = tile_grid(F, 32 - H2);
+        // at most one tile per SM: the kernel lasts as long as one tile does -- one node per thread (1024 threads)
+        if (s->t32_wide && (int)(g32.x * g32.y) <= s->num_sms)
+            LAUNCH_K(pdl_ok, (T32::k_presmooth<NU, 1>), g32, dim3(1024), tsm, st, F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t),
+                     VP(s, cv, cv.b), sw, scc);
+        else
+            LAUNCH_K(pdl_ok, (T32::k_presmooth<NU, 4>), g32, dim3(256), tsm, st, F, Cc, VP(s, lv, lv.b),
+                     VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
     } else {
-        const size_t tsm = 2 * TN64 * sizeof(double);
+        const size_t tsm = SM64_2, tsm3 = SM64_3;
         const dim3 g = tile_grid(F, 64 - H2);
         if ((int)(g.x * g.y) >= 2 * s->num_sms)
             LAUNCH_K(pdl_ok, (T64::k_presmooth<NU, 8>), g, dim3(512), tsm, st, F, Cc, VP(s, lv, lv.b), VP(s, lv, lv.t),
                      VP(s, cv, cv.b), sw, scc);
         else
-            LAUNCH_K(pdl_ok, (T64::k_presmooth<NU, 4>), g, dim3(1024), tsm + tsm / 2, st, F, Cc, VP(s, lv, lv.b),
+            LAUNCH_K(pdl_ok, (T64::k_presmooth<NU, 4>), g, dim3(1024), tsm3, st, F, Cc, VP(s, lv, lv.b),
                      VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
     }
     s->launches++;
@@ -2165,7 +2175,7 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
                 LevelDev Fp = F;
                 Fp.tlist = lv.rt_post.d_tlist; Fp.tl_gx = lv.rt_post.gx; Fp.tl_gy = lv.rt_post.gy;
 #define PERIM(DOT)                                                                                                       \
-    LAUNCH_K(false, (T64::k_postsmooth<NU, DOT, 8, HX>), dim3(lv.rt_post.nperim), dim3(512), 2 * TN64 * sizeof(double),    \
+    LAUNCH_K(false, (T64::k_postsmooth<NU, DOT, 8, HX>), dim3(lv.rt_post.nperim), dim3(512), SM64_2,    \
              s->rt_stream, Fp, Cc, (const double *)VP(s, lv, lv.b), (const double *)VP(s, lv, lv.t), VP(s, lv, lv.x),     \
              (const double *)VP(s, cv, cv.x), sw, s->sc, s->partials, s->counters + 1, out_dot)
                 if (l == 0) PERIM(true); else PERIM(false);
@@ -2190,15 +2200,18 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
              (const double *)VP(s, lv, lv.t), VP(s, lv, lv.x), (const double *)VP(s, cv, cv.x), sw, s->sc,        \
              s->partials, s->counters + 1, out_dot)
     if (use_t32(s, F, 64 - 2 * NU)) {
-        const size_t tsm = 3 * TN32 * sizeof(double);
+        const size_t tsm = SM32_3;
         const dim3 g = tile_grid(F, 32 - 2 * NU);
-        if (l == 0) POST(T32, true, 4, 256, g, tsm); else POST(T32, false, 4, 256, g, tsm);
+        const bool wide = s->t32_wide && (int)(g.x * g.y) <= s->num_sms;
+        if (l == 0) POST(T32, true, 4, 256, g, tsm);
+        else if (wide) POST(T32, false, 1, 1024, g, tsm);
+        else POST(T32, false, 4, 256, g, tsm);
     } else {
-        const size_t tsm = 2 * TN64 * sizeof(double);
+        const size_t tsm = SM64_2, tsm3 = SM64_3;
         const dim3 g = tile_grid(F, 64 - 2 * NU);
         const bool big = (int)(g.x * g.y) >= 2 * s->num_sms;
-        if (l == 0) { if (big) POST(T64, true, 8, 512, g, tsm); else POST(T64, true, 4, 1024, g, tsm + tsm / 2); }
-        else { if (big) POST(T64, false, 8, 512, g, tsm); else POST(T64, false, 4, 1024, g, tsm + tsm / 2); }
+        if (l == 0) { if (big) POST(T64, true, 8, 512, g, tsm); else POST(T64, true, 4, 1024, g, tsm3); }
+        else { if (big) POST(T64, false, 8, 512, g, tsm); else POST(T64, false, 4, 1024, g, tsm3); }
     }
 #undef POST
     s->launches++;
@@ -2224,10 +2237,17 @@ static void launch_coarsest(eqgpu_solver *s, cudaStream_t st, const CoarseW &cw)
     const int H2 = 2 * (cw.n - 1);
     xch(s, lv, lv.b, cw.n - 1);
     if (coarsest_t32(s, F, cw.n))
-        LAUNCH_K(true, (T32::k_coarsest<4>), tile_grid(F, 32 - H2), dim3(256), 3 * TN32 * sizeof(double), st, F,
-                 (const double *)VP(s, lv, lv.b), VP(s, lv, lv.x), cw, scc);
+    {
+        const dim3 gc = tile_grid(F, 32 - H2);
+        if (s->t32_wide && (int)(gc.x * gc.y) <= s->num_sms)
+            LAUNCH_K(true, (T32::k_coarsest<1>), tile_grid(F, 32 - H2), dim3(1024), SM32_3, st, F,
+                     (const double *)VP(s, lv, lv.b), VP(s, lv, lv.x), cw, scc);
+        else
+            LAUNCH_K(true, (T32::k_coarsest<4>), tile_grid(F, 32 - H2), dim3(256), SM32_3, st, F,
+                     (const double *)VP(s, lv, lv.b), VP(s, lv, lv.x), cw, scc);
+    }
     else
-        LAUNCH_K(true, (T64::k_coarsest<4>), tile_grid(F, 64 - H2), dim3(1024), 3 * TN64 * sizeof(double), st, F,
+        LAUNCH_K(true, (T64::k_coarsest<4>), tile_grid(F, 64 - H2), dim3(1024), SM64_3, st, F,
                  (const double *)VP(s, lv, lv.b), VP(s, lv, lv.x), cw, scc);
     s->launches++;
     trace_mark(st);
@@ -2517,6 +2537,18 @@ static int pcg(eqgpu_solver *s)
     if (ring && s->st.steps > 0) chunk = std::max(1, std::max(s->st.iterations, s->ring_prev_iters));
     s->graph_phase = 0;   // odd iterations leave their search direction in pv2, even ones in pv (k_update_x flush)
     double *const p_odd = s->pv2, *const p_even = s->pv;
+#ifdef EQ_KTRACE
+    if (s->st.steps == 6) {
+        unsigned long long h[256];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_ktrace, sizeof h);
+        for (int base = 0; base < 160; base += 32) {
+            fprintf(stderr, "ktrace base %d:", base);
+            for (int k = 1; k <= 10; ++k) fprintf(stderr, " %lld", (long long)(h[base + k] - h[base]));
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     if (fused && !s->slab && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
         std::vector<cudaEvent_t> ev;
         g_trace = &ev;

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out/c14
+cd /root/repo
+timeout 200 python bench.py --steps 10 --warmup 2 --no-cpu-baseline --no-side-legs > gpurun_out/c14/bench_kt.json 2> gpurun_out/c14/bench_kt.err
+grep ktrace gpurun_out/c14/bench_kt.err
+EQGPU_T32_WIDE=0 timeout 200 python bench.py --steps 10 --warmup 2 --no-cpu-baseline --no-side-legs > gpurun_out/c14/bench_kt0.json 2> gpurun_out/c14/bench_kt0.err
+grep ktrace gpurun_out/c14/bench_kt0.err
