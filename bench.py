@@ -208,6 +208,12 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as O
+    # all the host threads it can use: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would time one core
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    O.lib().eqo_set_num_threads(int(ncpu))
     p = O.Problem(nW=NW, nH=NH, h=H, dt=DT, D=D)
     total = args.warmup + args.steps
     nsets = min(total + 1, 64)
@@ -283,7 +289,7 @@ def cpu_baseline_subprocess(colony):
     work), run in a SUBPROCESS so that the GPU arm's own process never maps anything under oracle/."""
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3",
            "--bounded", "--colony", colony]
-    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS")}
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
         line = json.loads(r.stdout.strip().splitlines()[-1])

@@ -55,6 +55,8 @@ def lib():
         L.eqo_deposit_per_point.restype = C.c_double
         L.eqo_point_in_cell.restype = C.c_int
         L.eqo_num_threads.restype = C.c_int
+        L.eqo_set_num_threads.argtypes = [C.c_int]
+        L.eqo_set_num_threads.restype = None
         L.eqo_assemble.restype = C.c_int
         L.eqo_fd_bicgstab.restype = C.c_long
         _LIB = L
