@@ -133,6 +133,24 @@ __device__ __forceinline__ void band_halo(const double *exch, int buf, int w, in
     xa[0] = lo.x; xb[0] = lo.y; xa[RW + 1] = hi.x; xb[RW + 1] = hi.y;
 }
 
+// Between two passes a warp only needs its two neighbours' boundary rows.  Pairwise named barriers (boundary q, shared by
+// warps q-1 and q, hardware barrier q, 64 threads; lower boundary first, so the chain cannot deadlock) were MEASURED
+// SLOWER than one CTA-wide __syncthreads on the B200 (pre-smoother 39.0 against 32.9 us, post 45.3 against 40.9 us at
+// 2048^2, profiles/r02_register_tile.md): two barrier instructions per pass and a ripple of dependent releases cost more
+// than the slack they give.  Kept behind RT_PAIR_BARRIER for the record.
+#ifndef RT_PAIR_BARRIER
+#define RT_PAIR_BARRIER 0
+#endif
+__device__ __forceinline__ void band_sync(int w)
+{
+#if RT_PAIR_BARRIER
+    if (w > 0) asm volatile("bar.sync %0, 64;" ::"r"(w) : "memory");
+    if (w < NWARP - 1) asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
+#else
+    __syncthreads();
+#endif
+}
+
 // One pass over the band.  RESID false: x <- x + wd (b - A x) in place, wda / wdb = wd times the column masks;  true: the
 // residual b - A x of the band's rows (times the column masks wda / wdb) goes to rows row0 .. row0+RW-1 of the 64-column
 // shared array `rt`, x is left alone.  Rows whose bit in rowm is clear stay (are stored as) zero.
@@ -241,13 +259,13 @@ __device__ __forceinline__ void pre_sweeps(const Coef &c, const SmoothW &sw, dou
 #pragma unroll
     for (int s = 1; s < NU; ++s) {
         band_publish(exch, buf, w, lane, xa, xb);
-        __syncthreads();
+        band_sync(w);
         band_halo(exch, buf, w, lane, xa, xb);
         buf ^= 1;
         band_pass<false, MASKED>(c, sw.w[s] * icC * ma, sw.w[s] * icC * mb, L.rowm, ba, bb, xa, xb, nullptr, 0, lane);
     }
     band_publish(exch, buf, w, lane, xa, xb);
-    __syncthreads();
+    band_sync(w);
     band_halo(exch, buf, w, lane, xa, xb);
     buf ^= 1;
     band_pass<true, MASKED>(c, ma, mb, L.rowm, ba, bb, xa, xb, rt, w * RW, lane);
@@ -416,7 +434,7 @@ __device__ __forceinline__ void post_sweeps(const Coef &c, const SmoothW &sw, do
 #pragma unroll
     for (int s = 0; s < NU; ++s) {
         band_publish(exch, buf, w, lane, xa, xb);
-        __syncthreads();
+        band_sync(w);
         band_halo(exch, buf, w, lane, xa, xb);
         buf ^= 1;
         band_pass<false, MASKED>(c, sw.w[s] * icC * ma, sw.w[s] * icC * mb, L.rowm, ba, bb, xa, xb, nullptr, 0, lane);
