@@ -52,6 +52,9 @@ struct LevelDev {
     // closed form of the padded cell sizes (uniform cells, only the last one may be narrower): regular and last cell
     // widths / heights of the GLOBAL grid, so that set-up code needs no global loads (mg_stream.cuh)
     double hxr, hxl, hyr, hyl;
+    // variable tensor: the assembled rows, packed by symmetry -- centre, east, north, north-east coefficient of every node
+    // (west / south / south-west are the neighbour's east / north / north-east); null = evaluate the row from d11/d22/d12
+    const double *kC, *kE, *kN, *kNE;
     // tile-list launches (mg_rt.cuh): when set, a tile kernel's CTA q works on tile (tlist[2q], tlist[2q+1]) of the level's
     // tl_gx x tl_gy tile grid instead of (blockIdx.x, blockIdx.y), and a reduction it takes part in is shared with another
     // kernel: one partial per tile of the whole grid, tl_gx * tl_gy arrivals in all
@@ -96,6 +99,7 @@ struct Level {
     double *d_hx = nullptr, *d_ihx = nullptr, *d_hy = nullptr, *d_ihy = nullptr;
     double *x = nullptr, *b = nullptr, *t = nullptr;  // solution, rhs, scratch
     double *t11 = nullptr, *t22 = nullptr, *t12 = nullptr;
+    double *kC = nullptr, *kE = nullptr, *kN = nullptr, *kNE = nullptr;   // assembled tensor rows (solver_refresh_levels)
     // streaming smoothers (mg_stream.cuh): TMA descriptors of the level's b and t vectors (row pitch 16-byte aligned)
     CUtensorMap map_b{}, map_t{};
     bool tma = false;
@@ -462,11 +466,26 @@ __device__ __forceinline__ void stencil_tensor(const LevelDev &L, int i, int j, 
     c[B_C] += cc;
 }
 
-template <bool TENSOR>
+// Row of the operator.  TENSOR 0: isotropic closed form; 1: variable tensor evaluated on the fly (150 flops and 21 tensor
+// loads per node); 2: variable tensor read from the assembled arrays (LevelDev::kC ..., one evaluation per node and tensor
+// update instead of one per node, sweep and kernel -- and 40 registers instead of 96, i.e. four resident blocks, not two).
+template <int TENSOR>
 __device__ __forceinline__ void stencil_row(const LevelDev &L, int i, int j, double c[NBAND])
 {
-    if (TENSOR) stencil_tensor(L, i, j, c);
-    else stencil_iso(L, i, j, c);
+    if (TENSOR == 2) {
+        const size_t g = (size_t)i * L.nx + j;
+        c[B_C] = __ldg(L.kC + g);
+        c[B_E] = __ldg(L.kE + g);
+        c[B_N] = __ldg(L.kN + g);
+        c[B_NE] = __ldg(L.kNE + g);
+        c[B_W] = j > 0 ? __ldg(L.kE + g - 1) : 0.0;
+        c[B_S] = i > 0 ? __ldg(L.kN + g - L.nx) : 0.0;
+        c[B_SW] = (i > 0 && j > 0) ? __ldg(L.kNE + g - L.nx - 1) : 0.0;
+    } else if (TENSOR == 1) {
+        stencil_tensor(L, i, j, c);
+    } else {
+        stencil_iso(L, i, j, c);
+    }
 }
 
 // sum_k c[k] * x[nbr_k]; neighbours outside the grid carry zero coefficients

@@ -50,7 +50,7 @@ __device__ __forceinline__ double dir_value(const LevelDev &L, const DirData &d,
 // ---------------------------------------------------------------------------
 // operator apply: y = A x on free rows (Dirichlet rows -> 0), optional x.y
 // ---------------------------------------------------------------------------
-template <bool TENSOR, bool DOT>
+template <int TENSOR, bool DOT>
 __global__ void __launch_bounds__(BX *BY)
 k_apply(LevelDev L, const double *__restrict__ x, double *__restrict__ y, CGScalars *sc,
         double *partials, unsigned *counter, double *out_pAp)
@@ -132,7 +132,7 @@ __global__ void k_rhs_check(LevelDev L, const double *__restrict__ u0, double *_
 // quasi-steady state and poor right after large point deposits, where the
 // huge A*u0 would cap the attainable accuracy.
 // ---------------------------------------------------------------------------
-template <bool TENSOR>
+template <int TENSOR>
 __global__ void __launch_bounds__(BX *BY)
 k_init(LevelDev L, DirData dd, const double *__restrict__ u, double *__restrict__ rA,
        double *__restrict__ rB, double rs_l, double rs_r, CGScalars *sc, double *partials,
@@ -421,7 +421,7 @@ k_init_tile(LevelDev L, DirData dd, const double *__restrict__ u, const double *
 // Per-node version of k_init_tile for the variable-tensor operator (one GPU): the same candidates -- previous
 // solution (or the field as given without history), zero, linear and quadratic extrapolation -- with the row
 // of the operator evaluated once per node (stencil_row) and applied to every history vector.
-template <bool TENSOR>
+template <int TENSOR>
 __global__ void __launch_bounds__(BX *BY)
 k_init_hist(LevelDev L, DirData dd, const double *__restrict__ u, const double *__restrict__ h0,
             const double *__restrict__ h1, const double *__restrict__ h2, int nh, double *__restrict__ r1,
@@ -1150,7 +1150,7 @@ __global__ void k_book(CGScalars *sc)
 // multigrid pieces
 // ---------------------------------------------------------------------------
 // x = omega * D^-1 b   (first sweep from a zero guess)
-template <bool TENSOR>
+template <int TENSOR>
 __global__ void __launch_bounds__(BX *BY)
 k_jacobi0(LevelDev L, const double *__restrict__ b, double *__restrict__ x, double omega,
           const CGScalars *sc)
@@ -1169,7 +1169,7 @@ k_jacobi0(LevelDev L, const double *__restrict__ b, double *__restrict__ x, doub
 }
 
 // xout = xin + omega * D^-1 (b - A xin);  RESID: xout = b - A xin instead
-template <bool TENSOR, bool RESID>
+template <int TENSOR, bool RESID>
 __global__ void __launch_bounds__(BX *BY)
 k_jacobi(LevelDev L, const double *__restrict__ b, const double *__restrict__ xin,
          double *__restrict__ xout, double omega, const CGScalars *sc)
@@ -1239,6 +1239,19 @@ k_prolong_add(LevelDev F, LevelDev Cc, const double *__restrict__ xc, double *__
     else if (mi && !mj) add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx));
     else add = 0.5 * (__ldg(c0) + __ldg(c0 + Cc.nx + 1));
     xf[(size_t)i * F.nx + j] += add;
+}
+
+// assembled rows of the variable-tensor operator, packed by symmetry (LevelDev::kC ...)
+__global__ void __launch_bounds__(BX *BY)
+k_coef_assemble(LevelDev L, double *__restrict__ kC, double *__restrict__ kE, double *__restrict__ kN,
+                double *__restrict__ kNE)
+{
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.ny || j >= L.nx) return;
+    double c[NBAND];
+    stencil_tensor(L, i, j, c);
+    const size_t g = (size_t)i * L.nx + j;
+    kC[g] = c[B_C]; kE[g] = c[B_E]; kN[g] = c[B_N]; kNE[g] = c[B_NE];
 }
 
 // nodal injection of a tensor component to the coarse grid
@@ -1328,6 +1341,7 @@ static void fill_level_consts(eqgpu_solver *s, Level &lv)
     L.hxr = lv.hx_host.front(); L.hxl = lv.hx_host.back(); L.hyr = lv.hy_host.front(); L.hyl = lv.hy_host.back();
     L.hx = lv.d_hx; L.ihx = lv.d_ihx; L.hy = lv.d_hy; L.ihy = lv.d_ihy;
     L.d11 = lv.t11; L.d22 = lv.t22; L.d12 = lv.t12;
+    L.kC = nullptr; L.kE = nullptr; L.kN = nullptr; L.kNE = nullptr;   // set by solver_refresh_levels once assembled
     // global view for the tile kernels: whole-grid index logic, windows saying which rows are stored / owned
     LevelDev &G = lv.gdev;
     G = L;
@@ -1627,6 +1641,7 @@ void solver_teardown(eqgpu_solver *s)
         cudaFree(lv.t);
         if (&lv != &s->levels[0]) { cudaFree(lv.x); cudaFree(lv.b); }
         if (&lv != &s->levels[0]) { cudaFree(lv.t11); cudaFree(lv.t22); cudaFree(lv.t12); }
+        cudaFree(lv.kC); cudaFree(lv.kE); cudaFree(lv.kN); cudaFree(lv.kNE);
     }
     s->levels.clear();
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
@@ -1675,6 +1690,22 @@ int solver_refresh_levels(eqgpu_solver *s)
             }
         }
         fill_level_consts(s, lv);
+        // one GPU, consistent mass: assemble the rows once per tensor update; every kernel of the variable-tensor path then
+        // reads four coefficients per node (EQGPU_TENSOR_ASSEMBLE=0: evaluate them on the fly, as round 1 did)
+        static const bool assemble = getenv("EQGPU_TENSOR_ASSEMBLE") == nullptr || atoi(getenv("EQGPU_TENSOR_ASSEMBLE")) != 0;
+        if (s->tensor && !s->slab && assemble && lv.t11) {
+            const size_t bytes = sizeof(double) * lv.n();
+            if (!lv.kC) {
+                EQ_CUDA(cudaMalloc(&lv.kC, bytes));
+                EQ_CUDA(cudaMalloc(&lv.kE, bytes));
+                EQ_CUDA(cudaMalloc(&lv.kN, bytes));
+                EQ_CUDA(cudaMalloc(&lv.kNE, bytes));
+            }
+            k_coef_assemble<<<grid2d(lv.dev), dim3(BX, BY), 0, s->stream>>>(lv.dev, lv.kC, lv.kE, lv.kN, lv.kNE);
+            s->launches++;
+            lv.dev.kC = lv.kC; lv.dev.kE = lv.kE; lv.dev.kN = lv.kN; lv.dev.kNE = lv.kNE;
+            lv.gdev.kC = lv.kC; lv.gdev.kE = lv.kE; lv.gdev.kN = lv.kN; lv.gdev.kNE = lv.kNE;
+        }
     }
     {
         std::vector<LevelDev> host(MAX_LEVELS);
@@ -1715,12 +1746,14 @@ static void vcycle(eqgpu_solver *s)
     auto smooth_from_zero = [&](Level &lv, int sweeps, const double *w) {
         const dim3 g = grid2d(lv.dev);
         double *cur = (sweeps & 1) ? lv.x : lv.t;  // so that the last write lands in lv.x
-        k_jacobi0<T><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, w[0], s->sc);
+        if (T && lv.dev.kC) k_jacobi0<2><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, w[0], s->sc);
+        else k_jacobi0<T><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, w[0], s->sc);
         s->launches++;
         for (int k = 1; k < sweeps; ++k) {
             double *nxt = (cur == lv.x) ? lv.t : lv.x;
             xch(lv, cur);
-            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
+            if (T && lv.dev.kC) k_jacobi<2, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
+            else k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
             s->launches++;
             cur = nxt;
         }
@@ -1735,7 +1768,8 @@ static void vcycle(eqgpu_solver *s)
         for (int k = 0; k < sweeps; ++k) {
             double *nxt = (cur == lv.x) ? lv.t : lv.x;
             xch(lv, cur);
-            k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
+            if (T && lv.dev.kC) k_jacobi<2, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
+            else k_jacobi<T, false><<<g, blk, 0, st>>>(lv.dev, lv.b, cur, nxt, w[k], s->sc);
             s->launches++;
             cur = nxt;
         }
@@ -1744,7 +1778,8 @@ static void vcycle(eqgpu_solver *s)
         Level &lv = s->levels[l], &cv = s->levels[l + 1];
         smooth_from_zero(lv, s->nu, sw.w);
         xch(lv, lv.x);
-        k_jacobi<T, true><<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, lv.b, lv.x, lv.t, 0.0, s->sc);
+        if (T && lv.dev.kC) k_jacobi<2, true><<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, lv.b, lv.x, lv.t, 0.0, s->sc);
+        else k_jacobi<T, true><<<grid2d(lv.dev), blk, 0, st>>>(lv.dev, lv.b, lv.x, lv.t, 0.0, s->sc);
         xch(lv, lv.t);
         k_restrict<<<grid2d(cv.dev), blk, 0, st>>>(lv.dev, cv.dev, lv.t, cv.b, s->sc);
         s->launches += 2;
@@ -2489,11 +2524,23 @@ static int pcg(eqgpu_solver *s)
             s->launches++;
         }
     } else if (hist_tensor)
-        k_init_hist<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2, rs_l,
-                                           rs_r, s->partials, s->counters + 0, sc);
+    {
+        if (T && L.kC)
+            k_init_hist<2><<<g0, blk, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2, rs_l,
+                                               rs_r, s->partials, s->counters + 0, sc);
+        else
+            k_init_hist<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->uh[0], s->uh[1], s->uh[2], nh, s->r, s->z, s->Ap, s->pv2, rs_l,
+                                               rs_r, s->partials, s->counters + 0, sc);
+    }
     else
-        k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
-                                      sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
+    {
+        if (T && L.kC)
+            k_init<2><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
+                                          sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
+        else
+            k_init<T><<<g0, blk, 0, st>>>(L, dd, s->u, s->r, s->z, rs_l, rs_r, sc, s->partials, s->counters + 0,
+                                          sl ? &sc->part_rr0 : &sc->rr0, sl ? &sc->part_b2 : &sc->bnorm2);
+    }
     if (sl && !(!T && s->init_tile)) {  // per-node k_init: rank-sum the two start residuals
         slab_allreduce(s, &sc->part_rr0, &sc->rr0, 1);
         slab_allreduce(s, &sc->part_b2, &sc->bnorm2, 1);
@@ -2580,8 +2627,12 @@ static int pcg(eqgpu_solver *s)
                 if (sl) slab_allreduce(s, &sc->part_rz, &sc->rz_new, 1);
                 k_update_p<<<nb1, 256, 0, st>>>(on, s->z + ooff, s->pv + ooff, sc);
                 if (sl) slab_exchange(s, L, s->pv);
-                k_apply<T, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, sc, s->partials, s->counters + 2,
-                                                     sl ? &sc->part_pAp : &sc->pAp);
+                if (T && L.kC)
+                    k_apply<2, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, sc, s->partials, s->counters + 2,
+                                                         sl ? &sc->part_pAp : &sc->pAp);
+                else
+                    k_apply<T, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, sc, s->partials, s->counters + 2,
+                                                         sl ? &sc->part_pAp : &sc->pAp);
                 if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
                 k_update_xr<<<nb1, 256, 0, st>>>(on, s->u + ooff, s->r + ooff, s->pv + ooff, s->Ap + ooff, sc,
                                                  s->partials, s->counters + 3, sl ? 0 : 1,
