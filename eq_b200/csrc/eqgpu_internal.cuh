@@ -229,6 +229,7 @@ struct eqgpu_solver {
     // stats
     eqgpu_stats st{};
     int64_t launches = 0;
+    int nu1 = 3;                   // sweeps on level 1 (default: as the coarser levels)
     int nu = 3, nuc = 3, ncoarse = 24;  // smoothing sweeps on level 0 / on the coarser levels
     double omega = 0.8;
     bool tensor = false;

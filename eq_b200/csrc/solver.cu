@@ -1375,6 +1375,8 @@ int solver_setup(eqgpu_solver *s)
     s->nuc = p.smooth_sweeps > 0 ? s->nu : 4;
     if (const char *e = getenv("EQGPU_NU0")) s->nu = std::max(1, std::min(atoi(e), 4));   // tuning knobs
     if (const char *e = getenv("EQGPU_NUC")) s->nuc = std::max(1, std::min(atoi(e), 4));
+    s->nu1 = s->nuc;
+    if (const char *e = getenv("EQGPU_NU1")) s->nu1 = std::max(1, std::min(atoi(e), 4));
     // ---- hierarchy -------------------------------------------------------
     Level l0;
     l0.dev.nx = p.nW; l0.dev.gny = p.nH;
@@ -2288,7 +2290,7 @@ static void launch_coarsest(eqgpu_solver *s, cudaStream_t st, const CoarseW &cw)
     trace_mark(st);
 }
 
-static int nu_of(const eqgpu_solver *s, int l) { return l == 0 ? s->nu : s->nuc; }
+static int nu_of(const eqgpu_solver *s, int l) { return l == 0 ? s->nu : l == 1 ? s->nu1 : s->nuc; }
 
 // Fused V-cycle (isotropic): two kernels per large level + one tail kernel.
 // Leaves z = B r in levels[0].x and (when the fine level is tiled) r.z in sc->rz_new.
