@@ -36,6 +36,7 @@ API_SYMBOLS = [
     "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
     "eqgpu_last_guess", "eqgpu_cells_tensor", "eqgpu_get_tensor",
     "eqgpu_ls_solve3", "eqgpu_ring_solve", "eqgpu_cells_upload_device", "eqgpu_get_warm_start", "eqgpu_apply_preconditioner", "eqgpu_comm_stats",
+    "eqgpu_set_nonconvergence_policy", "eqgpu_unconverged_steps",
 ]
 
 
@@ -337,6 +338,15 @@ class GpuHSL:
         out = np.empty(self.ncells)
         self._ck(lib().eqgpu_cells_gather(self._h, _dp(out)))
         return out
+
+    def set_nonconvergence_policy(self, policy: int):
+        """0: a step that stops at max_iters above rtol raises (EQGPU_ENOCONV); 1: report and continue."""
+        self._ck(lib().eqgpu_set_nonconvergence_policy(self._h, int(policy)))
+
+    def unconverged_steps(self) -> int:
+        n = C.c_int64()
+        self._ck(lib().eqgpu_unconverged_steps(self._h, C.byref(n)))
+        return int(n.value)
 
     def set_warm_start(self, mode: int):
         """Starting guess of the PCG solve: 0 = field as given or zero, 1 = also the previous solution,

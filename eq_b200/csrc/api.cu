@@ -80,6 +80,21 @@ int eqgpu_solver_path(eqgpu_solver *s)
            (s->tile_coarsest ? 16 : 0) | (s->tensor ? 32 : 0) | (std::min(rt_levels, 15) << 8);
 }
 
+int eqgpu_set_nonconvergence_policy(eqgpu_solver *s, int policy)
+{
+    if (!s) return EQGPU_EINVAL;
+    if (policy != 0 && policy != 1) { s->set_error("non-convergence policy must be 0 or 1"); return EQGPU_EINVAL; }
+    s->noconv_policy = policy;
+    return 0;
+}
+
+int eqgpu_unconverged_steps(eqgpu_solver *s, int64_t *count)
+{
+    if (!s || !count) return EQGPU_EINVAL;
+    *count = s->unconverged;
+    return 0;
+}
+
 int eqgpu_set_warm_start(eqgpu_solver *s, int mode)
 {
     if (!s) return EQGPU_EINVAL;

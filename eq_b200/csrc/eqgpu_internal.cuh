@@ -233,6 +233,8 @@ struct eqgpu_solver {
     int nu = 3, nuc = 3, ncoarse = 24;  // smoothing sweeps on level 0 / on the coarser levels
     double omega = 0.8;
     bool tensor = false;
+    int noconv_policy = 0;         // 0: EQGPU_ENOCONV; 1: report and continue with the best iterate
+    int64_t unconverged = 0;
 
     void set_error(const std::string &m) { err = m; }
 };

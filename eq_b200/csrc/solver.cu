@@ -2739,7 +2739,9 @@ static int pcg(eqgpu_solver *s)
         snprintf(buf, sizeof buf, "PCG did not converge: %d iterations, relres %.3e (rtol %.1e)",
                  s->sc_host->iters, s->st.relres, rtol);
         s->set_error(buf);
-        return EQGPU_ENOCONV;
+        s->unconverged++;
+        if (s->noconv_policy == 0) return EQGPU_ENOCONV;
+        // policy 1: the best iterate stands, the message stays readable through eqgpu_last_error, the run goes on
     }
     return 0;
 }

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <fstream>
+#include <iostream>
 
 void gpuHSL::check(int rc, const char *what)
 {
@@ -145,6 +146,7 @@ void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
     int rc = eqgpu_create(&p, &h);
     if (rc != EQGPU_OK) throw std::runtime_error(std::string("gpuHSL: eqgpu_create failed: ") + eqgpu_last_error(nullptr));
     if (cfg.warmStart >= 0) check(eqgpu_set_warm_start(h, cfg.warmStart), "eqgpu_set_warm_start");
+    if (cfg.continueOnNoConvergence) check(eqgpu_set_nonconvergence_policy(h, 1), "eqgpu_set_nonconvergence_policy");
 
     const size_t N = nodesH * nodesW;
     solution_vector.assign(N, 0.0);  // src/fHSL.cpp:583-584
@@ -191,10 +193,22 @@ void gpuHSL::pushTensorIfChanged()
 }
 
 // src/fHSL.cpp:98-161: host vector in, solved field out
+// (continueOnNoConvergence) a step that did not reach rtol: say so once per step and go on, as the reference does
+void gpuHSL::reportUnconverged()
+{
+    int64_t n = 0;
+    if (eqgpu_unconverged_steps(h, &n) == EQGPU_OK && n > unconvergedSeen) {
+        unconvergedSeen = n;
+        std::cerr << "gpuHSL: " << eqgpu_last_error(h) << " -- continuing with the best iterate (" << n
+                  << " such steps so far)" << std::endl;
+    }
+}
+
 void gpuHSL::stepDiffusion()
 {
     pushTensorIfChanged();
     check(eqgpu_step_host(h, solution_vector.data()), "eqgpu_step_host");
+    reportUnconverged();
     eqgpu_stats st;
     check(eqgpu_get_stats(h, &st), "eqgpu_get_stats");
     totalBoundaryFlux = st.total_boundary_flux;
@@ -204,6 +218,7 @@ void gpuHSL::stepDiffusion()
 void gpuHSL::stepDiffusionResident()
 {
     check(eqgpu_step(h), "eqgpu_step");
+    reportUnconverged();
     eqgpu_stats st;
     check(eqgpu_get_stats(h, &st), "eqgpu_get_stats");
     totalBoundaryFlux = st.total_boundary_flux;

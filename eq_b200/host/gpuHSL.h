@@ -43,6 +43,9 @@ public:
         // starting guess of the iterative solve (eqgpu_set_warm_start): -1 = the library's default for the mesh size,
         // 0..7 as in include/eqgpu.h (7 = image ring, opt-in)
         int warmStart = -1;
+        // true: a step whose PCG stops at max_iters above rtol is reported on stderr and the run continues with the best
+        // iterate (what the reference does with its solver's diagnostics); false: stepDiffusion throws
+        bool continueOnNoConvergence = false;
     };
 
     // what simulation.cpp reads through `diffusionSolver->shell->...` (src/simulation.cpp:298-308)
@@ -109,8 +112,10 @@ private:
     bool tensorFromCells = false;
     double leftRate = 0.0, rightRate = 0.0, channelFlowVelocity = 0.0;
     bool tensorDirty = false, tensorPending = false;
+    int64_t unconvergedSeen = 0;
     void check(int rc, const char *what);
     void pushTensorIfChanged();
+    void reportUnconverged();
 };
 
 // The boundary-well model Simulation keeps next to a DIRICHLET_UPDATE layer (src/simulation.cpp:581-627):

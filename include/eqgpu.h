@@ -205,6 +205,12 @@ EQGPU_API int eqgpu_build_rhs(eqgpu_solver *s, const double *host_u0, double *ho
 /* Device pointer to the resident field (for benchmarks that stage inputs in HBM). */
 EQGPU_API int eqgpu_field_device_ptr(eqgpu_solver *s, void **dev_ptr);
 EQGPU_API int eqgpu_sync(eqgpu_solver *s);
+/* What a step does when PCG stops at max_iters above rtol.  policy 0 (default): the step returns EQGPU_ENOCONV (the field
+ * holds the best iterate).  policy 1: report and continue -- the step returns EQGPU_OK, stats.relres tells how far it got,
+ * and the step is counted in eqgpu_unconverged_steps.  The reference prints solver diagnostics and carries on
+ * (src/fHSL.cpp:104-108 has no error path); policy 1 is that behaviour for 24 000-step runs that must not abort. */
+EQGPU_API int eqgpu_set_nonconvergence_policy(eqgpu_solver *s, int policy);
+EQGPU_API int eqgpu_unconverged_steps(eqgpu_solver *s, int64_t *count);
 /* Which code path the solver selected (diagnostics / tests): bit 0 fused tile kernels, 1 row-slab mode,
  * 2 fused kernels in slab mode, 3 cluster tail, 4 tiled coarsest solve, 5 variable tensor active; bits 8-11: number of
  * multigrid levels whose interior tiles run on the register-tile smoothers (TMA-staged, smooth_rt.cu). */

@@ -522,3 +522,28 @@ def test_warm_start_survives_a_field_reset(oracle):
         g.step()
         assert rel(g.get_field(), s.u) < TOL
     g.close()
+
+
+@pytest.mark.gpu
+def test_nonconvergence_policy_report_and_continue():
+    """max_iters too small to reach rtol: policy 0 raises EQGPU_ENOCONV (the default), policy 1 reports and carries on
+    with the best iterate -- what the reference does with its solver's diagnostics (src/fHSL.cpp:104-108 has no error
+    path); the next, unconstrained solver reaches the tolerance again from that iterate."""
+    import eq_b200 as E
+    nW, nH = 257, 129
+    rng = np.random.default_rng(3)
+    u0 = rng.uniform(0.0, 10.0, nW * nH)
+    g = E.GpuHSL(nW, nH, device=0, max_iters=2)
+    g.set_warm_start(0)
+    g.set_field(u0)
+    with pytest.raises(E.EqGpuError):
+        g.step()
+    assert g.unconverged_steps() == 1
+    g.set_nonconvergence_policy(1)
+    g.set_field(u0)
+    g.step()                                   # no exception
+    assert g.unconverged_steps() == 2
+    st = g.stats()
+    assert st.iterations == 2 and st.relres > 1e-12
+    assert np.all(np.isfinite(g.get_field()))
+    g.close()
