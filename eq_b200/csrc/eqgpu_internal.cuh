@@ -187,6 +187,7 @@ struct eqgpu_solver {
     bool rt_smooth = true;         // register-tile smoothers (mg_rt.cuh) on the interior tiles of the large levels
     int rt_min_tiles = 148;        // ... of levels with at least this many regular tiles
     int rt_ctas = 0;               // persistent CTAs of a register-tile kernel (2 per SM)
+    bool rt_lean = false;          // TMA levels: the three-CTAs-per-SM instances (right-hand side in shared memory; opt-in)
     cudaStream_t rt_stream = nullptr;   // perimeter tiles run beside the interior ones
     cudaEvent_t ev_rt_fork = nullptr, ev_rt_join = nullptr;
     unsigned *rt_sched = nullptr;  // tile counters of the persistent kernels

@@ -157,7 +157,9 @@ __device__ __forceinline__ void band_sync(int w)
 // Lane 0's west partial and lane 31's east partial are their own values (the shuffle has no source): the outermost columns
 // of the tile belong to the ring that goes stale, one node per pass, like the outermost rows.
 // MASKED false (tiles strictly inside the walls): no masks, wda is the weight of both columns.
-template <bool RESID, bool MASKED>
+// BSM true (the three-CTAs-per-SM instances): the right-hand side is not held in registers but read from the shared tile
+// `rt` row by row (ba / bb unused), and the residual overwrites it in place.
+template <bool RESID, bool MASKED, bool BSM = false>
 __device__ __forceinline__ void band_pass(const Coef &c, double wda, double wdb, unsigned rowm, const double (&ba)[RW],
                                           const double (&bb)[RW], double (&xa)[RW + 2], double (&xb)[RW + 2], double *rt,
                                           int row0, int lane)
@@ -175,7 +177,14 @@ __device__ __forceinline__ void band_pass(const Coef &c, double wda, double wdb,
         const double qr = __shfl_down_sync(0xffffffffu, qown, 1);
         const double axa = fma(c.cC, ca, fma(c.cNS, na + oa, ea)) + pl;
         const double axb = fma(c.cC, cb, fma(c.cNS, nb + ob, wb)) + qr;
-        const double ra = ba[k - 1] - axa, rb = bb[k - 1] - axb;
+        double bka, bkb;
+        if (BSM) {
+            const double2 bv = *reinterpret_cast<const double2 *>(rt + (row0 + k - 1) * TS + 2 * lane);
+            bka = bv.x; bkb = bv.y;
+        } else {
+            bka = ba[k - 1]; bkb = bb[k - 1];
+        }
+        const double ra = bka - axa, rb = bkb - axb;
         if (!MASKED) {
             if (RESID) {
                 *reinterpret_cast<double2 *>(rt + (row0 + k - 1) * TS + 2 * lane) = make_double2(ra, rb);
@@ -548,6 +557,224 @@ k_post_rt(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorM
     sched_leave(sched);
 }
 
+// =====================================================================================================================
+// Three CTAs per SM ("lean" instances, TMA levels): the right-hand side tile stays in shared memory for the whole tile
+// (read row by row in every pass: 8 LDS.128 per lane and pass) instead of in 32 registers per thread, which brings the
+// kernels under 80 registers -- 24 warps per SM instead of 16.  The sweeps are latency-bound at four warps per scheduler
+// (profiles/r02_ncu_register_tile.md), so more resident warps buy more than the extra shared-memory reads cost.  The
+// price: one box buffer per CTA, so the next tile's copy can only start when the current tile is done with it (no
+// prefetch; the other two CTAs of the SM cover that wait), and the post-smoother's incoming iterate comes by 128-bit
+// global loads straight into registers.  The residual overwrites the right-hand side in place.
+// =====================================================================================================================
+template <int NU, bool MASKED>
+__device__ __forceinline__ void pre_sweeps3(const Coef &c, const SmoothW &sw, double icC, const Lane &L, double *exch, int &buf,
+                                            int w, int lane, double (&xa)[RW + 2], double (&xb)[RW + 2], double *bt)
+{
+    const double ma = MASKED ? L.cma : 1.0, mb = MASKED ? L.cmb : 1.0;
+    const double dummy[RW] = {};
+    {
+        const double wda = sw.w[0] * icC * ma, wdb = sw.w[0] * icC * mb;
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+            const double2 bv = *reinterpret_cast<const double2 *>(bt + (w * RW + k) * TS + 2 * lane);
+            const bool ok = !MASKED || ((L.rowm >> k) & 1u);
+            xa[k + 1] = ok ? wda * bv.x : 0.0;
+            xb[k + 1] = ok ? wdb * bv.y : 0.0;
+        }
+    }
+#pragma unroll
+    for (int s = 1; s < NU; ++s) {
+        band_publish(exch, buf, w, lane, xa, xb);
+        band_sync(w);
+        band_halo(exch, buf, w, lane, xa, xb);
+        buf ^= 1;
+        band_pass<false, MASKED, true>(c, sw.w[s] * icC * ma, sw.w[s] * icC * mb, L.rowm, dummy, dummy, xa, xb, bt, w * RW, lane);
+    }
+    band_publish(exch, buf, w, lane, xa, xb);
+    band_sync(w);
+    band_halo(exch, buf, w, lane, xa, xb);
+    buf ^= 1;
+    band_pass<true, MASKED, true>(c, ma, mb, L.rowm, dummy, dummy, xa, xb, bt, w * RW, lane);
+}
+
+template <int NU, int H>
+__global__ void __launch_bounds__(NT, 3)
+k_pre_rt3(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMap map_b, double *__restrict__ x,
+          double *__restrict__ bc, const SmoothW sw, const Geom G, unsigned *sched, const CGScalars *sc)
+{
+    static_assert(H % 2 == 0 && H >= NU + 1, "even halo of at least NU + 1 nodes");
+    constexpr int TO = TS - 2 * H, CT = TO / 2;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double *bt = reinterpret_cast<double *>(smraw);     // TMA box: right-hand side, then the residual in place
+    double *exch = bt + TS * TS;                        // 2 x NWARP x 2 x 64
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(exch + 2 * NWARP * 2 * TS);
+    int *ids = reinterpret_cast<int *>(bar + 1);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ntiles = G.n;
+    const int done = sc->done;
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    int cur = blockIdx.x, nxt = blockIdx.x + gridDim.x;
+    pdl_wait();
+    if (tid == 0 && cur < ntiles && !done) {
+        mbar_expect_tx(bar, TS * TS * 8);
+        tma_load_2d(bt, &map_b, bar, __ldg(G.tiles + 2 * cur) * TO - H, F.tbase + __ldg(G.tiles + 2 * cur + 1) * TO - H);
+    }
+    if (done) return;
+    __syncthreads();
+    unsigned phase = 0;
+    int it = 0, buf = 0;
+    const Coef c{F.cC, F.cEW, F.cNS, F.cD};
+    const double icC = F.icC;
+    while (cur < ntiles) {
+        const Lane L = lane_of<H>(F, G, cur, w, lane);
+        unsigned t_nn = 0;
+        if (tid == 0) t_nn = 2u * gridDim.x + atomicAdd(sched, 1u);   // the tile after the next one
+        double xa[RW + 2], xb[RW + 2];
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        if (L.ox >= 1 && L.ox + TS <= F.nx - 1 && L.oy >= 1 && L.oy + TS <= F.ny - 1)
+            pre_sweeps3<NU, false>(c, sw, icC, L, exch, buf, w, lane, xa, xb, bt);
+        else
+            pre_sweeps3<NU, true>(c, sw, icC, L, exch, buf, w, lane, xa, xb, bt);
+        if (tid == 0) ids[it & 1] = (int)t_nn;
+        band_store<H, true>(F, L, x, w, lane, xa, xb);
+        __syncthreads();   // residual tile complete (and ids[] visible)
+        {
+            const int I0 = (L.oy + H) >> 1, J0 = (L.ox + H) >> 1;
+            for (int q = tid; q < CT * CT; q += NT) {
+                const int cy = q / CT, cx = q - cy * CT;
+                const int gi = L.oy + H + 2 * cy, gj = L.ox + H + 2 * cx;
+                if (gi >= F.ny || gj >= F.nx) continue;
+                const int cc = (H + 2 * cy) * TS + H + 2 * cx;
+                const double h = bt[cc + 1] + bt[cc - 1] + bt[cc + TS] + bt[cc - TS] + bt[cc + TS + 1] + bt[cc - TS - 1];
+                bc[(size_t)(I0 + cy) * Cc.nx + J0 + cx] = is_dirichlet(Cc, I0 + cy, J0 + cx) ? 0.0 : bt[cc] + 0.5 * h;
+            }
+            const bool lastx = !(F.nx & 1) && L.ox + TS - H >= F.nx, lasty = !(F.ny & 1) && L.oy + TS - H >= F.ny;
+            if (lastx)
+                for (int cy = tid; cy < CT; cy += NT)
+                    if (L.oy + H + 2 * cy < F.ny) bc[(size_t)(I0 + cy) * Cc.nx + Cc.nx - 1] = 0.0;
+            if (lasty)
+                for (int cx = tid; cx < CT; cx += NT)
+                    if (L.ox + H + 2 * cx < F.nx) bc[(size_t)(Cc.ny - 1) * Cc.nx + J0 + cx] = 0.0;
+            if (lastx && lasty && tid == 0) bc[(size_t)Cc.ny * Cc.nx - 1] = 0.0;
+        }
+        const int nn = ids[it & 1];
+        __syncthreads();   // the box has been read to the end: refill it
+        if (tid == 0 && nxt < ntiles) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, TS * TS * 8);
+            tma_load_2d(bt, &map_b, bar, __ldg(G.tiles + 2 * nxt) * TO - H, F.tbase + __ldg(G.tiles + 2 * nxt + 1) * TO - H);
+        }
+        cur = nxt; nxt = nn;
+        ++it;
+    }
+    sched_leave(sched);
+}
+
+template <int NU, int H, bool DOT>
+__global__ void __launch_bounds__(NT, 3)
+k_post_rt3(const LevelDev F, const LevelDev Cc, const __grid_constant__ CUtensorMap map_b, const double *__restrict__ xin,
+           double *__restrict__ x, const double *__restrict__ xc, const SmoothW sw, const Geom G, unsigned *sched,
+           CGScalars *sc, double *partials, unsigned *counter, double *out_dot)
+{
+    static_assert(H % 2 == 0 && H >= NU, "even halo of at least NU nodes");
+    constexpr int TO = TS - 2 * H;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double *bt = reinterpret_cast<double *>(smraw);     // TMA box: right-hand side
+    double *exch = bt + TS * TS;                        // 2 x NWARP x 2 x 64
+    double *patch2 = exch + 2 * NWARP * 2 * TS;         // two buffers of PATCH rows of stride PS
+    double *red = patch2 + 2 * PATCH * PS;              // 32 doubles
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(red + 32);
+    int *ids = reinterpret_cast<int *>(bar + 1);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ntiles = G.n;
+    const int done = sc->done;
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    int cur = blockIdx.x, nxt = blockIdx.x + gridDim.x;
+    pdl_wait();
+    if (done) return;
+    if (cur < ntiles) {
+        const int ox = __ldg(G.tiles + 2 * cur) * TO - H, oy = F.tbase + __ldg(G.tiles + 2 * cur + 1) * TO - H;
+        if (tid == 0) {
+            mbar_expect_tx(bar, TS * TS * 8);
+            tma_load_2d(bt, &map_b, bar, ox, oy);
+        }
+        patch_copy_async(Cc, xc, ox, oy, tid, patch2);
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    unsigned phase = 0, mine = 0;
+    int it = 0, buf = 0;
+    const Coef c{F.cC, F.cEW, F.cNS, F.cD};
+    const double icC = F.icC;
+    const double dummy[RW] = {};
+    while (cur < ntiles) {
+        const Lane L = lane_of<H>(F, G, cur, w, lane);
+        unsigned t_nn = 0;
+        if (tid == 0) t_nn = 2u * gridDim.x + atomicAdd(sched, 1u);
+        // the incoming iterate: straight into the registers (even pitch and origin: 128-bit, the pair inside the grid or
+        // outside it together); in flight while the right-hand side box lands
+        double xa[RW + 2], xb[RW + 2];
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+            double2 u = make_double2(0.0, 0.0);
+            if (((L.rowin >> k) & 1u) && L.ina)
+                u = *reinterpret_cast<const double2 *>(xin + (size_t)(L.oy + w * RW + k) * F.nx + L.ox + 2 * lane);
+            xa[k + 1] = u.x; xb[k + 1] = u.y;
+        }
+        const double *patch = patch2 + (it & 1) * PATCH * PS;
+        const bool inner = L.ox >= 1 && L.ox + TS <= F.nx - 1 && L.oy >= 1 && L.oy + TS <= F.ny - 1;   // CTA-uniform
+        if (inner) post_prolong<false>(L, patch, w, lane, xa, xb);
+        else post_prolong<true>(L, patch, w, lane, xa, xb);
+        if (nxt < ntiles)   // the next tile's patch into the other buffer (last read during the previous tile)
+            patch_copy_async(Cc, xc, __ldg(G.tiles + 2 * nxt) * TO - H, F.tbase + __ldg(G.tiles + 2 * nxt + 1) * TO - H, tid,
+                             patch2 + ((it + 1) & 1) * PATCH * PS);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        const double ma = inner ? 1.0 : L.cma, mb = inner ? 1.0 : L.cmb;
+#pragma unroll
+        for (int s = 0; s < NU; ++s) {
+            band_publish(exch, buf, w, lane, xa, xb);
+            band_sync(w);
+            band_halo(exch, buf, w, lane, xa, xb);
+            buf ^= 1;
+            if (inner) band_pass<false, false, true>(c, sw.w[s] * icC, sw.w[s] * icC, L.rowm, dummy, dummy, xa, xb, bt, w * RW, lane);
+            else band_pass<false, true, true>(c, sw.w[s] * icC * ma, sw.w[s] * icC * mb, L.rowm, dummy, dummy, xa, xb, bt, w * RW, lane);
+        }
+        cp_async_wait<0>();
+        if (tid == 0) ids[it & 1] = (int)t_nn;
+        band_store<H, true>(F, L, x, w, lane, xa, xb);
+        double acc = 0.0;
+        if (DOT && lane >= H / 2 && lane < 32 - H / 2) {
+#pragma unroll
+            for (int k = 0; k < RW; ++k) {
+                const int ly = w * RW + k;
+                if (ly >= H && ly < TS - H) {
+                    const double2 bv = *reinterpret_cast<const double2 *>(bt + ly * TS + 2 * lane);
+                    acc += xa[k + 1] * bv.x + xb[k + 1] * bv.y;
+                }
+            }
+        }
+        if (DOT) {
+            const double t = cta_sum(acc, red);   // contains the __syncthreads after which the box may be refilled
+            if (tid == 0) partials[L.by * G.gx + L.bx] = t;
+            ++mine;
+        } else {
+            __syncthreads();
+        }
+        const int nn = ids[it & 1];
+        if (tid == 0 && nxt < ntiles) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, TS * TS * 8);
+            tma_load_2d(bt, &map_b, bar, __ldg(G.tiles + 2 * nxt) * TO - H, F.tbase + __ldg(G.tiles + 2 * nxt + 1) * TO - H);
+        }
+        cur = nxt; nxt = nn;
+        ++it;
+    }
+    if (DOT && mine) tiles_arrive(partials, counter, mine, (unsigned)(G.gx * G.gy), out_dot);
+    sched_leave(sched);
+}
+
 }  // namespace RT
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -585,6 +812,8 @@ static int rt_halo_pre(int nu) { return (nu + 2) & ~1; }    // even, >= nu + 1
 static int rt_halo_post(int nu) { return (nu + 1) & ~1; }   // even, >= nu
 
 static const size_t RT_SMEM_PRE = (size_t)(2 * RT::TS * RT::TS + 2 * RT::NWARP * 2 * RT::TS) * 8 + 64;
+static const size_t RT_SMEM_PRE3 = (size_t)(RT::TS * RT::TS + 2 * RT::NWARP * 2 * RT::TS) * 8 + 64;
+static const size_t RT_SMEM_POST3 = (size_t)(RT::TS * RT::TS + 2 * RT::NWARP * 2 * RT::TS + 2 * RT::PATCH * RT::PS + 32) * 8 + 64;
 static const size_t RT_SMEM_POST = (size_t)(2 * RT::TS * RT::TS + 2 * RT::NWARP * 2 * RT::TS + 2 * RT::PATCH * RT::PS + 32) * 8 + 64;
 
 // Splits the gx x gy tiling (halo h) of a level into the tiles the register-tile kernel takes -- every node of the 64 x 64
@@ -647,6 +876,14 @@ int rt_setup(eqgpu_solver *s)
     RT_SET(false);
 #undef RT_SET
     if (!ok) { s->rt_smooth = false; return 0; }
+    // three CTAs per SM: the lean instances (right-hand side in shared memory, under 80 registers) on TMA levels.  Opt-in
+    // (EQGPU_RT_LEAN=1): measured on the B200 at 2048^2, 24 warps per SM buy nothing -- 29.4 / 41.7 us against 28.0 / 37.0 us
+    // for the two-CTA instances with their prefetched boxes (profiles/r02_ncu_register_tile.md)
+    s->rt_lean = getenv("EQGPU_RT_LEAN") != nullptr && atoi(getenv("EQGPU_RT_LEAN")) != 0;
+    if (s->rt_lean)
+        s->rt_lean = set_smem(RT::k_pre_rt3<3, 4>, RT_SMEM_PRE3) && set_smem(RT::k_pre_rt3<4, 6>, RT_SMEM_PRE3) &&
+                     set_smem(RT::k_post_rt3<3, 4, true>, RT_SMEM_POST3) && set_smem(RT::k_post_rt3<3, 4, false>, RT_SMEM_POST3) &&
+                     set_smem(RT::k_post_rt3<4, 4, true>, RT_SMEM_POST3) && set_smem(RT::k_post_rt3<4, 4, false>, RT_SMEM_POST3);
     s->rt_ctas = 2 * s->num_sms;
     if (const char *e = getenv("EQGPU_RT_CTAS")) s->rt_ctas = std::max(1, atoi(e));
     EQ_CUDA(cudaMalloc(&s->rt_sched, sizeof(unsigned) * 4));
@@ -702,7 +939,7 @@ static RT::Geom geom_of(const Level::RtPlan &P)
 #define RT_LAUNCH(PDL_OK, KERN, SM, ST, ...)                                                              \
     do {                                                                                                  \
         cudaLaunchConfig_t cfg_{};                                                                        \
-        cfg_.gridDim = dim3(std::min(s->rt_ctas, G.n)); cfg_.blockDim = dim3(RT::NT);                     \
+        cfg_.gridDim = dim3(std::min(ctas, G.n)); cfg_.blockDim = dim3(RT::NT);                           \
         cfg_.dynamicSmemBytes = (SM); cfg_.stream = (ST);                                                 \
         cudaLaunchAttribute at_[1];                                                                       \
         if (s->pdl && (PDL_OK) && !s->pdl_block) {                                                        \
@@ -720,6 +957,13 @@ void rt_launch_pre(eqgpu_solver *s, cudaStream_t st, int l, int nu, const Smooth
     const RT::Geom G = geom_of(lv.rt_pre);
     const CGScalars *scc = s->sc;
     const double *b = lv.b;
+    const bool lean = s->rt_lean && lv.rt_tma;
+    const int ctas = lean ? (s->rt_ctas / 2) * 3 : s->rt_ctas;
+    if (lean) {
+        if (nu == 3) RT_LAUNCH(pdl_ok, (RT::k_pre_rt3<3, 4>), RT_SMEM_PRE3, st, lv.dev, cv.dev, lv.map_b64, lv.t, cv.b, sw, G, s->rt_sched, scc);
+        else RT_LAUNCH(pdl_ok, (RT::k_pre_rt3<4, 6>), RT_SMEM_PRE3, st, lv.dev, cv.dev, lv.map_b64, lv.t, cv.b, sw, G, s->rt_sched, scc);
+        return;
+    }
 #define RT_PRE(NU, H, TMA) \
     RT_LAUNCH(pdl_ok, (RT::k_pre_rt<NU, H, TMA>), RT_SMEM_PRE, st, lv.dev, cv.dev, lv.map_b64, b, lv.t, cv.b, sw, G, s->rt_sched, scc)
     if (nu == 3) { if (lv.rt_tma) RT_PRE(3, 4, true); else RT_PRE(3, 4, false); }
@@ -732,6 +976,17 @@ void rt_launch_post(eqgpu_solver *s, cudaStream_t st, int l, int nu, const Smoot
     Level &lv = s->levels[l], &cv = s->levels[l + 1];
     const RT::Geom G = geom_of(lv.rt_post);
     const double *xc = cv.x, *b = lv.b, *xin = lv.t;
+    const bool lean = s->rt_lean && lv.rt_tma;
+    const int ctas = lean ? (s->rt_ctas / 2) * 3 : s->rt_ctas;
+    if (lean) {
+#define RT_POST3(NU, DOT)                                                                                                  \
+    RT_LAUNCH(true, (RT::k_post_rt3<NU, 4, DOT>), RT_SMEM_POST3, st, lv.dev, cv.dev, lv.map_b64, xin, lv.x, xc, sw, G,       \
+              s->rt_sched + 2, s->sc, s->partials, s->counters + 1, out_dot)
+        if (nu == 3) { if (dot) RT_POST3(3, true); else RT_POST3(3, false); }
+        else { if (dot) RT_POST3(4, true); else RT_POST3(4, false); }
+#undef RT_POST3
+        return;
+    }
 #define RT_POST(NU, DOT, TMA)                                                                                              \
     RT_LAUNCH(true, (RT::k_post_rt<NU, 4, DOT, TMA>), RT_SMEM_POST, st, lv.dev, cv.dev, lv.map_b64, lv.map_t64, b, xin, lv.x, \
               xc, sw, G, s->rt_sched + 2, s->sc, s->partials, s->counters + 1, out_dot)

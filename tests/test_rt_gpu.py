@@ -25,6 +25,9 @@ CASES = [
     (640, 512, (D, N_, D, N_), (0, 0, 0, 0), {}, {"EQGPU_RT_MIN_TILES": "8"}),  # few tiles: more CTAs than tiles
     (1024, 1024, (D, D, D, D), (0, 0, 0, 0), {"discretisation": 1}, {}),        # diffusionPETSc's finite differences (cD = 0)
     (1536, 1100, (D, D, D, D), (0, 0, 0, 0), {}, {"EQGPU_RT_CTAS": "40"}),      # many tiles per persistent CTA
+    # the three-CTAs-per-SM instances (right-hand side in shared memory, no box prefetch; opt-in)
+    (2048, 2048, (D, D, D, D), (0, 0, 0, 0), {}, {"EQGPU_RT_LEAN": "1"}),
+    (1026, 770, (D, D, N_, N_), (0, 0, 0, 0), {}, {"EQGPU_RT_LEAN": "1", "EQGPU_RT_CTAS": "30"}),
 ]
 
 
