@@ -175,6 +175,7 @@ struct eqgpu_solver {
     int slab_rank = 0, slab_world = 1;
     void *nccl_comm = nullptr;
     long long comm_allreduce_calls = 0, comm_allreduce_doubles = 0, comm_exchange_groups = 0, comm_halo_bytes = 0;   // cumulative, this rank
+    int slab_group_depth = 0;      // open slab_group_begin() brackets
     int halo = 1;                  // halo rows kept per neighbour (1 unfused, 6 for the tile kernels)
     bool slab_fused = false;
     int scatter_mode = 0;          // 0 direct global atomics, 1 shared-memory-binned
@@ -264,6 +265,8 @@ void slab_destroy_comm(eqgpu_solver *s);
 int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth = 1);  // halo rows of a level vector (local view)
 int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count);  // sum over ranks, stream-ordered
 int slab_exchange2(eqgpu_solver *s, const LevelDev &L, double *v1, double *v2, int depth);   // two vectors, one NCCL group
+int slab_group_begin(eqgpu_solver *s);   // bracket several exchanges into one NCCL group (no kernel in between)
+int slab_group_end(eqgpu_solver *s);
 int slab_unique_id(void *out128);
 // ---- cells.cu ----
 int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap);

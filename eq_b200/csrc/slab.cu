@@ -121,7 +121,7 @@ int slab_exchange2(eqgpu_solver *s, const LevelDev &L, double *v1, double *v2, i
         }
     }
     note(g_nccl.GroupEnd());
-    s->comm_exchange_groups++;
+    if (s->slab_group_depth == 0) s->comm_exchange_groups++;
     if (bad != 0) {
         s->set_error(std::string("halo exchange: ") + g_nccl.GetErrorString(bad));
         return EQGPU_ECUDA;
@@ -130,6 +130,24 @@ int slab_exchange2(eqgpu_solver *s, const LevelDev &L, double *v1, double *v2, i
 }
 
 int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth) { return slab_exchange2(s, L, v, nullptr, depth); }
+
+// Several exchanges (different levels, different vectors) that have no kernel between them travel as ONE NCCL group: NCCL
+// groups nest, the sends and receives start at the outermost ncclGroupEnd -- one launch instead of one per exchange.
+int slab_group_begin(eqgpu_solver *s)
+{
+    if (!s->slab || s->slab_world < 2) return 0;
+    EQ_NCCL(g_nccl.GroupStart());
+    s->slab_group_depth++;
+    return 0;
+}
+int slab_group_end(eqgpu_solver *s)
+{
+    if (!s->slab || s->slab_world < 2 || s->slab_group_depth == 0) return 0;
+    s->slab_group_depth--;
+    EQ_NCCL(g_nccl.GroupEnd());
+    if (s->slab_group_depth == 0) s->comm_exchange_groups++;
+    return 0;
+}
 
 int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count)
 {

@@ -2230,8 +2230,10 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
             return;
         }
     }
+    if (s->slab) slab_group_begin(s);   // both exchanges in one NCCL group
     xch(s, cv, cv.x, NU + 1);   // coarse correction rows reached by the prolongation of my halo
     xch(s, lv, lv.t, NU);       // pre-smoothed iterate; lv.b halos are still valid from the pre-smoothing exchange
+    if (s->slab) slab_group_end(s);
 #define POST(NS, DOT, R, NT, G, SM)                                                                               \
     LAUNCH_K(true, (NS::k_postsmooth<NU, DOT, R>), G, dim3(NT), SM, st, F, Cc, (const double *)VP(s, lv, lv.b),   \
              (const double *)VP(s, lv, lv.t), VP(s, lv, lv.x), (const double *)VP(s, cv, cv.x), sw, s->sc,        \
@@ -2459,6 +2461,9 @@ static int pcg(eqgpu_solver *s)
     DirData dd = make_dirdata(s);
     const int nb1 = std::min<int>(s->max_blocks, 4 * s->num_sms);
     const bool fused = !T && s->fused;
+    // EQGPU_TENSOR_PRECOND=tensor: the unfused V-cycle of the tensor operator itself (round 1's preconditioner)
+    static const bool iso_env = getenv("EQGPU_TENSOR_PRECOND") == nullptr || std::string(getenv("EQGPU_TENSOR_PRECOND")) != "tensor";
+    const bool iso_precond = T && iso_env && s->fused && !s->slab && s->levels.size() >= 2;
     if (fused && !s->slab) {
         int rc = build_iteration_graph(s);
         if (rc) return rc;
@@ -2623,9 +2628,24 @@ static int pcg(eqgpu_solver *s)
             }
         } else {
             for (int k = 0; k < chunk && issued < max_iters; ++k, ++issued) {
-                vcycle<T>(s);
-                k_dot<<<nb1, 256, 0, st>>>(on, s->r + ooff, s->z + ooff, sc, s->partials, s->counters + 1,
-                                           sl ? &sc->part_rz : &sc->rz_new);
+                if (T && iso_precond) {
+                    // variable tensor, one GPU: the preconditioner is the fused V-cycle of the ISOTROPIC operator with the
+                    // same dt*D (spectrally equivalent to the tensor operator within the range of the tensor's
+                    // eigenvalues: identity outside the rods, the shipped scalings inside them).  PCG is exact for any
+                    // SPD preconditioner; the tensor operator itself is applied by k_apply below.
+                    const bool dx = s->defer_x;
+                    s->defer_x = false;   // (x is updated in line by k_update_xr on this path)
+                    vcycle_fused(s, st);
+                    s->defer_x = dx;
+                } else {
+                    vcycle<T>(s);
+                }
+                // (the fused cycle's level-0 post-smoother has left r.z in sc->rz_new, as in enqueue_fused_iteration)
+                const bool have_rz = T && iso_precond &&
+                                     !(!s->tile_coarsest && (s->use_cluster ? s->ctail_first : s->tail_first) == 0);
+                if (!have_rz)
+                    k_dot<<<nb1, 256, 0, st>>>(on, s->r + ooff, s->z + ooff, sc, s->partials, s->counters + 1,
+                                               sl ? &sc->part_rz : &sc->rz_new);
                 if (sl) slab_allreduce(s, &sc->part_rz, &sc->rz_new, 1);
                 k_update_p<<<nb1, 256, 0, st>>>(on, s->z + ooff, s->pv + ooff, sc);
                 if (sl) slab_exchange(s, L, s->pv);

@@ -5,7 +5,7 @@ timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "tensor" > gpurun
 tail -3 gpurun_out/c19/pytest_tensor.log
 run() { name=$1; shift; env "$@" timeout 300 python bench.py --config 7 --steps 20 --warmup 5 --no-cpu-baseline --no-side-legs > gpurun_out/c19/bench_$name.json 2> gpurun_out/c19/bench_$name.err; }
 run tensor_asm
-run tensor_fly EQGPU_TENSOR_ASSEMBLE=0
+run tensor_tprec EQGPU_TENSOR_PRECOND=tensor
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob("gpurun_out/c19/bench_*.json")):
