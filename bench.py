@@ -393,7 +393,12 @@ def run_slab_leg(args, rank, local_rank, world, stream, ids_fn):
             "allreduce_doubles_per_step": (c1["allreduce_doubles"] - c0["allreduce_doubles"]) / k_steps,
             "halo_exchanges_per_step": (c1["halo_exchanges"] - c0["halo_exchanges"]) / k_steps,
             "halo_bytes_sent_per_step_this_rank": (c1["halo_bytes_sent"] - c0["halo_bytes_sent"]) / k_steps,
-            "transport": "NCCL send/recv + all-reduce over NVLink/NVSwitch, stream-ordered"}
+            "peer_exchange_kernels_per_step": (c1["peer_exchange_kernels"] - c0["peer_exchange_kernels"]) / k_steps,
+            "peer_allreduces_per_step": (c1["peer_allreduces"] - c0["peer_allreduces"]) / k_steps,
+            "transport": ("peer memory over NVLink/NVSwitch (CUDA IPC): one kernel per halo exchange (boundary rows stored into the neighbours' staging buffers, theirs copied out of mine), scalar "
+                          "all-reduces by one warp summing every rank's partials in rank order; NCCL only for the set-up and "
+                          "the per-cell sample reduction" if c1["peer_exchange_kernels"] >= 0 else
+                          "NCCL send/recv + all-reduce over NVLink/NVSwitch, stream-ordered")}
     out.update({"metric": f"hsl_diffusion_steps_per_sec_{nW}x{nH}_row_slab", "value": 1e3 / ms, "unit": UNIT,
                 "ms_per_step": ms, "steps": k_steps, "warmup": k_warm, "scaling": "weak",
                 "workload": f"configs[4] style: {nW}x{nH} nodes in {world} row slabs of 2048 rows, {nrec} rods "

@@ -36,7 +36,7 @@ API_SYMBOLS = [
     "eqgpu_slab_plan", "eqgpu_set_scatter_mode", "eqgpu_solver_path", "eqgpu_set_warm_start",
     "eqgpu_last_guess", "eqgpu_cells_tensor", "eqgpu_get_tensor",
     "eqgpu_ls_solve3", "eqgpu_ring_solve", "eqgpu_cells_upload_device", "eqgpu_get_warm_start", "eqgpu_apply_preconditioner", "eqgpu_comm_stats",
-    "eqgpu_set_nonconvergence_policy", "eqgpu_unconverged_steps",
+    "eqgpu_set_nonconvergence_policy", "eqgpu_unconverged_steps", "eqgpu_comm_peer_stats",
 ]
 
 
@@ -361,8 +361,10 @@ class GpuHSL:
         """Row-slab mode: cumulative communication counters of this rank (eqgpu_comm_stats)."""
         out = (C.c_int64 * 4)()
         self._ck(lib().eqgpu_comm_stats(self._h, out))
+        peer = (C.c_int64 * 2)()
+        self._ck(lib().eqgpu_comm_peer_stats(self._h, peer))
         return {"allreduce_calls": int(out[0]), "allreduce_doubles": int(out[1]), "halo_exchanges": int(out[2]),
-                "halo_bytes_sent": int(out[3])}
+                "halo_bytes_sent": int(out[3]), "peer_exchange_kernels": int(peer[0]), "peer_allreduces": int(peer[1])}
 
     def warm_mode(self) -> int:
         return int(lib().eqgpu_get_warm_start(self._h))

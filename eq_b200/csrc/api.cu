@@ -112,6 +112,14 @@ int eqgpu_comm_stats(eqgpu_solver *s, int64_t out[4])
     return 0;
 }
 
+int eqgpu_comm_peer_stats(eqgpu_solver *s, int64_t out[2])
+{
+    if (!s || !out) return EQGPU_EINVAL;
+    out[0] = s->peer_ok ? s->comm_peer_pulls : -1;   // -1: the peer-memory path is not in use (NCCL carries everything)
+    out[1] = s->peer_ok ? s->comm_peer_allreduces : -1;
+    return 0;
+}
+
 int eqgpu_get_warm_start(eqgpu_solver *s) { return s ? s->warm : EQGPU_EINVAL; }
 
 int eqgpu_ls_solve3(const double *G, const double *f, double bb, double *c, double *pred)
@@ -179,6 +187,7 @@ static int create_common(const eqgpu_params *p, int rank, int world, const void 
     s->slab_world = world;
     auto fail = [&](int rc) {
         g_create_error = s->err;
+        slab_peer_teardown(s);
         slab_destroy_comm(s);
         solver_teardown(s);
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -208,6 +217,10 @@ static int create_common(const eqgpu_params *p, int rank, int world, const void 
     if (rc) return fail(rc);
     rc = solver_refresh_levels(s);
     if (rc) return fail(rc);
+    if (s->slab) {   // every vector exists now: map the other ranks' memory for the halo pulls and the scalar all-reduce
+        rc = slab_peer_setup(s);
+        if (rc) return fail(rc);
+    }
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) { s->set_error("setup sync failed"); return fail(EQGPU_ECUDA); }
     *out = s;
     return EQGPU_OK;
@@ -218,6 +231,7 @@ void eqgpu_destroy(eqgpu_solver *s)
     if (!s) return;
     cudaSetDevice(s->p.device);
     cudaStreamSynchronize(s->stream);
+    slab_peer_teardown(s);
     slab_destroy_comm(s);
     solver_teardown(s);
     cudaFree(s->cells); cudaFree(s->cell_vals); cudaFree(s->cell_counts); cudaFree(s->cell_amt); cudaFree(s->bin_ints); cudaFree(s->tensor_owner);

@@ -176,6 +176,20 @@ struct eqgpu_solver {
     void *nccl_comm = nullptr;
     long long comm_allreduce_calls = 0, comm_allreduce_doubles = 0, comm_exchange_groups = 0, comm_halo_bytes = 0;   // cumulative, this rank
     int slab_group_depth = 0;      // open slab_group_begin() brackets
+    // peer-memory halos and scalar all-reduce (slab.cu): the other ranks' flag blocks and staging buffers mapped through
+    // CUDA IPC; an exchange is one small kernel that stores my boundary rows into the neighbours' staging buffers and
+    // copies theirs out of mine once their arrival flag is up -- no NCCL call on the data path
+    unsigned long long *peer_flags = nullptr;                   // my flag block (PEER_FLAG_WORDS words)
+    unsigned long long *peer_flags_of[16] = {};                 // every rank's flag block as mapped here (mine included)
+    void *peer_stage = nullptr, *peer_stage_lo = nullptr, *peer_stage_hi = nullptr;   // my staging buffers, rank-1's, rank+1's
+    unsigned long long peer_stage_cap = 0, peer_batch_fill = 0;   // 16-byte slots per (side, parity) buffer; filled by the open batch
+    int *peer_err = nullptr;                                    // mapped pinned: set by a kernel whose wait timed out
+    std::vector<void *> peer_opened;                            // cudaIpcOpenMemHandle results to close
+    bool peer_ok = false;
+    unsigned long long peer_xseq = 0, peer_arseq = 0;           // exchanges / all-reduces issued so far (same on every rank)
+    long long peer_timeout_ns = 20000000000LL;
+    void *peer_batch = nullptr;                                 // jobs collected between slab_group_begin/end
+    long long comm_peer_pulls = 0, comm_peer_allreduces = 0;
     int halo = 1;                  // halo rows kept per neighbour (1 unfused, 6 for the tile kernels)
     bool slab_fused = false;
     int scatter_mode = 0;          // 0 direct global atomics, 1 shared-memory-binned
@@ -267,6 +281,10 @@ int slab_allreduce(eqgpu_solver *s, const double *src, double *dst, int count); 
 int slab_exchange2(eqgpu_solver *s, const LevelDev &L, double *v1, double *v2, int depth);   // two vectors, one NCCL group
 int slab_group_begin(eqgpu_solver *s);   // bracket several exchanges into one NCCL group (no kernel in between)
 int slab_group_end(eqgpu_solver *s);
+void solver_trace_mark(cudaStream_t st, const char *label);   // EQGPU_TRACE debugging aid (solver.cu)
+int slab_peer_setup(eqgpu_solver *s);     // after every vector exists: map the neighbours' memory (no-op unless enabled)
+void slab_peer_teardown(eqgpu_solver *s);
+int slab_peer_check(eqgpu_solver *s);     // after a stream sync: did a peer wait time out?  (error set, peer path switched off)
 int slab_unique_id(void *out128);
 // ---- cells.cu ----
 int cells_raster(eqgpu_solver *s, int32_t *d_counts, long long *d_nodes, int cap);

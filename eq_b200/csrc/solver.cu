@@ -1858,14 +1858,17 @@ static CoarseW coarse_weights(eqgpu_solver *s)
 }
 
 static std::vector<cudaEvent_t> *g_trace = nullptr;  // debugging aid (EQGPU_TRACE): event after each launch
-static void trace_mark(cudaStream_t st)
+static std::vector<const char *> g_trace_labels;
+void solver_trace_mark(cudaStream_t st, const char *label)
 {
     if (!g_trace) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, st);
     g_trace->push_back(e);
+    g_trace_labels.push_back(label);
 }
+static void trace_mark(cudaStream_t st, const char *label = "kernel") { solver_trace_mark(st, label); }
 
 static SmoothW smooth_weights_n(int n)
 {
@@ -2134,7 +2137,7 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
         if (s->stream_pipe && lv.tma && NU >= 3) launch_pre_pipe<(NU >= 3 ? NU : 3)>(s, st, l, pdl_ok);
         else launch_pre_stream<NU>(s, st, l, pdl_ok);
         s->launches++;
-        trace_mark(st);
+        trace_mark(st, "pre");
         return;
     }
     if constexpr (NU == 3 || NU == 4) {
@@ -2159,7 +2162,7 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
                 s->pdl_block = true;
             }
             s->launches++;
-            trace_mark(st);
+            trace_mark(st, "pre");
             return;
         }
     }
@@ -2185,7 +2188,7 @@ static void launch_pre(eqgpu_solver *s, cudaStream_t st, int l)
                      VP(s, lv, lv.t), VP(s, cv, cv.b), sw, scc);
     }
     s->launches++;
-    trace_mark(st);
+    trace_mark(st, "pre");
 }
 
 template <int NU>
@@ -2198,7 +2201,7 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
         if (s->stream_pipe && lv.tma && NU >= 3) launch_post_pipe<(NU >= 3 ? NU : 3)>(s, st, l);
         else launch_post_stream<NU>(s, st, l);
         s->launches++;
-        trace_mark(st);
+        trace_mark(st, "post");
         return;
     }
     double *out_dot = s->slab ? &s->sc->part_rz : &s->sc->rz_new;
@@ -2226,7 +2229,7 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
                 s->pdl_block = true;
             }
             s->launches++;
-            trace_mark(st);
+            trace_mark(st, "post");
             return;
         }
     }
@@ -2254,7 +2257,7 @@ static void launch_post(eqgpu_solver *s, cudaStream_t st, int l)
     }
 #undef POST
     s->launches++;
-    trace_mark(st);
+    trace_mark(st, "post");
 }
 
 // Coarsest level: cw.n Chebyshev-Jacobi sweeps in one tile pass (halo cw.n-1).  32-node tiles while they
@@ -2289,7 +2292,7 @@ static void launch_coarsest(eqgpu_solver *s, cudaStream_t st, const CoarseW &cw)
         LAUNCH_K(true, (T64::k_coarsest<4>), tile_grid(F, 64 - H2), dim3(1024), SM64_3, st, F,
                  (const double *)VP(s, lv, lv.b), VP(s, lv, lv.x), cw, scc);
     s->launches++;
-    trace_mark(st);
+    trace_mark(st, "coarsest");
 }
 
 static int nu_of(const eqgpu_solver *s, int l) { return l == 0 ? s->nu : l == 1 ? s->nu1 : s->nuc; }
@@ -2399,20 +2402,20 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     if (use_stream(s, l0) && s->stream_apply)
         launch_apply_stream(s, st, !s->defer_x || s->join_pdl, s->pv, s->pv2);
     else
-        LAUNCH_K(!sl && (!s->defer_x || s->join_pdl), T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
+        LAUNCH_K((!sl || s->peer_ok) && (!s->defer_x || s->join_pdl), T64::k_apply_p, tg, dim3(256), 0, st, L, (const double *)VP(s, l0, s->z),
                  (const double *)VP(s, l0, s->pv), VP(s, l0, s->pv2), VP(s, l0, s->Ap), sc, s->partials, s->counters + 2,
                  sl ? &sc->part_pAp : &sc->pAp);
-    trace_mark(st);
+    trace_mark(st, "apply_p");
     std::swap(s->pv, s->pv2);
     if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
     if (s->defer_x)
         LAUNCH_K(true, k_update_r, dim3(nb1), dim3(256), 0, st, on, s->r + ooff, (const double *)(s->Ap + ooff), sc,
                  s->partials, s->counters + 3);
     else
-        LAUNCH_K(!sl, k_update_xr, dim3(nb1), dim3(256), 0, st, on, s->u + ooff, s->r + ooff,
+        LAUNCH_K(!sl || s->peer_ok, k_update_xr, dim3(nb1), dim3(256), 0, st, on, s->u + ooff, s->r + ooff,
                  (const double *)(s->pv + ooff), (const double *)(s->Ap + ooff), sc, s->partials, s->counters + 3,
                  sl ? 0 : 1, sl ? &sc->part_rr : &sc->rr);
-    trace_mark(st);
+    trace_mark(st, "update_xr");
     if (sl) {
         slab_allreduce(s, &sc->part_rr, &sc->rr, 1);
         k_book<<<1, 1, 0, st>>>(sc);
@@ -2603,10 +2606,11 @@ static int pcg(eqgpu_solver *s)
         }
     }
 #endif
-    if (fused && !s->slab && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
+    if (fused && getenv("EQGPU_TRACE") && s->st.steps == 5) {  // debugging aid: in-situ per-kernel times
         std::vector<cudaEvent_t> ev;
         g_trace = &ev;
-        trace_mark(st);
+        g_trace_labels.clear();
+        trace_mark(st, "start");
         for (int k = 0; k < 2; ++k, ++issued) { enqueue_fused_iteration(s, st); }
         g_trace = nullptr;
         s->graph_phase = 0;
@@ -2614,7 +2618,7 @@ static int pcg(eqgpu_solver *s)
         for (size_t k = 1; k < ev.size(); ++k) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
-            fprintf(stderr, "trace kernel %2zu: %7.1f us\n", k, ms * 1e3);
+            fprintf(stderr, "trace rank %d %2zu %-12s %7.1f us\n", s->slab_rank, k, g_trace_labels[k], ms * 1e3);
         }
         for (auto e : ev) cudaEventDestroy(e);
     }
@@ -2686,6 +2690,7 @@ static int pcg(eqgpu_solver *s)
             if (rc) return rc;
         }
         EQ_CUDA(cudaStreamSynchronize(st));
+        if (s->slab) { int rc = slab_peer_check(s); if (rc) return rc; }
         s->functional_enqueued = spec;
         if (s->sc_host->done || issued >= max_iters) break;
         chunk = 1;

@@ -236,6 +236,13 @@ EQGPU_API int eqgpu_set_warm_start(eqgpu_solver *s, int mode);
 /* Row-slab mode: cumulative communication counters of this rank since creation -- out[0] all-reduce calls,
  * out[1] doubles all-reduced, out[2] halo exchanges (one NCCL group each), out[3] halo bytes sent.  Zeros on one GPU. */
 EQGPU_API int eqgpu_comm_stats(eqgpu_solver *s, int64_t out[4]);
+/* Row-slab mode, transport of the data path.  By default the ranks of one box map each other's vectors (CUDA IPC over
+ * NVLink / NVSwitch) and a halo exchange is one small kernel that stores my boundary rows into the neighbours' staging buffers and copies theirs out of mine, a scalar
+ * all-reduce one warp that sums every rank's partials in rank order -- no NCCL call per exchange; NCCL remains the
+ * transport of the set-up, of long reductions (per-cell samples) and of everything when peer mapping is unavailable or
+ * EQGPU_SLAB_PEER=0.  out[0] halo-exchange kernels, out[1] peer all-reduces so far; -1, -1 when NCCL carries everything.
+ * The reference's counterpart is PETSc's DMDA ghost update and the KSP's MPI_Allreduce (diffuclass.cpp:364-370,410). */
+EQGPU_API int eqgpu_comm_peer_stats(eqgpu_solver *s, int64_t out[2]);
 /* Verification hook (single GPU, isotropic operator): z = B r, one application of the multigrid preconditioner
  * (the V-cycle of the PCG iteration) to a host vector r (zero on Dirichlet rows); host arrays of nW*nH doubles.
  * Lets the tests compare the streaming smoothers with the shared-memory tile kernels and check the symmetry of B. */

@@ -24,8 +24,10 @@ def problem(D):
     return O, p, cells
 
 
-def worker(rank, world, q_id, q_out, kase):
+def worker(rank, world, q_id, q_out, kase, transport="peer"):
     sys.path.insert(0, ROOT)
+    os.environ["EQGPU_SLAB_PEER"] = "1" if transport == "peer" else "0"
+    os.environ.setdefault("EQGPU_PEER_TIMEOUT_MS", "5000")   # a lost flag fails the test in seconds, it never hangs the GPU
     import torch
     torch.cuda.set_device(rank)
     import eq_b200 as E
@@ -52,12 +54,15 @@ def worker(rank, world, q_id, q_out, kase):
         hist.append((s, g.totalBoundaryFlux, g.stats().iterations, g.last_guess()))
     out = np.zeros(NW * NH)
     g.get_field(out)
-    q_out.put((rank, g0, g1, out[g0 * NW:g1 * NW].copy(), hist))
+    q_out.put((rank, g0, g1, out[g0 * NW:g1 * NW].copy(), hist, g.comm_stats()))
     g.close()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("kase", list(CASES))
-def test_two_gpu_slab_equals_single_gpu_and_oracle(kase):
+def test_two_gpu_slab_equals_single_gpu_and_oracle(kase, transport):
+    """transport "peer": halo rows pulled from the neighbour's memory (CUDA IPC) and scalar all-reduces by one warp over
+    peer memory, no NCCL call on the data path; "nccl": ncclSend/Recv + ncclAllReduce (EQGPU_SLAB_PEER=0)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -66,7 +71,7 @@ def test_two_gpu_slab_equals_single_gpu_and_oracle(kase):
     O, p, cells = problem(CASES[kase])
     ctx = mp.get_context("spawn")
     q_id, q_out = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, 2, q_id, q_out, kase)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, q_id, q_out, kase, transport)) for r in range(2)]
     for pr in procs:
         pr.start()
     res = sorted([q_out.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
@@ -74,6 +79,13 @@ def test_two_gpu_slab_equals_single_gpu_and_oracle(kase):
         pr.join(timeout=60)
         assert pr.exitcode == 0
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == NH   # contiguous partition
+    for r in range(2):   # the transport asked for is the one that ran
+        cs = res[r][5]
+        if transport == "peer":
+            assert cs["peer_exchange_kernels"] > 0 and cs["peer_allreduces"] > 0, cs
+        else:
+            assert cs["peer_exchange_kernels"] == -1, cs
+        assert cs["halo_bytes_sent"] > 0 and cs["allreduce_calls"] > 0, cs
     field = np.concatenate([res[0][3], res[1][3]])
     # oracle with the same coupling
     rng = np.random.default_rng(3)
