@@ -1026,7 +1026,7 @@ k_update_xr(size_t n, double *__restrict__ x, double *__restrict__ r, const doub
 // levels -- that window leaves most of the HBM bandwidth idle.
 __global__ void __launch_bounds__(256)
 k_update_r(size_t n, double *__restrict__ r, const double *__restrict__ Ap, CGScalars *sc, double *partials,
-           unsigned *counter)
+           unsigned *counter, double *out_part = nullptr)
 {
     pdl_trigger();
     pdl_wait();
@@ -1060,6 +1060,10 @@ k_update_r(size_t n, double *__restrict__ r, const double *__restrict__ Ap, CGSc
     }
     double tot[1];
     if (grid_reduce<1>(v, partials, counter, tot)) {
+        if (out_part) {   // row slabs: this rank's share; summed over the ranks, then k_book_x does the bookkeeping
+            *out_part = tot[0];
+            return;
+        }
         sc->rr = tot[0];
         sc->rz_old = sc->rz_new;
         sc->iters += 1;
@@ -1143,6 +1147,17 @@ __global__ void k_book(CGScalars *sc)
     if (sc->done) return;
     sc->rz_old = sc->rz_new;
     sc->iters += 1;
+    if (sc->rr <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
+}
+
+// ... and with the deferred x update (k_update_r / k_update_x) on slabs: the step length and its stamp as k_update_r leaves them
+__global__ void k_book_x(CGScalars *sc)
+{
+    if (sc->done) return;
+    sc->alpha_x = sc->rz_new / sc->pAp;
+    sc->rz_old = sc->rz_new;
+    sc->iters += 1;
+    sc->x_stamp = sc->iters;
     if (sc->rr <= sc->stop2 || sc->iters >= sc->max_iters) sc->done = 1;
 }
 
@@ -1587,8 +1602,15 @@ int solver_setup(eqgpu_solver *s)
         if (const char *e = getenv("EQGPU_T32_BELOW")) s->t32_below = atoi(e);
         if (const char *e = getenv("EQGPU_T32_WIDE")) s->t32_wide = atoi(e) != 0;
         if (const char *e = getenv("EQGPU_INIT_TILE")) s->init_tile = atoi(e) != 0;
-        s->defer_x = !s->slab;
+        // (row slabs: the same split, on the owned rows; EQGPU_SLAB_DEFER_X=0 falls back to the combined k_update_xr)
+        s->defer_x = !s->slab || s->slab_fused;
         if (const char *e = getenv("EQGPU_DEFER_X")) s->defer_x = atoi(e) != 0 && !s->slab;
+        if (s->slab) {
+            if (const char *e = getenv("EQGPU_SLAB_DEFER_X")) s->defer_x = atoi(e) != 0 && s->slab_fused;
+            // (k_update_r / k_update_x use 128-bit accesses from the first owned node on)
+            const LevelDev &L0 = s->levels[0].dev;
+            if (((size_t)L0.own0 * L0.nx) & 1) s->defer_x = false;
+        }
         // Least-squares combination on top of the extrapolations: measured (profiles/r01_ls_guess.md) 3.1 vs 5.3
         // iterations per step at 257^2 and 4.5 vs 5.1 at 512^2 over 40 steps of the bench colony, but 4.9 vs 4.5
         // at 2048^2, where the field is far from steady and PCG converges more slowly from the residual-optimal
@@ -2320,7 +2342,9 @@ static void vcycle_fused(eqgpu_solver *s, cudaStream_t st)
             // few CTAs: it must not crowd the coarse-level kernels out of the SMs, and has ~70 us to finish
             cudaEventRecord(s->ev_fork, st);
             cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
-            k_update_x<<<s->xupd_blocks, 256, 0, s->side_stream>>>(l0.n(), s->u, s->pv, s->pv, s->sc);
+            const size_t xoff = s->slab ? (size_t)l0.dev.own0 * l0.dev.nx : 0;   // slabs: owned rows only (halo rows of p are stale)
+            const size_t xn = s->slab ? (size_t)(l0.dev.own1 - l0.dev.own0) * l0.dev.nx : l0.n();
+            k_update_x<<<s->xupd_blocks, 256, 0, s->side_stream>>>(xn, s->u + xoff, s->pv + xoff, s->pv + xoff, s->sc);
             cudaEventRecord(s->ev_join, s->side_stream);
             s->x_forked = true;
             s->launches++;
@@ -2395,7 +2419,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     if (s->defer_x) {
         if (s->x_forked) cudaStreamWaitEvent(st, s->ev_join, 0);
         else {   // no tiled level ran (tiny grid): nothing to hide behind, update x in line
-            k_update_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, s->pv, s->pv, sc);
+            k_update_x<<<nb1, 256, 0, st>>>(on, s->u + ooff, s->pv + ooff, s->pv + ooff, sc);
             s->launches++;
         }
     }
@@ -2410,7 +2434,7 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     if (sl) slab_allreduce(s, &sc->part_pAp, &sc->pAp, 1);
     if (s->defer_x)
         LAUNCH_K(true, k_update_r, dim3(nb1), dim3(256), 0, st, on, s->r + ooff, (const double *)(s->Ap + ooff), sc,
-                 s->partials, s->counters + 3);
+                 s->partials, s->counters + 3, sl ? &sc->part_rr : (double *)nullptr);
     else
         LAUNCH_K(!sl || s->peer_ok, k_update_xr, dim3(nb1), dim3(256), 0, st, on, s->u + ooff, s->r + ooff,
                  (const double *)(s->pv + ooff), (const double *)(s->Ap + ooff), sc, s->partials, s->counters + 3,
@@ -2418,7 +2442,8 @@ static void enqueue_fused_iteration(eqgpu_solver *s, cudaStream_t st)
     trace_mark(st, "update_xr");
     if (sl) {
         slab_allreduce(s, &sc->part_rr, &sc->rr, 1);
-        k_book<<<1, 1, 0, st>>>(sc);
+        if (s->defer_x) k_book_x<<<1, 1, 0, st>>>(sc);
+        else k_book<<<1, 1, 0, st>>>(sc);
     }
     s->launches += 2;
 }
@@ -2681,7 +2706,10 @@ static int pcg(eqgpu_solver *s)
             // ... and, for the next step's warm start, leave a copy of the solution in the older history slot
             // (ring mode: into the ring's oldest slot, which becomes the newest once the step has converged)
             double *const ring_slot = ring ? s->ring_h[(s->ring_head + RING_MAX - 1) % RING_MAX] : nullptr;
-            k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[4] : ring_slot);
+            if (sl)   // owned rows; the history copy of a slab is made below, once the step has converged (its halo rows are exchanged)
+                k_finish_x<<<nb1, 256, 0, st>>>(on, s->u + ooff, p_odd + ooff, p_even + ooff, sc, (double *)nullptr);
+            else
+                k_finish_x<<<nb1, 256, 0, st>>>(l0.n(), s->u, p_odd, p_even, sc, keep_hist ? s->uh[4] : ring_slot);
             k_mark_x<<<1, 1, 0, st>>>(sc);
             s->launches += 2;
         }
