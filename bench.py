@@ -413,10 +413,11 @@ def run_slab_leg(args, rank, local_rank, world, stream, ids_fn):
 def run_slab_baseline(args, local_rank, stream):
     """N = 1: the weak-scaling baseline of the slab leg -- ONE GPU solving what one rank of the slab leg owns (16384 x 2048
     nodes, 25k moving rods), so that the driver's 1/2/4/8 runs give the slab curve from its first point.  Two figures:
-    `value` is the SAME code path as the N > 1 leg (eqgpu_create_slab with one rank: the slab kernels, no neighbour to
-    exchange with) -- the denominator of weak-scaling efficiency; `single_gpu_path` is the tuned one-GPU path on the same
-    mesh (register-tile smoothers, iteration graph, programmatic launches, deeper warm starts), i.e. what the decomposition
-    costs beyond its communication.  Same step, same timing as run_slab_leg."""
+    `value` goes through eqgpu_create_slab with one rank, which resolves to the one-GPU path (a single rank has no slab:
+    register-tile smoothers, iteration graph) -- the denominator of weak-scaling efficiency is therefore the BEST one-GPU
+    time for a rank's share, and everything a rank of the N > 1 leg loses (tile smoothers instead of register tiles, no
+    iteration graph, exchanges, reductions, rank skew) counts against the efficiency; `single_gpu_path` is the same solve
+    through eqgpu_create, as a cross-check.  Same step, same timing as run_slab_leg."""
     import torch
     import eq_b200 as E
     nW, nH, ncells = args.slab_cols, 2048, 25000
@@ -465,7 +466,7 @@ def run_slab_baseline(args, local_rank, stream):
         ms, it, st = leg(g)
         out.update({"value": 1e3 / ms, "ms_per_step": ms, "pcg_iterations_mean": it, "relres": st.relres,
                     "mg_levels": int(st.levels), "dof_updates_per_sec": nW * nH * 1e3 / ms,
-                    "note": "eqgpu_create_slab with one rank: the code path of the N > 1 leg without a neighbour"})
+                    "note": "eqgpu_create_slab with one rank = the one-GPU path (no decomposition): the best one-GPU time for a rank's share"})
         g.close()
     except Exception as e:   # no NCCL library: the tuned path is all there is to report
         out.update({"value": 1e3 / ms1, "ms_per_step": ms1, "pcg_iterations_mean": it1, "relres": st1.relres,
