@@ -75,6 +75,43 @@ k_apply(LevelDev L, const double *__restrict__ x, double *__restrict__ y, CGScal
     }
 }
 
+// Variable tensor with assembled rows, one GPU: p' = z + beta p and Ap = A p' in ONE pass (the unfused pair k_update_p +
+// k_apply<2> reads and writes p twice).  p' is needed at the six neighbours too, so each thread forms it there from z and
+// the OLD p -- which is why the new direction goes to a second buffer (the p ping-pong of the isotropic path); the
+// neighbours' loads hit L1/L2 (a 32 x 8 block re-reads a one-node rim).  Dirichlet rows: p' = 0 (r and z vanish there).
+__global__ void __launch_bounds__(BX *BY)
+k_apply_p_asm(LevelDev L, const double *__restrict__ z, const double *__restrict__ pin, double *__restrict__ p,
+              double *__restrict__ Ap, CGScalars *sc, double *partials, unsigned *counter, double *out_pAp)
+{
+    if (sc->done) return;
+    const double beta = sc->iters == 0 ? 0.0 : sc->rz_new / sc->rz_old;
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    double v[1] = {0.0};
+    if (i >= L.own0 && i < L.own1 && j < L.nx) {
+        const size_t g = (size_t)i * L.nx + j, nx = (size_t)L.nx;
+        auto pn = [&](size_t q) { return __ldg(z + q) + beta * __ldg(pin + q); };
+        const double pc = pn(g);
+        double out = 0.0;
+        if (!is_dirichlet(L, i, j)) {
+            double c[NBAND];
+            stencil_row<2>(L, i, j, c);
+            const bool hasW = j > 0, hasE = j < L.nx - 1, hasS = i > 0, hasN = i < L.ny - 1;
+            out = c[B_C] * pc;
+            if (hasE) out += c[B_E] * pn(g + 1);
+            if (hasW) out += c[B_W] * pn(g - 1);
+            if (hasN) out += c[B_N] * pn(g + nx);
+            if (hasS) out += c[B_S] * pn(g - nx);
+            if (hasN && hasE) out += c[B_NE] * pn(g + nx + 1);
+            if (hasS && hasW) out += c[B_SW] * pn(g - nx - 1);
+            v[0] = out * pc;
+        }
+        p[g] = pc;
+        Ap[g] = out;
+    }
+    double tot[1];
+    if (grid_reduce<1>(v, partials, counter, tot)) *out_pAp = tot[0];
+}
+
 // Verification hook: y = A x with explicit handling of constrained rows/cols.
 // mode 0: unconstrained operator.  mode 1: Dirichlet rows = identity, columns
 // to Dirichlet nodes dropped (the symmetric elimination CG works with).
@@ -2619,6 +2656,7 @@ static int pcg(eqgpu_solver *s)
     if (ring && s->st.steps > 0) chunk = std::max(1, std::max(s->st.iterations, s->ring_prev_iters));
     s->graph_phase = 0;   // odd iterations leave their search direction in pv2, even ones in pv (k_update_x flush)
     double *const p_odd = s->pv2, *const p_even = s->pv;
+    int tensor_swaps = 0;   // k_apply_p_asm ping-pongs the host's view of pv / pv2; restored after the loop (the isotropic iteration graphs hold the buffers by address)
 #ifdef EQ_KTRACE
     if (s->st.steps == 6) {
         unsigned long long h[256];
@@ -2676,9 +2714,17 @@ static int pcg(eqgpu_solver *s)
                     k_dot<<<nb1, 256, 0, st>>>(on, s->r + ooff, s->z + ooff, sc, s->partials, s->counters + 1,
                                                sl ? &sc->part_rz : &sc->rz_new);
                 if (sl) slab_allreduce(s, &sc->part_rz, &sc->rz_new, 1);
+                static const bool fuse_p = getenv("EQGPU_TENSOR_FUSE_P") == nullptr || atoi(getenv("EQGPU_TENSOR_FUSE_P")) != 0;
+                const bool fused_p = T && L.kC && !sl && fuse_p;
+                if (fused_p) {   // p' = z + beta p and A p' in one pass, p ping-pong
+                    k_apply_p_asm<<<g0, blk, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, sc, s->partials, s->counters + 2, &sc->pAp);
+                    std::swap(s->pv, s->pv2);
+                    ++tensor_swaps;
+                } else
                 k_update_p<<<nb1, 256, 0, st>>>(on, s->z + ooff, s->pv + ooff, sc);
                 if (sl) slab_exchange(s, L, s->pv);
-                if (T && L.kC)
+                if (fused_p) { /* done above */ }
+                else if (T && L.kC)
                     k_apply<2, true><<<g0, blk, 0, st>>>(L, s->pv, s->Ap, sc, s->partials, s->counters + 2,
                                                          sl ? &sc->part_pAp : &sc->pAp);
                 else
@@ -2723,6 +2769,7 @@ static int pcg(eqgpu_solver *s)
         if (s->sc_host->done || issued >= max_iters) break;
         chunk = 1;
     }
+    if (tensor_swaps & 1) std::swap(s->pv, s->pv2);
     s->ring_prev_iters = s->st.iterations;
     s->st.iterations = s->sc_host->iters;
     s->last_guess = s->sc_host->guess;
