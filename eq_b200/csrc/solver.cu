@@ -76,7 +76,7 @@ k_apply(LevelDev L, const double *__restrict__ x, double *__restrict__ y, CGScal
 }
 
 // Variable tensor with assembled rows, one GPU: p' = z + beta p and Ap = A p' in ONE pass (the unfused pair k_update_p +
-// k_apply<2> reads and writes p twice).  p' is needed at the six neighbours too, so each thread forms it there from z and
+// k_apply<2> reads and writes p twice).  Kept opt-in: measured slower than the pair (see the call site).  p' is needed at the six neighbours too, so each thread forms it there from z and
 // the OLD p -- which is why the new direction goes to a second buffer (the p ping-pong of the isotropic path); the
 // neighbours' loads hit L1/L2 (a 32 x 8 block re-reads a one-node rim).  Dirichlet rows: p' = 0 (r and z vanish there).
 __global__ void __launch_bounds__(BX *BY)
@@ -2714,7 +2714,9 @@ static int pcg(eqgpu_solver *s)
                     k_dot<<<nb1, 256, 0, st>>>(on, s->r + ooff, s->z + ooff, sc, s->partials, s->counters + 1,
                                                sl ? &sc->part_rz : &sc->rz_new);
                 if (sl) slab_allreduce(s, &sc->part_rz, &sc->rz_new, 1);
-                static const bool fuse_p = getenv("EQGPU_TENSOR_FUSE_P") == nullptr || atoi(getenv("EQGPU_TENSOR_FUSE_P")) != 0;
+                // opt-in (EQGPU_TENSOR_FUSE_P=1): measured slower on the B200 at 2048^2 -- 195.9 against 208.0 steps/s for the
+                // unfused pair, bit-identical results; fourteen neighbour loads through L1 cost more than a second pass over p
+                static const bool fuse_p = getenv("EQGPU_TENSOR_FUSE_P") != nullptr && atoi(getenv("EQGPU_TENSOR_FUSE_P")) != 0;
                 const bool fused_p = T && L.kC && !sl && fuse_p;
                 if (fused_p) {   // p' = z + beta p and A p' in one pass, p ping-pong
                     k_apply_p_asm<<<g0, blk, 0, st>>>(L, s->z, s->pv, s->pv2, s->Ap, sc, s->partials, s->counters + 2, &sc->pAp);
