@@ -172,7 +172,7 @@ int slab_exchange(eqgpu_solver *s, const LevelDev &L, double *v, int depth) { re
 // synchronisation, instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------------------------------------
 enum { PEER_MAX_JOBS = 4, PEER_F_SLOTS = 8, PEER_AR_MAX = 8, PEER_MAX_WORLD = 16,
-       PEER_FLAG_WORDS = PEER_F_SLOTS + PEER_MAX_WORLD * 2 * PEER_AR_MAX * 2, PEER_PUSH_BLOCKS = 64 };
+       PEER_FLAG_WORDS = PEER_F_SLOTS + PEER_MAX_WORLD * 2 * PEER_AR_MAX * 2, PEER_PUSH_BLOCKS = 148 };
 
 struct PushJob {
     const double *snd_lo, *snd_hi;      // my first / last `depth` owned rows (go to rank-1 / rank+1); null: no neighbour there
@@ -490,7 +490,11 @@ static int peer_flush(eqgpu_solver *s)
     const int R = s->slab_rank, W = s->slab_world;
     const unsigned long long cap = s->peer_stage_cap;
     const int sides = B.n * ((R > 0 ? 1 : 0) + (R + 1 < W ? 1 : 0));
-    const int blocks = (int)std::min<unsigned long long>(PEER_PUSH_BLOCKS, std::max<unsigned long long>(sides, s->peer_batch_fill * (unsigned long long)sides / B.n / 4096));
+    static const int max_blocks = getenv("EQGPU_PEER_BLOCKS") ? std::max(1, atoi(getenv("EQGPU_PEER_BLOCKS"))) : (int)PEER_PUSH_BLOCKS;   // tuning knob
+    // measured, 2 x B200, 16384 x 4096: 16 blocks of 16384 doubles 72.6 steps/s, 32 x 8192 77.8, 64 x 4096 80.9, 128 x 2048 83.0,
+    // 148 x 1024 84.1, 148 x 256 .. 592 x 256 84.5-84.6 -- the exchange wants every SM's load/store slots, not few fat blocks
+    static const int per_block = getenv("EQGPU_PEER_PER_BLOCK") ? std::max(256, atoi(getenv("EQGPU_PEER_PER_BLOCK"))) : 512;
+    const int blocks = (int)std::min<unsigned long long>(max_blocks, std::max<unsigned long long>(sides, s->peer_batch_fill * (unsigned long long)sides / B.n / per_block));
     ++s->peer_xseq;
     // staging: mine is [from_lo: parity 0, 1][from_hi: parity 0, 1]; a neighbour's has the same layout
     uint4 *mine = (uint4 *)s->peer_stage, *lo = (uint4 *)s->peer_stage_lo, *hi = (uint4 *)s->peer_stage_hi;
