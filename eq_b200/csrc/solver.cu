@@ -2785,7 +2785,10 @@ static int pcg(eqgpu_solver *s)
                 sqrt(fabs(h.rrE) / b2), sqrt(fabs(h.rrF) / b2), sqrt(fabs(h.rrL) / b2), h.guess,
                 sqrt(fabs(h.rr_init) / b2), h.lsc[0], h.lsc[1], h.lsc[2], h.iters, sqrt(h.rr / b2));
     }
-    if (s->warm_adaptive && keep_hist && !T && !sl) {
+    // (row slabs too: the norms below are the rank-summed ones, bit-identical on every rank, so all ranks decide alike;
+    // EQGPU_SLAB_ADAPTIVE=0 keeps the full history depth on slabs)
+    static const bool slab_adaptive = getenv("EQGPU_SLAB_ADAPTIVE") == nullptr || atoi(getenv("EQGPU_SLAB_ADAPTIVE")) != 0;
+    if (s->warm_adaptive && keep_hist && !T && (!sl || slab_adaptive)) {
         // Did the extrapolations pay?  gain = squared residual of the previous solution over the best higher candidate's.
         // Below 4 (a factor 2 in norm, a fifth of a PCG iteration) for three steps running, the operator walks over the
         // older solutions cost more than they save: walk the newest one only.  The history keeps rotating at full depth,
