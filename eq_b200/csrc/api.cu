@@ -115,7 +115,7 @@ int eqgpu_comm_stats(eqgpu_solver *s, int64_t out[4])
 int eqgpu_comm_peer_stats(eqgpu_solver *s, int64_t out[2])
 {
     if (!s || !out) return EQGPU_EINVAL;
-    out[0] = s->peer_ok ? s->comm_peer_pulls : -1;   // -1: the peer-memory path is not in use (NCCL carries everything)
+    out[0] = s->peer_ok ? s->comm_peer_exchanges : -1;   // -1: the peer-memory path is not in use (NCCL carries everything)
     out[1] = s->peer_ok ? s->comm_peer_allreduces : -1;
     return 0;
 }

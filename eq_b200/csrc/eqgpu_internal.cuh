@@ -189,7 +189,7 @@ struct eqgpu_solver {
     unsigned long long peer_xseq = 0, peer_arseq = 0;           // exchanges / all-reduces issued so far (same on every rank)
     long long peer_timeout_ns = 20000000000LL;
     void *peer_batch = nullptr;                                 // jobs collected between slab_group_begin/end
-    long long comm_peer_pulls = 0, comm_peer_allreduces = 0;
+    long long comm_peer_exchanges = 0, comm_peer_allreduces = 0;
     int halo = 1;                  // halo rows kept per neighbour (1 unfused, 6 for the tile kernels)
     bool slab_fused = false;
     int scatter_mode = 0;          // 0 direct global atomics, 1 shared-memory-binned

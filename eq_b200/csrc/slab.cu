@@ -508,7 +508,7 @@ static int peer_flush(eqgpu_solver *s)
                                (const uint4 *)(mine + 2 * cap), cap, s->peer_xseq, s->peer_timeout_ns, s->peer_err));
     B.n = 0;
     s->peer_batch_fill = 0;
-    s->comm_peer_pulls++;
+    s->comm_peer_exchanges++;
     s->launches++;
     solver_trace_mark(s->stream, "peer-xch");
     EQ_CUDA(cudaGetLastError());
