@@ -1,7 +1,8 @@
-// Row-slab decomposition plumbing: one-row halo exchange and scalar all-reduce over NCCL
-// (NVLink 5 / NVSwitch between the GPUs of one box).  The reference's precedent is the PETSc DMDA
-// star-stencil halo of diffuclass.cpp:364-370,659-669 and the KSP's internal dot-product
-// MPI_Allreduce (diffuclass.cpp:410 [ext]).
+// Row-slab decomposition plumbing: halo exchange and scalar all-reduce between the GPUs of one box
+// (NVLink 5 / NVSwitch).  The reference's precedent is the PETSc DMDA star-stencil halo of
+// diffuclass.cpp:364-370,659-669 and the KSP's internal dot-product MPI_Allreduce (diffuclass.cpp:410 [ext]).
+// Two transports: peer memory (the default: own kernels over CUDA IPC mappings, second half of this file) and NCCL
+// (set-up, long reductions, fallback).
 //
 // NCCL is resolved at run time (dlopen of libnccl.so.2 -- the copy torch has already loaded in the
 // calling process, or the system one), so libeqgpu.so itself has no link-time dependency on it and
@@ -110,7 +111,7 @@ int slab_exchange2(eqgpu_solver *s, const LevelDev &L, double *v1, double *v2, i
     if (s->peer_ok) {   // peer-memory exchange (a vector too long for the staging buffers goes through NCCL below)
         if (v1 && peer_add(s, L, v1, depth)) v1 = nullptr;
         if (v2 && peer_add(s, L, v2, depth)) v2 = nullptr;
-        if (s->slab_group_depth == 0) {   // not inside a bracket: the pull goes out now
+        if (s->slab_group_depth == 0) {   // not inside a bracket: the exchange kernel goes out now
             int rc = peer_flush(s);
             if (rc) return rc;
         }
