@@ -143,7 +143,7 @@ void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
     myParams = initParams;
     eqgpu_params p;
     decodeParameters(p);
-    int rc = eqgpu_create(&p, &h);
+    int rc = cfg.slabWorld > 1 ? eqgpu_create_slab(&p, cfg.slabRank, cfg.slabWorld, cfg.slabId, &h) : eqgpu_create(&p, &h);
     if (rc != EQGPU_OK) throw std::runtime_error(std::string("gpuHSL: eqgpu_create failed: ") + eqgpu_last_error(nullptr));
     if (cfg.warmStart >= 0) check(eqgpu_set_warm_start(h, cfg.warmStart), "eqgpu_set_warm_start");
     if (cfg.continueOnNoConvergence) check(eqgpu_set_nonconvergence_policy(h, 1), "eqgpu_set_nonconvergence_policy");
@@ -167,6 +167,19 @@ void gpuHSL::initDiffusion(eQ::diffusionSolver::params &initParams)
             shell->mesh_coords[2 * v + 1] = double(i) * p.hy;
             shell->dof_from_vertex[v] = int(v);
         }
+}
+
+void gpuHSL::makeSlabId(unsigned char out[128])
+{
+    if (eqgpu_nccl_unique_id(out) != EQGPU_OK)
+        throw std::runtime_error("gpuHSL::makeSlabId: eqgpu_nccl_unique_id failed (is libnccl.so.2 loadable?)");
+}
+
+void gpuHSL::slabRows(int &g0, int &g1)
+{
+    int32_t a = 0, b = 0;
+    check(eqgpu_slab_rows(h, &a, &b), "eqgpu_slab_rows");
+    g0 = a; g1 = b;
 }
 
 void gpuHSL::pushTensorIfChanged()

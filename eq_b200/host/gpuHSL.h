@@ -46,7 +46,18 @@ public:
         // true: a step whose PCG stops at max_iters above rtol is reported on stderr and the run continues with the best
         // iterate (what the reference does with its solver's diagnostics); false: stepDiffusion throws
         bool continueOnNoConvergence = false;
+        // One large mesh over several GPUs (the reference's precedent is the DMDA split of
+        // diffuclass.cpp:364-370): every MPI rank that owns a GPU builds its gpuHSL with the same slabWorld, its own
+        // slabRank and the 128-byte id made by gpuHSL::makeSlabId on rank 0 and broadcast by the controller (MPI_Bcast).
+        // solution_vector then stays the WHOLE field on every rank: stepDiffusion reads this rank's window of it and
+        // writes back the rows slabRows() names; the controller assembles the rest as it does for its own data.
+        int slabRank = 0, slabWorld = 1;
+        unsigned char slabId[128] = {};
     };
+    // rank 0, before constructing the solvers: the id every rank of a slab group must share (eqgpu_nccl_unique_id)
+    static void makeSlabId(unsigned char out[128]);
+    // the rows [g0, g1) of the mesh this rank owns (the whole mesh without slabs)
+    void slabRows(int &g0, int &g1);
 
     // what simulation.cpp reads through `diffusionSolver->shell->...` (src/simulation.cpp:298-308)
     struct meshShell {

@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <string>
 #include <vector>
 
 #include "gpuFD.h"
@@ -180,6 +182,27 @@ int main(int argc, char **argv)
         memcpy(cfg.boundaries[2], chan, sizeof chan); memcpy(cfg.boundaries[3], chan, sizeof chan);
     } else { fprintf(stderr, "unknown case\n"); return 2; }
 
+    // EQ_TEST_SLAB=<rank>,<world>,<id file>: this process is one rank of a row-slab group (gpuHSL::config::slabRank ...;
+    // INTEGRATION 4d).  Rank 0 makes the id and leaves it in the file -- the stand-in for the controller's MPI_Bcast.
+    if (const char *sl = getenv("EQ_TEST_SLAB")) {
+        int rank = 0, world = 1;
+        char path[512] = {0};
+        if (sscanf(sl, "%d,%d,%511s", &rank, &world, path) != 3) { fprintf(stderr, "bad EQ_TEST_SLAB\n"); return 2; }
+        cfg.slabRank = rank; cfg.slabWorld = world; cfg.device = rank;
+        if (rank == 0) {
+            try { gpuHSL::makeSlabId(cfg.slabId); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return 1; }
+            const std::string tmp = std::string(path) + ".tmp";
+            FILE *f = fopen(tmp.c_str(), "wb");
+            if (!f || fwrite(cfg.slabId, 1, 128, f) != 128) { perror(tmp.c_str()); return 2; }
+            fclose(f);
+            rename(tmp.c_str(), path);
+        } else {
+            FILE *f = nullptr;
+            for (int tries = 0; tries < 600 && !(f = fopen(path, "rb")); ++tries) { struct timespec ts = {0, 100000000}; nanosleep(&ts, nullptr); }
+            if (!f || fread(cfg.slabId, 1, 128, f) != 128) { fprintf(stderr, "no slab id in %s\n", path); return 2; }
+            fclose(f);
+        }
+    }
     std::shared_ptr<gpuHSL> solver = std::make_shared<gpuHSL>(cfg);  // simulation.cpp:207
     // EQ_TEST_SNAPSHOT=<prefix>: the controller's field snapshot (src/main.cpp:148-162 -> writeDiffusionFiles,
     // src/fHSL.cpp:630-636) after the last step, for the read-back test

@@ -109,8 +109,9 @@ EQGPU_API int eqgpu_create(const eqgpu_params *p, eqgpu_solver **out);
 /* Row-slab variant for meshes split over the GPUs of one box (BASELINE configs[4]; the reference's
  * precedent is the DMDA decomposition of diffuclass.cpp:364-370 and the per-layer sub-communicator of
  * src/simulation.cpp:657-666).  One process per GPU calls this with its rank; rank r owns a contiguous
- * block of rows, keeps one halo row per neighbour, exchanges halos and sums the CG scalars over NCCL
- * (loaded at run time from the calling process).  nccl_unique_id: 128 bytes from eqgpu_nccl_unique_id
+ * block of rows, keeps halo rows per neighbour (six with the fused tile kernels), exchanges halos and sums the CG
+ * scalars through peer memory over NVLink (eqgpu_comm_peer_stats) or, as fallback, over NCCL (loaded at run time
+ * from the calling process; also used for the set-up).  nccl_unique_id: 128 bytes from eqgpu_nccl_unique_id
  * on rank 0, distributed by the caller.  Host field pointers always address the WHOLE nW x nH field;
  * a slab reads its window and writes back its owned rows (eqgpu_slab_rows).  Per-cell calls take the
  * full cell list on every rank and return rank-summed samples. */

@@ -165,3 +165,55 @@ def test_field_snapshot_reads_back_to_the_last_digit(oracle, tmp_path, monkeypat
         s.u = s.u + deposit
         s = oracle.step(p, s)
     assert rel(vals, s.u) < 1e-8
+
+
+def test_gpuHSL_row_slabs_two_ranks(oracle, tmp_path):
+    """gpuHSL::config::slabRank / slabWorld / slabId (INTEGRATION 4d): two processes, one GPU each, drive ONE mesh through the
+    C++ class the way two MPI ranks of eQ would -- the id made by gpuHSL::makeSlabId on rank 0 reaches rank 1 through a file
+    (the stand-in for the controller's MPI_Bcast).  Every rank holds the whole solution_vector, steps, and owns the rows
+    eqgpu_slab_plan names; the rows assembled from both ranks equal the oracle's step, and so does the fused tail (rank-summed
+    gather, scatter, resident step)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import eq_b200 as E
+    if not os.path.exists(EXE):
+        subprocess.run(["make", "-C", os.path.dirname(EXE), "all"], check=True)
+    W, H, npm, dt, D, nsteps, world = 100.0, 40.0, 2.0, 0.1, 1200.0, 1, 2
+    p = oracle.Problem(nW=201, nH=81, h=0.5, dt=dt, D=D, bc_type=(1, 1, 1, 1))
+    rng = np.random.default_rng(18)
+    n = 60
+    cells = oracle.make_cells(np.c_[rng.uniform(3, W - 3, n), rng.uniform(3, H - 3, n)], rng.uniform(0, 2 * np.pi, n),
+                              (1 + rng.uniform(size=n)) * 2.1, W, H)
+    deposit = oracle.scatter(cells, npm, p.nH, p.nW, np.full(n, 100.0), np.zeros(p.N))
+    inp = np.concatenate([[W, H, npm, dt, D, nsteps, len(cells)], cells.ravel(), deposit])
+    fin = tmp_path / "in.bin"
+    inp.astype(np.float64).tofile(fin)
+    idfile = tmp_path / "slab.id"
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, EQ_TEST_SLAB=f"{r},{world},{idfile}", EQGPU_PEER_TIMEOUT_MS="5000")
+        procs.append(subprocess.Popen([EXE, "default", str(fin), str(tmp_path / f"out{r}.bin")], env=env))
+    for pr in procs:
+        assert pr.wait(timeout=180) == 0
+    N = p.N
+    u, u_fused, gathered = np.zeros(N), np.zeros(N), []
+    for r in range(world):
+        out = np.fromfile(tmp_path / f"out{r}.bin")
+        assert (int(out[0]), int(out[1])) == (201, 81)
+        g0, g1, _ = E.slab_plan(p.nH, world, r)[0]
+        o = 3
+        u[g0 * p.nW:g1 * p.nW] = out[o:o + N][g0 * p.nW:g1 * p.nW]
+        o += N + 2 * p.nW + nsteps
+        gathered.append(out[o:o + n])
+        u_fused[g0 * p.nW:g1 * p.nW] = out[o + n:o + n + N][g0 * p.nW:g1 * p.nW]
+    s = oracle.new_state(p)
+    s.u = s.u + deposit
+    s = oracle.step(p, s)
+    assert rel(u, s.u) < 1e-8
+    g = oracle.gather(cells, npm, p.nH, p.nW, s.u)
+    for r in range(world):
+        assert rel(gathered[r], g) < 1e-8          # rank-summed: the same on both ranks
+    s.u = oracle.scatter(cells, npm, p.nH, p.nW, np.full(n, 100.0), s.u)
+    s = oracle.step(p, s)
+    assert rel(u_fused, s.u) < 1e-8
